@@ -1,0 +1,196 @@
+"""Pins oracle/ssunet_oracle.py against fixtures produced by the unmodified reference
+(oracle/make_golden.py).  CPU only."""
+import json
+import os
+
+import numpy as np
+import torch
+
+import ssunet_oracle as O
+
+torch.set_num_threads(max(1, min(8, os.cpu_count() or 1)))
+
+
+def _csum(t):
+    t = t.detach().double()
+    return np.array([float(t.sum()), float(t.abs().sum()), float((t * t).sum())])
+
+
+def _close(a, b, rtol=2e-4, atol=1e-6):
+    np.testing.assert_allclose(np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64), rtol=rtol, atol=atol)
+
+
+def test_state_dict_layout_matches_reference(golden_dir):
+    lay = json.load(open(os.path.join(golden_dir, "state_layout.json")))
+    g = [[k, list(s)] for k, s in O.unet_r_ss_v2_spec(3, 3, prefix="net.")]
+    d = [[k, list(s)] for k, s in O.discriminator_spec(3)]
+    assert g == lay["generator"]
+    assert d == lay["discriminator"]
+    assert len(g) == 269
+
+
+def test_generator_fwd_bwd_matches_reference(golden_dir):
+    z = np.load(os.path.join(golden_dir, "generator_fwd_bwd_2x64.npz"))
+    sd = O.portable_state_dict(O.unet_r_ss_v2_spec(3, 3, prefix="net."))
+    x, t = O.synthetic_batch(2, 3, 64, 64, seed=1234)
+    _leaf = O._leafify
+    _leaf(sd)
+    out = O.unet_r_ss_v2(sd, x, True, prefix="net.")
+    loss = O.bce_dice_loss(out, t)
+    keys = O.trainable_keys(sd)
+    grads = torch.autograd.grad(loss, [sd[k] for k in keys], allow_unused=True)
+    _close(out.detach().numpy(), z["logits"], rtol=1e-4, atol=2e-5)
+    _close(float(loss.detach()), float(z["loss"]), rtol=1e-5)
+    assert O.iou_score(out[:, 1:], t[:, 1:]) == float(z["iou"])
+    _close(O.dice_coef(out[:, 1:], t[:, 1:]), z["dice"], rtol=1e-6)
+    gmap = dict(zip(keys, grads))
+    for k, c in zip(z["grad_keys"], z["grad_csum"]):
+        _close(_csum(gmap[str(k)])[1:], c[1:], rtol=2e-3, atol=1e-7)
+    _close(sd["net.conv0_0.bn1.running_mean"].numpy(), z["bn_running_mean"], rtol=1e-5, atol=1e-7)
+    _close(sd["net.conv2_1.bn2.running_var"].numpy(), z["bn_running_var"], rtol=1e-5, atol=1e-7)
+
+
+def test_generator_eval_matches_reference(golden_dir):
+    z = np.load(os.path.join(golden_dir, "generator_eval_1x96.npz"))
+    sd = O.portable_state_dict(O.unet_r_ss_v2_spec(3, 3, prefix="net."))
+    x, _ = O.synthetic_batch(1, 3, 96, 96, seed=77)
+    with torch.no_grad():
+        out = O.unet_r_ss_v2(sd, x, False, prefix="net.")
+    _close(out.numpy(), z["logits"], rtol=1e-4, atol=2e-6)
+
+
+def test_discriminator_matches_reference(golden_dir):
+    z = np.load(os.path.join(golden_dir, "discriminator_fwd_bwd_3x96.npz"))
+    sd = O.portable_state_dict(O.discriminator_spec(3))
+    O._leafify(sd)
+    x, _ = O.synthetic_batch(3, 3, 96, 96, seed=5)
+    x.requires_grad_(True)
+    lo = O.discriminator(sd, x, True)
+    l = torch.nn.functional.binary_cross_entropy_with_logits(lo, torch.ones_like(lo))
+    keys = O.trainable_keys(sd)
+    grads = torch.autograd.grad(l, [x] + [sd[k] for k in keys])
+    _close(lo.detach().numpy(), z["logit"], rtol=1e-4, atol=1e-6)
+    _close(float(l), float(z["loss"]), rtol=1e-5)
+    _close(grads[0].numpy(), z["dx"], rtol=1e-3, atol=1e-9)
+    gmap = dict(zip(keys, grads[1:]))
+    for k, c in zip(z["grad_keys"], z["grad_csum"]):
+        _close(_csum(gmap[str(k)])[1:], c[1:], rtol=2e-3, atol=1e-9)
+
+
+def test_gan_step_matches_reference(golden_dir):
+    z = np.load(os.path.join(golden_dir, "gan_step_2it_2x64.npz"))
+    sd_g = O.portable_state_dict(O.unet_r_ss_v2_spec(3, 3, prefix="net."))
+    sd_d = O.portable_state_dict(O.discriminator_spec(3))
+    # the oracle's generator keys carry the Generator wrapper's "net." prefix
+    og = O.AdamState(O.trainable_keys(sd_g), 2e-5)
+    od = O.AdamState(O.trainable_keys(sd_d), 2e-5)
+    for it in range(2):
+        x, t = O.synthetic_batch(2, 3, 64, 64, seed=1234 + it, blobby=(it == 1))
+        r = _step_prefixed(sd_g, sd_d, og, od, x, t)
+        want = z["it%d_scalars" % it]
+        _close([r["loss"], r["content"], r["adv_g"], r["adv_d"]], want[:4], rtol=2e-5)
+        assert r["iou"] == want[4]
+        _close(r["dice"], want[5], rtol=1e-6)
+        _close(r["logits"].numpy(), z["it%d_logits" % it], rtol=2e-4, atol=3e-5)
+    for k, c in zip(z["g_keys"], z["g_csum"]):
+        # Adam's g/sqrt(v) is sign-like on the first steps, so the plain sum carries +-lr noise
+        # per near-zero-gradient element; |.| and squared sums pin the update magnitude.
+        got = _csum(sd_g[str(k)].double())
+        _close(got[1:], c[1:], rtol=1e-4, atol=1e-4)
+        _close(got[0], c[0], rtol=1e-4, atol=4e-5 * max(1, sd_g[str(k)].numel()) ** 0.5 + 1e-4)
+    for k, c in zip(z["d_keys"], z["d_csum"]):
+        got = _csum(sd_d[str(k)].double())
+        _close(got[1:], c[1:], rtol=1e-4, atol=1e-4)
+        _close(got[0], c[0], rtol=1e-4, atol=4e-5 * max(1, sd_d[str(k)].numel()) ** 0.5 + 1e-4)
+    _close(sd_g["net.final.weight"].detach().numpy(), z["final_weight"], rtol=1e-5, atol=1e-7)
+    _close(sd_d["fc2.weight"].detach().numpy(), z["d_fc2_weight"], rtol=1e-5, atol=1e-7)
+    assert int(sd_d["conv_blocks.1.conv_block.1.num_batches_tracked"]) == 6
+
+
+def _step_prefixed(sd_g, sd_d, og, od, x, t):
+    import functools
+    orig = O.unet_r_ss_v2
+    O.unet_r_ss_v2 = functools.partial(orig, prefix="net.")
+    try:
+        return O.gan_train_step(sd_g, sd_d, og, od, x, t)
+    finally:
+        O.unet_r_ss_v2 = orig
+
+
+def test_syncbn_matches_reference(golden_dir):
+    z = np.load(os.path.join(golden_dir, "syncbn_3shards.npz"))
+    x = torch.from_numpy(z["x"])
+    sd = {"bn.weight": O.portable_tensor("sbn.weight", (8,)), "bn.bias": O.portable_tensor("sbn.bias", (8,)),
+          "bn.running_mean": torch.zeros(8), "bn.running_var": torch.ones(8),
+          "bn.num_batches_tracked": torch.zeros((), dtype=torch.int64)}
+    shards = x.chunk(3, 0)
+
+    # emulate 3 replicas: each sees a shard; the "all-reduce" sums the per-shard statistics
+    def make_sync(all_shards):
+        def sync(s, ss, n):
+            S = sum(sh.reshape(sh.shape[0], 8, -1).sum(0).sum(-1) for sh in all_shards)
+            SS = sum((sh.reshape(sh.shape[0], 8, -1) ** 2).sum(0).sum(-1) for sh in all_shards)
+            return S, SS, sum(sh.shape[0] * sh[0, 0].numel() for sh in all_shards)
+        return sync
+
+    ys = []
+    for sh in shards:
+        sdk = dict(sd)
+        ys.append(O.batch_norm(sdk, "bn", sh, True, sync_stats=make_sync(shards)))
+    _close(torch.cat(ys).numpy(), z["y"], rtol=1e-5, atol=1e-6)
+    _close(sdk["bn.running_mean"].numpy(), z["running_mean"], rtol=1e-6, atol=1e-8)
+    _close(sdk["bn.running_var"].numpy(), z["running_var"], rtol=1e-6, atol=1e-8)
+    assert int(sdk["bn.num_batches_tracked"]) == 0     # parallel path never increments it
+
+
+def test_spectral_norm_matches_reference(golden_dir):
+    z = np.load(os.path.join(golden_dir, "spectral_norm_conv.npz"))
+    w0 = torch.from_numpy(z["w_orig"]).requires_grad_(True)
+    w1, u1, v1, sigma = O.spectral_weight(w0, torch.from_numpy(z["u0"]), torch.from_numpy(z["v0"]), True)
+    _close(w1.detach().numpy(), z["w1"], rtol=1e-5, atol=1e-7)
+    _close(u1.numpy(), z["u1"], rtol=1e-5, atol=1e-7)
+    _close(v1.numpy(), z["v1"], rtol=1e-5, atol=1e-7)
+    y = torch.nn.functional.conv2d(torch.from_numpy(z["x"]), w1, O.portable_tensor("none", (10,)) * 0, 1, 1)
+    (gw,) = torch.autograd.grad(y.sum(), [w0])
+    _close(gw.numpy(), z["gw_orig"], rtol=1e-3, atol=1e-5)
+    assert list(z["sd_keys"]) == ["bias", "weight_orig", "weight_u", "weight_v"]
+
+
+def test_metrics_and_losses_match_reference(golden_dir):
+    z = np.load(os.path.join(golden_dir, "metrics_loss.npz"))
+    lg, tg = torch.from_numpy(z["logits"]), torch.from_numpy(z["target"])
+    assert O.iou_score(lg, tg) == float(z["iou"])
+    assert np.float32(O.dice_coef(lg, tg)) == z["dice"]
+    assert isinstance(O.dice_coef(lg, tg), np.float32)
+    hard = torch.where(lg > 0, torch.full_like(lg, 200.0), torch.full_like(lg, -200.0))
+    assert O.iou_score(hard, tg) == float(z["iou_hard"])
+    assert np.float32(O.dice_coef(hard, tg)) == z["dice_hard"]
+    l3, t3 = torch.from_numpy(z["logits3"]), torch.from_numpy(z["target3"])
+    _close(float(O.bce_dice_loss(l3, t3)), float(z["bcedice"]), rtol=1e-6)
+    _close(float(O.stable_bce(l3, t3)), float(z["stable_bce"]), rtol=1e-6)
+    # numpy's float32 pairwise tree, restated (what the CUDA metric kernel reproduces bit-for-bit)
+    p = z["probs"].reshape(-1)
+    t = z["target"].reshape(-1)
+    assert O.numpy_pairwise_sum_f32(p) == p.sum()
+    assert O.numpy_pairwise_sum_f32(p * t) == (p * t).sum()
+    for n in (0, 1, 7, 8, 9, 127, 128, 129, 255, 1000, 4099):
+        a = np.random.RandomState(n).rand(n).astype(np.float32)
+        assert O.numpy_pairwise_sum_f32(a) == a.sum(), n
+
+
+def test_bce_dice_nan_branch():
+    x = torch.tensor([[[[float("inf"), 1.0], [0.5, -2.0]]]])
+    t = torch.tensor([[[[0.0, 1.0], [1.0, 0.0]]]])
+    out = O.bce_dice_loss(x, t)   # bce = inf -> 2 * dice (losses.py:297-298)
+    p = torch.sigmoid(x).reshape(1, -1)
+    dice = 1 - ((2 * (p * t.reshape(1, -1)).sum(1) + 1e-5) / (p.sum(1) + t.sum() + 1e-5)).sum()
+    assert torch.isfinite(out)
+    _close(float(out), float(2 * dice), rtol=1e-6)
+
+
+def test_xresidual_matches_reference(golden_dir):
+    z = np.load(os.path.join(golden_dir, "xresidual_2x16x20.npz"))
+    sd = O.portable_state_dict(O.xresidual_block_spec(16, 16))
+    x = torch.randn(2, 16, 20, 20, generator=torch.Generator().manual_seed(8))
+    y = O.xresidual_block(sd, x, True)
+    _close(y.numpy(), z["y"], rtol=1e-4, atol=1e-5)
