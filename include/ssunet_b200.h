@@ -1,0 +1,186 @@
+/* ssunet_b200.h — C ABI of libssunet_b200.so (hand-written sm_100a CUDA for the ssUnet-GAN
+ * data-parallel training-step hot path).
+ *
+ * The reference (ideafisher/ssUnet-GAN) has no FFI of its own: every device operation on the
+ * path is an ATen/cuDNN call issued from Python.  Each entry point below
+ * replaces one such call site; the comment above it cites the reference file:line
+ * (relative to scripts/).  The Python host modules in ssunet-gan_b200/ bind these with ctypes.
+ *
+ * Conventions
+ *  - plain pointers + sizes; no torch / C++ types.  All pointers are DEVICE pointers unless the
+ *    name ends in _host.  The caller owns every buffer (inputs, outputs, workspaces).
+ *  - activations are NHWC ("channels last") contiguous: element (n,h,w,c) at ((n*H+h)*W+w)*C+c.
+ *    `dtype` selects their storage type: SSG_F32 or SSG_BF16.  Arithmetic is always fp32.
+ *  - every launch is asynchronous on `stream` (a cudaStream_t passed as void*); no hidden syncs.
+ *  - return value: 0 on success, negative ssg_status on error; ssg_last_error() describes it.
+ *    Nothing throws across the ABI.
+ */
+#ifndef SSUNET_B200_H
+#define SSUNET_B200_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* ssg_stream_t; /* cudaStream_t */
+
+enum ssg_status { SSG_OK = 0, SSG_ERR_INVALID_ARG = -1, SSG_ERR_CUDA = -2, SSG_ERR_UNSUPPORTED = -3 };
+enum ssg_dtype { SSG_F32 = 0, SSG_BF16 = 1 };
+enum ssg_act { SSG_ACT_NONE = 0, SSG_ACT_RELU = 1, SSG_ACT_LEAKY = 2 };
+/* packed-weight layouts produced by ssg_pack_conv_weight */
+enum ssg_wlayout {
+    SSG_W_RSCK = 0, /* [kh][kw][cin][cout]  : forward operand of the SIMT kernels            */
+    SSG_W_RSKC = 1, /* [kh][kw][cout][cin]  : dgrad operand of the SIMT kernels,
+                                              forward (K-major) operand of the tcgen05 kernels */
+    SSG_W_RSCK_FLIP = 2 /* [kh-1-r][kw-1-s][cin][cout]: tcgen05 dgrad (K-major in cout)       */
+};
+
+int ssg_version(void);
+const char* ssg_last_error(void);
+/* SM count / compute capability of the current device (host query). */
+int ssg_device_info(int* sm_count, int* cc_major, int* cc_minor);
+
+/* ---- layout ------------------------------------------------------------------------------ */
+/* module boundary: reference tensors are NCHW fp32 (dataset.py:126-142, archs.py:623). */
+int ssg_nchw_to_nhwc(const float* src, void* dst, int dtype, int n, int c, int h, int w, ssg_stream_t s);
+int ssg_nhwc_to_nchw(const void* src, int dtype, float* dst, int n, int c, int h, int w, ssg_stream_t s);
+/* dtype cast of a flat buffer (fp32 <-> bf16), n elements */
+int ssg_cast(const void* src, int src_dtype, void* dst, int dst_dtype, long long n, ssg_stream_t s);
+/* torch.cat([a, b], 1) (archs.py:651,656,661,664,667) and its adjoint; rows = N*H*W */
+int ssg_concat2(const void* a, int ca, const void* b, int cb, void* out, int dtype, long long rows, ssg_stream_t s);
+int ssg_split2(const void* in, void* a, int ca, void* b, int cb, int dtype, long long rows, ssg_stream_t s);
+/* OIHW fp32 parameter -> packed operand (see ssg_wlayout); `scale_dev` (optional, device float)
+ * multiplies every element (spectral norm's 1/sigma, spectral_norm.py:86-87). */
+int ssg_pack_conv_weight(const float* w_oihw, void* dst, int dtype, int layout, int cout, int cin, int kh, int kw,
+                         const float* inv_scale_dev, ssg_stream_t s);
+
+/* ---- convolution, CUDA-core implicit GEMM (any shape; the only path for tiny channel counts) */
+/* nn.Conv2d forward (archs.py:210,212,218; normalization.py:93-98; models_seg_gan.py:38-39).
+ * w: SSG_W_RSCK in `dtype`; bias fp32 or NULL; y = act(conv(x) + bias). */
+int ssg_conv2d_fwd_simt(const void* x, const void* w, const float* bias, void* y, int dtype, int n, int h, int w_,
+                        int cin, int cout, int kh, int kw, int stride, int pad, int act, float slope, ssg_stream_t s);
+/* dL/dx of the same convolution; w: SSG_W_RSKC; (h,w_) are the INPUT spatial dims, dy is [n,oh,ow,cout]. */
+int ssg_conv2d_dgrad_simt(const void* dy, const void* w, void* dx, int dtype, int n, int h, int w_, int cin, int cout,
+                          int kh, int kw, int stride, int pad, ssg_stream_t s);
+/* dL/dW written as OIHW fp32 (overwrites dw); dy is [n,oh,ow,cout]. */
+int ssg_conv2d_wgrad_simt(const void* x, const void* dy, float* dw_oihw, int dtype, int n, int h, int w_, int cin,
+                          int cout, int kh, int kw, int stride, int pad, ssg_stream_t s);
+
+/* ---- per-channel statistics / batch norm -------------------------------------------------- */
+/* batchnorm.py:59-64 (_sum_ft of x and x**2): sums[0:C] = sum x, sums[C:2C] = sum x^2 (fp64,
+ * overwritten).  With with_sq == 0 only sums[0:C] is produced (bias gradients). */
+int ssg_channel_stats(const void* x, int dtype, long long rows, int c, double* sums, int with_sq, ssg_stream_t s);
+/* batchnorm.py:115-127 (_compute_mean_std) when sync_quirk != 0: inv_std = clamp(var, eps)^-1/2;
+ * otherwise F.batch_norm semantics (var + eps), batchnorm.py:52-55.  Updates running stats in
+ * place (momentum; unbiased variance) when running_mean != NULL. */
+int ssg_bn_finalize(const double* sums, double count, int c, float eps, float momentum, int sync_quirk,
+                    float* running_mean, float* running_var, float* mean, float* inv_std, ssg_stream_t s);
+/* y = act((x - mean) * inv_std * gamma + beta + residual)   (archs.py:231-234, batchnorm.py:73-77,
+ * models_seg_gan.py:43-49).  gamma/beta/residual may be NULL. */
+int ssg_bn_apply(const void* x, const void* residual, void* y, int dtype, long long rows, int c, const float* mean,
+                 const float* inv_std, const float* gamma, const float* beta, int act, float slope, ssg_stream_t s);
+/* eval-mode BN (running stats): same as ssg_bn_apply with inv_std = rsqrt(var + eps) computed inline */
+int ssg_bn_eval_prepare(const float* running_mean, const float* running_var, int c, float eps, float* mean,
+                        float* inv_std, ssg_stream_t s);
+/* backward, pass 1: dz = dy * act'(y); sums[0:C] = sum dz, sums[C:2C] = sum dz * xhat (fp64, overwritten) */
+int ssg_bn_bwd_reduce(const void* dy, const void* y, const void* x, int dtype, long long rows, int c,
+                      const float* mean, const float* inv_std, int act, float slope, double* sums, ssg_stream_t s);
+/* backward, pass 2: dx = gamma*inv_std*(dz - sums0/count - xhat*sums1/count); dres = dz (optional).
+ * With training == 0 (eval mode): dx = gamma*inv_std*dz. */
+int ssg_bn_bwd_apply(const void* dy, const void* y, const void* x, void* dx, void* dres, int dtype, long long rows,
+                     int c, const float* mean, const float* inv_std, const float* gamma, const double* sums,
+                     double count, int act, float slope, int training, ssg_stream_t s);
+/* dgamma = sums[C:2C], dbeta = sums[0:C] as fp32 */
+int ssg_bn_param_grads(const double* sums, int c, float* dgamma, float* dbeta, ssg_stream_t s);
+
+/* ---- pooling / resampling ------------------------------------------------------------------ */
+/* nn.MaxPool2d(2,2,return_indices=True) (archs.py:571): y [n,h/2,w/2,c]; code in {0..3} = 2*dy+dx of the
+ * first maximum in row-major window order (ATen tie rule). */
+int ssg_maxpool2x2_fwd(const void* x, void* y, uint8_t* code, int dtype, int n, int h, int w, int c, ssg_stream_t s);
+/* nn.MaxUnpool2d(2,2) forward (archs.py:572,648,654,659) == max-pool backward: dst [n,2h,2w,c] */
+int ssg_scatter2x2(const void* src, const uint8_t* code, void* dst, int dtype, int n, int h, int w, int c, ssg_stream_t s);
+/* max-unpool backward == gather by code: src [n,2h,2w,c] -> dst [n,h,w,c] */
+int ssg_gather2x2(const void* src, const uint8_t* code, void* dst, int dtype, int n, int h, int w, int c, ssg_stream_t s);
+/* nn.Upsample(scale_factor=2, bilinear, align_corners=True) (archs.py:573,664,667) and adjoint */
+int ssg_upsample2x_fwd(const void* x, void* y, int dtype, int n, int h, int w, int c, ssg_stream_t s);
+int ssg_upsample2x_bwd(const void* dy, void* dx, int dtype, int n, int h, int w, int c, ssg_stream_t s);
+/* nn.AdaptiveAvgPool2d((oh,ow)) + view(batch,-1) (models_seg_gan.py:277,295-296): y is [n, c*oh*ow] in the
+ * reference's NCHW flatten order (channel-major). */
+int ssg_adaptive_avgpool_flat_fwd(const void* x, void* y, int dtype, int n, int h, int w, int c, int oh, int ow, ssg_stream_t s);
+int ssg_adaptive_avgpool_flat_bwd(const void* dy, void* dx, int dtype, int n, int h, int w, int c, int oh, int ow, ssg_stream_t s);
+
+/* ---- SPADE modulation (normalization.py:120) ------------------------------------------------ */
+/* gb is [rows, 2C]: gamma = gb[:, :C], beta = gb[:, C:]; y = x * (1 + gamma) + beta */
+int ssg_spade_modulate_fwd(const void* x, const void* gb, void* y, int dtype, long long rows, int c, ssg_stream_t s);
+/* dx_part = dy*(1+gamma); dgb = [dy*x, dy] */
+int ssg_spade_modulate_bwd(const void* dy, const void* x, const void* gb, void* dx, void* dgb, int dtype, long long rows,
+                           int c, ssg_stream_t s);
+
+/* ---- elementwise ---------------------------------------------------------------------------- */
+int ssg_act_fwd(const void* x, void* y, int dtype, long long n, int act, float slope, ssg_stream_t s);
+int ssg_act_bwd(const void* dy, const void* y, void* dx, int dtype, long long n, int act, float slope, ssg_stream_t s);
+/* out = a + b */
+int ssg_add(const void* a, const void* b, void* out, int dtype, long long n, ssg_stream_t s);
+/* generator_output[isnan] = 0 (train_seg_gan.py:190,269); fp32; bwd zeroes the gradient there */
+int ssg_nan_scrub_fwd(const float* x, float* y, long long n, ssg_stream_t s);
+int ssg_nan_scrub_bwd(const float* dy, const float* x, float* dx, long long n, ssg_stream_t s);
+
+/* ---- linear layers (models_seg_gan.py:279-283,296-298); w fp32 [nout, k] ---------------------- */
+int ssg_linear_fwd(const void* x, const float* w, const float* bias, void* y, int dtype, int m, int k, int nout,
+                   int act, float slope, const float* inv_scale_dev, ssg_stream_t s);
+/* dx32 is ALWAYS fp32 [m][k] (accumulated with atomics over output-feature splits); dy is `dtype` */
+int ssg_linear_dgrad(const void* dy, const float* w, float* dx32, int dtype, int m, int k, int nout,
+                     const float* inv_scale_dev, ssg_stream_t s);
+int ssg_linear_wgrad(const void* x, const void* dy, float* dw, float* dbias, int dtype, int m, int k, int nout, ssg_stream_t s);
+
+/* ---- losses (losses.py:130-136,274-302; train_seg_gan.py:194-195,204-205,221-222) ------------- */
+/* logits/target: fp32 [batch, per_sample] (NCHW flatten).  sums: fp64 [batch][5] =
+ * {sum bce_elem, sum sigmoid*t, sum sigmoid, sum t, sum (x-t)^2}, overwritten. */
+int ssg_seg_loss_sums(const float* logits, const float* target, int batch, long long per_sample, double* sums, ssg_stream_t s);
+/* out[0] = BCEDiceLoss (with the NaN/Inf -> 2*dice branch), out[1] = bce, out[2] = dice term,
+ * out[3] = MSELoss, out[4] = 1.0 if the NaN/Inf branch was taken */
+int ssg_seg_loss_finalize(const double* sums, int batch, long long per_sample, float* out, ssg_stream_t s);
+/* dlogits = g[0] * dBCEDice/dx + g[1] * dMSE/dx + g[2] * dStableBCE/dx ; g_loss is a device float[3] */
+int ssg_seg_loss_bwd(const float* logits, const float* target, const double* sums, const float* out, const float* g_loss,
+                     int batch, long long per_sample, float* dlogits, ssg_stream_t s);
+/* nn.BCEWithLogitsLoss(x, full_like(x, target_value)) mean over n (n small); out: device float */
+int ssg_bce_logits_fwd(const float* x, float target_value, int n, float* out, ssg_stream_t s);
+int ssg_bce_logits_bwd(const float* x, float target_value, int n, const float* g, float* dx, ssg_stream_t s);
+
+/* ---- metrics (metrics.py:6-35) ---------------------------------------------------------------- */
+/* counts[0] = sum((sigmoid(x) > .5) & (t > .5)), counts[1] = sum(|) ; int64, overwritten */
+int ssg_iou_counts(const float* logits, const float* target, long long n, long long* counts, ssg_stream_t s);
+/* NumPy float32 pairwise-summation tree (PW_BLOCKSIZE 128): host helpers + leaf kernel.
+ * ssg_pairwise_leaves_host returns the number of leaves and fills offsets[0..leaves] (offsets[leaves] = n). */
+long long ssg_pairwise_leaves_host(long long n, long long* offsets_host, long long capacity);
+/* leaf_sums: float [3][n_leaves] = per-leaf sums of sigmoid(x)*t, sigmoid(x), t in NumPy's order.
+ * If probs_out != NULL the fp32 probabilities are also written (for oracle comparison). */
+int ssg_dice_leaf_sums(const float* logits, const float* target, const long long* offsets_dev, long long n_leaves,
+                       float* leaf_sums, float* probs_out, ssg_stream_t s);
+/* combines leaf sums (host memory) up the same tree; returns the float32 total */
+float ssg_pairwise_combine_host(const float* leaf_sums_host, long long n);
+
+/* ---- optimiser (srgan_utils.py:186-195 + torch.optim.Adam, train_seg_gan.py:452,468) ---------- */
+int ssg_clamp_(float* g, long long n, float clip, ssg_stream_t s);
+/* g <- clamp(g*grad_scale, +-clip) (clip <= 0: no clamp); Adam update of p, m, v in place */
+int ssg_clamp_adam(float* p, float* g, float* m, float* v, long long n, float lr, float beta1, float beta2, float eps,
+                   float bias_corr1, float bias_corr2, float clip, float grad_scale, ssg_stream_t s);
+
+/* ---- spectral norm (spectral_norm.py:38-88) ---------------------------------------------------- */
+/* One power iteration on W [rows, cols] fp32: v = normalize(W^T u); u = normalize(W v); sigma = u.(W v).
+ * u, v updated in place when do_power_iteration != 0.  inv_sigma: device float[2] = {1/sigma, sigma}.
+ * workspace: (rows + cols) floats. */
+int ssg_spectral_sigma(const float* w, float* u, float* v, int rows, int cols, float eps, int do_power_iteration,
+                       float* inv_sigma, float* workspace, ssg_stream_t s);
+/* dW_orig = (dW_sn - <dW_sn, W_orig> * inv_sigma * u v^T) * inv_sigma ; dot_ws: device double[1] */
+int ssg_spectral_weight_bwd(const float* dw_sn, const float* w_orig, const float* u, const float* v, int rows, int cols,
+                            const float* inv_sigma, double* dot_ws, float* dw_orig, ssg_stream_t s);
+/* out = w * inv_sigma[0] */
+int ssg_scale_by_dev(const float* w, const float* inv_sigma, float* out, long long n, ssg_stream_t s);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SSUNET_B200_H */

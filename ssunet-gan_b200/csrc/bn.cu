@@ -1,0 +1,352 @@
+// Per-channel statistics and (Sync)BatchNorm forward/backward on NHWC activations.
+// HBM-bound: every kernel streams its operands once with 16-byte vector accesses; per-thread
+// fp32 partials -> shared-memory fp32 -> one fp64 atomic per channel per block.
+#include "common.cuh"
+
+namespace ssg {
+
+constexpr int BN_THREADS = 256;
+
+// Generic "reduce over rows, per channel" skeleton.  F(c, vals...) is applied by the callers.
+// REDUCE_MODE 0: stats (sum x, sum x^2); 1: BN backward (sum dz, sum dz*xhat)
+template <typename T, int MODE>
+__global__ void __launch_bounds__(BN_THREADS) channel_reduce_vec_kernel(
+    const T* __restrict__ a,      // MODE0: x        MODE1: dy
+    const T* __restrict__ yout,   // MODE1: post-activation output (may be null when act == none)
+    const T* __restrict__ xin,    // MODE1: BN input x
+    long long rows, int C, long long rows_per_block, const float* __restrict__ mean, const float* __restrict__ inv_std,
+    int act, float slope, int with_sq, double* __restrict__ sums) {
+    constexpr int V = Vec<T>::N;
+    extern __shared__ float sm[];  // [2][C]
+    float* s0 = sm;
+    float* s1 = sm + C;
+    for (int i = threadIdx.x; i < 2 * C; i += BN_THREADS) sm[i] = 0.f;
+    __syncthreads();
+    const int vpr = C / V;
+    const int lanes = vpr < BN_THREADS ? vpr : BN_THREADS;   // threads cooperating on one row
+    const int rpb = BN_THREADS / lanes;                       // rows processed per iteration
+    const int lane = threadIdx.x % lanes, rsub = threadIdx.x / lanes;
+    const long long r_begin = (long long)blockIdx.x * rows_per_block;
+    long long r_end = r_begin + rows_per_block;
+    if (r_end > rows) r_end = rows;
+    if (rsub < rpb) {
+        for (int v = lane; v < vpr; v += lanes) {
+            float acc0[V], acc1[V], mu[V], is[V];
+#pragma unroll
+            for (int i = 0; i < V; ++i) { acc0[i] = 0.f; acc1[i] = 0.f; mu[i] = 0.f; is[i] = 1.f; }
+            if (MODE == 1) {
+#pragma unroll
+                for (int i = 0; i < V; ++i) { mu[i] = mean[v * V + i]; is[i] = inv_std[v * V + i]; }
+            }
+            for (long long r = r_begin + rsub; r < r_end; r += rpb) {
+                const long long off = r * C + (long long)v * V;
+                Vec<T> va; va.load(a + off);
+                float fa[V]; va.get(fa);
+                if (MODE == 0) {
+#pragma unroll
+                    for (int i = 0; i < V; ++i) { acc0[i] += fa[i]; acc1[i] = fmaf(fa[i], fa[i], acc1[i]); }
+                } else {
+                    Vec<T> vx; vx.load(xin + off);
+                    float fx[V]; vx.get(fx);
+                    if (act != SSG_ACT_NONE) {
+                        Vec<T> vy; vy.load(yout + off);
+                        float fy[V]; vy.get(fy);
+#pragma unroll
+                        for (int i = 0; i < V; ++i) fa[i] *= act_grad_from_out(fy[i], act, slope);
+                    }
+#pragma unroll
+                    for (int i = 0; i < V; ++i) {
+                        acc0[i] += fa[i];
+                        acc1[i] = fmaf(fa[i], (fx[i] - mu[i]) * is[i], acc1[i]);
+                    }
+                }
+            }
+#pragma unroll
+            for (int i = 0; i < V; ++i) {
+                atomicAdd(&s0[v * V + i], acc0[i]);
+                if (with_sq) atomicAdd(&s1[v * V + i], acc1[i]);
+            }
+        }
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < C; c += BN_THREADS) {
+        atomicAdd(&sums[c], (double)s0[c]);
+        if (with_sq) atomicAdd(&sums[C + c], (double)s1[c]);
+    }
+}
+
+// Any C (tiny or not a multiple of the vector width): element-strided, shared-memory atomics.
+template <typename T, int MODE>
+__global__ void __launch_bounds__(BN_THREADS) channel_reduce_scalar_kernel(
+    const T* __restrict__ a, const T* __restrict__ yout, const T* __restrict__ xin, long long rows, int C,
+    long long rows_per_block, const float* __restrict__ mean, const float* __restrict__ inv_std, int act, float slope,
+    int with_sq, double* __restrict__ sums) {
+    extern __shared__ float sm[];
+    float* s0 = sm;
+    float* s1 = sm + C;
+    for (int i = threadIdx.x; i < 2 * C; i += BN_THREADS) sm[i] = 0.f;
+    __syncthreads();
+    const long long e_begin = (long long)blockIdx.x * rows_per_block * C;
+    long long e_end = e_begin + rows_per_block * C;
+    if (e_end > rows * C) e_end = rows * C;
+    for (long long e = e_begin + threadIdx.x; e < e_end; e += BN_THREADS) {
+        const int c = (int)(e % C);
+        float v = to_f(a[e]);
+        if (MODE == 0) {
+            atomicAdd(&s0[c], v);
+            if (with_sq) atomicAdd(&s1[c], v * v);
+        } else {
+            if (act != SSG_ACT_NONE) v *= act_grad_from_out(to_f(yout[e]), act, slope);
+            atomicAdd(&s0[c], v);
+            atomicAdd(&s1[c], v * (to_f(xin[e]) - mean[c]) * inv_std[c]);
+        }
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < C; c += BN_THREADS) {
+        atomicAdd(&sums[c], (double)s0[c]);
+        if (with_sq) atomicAdd(&sums[C + c], (double)s1[c]);
+    }
+}
+
+template <typename T, int MODE>
+static int launch_channel_reduce(const T* a, const T* y, const T* x, long long rows, int C, const float* mean,
+                                 const float* inv_std, int act, float slope, int with_sq, double* sums, cudaStream_t st) {
+    constexpr int V = Vec<T>::N;
+    SSG_CHECK_ARG(rows > 0 && C > 0 && C <= 8192, "channel reduce: rows=%lld C=%d unsupported", rows, C);
+    SSG_CHECK_CUDA(cudaMemsetAsync(sums, 0, sizeof(double) * 2 * C, st));
+    // aim for ~8 waves of blocks, but keep >= 64 rows per block so the fp64 atomics stay negligible
+    long long blocks = (long long)sm_count_cached() * 8;
+    long long rpb = (rows + blocks - 1) / blocks;
+    if (rpb < 64) rpb = 64;
+    blocks = (rows + rpb - 1) / rpb;
+    size_t smem = sizeof(float) * 2 * C;
+    if (C % V == 0)
+        channel_reduce_vec_kernel<T, MODE><<<(unsigned)blocks, BN_THREADS, smem, st>>>(a, y, x, rows, C, rpb, mean, inv_std, act, slope, with_sq, sums);
+    else
+        channel_reduce_scalar_kernel<T, MODE><<<(unsigned)blocks, BN_THREADS, smem, st>>>(a, y, x, rows, C, rpb, mean, inv_std, act, slope, with_sq, sums);
+    SSG_CHECK_LAUNCH();
+    return SSG_OK;
+}
+
+__global__ void bn_finalize_kernel(const double* __restrict__ sums, double count, int C, float eps, float momentum,
+                                   int sync_quirk, float* running_mean, float* running_var, float* mean, float* inv_std) {
+    int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    const double s = sums[c], ss = sums[C + c];
+    const double mu = s / count;
+    double sumvar = ss - s * mu;              // batchnorm.py:119
+    if (sumvar < 0) sumvar = 0;
+    const double bias_var = sumvar / count;
+    const double unbias_var = count > 1 ? sumvar / (count - 1) : bias_var;
+    mean[c] = (float)mu;
+    if (sync_quirk) {                         // batchnorm.py:127: bias_var.clamp(eps) ** -0.5
+        float bv = (float)bias_var;
+        inv_std[c] = 1.0f / sqrtf(bv < eps ? eps : bv);
+    } else {
+        inv_std[c] = 1.0f / sqrtf((float)bias_var + eps);
+    }
+    if (running_mean) {
+        running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * (float)mu;
+        running_var[c] = (1.f - momentum) * running_var[c] + momentum * (float)unbias_var;
+    }
+}
+
+__global__ void bn_eval_prepare_kernel(const float* rm, const float* rv, int C, float eps, float* mean, float* inv_std) {
+    int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    mean[c] = rm[c];
+    inv_std[c] = 1.0f / sqrtf(rv[c] + eps);
+}
+
+// y = act(x * sc[c] + sh[c] + residual)
+template <typename T, bool VEC>
+__global__ void __launch_bounds__(256) bn_apply_kernel(const T* __restrict__ x, const T* __restrict__ res, T* __restrict__ y,
+                                                        long long rows, int C, const float* __restrict__ mean,
+                                                        const float* __restrict__ inv_std, const float* __restrict__ gamma,
+                                                        const float* __restrict__ beta, int act, float slope) {
+    extern __shared__ float sm[];
+    float* sc = sm;
+    float* sh = sm + C;
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        float s = inv_std[c] * (gamma ? gamma[c] : 1.f);
+        sc[c] = s;
+        sh[c] = (beta ? beta[c] : 0.f) - mean[c] * s;
+    }
+    __syncthreads();
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    if (VEC) {
+        constexpr int V = Vec<T>::N;
+        const int vpr = C / V;
+        const long long total = rows * vpr;
+        for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+            const int c0 = (int)(i % vpr) * V;
+            Vec<T> vx; vx.load(x + i * V);
+            float f[V]; vx.get(f);
+            float r[V];
+            if (res) { Vec<T> vr; vr.load(res + i * V); vr.get(r); }
+#pragma unroll
+            for (int k = 0; k < V; ++k) {
+                float v = fmaf(f[k], sc[c0 + k], sh[c0 + k]);
+                if (res) v += r[k];
+                f[k] = apply_act(v, act, slope);
+            }
+            Vec<T> vo; vo.set(f); vo.store(y + i * V);
+        }
+    } else {
+        const long long total = rows * C;
+        for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+            const int c = (int)(i % C);
+            float v = fmaf(to_f(x[i]), sc[c], sh[c]);
+            if (res) v += to_f(res[i]);
+            y[i] = from_f<T>(apply_act(v, act, slope));
+        }
+    }
+}
+
+// dz = dy*act'(y); dx = g*is*(dz - m0 - xhat*m1) with m0 = sum0/count, m1 = sum1/count (training) or g*is*dz (eval)
+template <typename T, bool VEC>
+__global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const T* __restrict__ dy, const T* __restrict__ yout,
+                                                            const T* __restrict__ x, T* __restrict__ dx, T* __restrict__ dres,
+                                                            long long rows, int C, const float* __restrict__ mean,
+                                                            const float* __restrict__ inv_std, const float* __restrict__ gamma,
+                                                            const double* __restrict__ sums, double count, int act, float slope,
+                                                            int training) {
+    extern __shared__ float sm[];
+    float* k_scale = sm;          // gamma*inv_std
+    float* k_m0 = sm + C;         // sum dz / count
+    float* k_m1 = sm + 2 * C;     // inv_std * sum(dz xhat) / count
+    float* k_mu = sm + 3 * C;
+    float* k_is = sm + 4 * C;
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        k_scale[c] = inv_std[c] * (gamma ? gamma[c] : 1.f);
+        k_m0[c] = training ? (float)(sums[c] / count) : 0.f;
+        k_m1[c] = training ? (float)(sums[C + c] / count) : 0.f;
+        k_mu[c] = mean[c];
+        k_is[c] = inv_std[c];
+    }
+    __syncthreads();
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    if (VEC) {
+        constexpr int V = Vec<T>::N;
+        const int vpr = C / V;
+        const long long total = rows * vpr;
+        for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+            const int c0 = (int)(i % vpr) * V;
+            Vec<T> vd; vd.load(dy + i * V);
+            float d[V]; vd.get(d);
+            if (act != SSG_ACT_NONE) {
+                Vec<T> vy; vy.load(yout + i * V);
+                float fy[V]; vy.get(fy);
+#pragma unroll
+                for (int k = 0; k < V; ++k) d[k] *= act_grad_from_out(fy[k], act, slope);
+            }
+            if (dres) { Vec<T> vr; vr.set(d); vr.store(dres + i * V); }
+            Vec<T> vx; vx.load(x + i * V);
+            float fx[V]; vx.get(fx);
+#pragma unroll
+            for (int k = 0; k < V; ++k) {
+                const int c = c0 + k;
+                const float xhat = (fx[k] - k_mu[c]) * k_is[c];
+                d[k] = k_scale[c] * (d[k] - k_m0[c] - xhat * k_m1[c]);
+            }
+            Vec<T> vo; vo.set(d); vo.store(dx + i * V);
+        }
+    } else {
+        const long long total = rows * C;
+        for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+            const int c = (int)(i % C);
+            float d = to_f(dy[i]);
+            if (act != SSG_ACT_NONE) d *= act_grad_from_out(to_f(yout[i]), act, slope);
+            if (dres) dres[i] = from_f<T>(d);
+            const float xhat = (to_f(x[i]) - k_mu[c]) * k_is[c];
+            dx[i] = from_f<T>(k_scale[c] * (d - k_m0[c] - xhat * k_m1[c]));
+        }
+    }
+}
+
+__global__ void bn_param_grads_kernel(const double* sums, int C, float* dgamma, float* dbeta) {
+    int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    if (dbeta) dbeta[c] = (float)sums[c];
+    if (dgamma) dgamma[c] = (float)sums[C + c];
+}
+
+}  // namespace ssg
+using namespace ssg;
+
+extern "C" {
+
+int ssg_channel_stats(const void* x, int dtype, long long rows, int c, double* sums, int with_sq, ssg_stream_t s) {
+    SSG_DISPATCH_DTYPE(dtype, return (launch_channel_reduce<T, 0>((const T*)x, nullptr, nullptr, rows, c, nullptr, nullptr,
+                                                                  SSG_ACT_NONE, 0.f, with_sq, sums, (cudaStream_t)s)));
+    return SSG_OK;
+}
+
+int ssg_bn_finalize(const double* sums, double count, int c, float eps, float momentum, int sync_quirk, float* running_mean,
+                    float* running_var, float* mean, float* inv_std, ssg_stream_t s) {
+    SSG_CHECK_ARG(c > 0 && count > 0, "bn_finalize: bad args");
+    bn_finalize_kernel<<<(c + 127) / 128, 128, 0, (cudaStream_t)s>>>(sums, count, c, eps, momentum, sync_quirk, running_mean,
+                                                                     running_var, mean, inv_std);
+    SSG_CHECK_LAUNCH();
+    return SSG_OK;
+}
+
+int ssg_bn_eval_prepare(const float* rm, const float* rv, int c, float eps, float* mean, float* inv_std, ssg_stream_t s) {
+    bn_eval_prepare_kernel<<<(c + 127) / 128, 128, 0, (cudaStream_t)s>>>(rm, rv, c, eps, mean, inv_std);
+    SSG_CHECK_LAUNCH();
+    return SSG_OK;
+}
+
+int ssg_bn_apply(const void* x, const void* residual, void* y, int dtype, long long rows, int c, const float* mean,
+                 const float* inv_std, const float* gamma, const float* beta, int act, float slope, ssg_stream_t s) {
+    SSG_CHECK_ARG(rows > 0 && c > 0 && c <= 8192, "bn_apply: bad shape");
+    size_t smem = sizeof(float) * 2 * c;
+    SSG_DISPATCH_DTYPE(dtype, {
+        constexpr int V = Vec<T>::N;
+        if (c % V == 0) {
+            unsigned g = grid_for(rows * (c / V), 256 * 2);
+            bn_apply_kernel<T, true><<<g, 256, smem, (cudaStream_t)s>>>((const T*)x, (const T*)residual, (T*)y, rows, c, mean, inv_std, gamma, beta, act, slope);
+        } else {
+            unsigned g = grid_for(rows * c, 256 * 4);
+            bn_apply_kernel<T, false><<<g, 256, smem, (cudaStream_t)s>>>((const T*)x, (const T*)residual, (T*)y, rows, c, mean, inv_std, gamma, beta, act, slope);
+        }
+    });
+    SSG_CHECK_LAUNCH();
+    return SSG_OK;
+}
+
+int ssg_bn_bwd_reduce(const void* dy, const void* y, const void* x, int dtype, long long rows, int c, const float* mean,
+                      const float* inv_std, int act, float slope, double* sums, ssg_stream_t s) {
+    SSG_CHECK_ARG(act == SSG_ACT_NONE || y != nullptr, "bn_bwd_reduce: activation needs the forward output");
+    SSG_DISPATCH_DTYPE(dtype, return (launch_channel_reduce<T, 1>((const T*)dy, (const T*)y, (const T*)x, rows, c, mean, inv_std,
+                                                                  act, slope, 1, sums, (cudaStream_t)s)));
+    return SSG_OK;
+}
+
+int ssg_bn_bwd_apply(const void* dy, const void* y, const void* x, void* dx, void* dres, int dtype, long long rows, int c,
+                     const float* mean, const float* inv_std, const float* gamma, const double* sums, double count, int act,
+                     float slope, int training, ssg_stream_t s) {
+    SSG_CHECK_ARG(rows > 0 && c > 0 && c <= 2048, "bn_bwd_apply: bad shape");
+    SSG_CHECK_ARG(act == SSG_ACT_NONE || y != nullptr, "bn_bwd_apply: activation needs the forward output");
+    size_t smem = sizeof(float) * 5 * c;
+    SSG_DISPATCH_DTYPE(dtype, {
+        constexpr int V = Vec<T>::N;
+        if (c % V == 0) {
+            unsigned g = grid_for(rows * (c / V), 256 * 2);
+            bn_bwd_apply_kernel<T, true><<<g, 256, smem, (cudaStream_t)s>>>((const T*)dy, (const T*)y, (const T*)x, (T*)dx, (T*)dres, rows, c, mean, inv_std, gamma, sums, count, act, slope, training);
+        } else {
+            unsigned g = grid_for(rows * c, 256 * 4);
+            bn_bwd_apply_kernel<T, false><<<g, 256, smem, (cudaStream_t)s>>>((const T*)dy, (const T*)y, (const T*)x, (T*)dx, (T*)dres, rows, c, mean, inv_std, gamma, sums, count, act, slope, training);
+        }
+    });
+    SSG_CHECK_LAUNCH();
+    return SSG_OK;
+}
+
+int ssg_bn_param_grads(const double* sums, int c, float* dgamma, float* dbeta, ssg_stream_t s) {
+    bn_param_grads_kernel<<<(c + 127) / 128, 128, 0, (cudaStream_t)s>>>(sums, c, dgamma, dbeta);
+    SSG_CHECK_LAUNCH();
+    return SSG_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,178 @@
+// Layout / dtype plumbing kernels: NCHW<->NHWC, casts, concat/split, weight packing.
+#include "common.cuh"
+
+namespace ssg {
+
+// [n][C][HW] (float) -> [n][HW][C] (T): 32x32 smem tile transpose, coalesced on both sides.
+template <typename T>
+__global__ void nchw_to_nhwc_kernel(const float* __restrict__ src, T* __restrict__ dst, int C, long long HW) {
+    __shared__ float tile[32][33];
+    const int n = blockIdx.z;
+    const long long p0 = (long long)blockIdx.x * 32;
+    const int c0 = blockIdx.y * 32;
+    const float* s = src + (long long)n * C * HW;
+    T* d = dst + (long long)n * C * HW;
+    for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+        int c = c0 + i;
+        long long p = p0 + threadIdx.x;
+        tile[i][threadIdx.x] = (c < C && p < HW) ? s[(long long)c * HW + p] : 0.f;
+    }
+    __syncthreads();
+    for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+        long long p = p0 + i;
+        int c = c0 + threadIdx.x;
+        if (c < C && p < HW) d[p * C + c] = from_f<T>(tile[threadIdx.x][i]);
+    }
+}
+
+template <typename T>
+__global__ void nhwc_to_nchw_kernel(const T* __restrict__ src, float* __restrict__ dst, int C, long long HW) {
+    __shared__ float tile[32][33];
+    const int n = blockIdx.z;
+    const long long p0 = (long long)blockIdx.x * 32;
+    const int c0 = blockIdx.y * 32;
+    const T* s = src + (long long)n * C * HW;
+    float* d = dst + (long long)n * C * HW;
+    for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+        long long p = p0 + i;
+        int c = c0 + threadIdx.x;
+        tile[i][threadIdx.x] = (c < C && p < HW) ? to_f(s[p * C + c]) : 0.f;
+    }
+    __syncthreads();
+    for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+        int c = c0 + i;
+        long long p = p0 + threadIdx.x;
+        if (c < C && p < HW) d[(long long)c * HW + p] = tile[threadIdx.x][i];
+    }
+}
+
+template <typename S, typename D>
+__global__ void cast_kernel(const S* __restrict__ src, D* __restrict__ dst, long long n) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (; i < n; i += stride) dst[i] = from_f<D>(to_f(src[i]));
+}
+
+// out[row][0:ca] = a[row], out[row][ca:ca+cb] = b[row]; 16-byte vectors when channels allow.
+template <typename T, bool SPLIT>
+__global__ void concat2_kernel(T* __restrict__ a, int ca, T* __restrict__ b, int cb, T* __restrict__ cat, long long rows) {
+    constexpr int V = Vec<T>::N;
+    const int ct = ca + cb;
+    const int vpr = ct / V;  // vectors per row
+    const long long total = rows * vpr;
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (; i < total; i += stride) {
+        long long r = i / vpr;
+        int cv = (int)(i - r * vpr) * V;
+        T* part = (cv < ca) ? (a + r * ca + cv) : (b + r * cb + (cv - ca));
+        T* whole = cat + r * ct + cv;
+        Vec<T> v;
+        if (SPLIT) { v.load(whole); v.store(part); }
+        else { v.load(part); v.store(whole); }
+    }
+}
+template <typename T, bool SPLIT>
+__global__ void concat2_scalar_kernel(T* __restrict__ a, int ca, T* __restrict__ b, int cb, T* __restrict__ cat, long long rows) {
+    const int ct = ca + cb;
+    const long long total = rows * ct;
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (; i < total; i += stride) {
+        long long r = i / ct;
+        int c = (int)(i - r * ct);
+        T* part = (c < ca) ? (a + r * ca + c) : (b + r * cb + (c - ca));
+        if (SPLIT) *part = cat[i]; else cat[i] = *part;
+    }
+}
+
+// OIHW fp32 -> packed layouts.  One thread per destination element.
+template <typename T>
+__global__ void pack_weight_kernel(const float* __restrict__ w, T* __restrict__ dst, int layout, int cout, int cin, int kh,
+                                   int kw, const float* __restrict__ inv_scale) {
+    const long long total = (long long)cout * cin * kh * kw;
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    const float sc = inv_scale ? inv_scale[0] : 1.f;
+    int r, s, c, k;
+    long long t = i;
+    if (layout == SSG_W_RSKC) {  // [r][s][k][c]
+        c = (int)(t % cin); t /= cin; k = (int)(t % cout); t /= cout; s = (int)(t % kw); r = (int)(t / kw);
+    } else {                     // [r][s][c][k] (optionally flipped taps)
+        k = (int)(t % cout); t /= cout; c = (int)(t % cin); t /= cin; s = (int)(t % kw); r = (int)(t / kw);
+        if (layout == SSG_W_RSCK_FLIP) { r = kh - 1 - r; s = kw - 1 - s; }
+    }
+    dst[i] = from_f<T>(w[(((long long)k * cin + c) * kh + r) * kw + s] * sc);
+}
+
+}  // namespace ssg
+using namespace ssg;
+
+template <bool SPLIT>
+static int concat_impl(void* a, int ca, void* b, int cb, void* cat, int dtype, long long rows, ssg_stream_t s) {
+    SSG_CHECK_ARG(ca > 0 && cb > 0 && rows > 0, "concat2: bad shape");
+    SSG_DISPATCH_DTYPE(dtype, {
+        constexpr int V = Vec<T>::N;
+        if (ca % V == 0 && cb % V == 0) {
+            unsigned g = grid_for(rows * ((ca + cb) / V), 256);
+            concat2_kernel<T, SPLIT><<<g, 256, 0, (cudaStream_t)s>>>((T*)a, ca, (T*)b, cb, (T*)cat, rows);
+        } else {
+            unsigned g = grid_for(rows * (ca + cb), 256);
+            concat2_scalar_kernel<T, SPLIT><<<g, 256, 0, (cudaStream_t)s>>>((T*)a, ca, (T*)b, cb, (T*)cat, rows);
+        }
+    });
+    SSG_CHECK_LAUNCH();
+    return SSG_OK;
+}
+
+extern "C" {
+
+int ssg_nchw_to_nhwc(const float* src, void* dst, int dtype, int n, int c, int h, int w, ssg_stream_t s) {
+    SSG_CHECK_ARG(n > 0 && c > 0 && h > 0 && w > 0 && n <= 65535, "nchw_to_nhwc: bad shape");
+    long long hw = (long long)h * w;
+    dim3 grid((unsigned)((hw + 31) / 32), (unsigned)((c + 31) / 32), (unsigned)n), block(32, 8);
+    SSG_DISPATCH_DTYPE(dtype, nchw_to_nhwc_kernel<T><<<grid, block, 0, (cudaStream_t)s>>>(src, (T*)dst, c, hw));
+    SSG_CHECK_LAUNCH();
+    return SSG_OK;
+}
+
+int ssg_nhwc_to_nchw(const void* src, int dtype, float* dst, int n, int c, int h, int w, ssg_stream_t s) {
+    SSG_CHECK_ARG(n > 0 && c > 0 && h > 0 && w > 0 && n <= 65535, "nhwc_to_nchw: bad shape");
+    long long hw = (long long)h * w;
+    dim3 grid((unsigned)((hw + 31) / 32), (unsigned)((c + 31) / 32), (unsigned)n), block(32, 8);
+    SSG_DISPATCH_DTYPE(dtype, nhwc_to_nchw_kernel<T><<<grid, block, 0, (cudaStream_t)s>>>((const T*)src, dst, c, hw));
+    SSG_CHECK_LAUNCH();
+    return SSG_OK;
+}
+
+int ssg_cast(const void* src, int sd, void* dst, int dd, long long n, ssg_stream_t s) {
+    if (n <= 0) return SSG_OK;
+    unsigned g = grid_for(n, 256 * 4);
+    cudaStream_t st = (cudaStream_t)s;
+    if (sd == SSG_F32 && dd == SSG_BF16) cast_kernel<float, bf16><<<g, 256, 0, st>>>((const float*)src, (bf16*)dst, n);
+    else if (sd == SSG_BF16 && dd == SSG_F32) cast_kernel<bf16, float><<<g, 256, 0, st>>>((const bf16*)src, (float*)dst, n);
+    else if (sd == SSG_F32 && dd == SSG_F32) cast_kernel<float, float><<<g, 256, 0, st>>>((const float*)src, (float*)dst, n);
+    else if (sd == SSG_BF16 && dd == SSG_BF16) cast_kernel<bf16, bf16><<<g, 256, 0, st>>>((const bf16*)src, (bf16*)dst, n);
+    else { set_error("cast: bad dtypes"); return SSG_ERR_INVALID_ARG; }
+    SSG_CHECK_LAUNCH();
+    return SSG_OK;
+}
+
+int ssg_concat2(const void* a, int ca, const void* b, int cb, void* out, int dtype, long long rows, ssg_stream_t s) {
+    return concat_impl<false>((void*)a, ca, (void*)b, cb, out, dtype, rows, s);
+}
+int ssg_split2(const void* in, void* a, int ca, void* b, int cb, int dtype, long long rows, ssg_stream_t s) {
+    return concat_impl<true>(a, ca, b, cb, (void*)in, dtype, rows, s);
+}
+
+int ssg_pack_conv_weight(const float* w, void* dst, int dtype, int layout, int cout, int cin, int kh, int kw,
+                         const float* inv_scale_dev, ssg_stream_t s) {
+    SSG_CHECK_ARG(cout > 0 && cin > 0 && kh > 0 && kw > 0 && layout >= 0 && layout <= 2, "pack_conv_weight: bad args");
+    long long total = (long long)cout * cin * kh * kw;
+    unsigned g = (unsigned)((total + 255) / 256);
+    SSG_DISPATCH_DTYPE(dtype, pack_weight_kernel<T><<<g, 256, 0, (cudaStream_t)s>>>(w, (T*)dst, layout, cout, cin, kh, kw, inv_scale_dev));
+    SSG_CHECK_LAUNCH();
+    return SSG_OK;
+}
+
+}  // extern "C"

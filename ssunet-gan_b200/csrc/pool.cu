@@ -1,0 +1,304 @@
+// Max-pool 2x2 with a 2-bit argmax code (instead of ATen's int64 flat indices), max-unpool,
+// bilinear x2 (align_corners=True) and adaptive average pooling.  All HBM-bound, NHWC.
+#include "common.cuh"
+
+namespace ssg {
+
+// ---- max pool / unpool -----------------------------------------------------------------------
+// One thread per (output pixel, channel vector).  Tie rule = ATen max_pool2d: scan the window in
+// row-major order, replace when (val > max) || isnan(val).
+template <typename T, bool VEC>
+__global__ void __launch_bounds__(256) maxpool2x2_kernel(const T* __restrict__ x, T* __restrict__ y, uint8_t* __restrict__ code,
+                                                          int n, int h, int w, int c) {
+    constexpr int V = VEC ? Vec<T>::N : 1;
+    const int oh = h / 2, ow = w / 2, vpr = c / V;
+    const long long total = (long long)n * oh * ow * vpr;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+        const int cv = (int)(i % vpr);
+        long long p = i / vpr;
+        const int ox = (int)(p % ow); p /= ow;
+        const int oy = (int)(p % oh);
+        const int nn = (int)(p / oh);
+        const long long base = (((long long)nn * h + 2 * oy) * w + 2 * ox) * c + (long long)cv * V;
+        float best[V]; int arg[V];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const long long off = base + ((long long)(q >> 1) * w + (q & 1)) * c;
+            float f[V];
+            if (VEC) { Vec<T> v; v.load(x + off); v.get(f); } else { f[0] = to_f(x[off]); }
+#pragma unroll
+            for (int k = 0; k < V; ++k) {
+                if (q == 0 || f[k] > best[k] || f[k] != f[k]) { best[k] = f[k]; arg[k] = q; }
+            }
+        }
+        const long long o = i * V;
+        if (VEC) {
+            Vec<T> v; v.set(best); v.store(y + o);
+            if (V == 8) {
+                uint2 cc;
+                cc.x = arg[0] | (arg[1] << 8) | (arg[2] << 16) | (arg[3] << 24);
+                cc.y = arg[4] | (arg[5] << 8) | (arg[6] << 16) | (arg[7] << 24);
+                *reinterpret_cast<uint2*>(code + o) = cc;
+            } else {
+                *reinterpret_cast<uint32_t*>(code + o) = arg[0] | (arg[1] << 8) | (arg[2] << 16) | (arg[3] << 24);
+            }
+        } else {
+            y[o] = from_f<T>(best[0]);
+            code[o] = (uint8_t)arg[0];
+        }
+    }
+}
+
+// dst[n, 2y+dy, 2x+dx, c] = src[n,y,x,c] if code == 2*dy+dx else 0.  One thread writes all four.
+template <typename T, bool VEC>
+__global__ void __launch_bounds__(256) scatter2x2_kernel(const T* __restrict__ src, const uint8_t* __restrict__ code,
+                                                          T* __restrict__ dst, int n, int h, int w, int c) {
+    constexpr int V = VEC ? Vec<T>::N : 1;
+    const int vpr = c / V;
+    const long long total = (long long)n * h * w * vpr;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+        const int cv = (int)(i % vpr);
+        long long p = i / vpr;
+        const int x_ = (int)(p % w); p /= w;
+        const int y_ = (int)(p % h);
+        const int nn = (int)(p / h);
+        float f[V]; uint8_t cd[V];
+        if (VEC) { Vec<T> v; v.load(src + i * V); v.get(f); } else { f[0] = to_f(src[i]); }
+#pragma unroll
+        for (int k = 0; k < V; ++k) cd[k] = code[i * V + k];
+        const long long base = (((long long)nn * 2 * h + 2 * y_) * 2 * w + 2 * x_) * c + (long long)cv * V;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            float o[V];
+#pragma unroll
+            for (int k = 0; k < V; ++k) o[k] = (cd[k] == q) ? f[k] : 0.f;
+            const long long off = base + ((long long)(q >> 1) * 2 * w + (q & 1)) * c;
+            if (VEC) { Vec<T> v; v.set(o); v.store(dst + off); } else { dst[off] = from_f<T>(o[0]); }
+        }
+    }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) gather2x2_kernel(const T* __restrict__ src, const uint8_t* __restrict__ code,
+                                                         T* __restrict__ dst, int n, int h, int w, int c) {
+    const long long total = (long long)n * h * w * c;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+        const int cc = (int)(i % c);
+        long long p = i / c;
+        const int x_ = (int)(p % w); p /= w;
+        const int y_ = (int)(p % h);
+        const int nn = (int)(p / h);
+        const int q = code[i];
+        dst[i] = src[(((long long)nn * 2 * h + 2 * y_ + (q >> 1)) * 2 * w + 2 * x_ + (q & 1)) * c + cc];
+    }
+}
+
+// ---- bilinear x2, align_corners=True (ATen upsample_bilinear2d: scale = (in-1)/(out-1)) ----------
+__device__ __forceinline__ void src_index(int o, float scale, int in_size, int& i0, int& i1, float& l1) {
+    const float s = scale * (float)o;
+    i0 = (int)s;
+    if (i0 > in_size - 1) i0 = in_size - 1;
+    i1 = i0 + (i0 < in_size - 1 ? 1 : 0);
+    l1 = s - (float)i0;
+}
+
+template <typename T, bool VEC>
+__global__ void __launch_bounds__(256) upsample2x_fwd_kernel(const T* __restrict__ x, T* __restrict__ y, int n, int h, int w, int c) {
+    constexpr int V = VEC ? Vec<T>::N : 1;
+    const int oh = 2 * h, ow = 2 * w, vpr = c / V;
+    const float sy = oh > 1 ? (float)(h - 1) / (float)(oh - 1) : 0.f;
+    const float sx = ow > 1 ? (float)(w - 1) / (float)(ow - 1) : 0.f;
+    const long long total = (long long)n * oh * ow * vpr;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+        const int cv = (int)(i % vpr);
+        long long p = i / vpr;
+        const int ox = (int)(p % ow); p /= ow;
+        const int oy = (int)(p % oh);
+        const int nn = (int)(p / oh);
+        int y0, y1, x0, x1; float ly, lx;
+        src_index(oy, sy, h, y0, y1, ly);
+        src_index(ox, sx, w, x0, x1, lx);
+        const float hy = 1.f - ly, hx = 1.f - lx;
+        const T* b = x + (long long)nn * h * w * c + (long long)cv * V;
+        float f00[V], f01[V], f10[V], f11[V], o[V];
+        if (VEC) {
+            Vec<T> v;
+            v.load(b + ((long long)y0 * w + x0) * c); v.get(f00);
+            v.load(b + ((long long)y0 * w + x1) * c); v.get(f01);
+            v.load(b + ((long long)y1 * w + x0) * c); v.get(f10);
+            v.load(b + ((long long)y1 * w + x1) * c); v.get(f11);
+        } else {
+            f00[0] = to_f(b[((long long)y0 * w + x0) * c]); f01[0] = to_f(b[((long long)y0 * w + x1) * c]);
+            f10[0] = to_f(b[((long long)y1 * w + x0) * c]); f11[0] = to_f(b[((long long)y1 * w + x1) * c]);
+        }
+#pragma unroll
+        for (int k = 0; k < V; ++k) o[k] = hy * (hx * f00[k] + lx * f01[k]) + ly * (hx * f10[k] + lx * f11[k]);
+        if (VEC) { Vec<T> v; v.set(o); v.store(y + i * V); } else { y[i] = from_f<T>(o[0]); }
+    }
+}
+
+// Adjoint in gather form: every input pixel scans the (few) output rows/cols whose stencil touches it,
+// recomputing the forward's index arithmetic exactly.
+template <typename T, bool VEC>
+__global__ void __launch_bounds__(256) upsample2x_bwd_kernel(const T* __restrict__ dy, T* __restrict__ dx, int n, int h, int w, int c) {
+    constexpr int V = VEC ? Vec<T>::N : 1;
+    const int oh = 2 * h, ow = 2 * w, vpr = c / V;
+    const float sy = oh > 1 ? (float)(h - 1) / (float)(oh - 1) : 0.f;
+    const float sx = ow > 1 ? (float)(w - 1) / (float)(ow - 1) : 0.f;
+    const long long total = (long long)n * h * w * vpr;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+        const int cv = (int)(i % vpr);
+        long long p = i / vpr;
+        const int ix = (int)(p % w); p /= w;
+        const int iy = (int)(p % h);
+        const int nn = (int)(p / h);
+        // candidate outputs: those with floor(scale*o) in {i-1, i}; scale < 0.5 so o is within [2i-3, 2i+4]
+        int oy_lo = 2 * iy - 3, oy_hi = 2 * iy + 4, ox_lo = 2 * ix - 3, ox_hi = 2 * ix + 4;
+        if (h == 1) { oy_lo = 0; oy_hi = oh - 1; }
+        if (w == 1) { ox_lo = 0; ox_hi = ow - 1; }
+        oy_lo = oy_lo < 0 ? 0 : oy_lo; ox_lo = ox_lo < 0 ? 0 : ox_lo;
+        oy_hi = oy_hi > oh - 1 ? oh - 1 : oy_hi; ox_hi = ox_hi > ow - 1 ? ow - 1 : ox_hi;
+        float acc[V];
+#pragma unroll
+        for (int k = 0; k < V; ++k) acc[k] = 0.f;
+        const T* b = dy + (long long)nn * oh * ow * c + (long long)cv * V;
+        for (int oy = oy_lo; oy <= oy_hi; ++oy) {
+            int y0, y1; float ly;
+            src_index(oy, sy, h, y0, y1, ly);
+            float wy = 0.f;
+            if (y0 == iy) wy += 1.f - ly;
+            if (y1 == iy) wy += ly;
+            if (wy == 0.f) continue;
+            for (int ox = ox_lo; ox <= ox_hi; ++ox) {
+                int x0, x1; float lx;
+                src_index(ox, sx, w, x0, x1, lx);
+                float wx = 0.f;
+                if (x0 == ix) wx += 1.f - lx;
+                if (x1 == ix) wx += lx;
+                if (wx == 0.f) continue;
+                float f[V];
+                if (VEC) { Vec<T> v; v.load(b + ((long long)oy * ow + ox) * c); v.get(f); }
+                else { f[0] = to_f(b[((long long)oy * ow + ox) * c]); }
+#pragma unroll
+                for (int k = 0; k < V; ++k) acc[k] = fmaf(wy * wx, f[k], acc[k]);
+            }
+        }
+        if (VEC) { Vec<T> v; v.set(acc); v.store(dx + i * V); } else { dx[i] = from_f<T>(acc[0]); }
+    }
+}
+
+// ---- adaptive average pool to (oh, ow), flattened channel-major like NCHW .view(batch, -1) -----------
+// ATen window: [floor(o*in/out), ceil((o+1)*in/out))
+template <typename T>
+__global__ void __launch_bounds__(256) adaptive_avgpool_flat_fwd_kernel(const T* __restrict__ x, T* __restrict__ y, int n, int h,
+                                                                         int w, int c, int oh, int ow) {
+    const long long total = (long long)n * oh * ow * c;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+        const int cc = (int)(i % c);       // threads adjacent in c -> coalesced reads
+        long long p = i / c;
+        const int ox = (int)(p % ow); p /= ow;
+        const int oy = (int)(p % oh);
+        const int nn = (int)(p / oh);
+        const int y0 = (oy * h) / oh, y1 = ((oy + 1) * h + oh - 1) / oh;
+        const int x0 = (ox * w) / ow, x1 = ((ox + 1) * w + ow - 1) / ow;
+        float acc = 0.f;
+        for (int yy = y0; yy < y1; ++yy)
+            for (int xx = x0; xx < x1; ++xx) acc += to_f(x[(((long long)nn * h + yy) * w + xx) * c + cc]);
+        y[(long long)nn * c * oh * ow + (long long)cc * oh * ow + oy * ow + ox] = from_f<T>(acc / (float)((y1 - y0) * (x1 - x0)));
+    }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) adaptive_avgpool_flat_bwd_kernel(const T* __restrict__ dy, T* __restrict__ dx, int n, int h,
+                                                                         int w, int c, int oh, int ow) {
+    const long long total = (long long)n * h * w * c;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+        const int cc = (int)(i % c);
+        long long p = i / c;
+        const int xx = (int)(p % w); p /= w;
+        const int yy = (int)(p % h);
+        const int nn = (int)(p / h);
+        float acc = 0.f;
+        // windows may overlap when in % out != 0: scan candidate outputs
+        int oy_lo = (yy * oh) / h - 1, oy_hi = ((yy + 1) * oh + h - 1) / h;
+        int ox_lo = (xx * ow) / w - 1, ox_hi = ((xx + 1) * ow + w - 1) / w;
+        oy_lo = oy_lo < 0 ? 0 : oy_lo; ox_lo = ox_lo < 0 ? 0 : ox_lo;
+        oy_hi = oy_hi > oh - 1 ? oh - 1 : oy_hi; ox_hi = ox_hi > ow - 1 ? ow - 1 : ox_hi;
+        for (int oy = oy_lo; oy <= oy_hi; ++oy) {
+            const int y0 = (oy * h) / oh, y1 = ((oy + 1) * h + oh - 1) / oh;
+            if (yy < y0 || yy >= y1) continue;
+            for (int ox = ox_lo; ox <= ox_hi; ++ox) {
+                const int x0 = (ox * w) / ow, x1 = ((ox + 1) * w + ow - 1) / ow;
+                if (xx < x0 || xx >= x1) continue;
+                acc += to_f(dy[(long long)nn * c * oh * ow + (long long)cc * oh * ow + oy * ow + ox]) / (float)((y1 - y0) * (x1 - x0));
+            }
+        }
+        dx[i] = from_f<T>(acc);
+    }
+}
+
+}  // namespace ssg
+using namespace ssg;
+
+#define SSG_VEC_LAUNCH(kernel, total_expr, ...)                                                         \
+    SSG_DISPATCH_DTYPE(dtype, {                                                                         \
+        constexpr int V = Vec<T>::N;                                                                    \
+        if (c % V == 0) {                                                                               \
+            unsigned g = grid_for((total_expr) / V, 256);                                               \
+            kernel<T, true><<<g, 256, 0, (cudaStream_t)s>>>(__VA_ARGS__);                               \
+        } else {                                                                                        \
+            unsigned g = grid_for((total_expr), 256);                                                   \
+            kernel<T, false><<<g, 256, 0, (cudaStream_t)s>>>(__VA_ARGS__);                              \
+        }                                                                                               \
+    });                                                                                                 \
+    SSG_CHECK_LAUNCH();                                                                                 \
+    return SSG_OK
+
+extern "C" {
+
+int ssg_maxpool2x2_fwd(const void* x, void* y, uint8_t* code, int dtype, int n, int h, int w, int c, ssg_stream_t s) {
+    SSG_CHECK_ARG(n > 0 && h >= 2 && w >= 2 && c > 0, "maxpool2x2: bad shape");
+    SSG_VEC_LAUNCH(maxpool2x2_kernel, (long long)n * (h / 2) * (w / 2) * c, (const T*)x, (T*)y, code, n, h, w, c);
+}
+int ssg_scatter2x2(const void* src, const uint8_t* code, void* dst, int dtype, int n, int h, int w, int c, ssg_stream_t s) {
+    SSG_CHECK_ARG(n > 0 && h > 0 && w > 0 && c > 0, "scatter2x2: bad shape");
+    SSG_VEC_LAUNCH(scatter2x2_kernel, (long long)n * h * w * c, (const T*)src, code, (T*)dst, n, h, w, c);
+}
+int ssg_gather2x2(const void* src, const uint8_t* code, void* dst, int dtype, int n, int h, int w, int c, ssg_stream_t s) {
+    SSG_CHECK_ARG(n > 0 && h > 0 && w > 0 && c > 0, "gather2x2: bad shape");
+    unsigned g = grid_for((long long)n * h * w * c, 256);
+    SSG_DISPATCH_DTYPE(dtype, gather2x2_kernel<T><<<g, 256, 0, (cudaStream_t)s>>>((const T*)src, code, (T*)dst, n, h, w, c));
+    SSG_CHECK_LAUNCH();
+    return SSG_OK;
+}
+int ssg_upsample2x_fwd(const void* x, void* y, int dtype, int n, int h, int w, int c, ssg_stream_t s) {
+    SSG_CHECK_ARG(n > 0 && h > 0 && w > 0 && c > 0, "upsample2x: bad shape");
+    SSG_VEC_LAUNCH(upsample2x_fwd_kernel, (long long)n * 4 * h * w * c, (const T*)x, (T*)y, n, h, w, c);
+}
+int ssg_upsample2x_bwd(const void* dy, void* dx, int dtype, int n, int h, int w, int c, ssg_stream_t s) {
+    SSG_CHECK_ARG(n > 0 && h > 0 && w > 0 && c > 0, "upsample2x: bad shape");
+    SSG_VEC_LAUNCH(upsample2x_bwd_kernel, (long long)n * h * w * c, (const T*)dy, (T*)dx, n, h, w, c);
+}
+int ssg_adaptive_avgpool_flat_fwd(const void* x, void* y, int dtype, int n, int h, int w, int c, int oh, int ow, ssg_stream_t s) {
+    SSG_CHECK_ARG(n > 0 && h > 0 && w > 0 && c > 0 && oh > 0 && ow > 0, "adaptive_avgpool: bad shape");
+    unsigned g = grid_for((long long)n * oh * ow * c, 256);
+    SSG_DISPATCH_DTYPE(dtype, adaptive_avgpool_flat_fwd_kernel<T><<<g, 256, 0, (cudaStream_t)s>>>((const T*)x, (T*)y, n, h, w, c, oh, ow));
+    SSG_CHECK_LAUNCH();
+    return SSG_OK;
+}
+int ssg_adaptive_avgpool_flat_bwd(const void* dy, void* dx, int dtype, int n, int h, int w, int c, int oh, int ow, ssg_stream_t s) {
+    SSG_CHECK_ARG(n > 0 && h > 0 && w > 0 && c > 0 && oh > 0 && ow > 0, "adaptive_avgpool: bad shape");
+    unsigned g = grid_for((long long)n * h * w * c, 256);
+    SSG_DISPATCH_DTYPE(dtype, adaptive_avgpool_flat_bwd_kernel<T><<<g, 256, 0, (cudaStream_t)s>>>((const T*)dy, (T*)dx, n, h, w, c, oh, ow));
+    SSG_CHECK_LAUNCH();
+    return SSG_OK;
+}
+
+}  // extern "C"

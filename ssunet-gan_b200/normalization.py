@@ -1,0 +1,50 @@
+"""SPADE block, self-conditioned as the reference uses it (normalization.py:67-122).
+
+forward(x, segmap): segmap -> x2map (C->label_nc) -> mlp_shared (label_nc->h, ReLU) -> gamma, beta
+(h->C each) -> x * (1 + gamma) + beta.  The reference constructs `param_free_norm` but never
+calls it (normalization.py:110); it is kept so state_dict keys match.
+gamma and beta are produced by ONE convolution with 2C output channels (weights concatenated),
+and the modulation is one elementwise kernel; neither 1+gamma nor the product is materialised.
+"""
+import re
+
+import torch
+from torch import nn
+
+from . import ops
+from ._lib import ACT_RELU
+from .batchnorm import SynchronizedBatchNorm2d
+from .nn_layers import BatchNorm2d, Conv2d, ReLU
+
+
+class SPADE(nn.Module):
+    def __init__(self, config_text, norm_nc, label_nc, nhidden=64):
+        super().__init__()
+        assert config_text.startswith("spade")
+        parsed = re.search(r"spade(\D+)(\d)x\d", config_text)
+        norm_type = str(parsed.group(1))
+        ks = int(parsed.group(2))
+        if norm_type == "instance":
+            self.param_free_norm = nn.InstanceNorm2d(norm_nc, affine=False)
+        elif norm_type == "syncbatch":
+            self.param_free_norm = SynchronizedBatchNorm2d(norm_nc, affine=False)
+        elif norm_type == "batch":
+            self.param_free_norm = BatchNorm2d(norm_nc, affine=False)
+        else:
+            raise ValueError("%s is not a recognized param-free norm type in SPADE" % norm_type)
+        nhidden = int(max(nhidden, 4))
+        pw = ks // 2
+        self.mlp_shared = nn.Sequential(Conv2d(label_nc, nhidden, kernel_size=ks, padding=pw), ReLU())
+        self.x2map = Conv2d(norm_nc, label_nc, kernel_size=ks, padding=pw)
+        self.mlp_gamma = Conv2d(nhidden, norm_nc, kernel_size=ks, padding=pw)
+        self.mlp_beta = Conv2d(nhidden, norm_nc, kernel_size=ks, padding=pw)
+        self._pw = pw
+
+    def forward(self, x, segmap):
+        x = ops.to_nhwc(x)
+        seg = self.x2map(segmap)
+        actv = self.mlp_shared[0](seg, act=ACT_RELU)
+        w_gb = torch.cat([self.mlp_gamma.weight, self.mlp_beta.weight], 0)
+        b_gb = torch.cat([self.mlp_gamma.bias, self.mlp_beta.bias], 0)
+        gb = ops.conv2d(actv, w_gb, b_gb, 1, self._pw)
+        return ops.spade_modulate(x, gb)

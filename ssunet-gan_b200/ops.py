@@ -1,0 +1,677 @@
+"""Autograd operators over the C-ABI kernels (include/ssunet_b200.h).
+
+Activation tensors keep the reference's logical NCHW shape but live in NHWC ("channels last")
+storage in the compute dtype (bf16 by default, fp32 for the 1e-4 parity mode); `to_nhwc` /
+`to_nchw_f32` convert at module boundaries.  Every op launches hand-written CUDA through
+`_lib.call`; nothing here computes with torch kernels on the data path.
+"""
+import math
+
+import torch
+import torch.distributed as dist
+
+from . import _lib
+from ._lib import ACT_LEAKY, ACT_NONE, ACT_RELU, W_RSCK, W_RSCK_FLIP, W_RSKC, call, dtype_code
+
+_COMPUTE_DTYPE = torch.bfloat16
+_WEIGHT_EPOCH = 0          # bumped by the fused optimiser: invalidates packed-weight caches
+_CONV_IMPL = "auto"        # "auto" | "simt" (force the CUDA-core implicit GEMM everywhere)
+
+
+def set_compute_dtype(dt):
+    global _COMPUTE_DTYPE
+    assert dt in (torch.bfloat16, torch.float32)
+    _COMPUTE_DTYPE = dt
+
+
+def compute_dtype():
+    return _COMPUTE_DTYPE
+
+
+def set_conv_impl(name):
+    global _CONV_IMPL
+    assert name in ("auto", "simt")
+    _CONV_IMPL = name
+
+
+def bump_weight_epoch():
+    global _WEIGHT_EPOCH
+    _WEIGHT_EPOCH += 1
+
+
+# ----------------------------------------------------------------------------------------------
+# storage helpers
+# ----------------------------------------------------------------------------------------------
+def empty_nhwc(n, c, h, w, dtype=None, device="cuda"):
+    """Uninitialised NCHW-shaped tensor whose storage is NHWC contiguous."""
+    return torch.empty((n, h, w, c), dtype=dtype or _COMPUTE_DTYPE, device=device).permute(0, 3, 1, 2)
+
+
+def is_nhwc(x):
+    return x.dim() == 4 and x.permute(0, 2, 3, 1).is_contiguous()
+
+
+def _rows(x):
+    return x.shape[0] * x.shape[2] * x.shape[3]
+
+
+class _ToNHWC(torch.autograd.Function):
+    """NCHW fp32 contiguous -> NHWC compute dtype (module entry); backward is the inverse."""
+
+    @staticmethod
+    def forward(ctx, x, dtype):
+        x = x.contiguous()
+        if x.dtype != torch.float32:
+            x = x.float()
+        n, c, h, w = x.shape
+        y = empty_nhwc(n, c, h, w, dtype, x.device)
+        call("ssg_nchw_to_nhwc", x, y, dtype_code(dtype), n, c, h, w)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        n, c, h, w = dy.shape
+        dy = _as_storage(dy)
+        dx = torch.empty((n, c, h, w), dtype=torch.float32, device=dy.device)
+        call("ssg_nhwc_to_nchw", dy, dtype_code(dy.dtype), dx, n, c, h, w)
+        return dx, None
+
+
+class _ToNCHW(torch.autograd.Function):
+    """NHWC compute dtype -> NCHW fp32 contiguous (module exit)."""
+
+    @staticmethod
+    def forward(ctx, x):
+        n, c, h, w = x.shape
+        ctx.dt = x.dtype
+        y = torch.empty((n, c, h, w), dtype=torch.float32, device=x.device)
+        call("ssg_nhwc_to_nchw", x, dtype_code(x.dtype), y, n, c, h, w)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        dy = dy.contiguous().float()
+        n, c, h, w = dy.shape
+        dx = empty_nhwc(n, c, h, w, ctx.dt, dy.device)
+        call("ssg_nchw_to_nhwc", dy, dx, dtype_code(ctx.dt), n, c, h, w)
+        return dx
+
+
+def to_nhwc(x, dtype=None):
+    """Accept whatever the caller has (reference API: NCHW fp32) and return NHWC storage in compute dtype."""
+    dtype = dtype or _COMPUTE_DTYPE
+    if not x.is_cuda:
+        raise _lib.SsgError("ssunet-gan_b200 ops need CUDA tensors (there is no CPU path)")
+    if x.dtype == dtype and is_nhwc(x):
+        return x
+    if is_nhwc(x) and x.dtype != dtype:       # NHWC but other dtype: go through NCHW fp32 (rare, boundary only)
+        x = _ToNCHW.apply(x)
+    return _ToNHWC.apply(x, dtype)
+
+
+def to_nchw_f32(x):
+    if x.dtype == torch.float32 and x.is_contiguous():
+        return x
+    return _ToNCHW.apply(to_nhwc(x, x.dtype if x.dtype in (torch.float32, torch.bfloat16) else None))
+
+
+def _as_storage(t, dtype=None):
+    """Gradient tensors arriving from autograd: make sure they are NHWC storage in the right dtype."""
+    if dtype is not None and t.dtype != dtype:
+        t = t.to(dtype)
+    if not is_nhwc(t):
+        t = t.contiguous(memory_format=torch.channels_last)
+        if not is_nhwc(t):   # degenerate shapes (C == 1 or H == W == 1): force the layout explicitly
+            t = t.permute(0, 2, 3, 1).contiguous().permute(0, 3, 1, 2)
+    return t
+
+
+# ----------------------------------------------------------------------------------------------
+# packed weights
+# ----------------------------------------------------------------------------------------------
+def packed_weight(w, layout, dtype, inv_scale=None):
+    """OIHW fp32 parameter -> kernel operand, cached on the tensor until it changes."""
+    key = (layout, dtype)
+    token = (w._version, _WEIGHT_EPOCH, w.data_ptr())
+    cache = getattr(w, "_ssg_pack", None)
+    if cache is None:
+        cache = {}
+        try:
+            w._ssg_pack = cache
+        except Exception:
+            pass
+    hit = cache.get(key)
+    if hit is not None and hit[0] == token and inv_scale is None:
+        return hit[1]
+    cout, cin, kh, kw = w.shape
+    out = torch.empty(w.numel(), dtype=dtype, device=w.device)
+    call("ssg_pack_conv_weight", w.detach(), out, dtype_code(dtype), layout, cout, cin, kh, kw, inv_scale)
+    if inv_scale is None:
+        cache[key] = (token, out)
+    return out
+
+
+# ----------------------------------------------------------------------------------------------
+# convolution
+# ----------------------------------------------------------------------------------------------
+def _conv_out_hw(h, w, k, stride, pad):
+    return (h + 2 * pad - k) // stride + 1, (w + 2 * pad - k) // stride + 1
+
+
+def _tc_eligible(cin, cout, k, stride, dtype):
+    if _CONV_IMPL == "simt" or dtype != torch.bfloat16:
+        return False
+    from . import conv_tc
+    return conv_tc.eligible(cin, cout, k, stride)
+
+
+class _Conv2d(torch.autograd.Function):
+    """nn.Conv2d (square kernel, symmetric padding, groups=1) with optional fused bias + activation."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, stride, pad, act, slope):
+        n, cin, h, w = x.shape
+        cout, cin_w, kh, kw = weight.shape
+        assert cin == cin_w and kh == kw, "conv2d: shape mismatch %s vs %s" % (tuple(x.shape), tuple(weight.shape))
+        oh, ow = _conv_out_hw(h, w, kh, stride, pad)
+        dt = x.dtype
+        y = empty_nhwc(n, cout, oh, ow, dt, x.device)
+        use_tc = _tc_eligible(cin, cout, kh, stride, dt)
+        if use_tc:
+            from . import conv_tc
+            conv_tc.forward(x, weight, bias, y, stride, pad, act, slope)
+        else:
+            wp = packed_weight(weight, W_RSCK, dt)
+            call("ssg_conv2d_fwd_simt", x, wp, bias, y, dtype_code(dt), n, h, w, cin, cout, kh, kw, stride, pad, act, slope)
+        ctx.save_for_backward(x, weight, y if act != ACT_NONE else None)
+        ctx.cfg = (stride, pad, act, slope, bias is not None, use_tc)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, weight, y = ctx.saved_tensors
+        stride, pad, act, slope, has_bias, use_tc = ctx.cfg
+        n, cin, h, w = x.shape
+        cout, _, kh, kw = weight.shape
+        dt = x.dtype
+        dy = _as_storage(dy, dt)
+        if act != ACT_NONE:
+            dz = torch.empty_like(dy)
+            call("ssg_act_bwd", dy, y, dz, dtype_code(dt), dy.numel(), act, slope)
+            dy = dz
+        dx = dw = db = None
+        if ctx.needs_input_grad[0]:
+            dx = empty_nhwc(n, cin, h, w, dt, x.device)
+            if use_tc and _tc_eligible(cout, cin, kh, stride, dt) and stride == 1:
+                from . import conv_tc
+                conv_tc.dgrad(dy, weight, dx, stride, pad)
+            else:
+                wp = packed_weight(weight, W_RSKC, dt)
+                call("ssg_conv2d_dgrad_simt", dy, wp, dx, dtype_code(dt), n, h, w, cin, cout, kh, kw, stride, pad)
+        if ctx.needs_input_grad[1]:
+            dw = torch.empty_like(weight, dtype=torch.float32)
+            done = False
+            if use_tc:
+                from . import conv_tc
+                done = conv_tc.wgrad(x, dy, dw, stride, pad)
+            if not done:
+                call("ssg_conv2d_wgrad_simt", x, dy, dw, dtype_code(dt), n, h, w, cin, cout, kh, kw, stride, pad)
+        if has_bias and ctx.needs_input_grad[2]:
+            sums = torch.empty(2 * cout, dtype=torch.float64, device=x.device)
+            call("ssg_channel_stats", dy, dtype_code(dt), _rows(dy), cout, sums, 0)
+            db = sums[:cout].float()
+        return dx, dw, db, None, None, None, None
+
+
+def conv2d(x, weight, bias=None, stride=1, pad=0, act=ACT_NONE, slope=0.0):
+    return _Conv2d.apply(to_nhwc(x), weight, bias, stride, pad, act, slope)
+
+
+# ----------------------------------------------------------------------------------------------
+# batch norm (single device and synchronised)
+# ----------------------------------------------------------------------------------------------
+def _all_reduce_sum(t, group):
+    if group is not None and dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+        return dist.get_world_size(group)
+    return 1
+
+
+class _BatchNorm(torch.autograd.Function):
+    """Training-mode BN (+ optional residual add + activation) with cross-rank statistics when
+    ``group`` spans more than one rank.  ``sync_quirk`` selects batchnorm.py:127's clamp(eps)."""
+
+    @staticmethod
+    def forward(ctx, x, gamma, beta, residual, running_mean, running_var, momentum, eps, act, slope, group, sync_quirk):
+        n, c, h, w = x.shape
+        dt = x.dtype
+        rows = _rows(x)
+        dev = x.device
+        sums = torch.empty(2 * c, dtype=torch.float64, device=dev)
+        call("ssg_channel_stats", x, dtype_code(dt), rows, c, sums, 1)
+        world = _all_reduce_sum(sums, group)
+        count = float(rows * world)
+        mean = torch.empty(c, dtype=torch.float32, device=dev)
+        inv_std = torch.empty(c, dtype=torch.float32, device=dev)
+        call("ssg_bn_finalize", sums, count, c, eps, momentum if momentum is not None else 0.0, int(sync_quirk),
+             running_mean, running_var, mean, inv_std)
+        y = empty_nhwc(n, c, h, w, dt, dev)
+        call("ssg_bn_apply", x, residual, y, dtype_code(dt), rows, c, mean, inv_std, gamma, beta, act, slope)
+        ctx.save_for_backward(x, y if act != ACT_NONE else None, mean, inv_std, gamma)
+        ctx.cfg = (act, slope, group, count, residual is not None)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, y, mean, inv_std, gamma = ctx.saved_tensors
+        act, slope, group, count, has_res = ctx.cfg
+        n, c, h, w = x.shape
+        dt = x.dtype
+        rows = _rows(x)
+        dy = _as_storage(dy, dt)
+        sums = torch.empty(2 * c, dtype=torch.float64, device=x.device)
+        call("ssg_bn_bwd_reduce", dy, y, x, dtype_code(dt), rows, c, mean, inv_std, act, slope, sums)
+        dgamma = dbeta = None
+        if gamma is not None:
+            dgamma = torch.empty(c, dtype=torch.float32, device=x.device)
+            dbeta = torch.empty(c, dtype=torch.float32, device=x.device)
+            call("ssg_bn_param_grads", sums, c, dgamma, dbeta)      # local sums: the gradient all-reduce adds ranks
+        _all_reduce_sum(sums, group)
+        dx = empty_nhwc(n, c, h, w, dt, x.device)
+        dres = empty_nhwc(n, c, h, w, dt, x.device) if has_res else None
+        call("ssg_bn_bwd_apply", dy, y, x, dx, dres, dtype_code(dt), rows, c, mean, inv_std, gamma, sums, count, act, slope, 1)
+        return dx, dgamma, dbeta, dres, None, None, None, None, None, None, None, None
+
+
+class _BatchNormEval(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, gamma, beta, residual, running_mean, running_var, eps, act, slope):
+        n, c, h, w = x.shape
+        dt = x.dtype
+        mean = torch.empty(c, dtype=torch.float32, device=x.device)
+        inv_std = torch.empty(c, dtype=torch.float32, device=x.device)
+        call("ssg_bn_eval_prepare", running_mean, running_var, c, eps, mean, inv_std)
+        y = empty_nhwc(n, c, h, w, dt, x.device)
+        call("ssg_bn_apply", x, residual, y, dtype_code(dt), _rows(x), c, mean, inv_std, gamma, beta, act, slope)
+        ctx.save_for_backward(x, y if act != ACT_NONE else None, mean, inv_std, gamma)
+        ctx.cfg = (act, slope, residual is not None)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, y, mean, inv_std, gamma = ctx.saved_tensors
+        act, slope, has_res = ctx.cfg
+        n, c, h, w = x.shape
+        dt = x.dtype
+        dy = _as_storage(dy, dt)
+        sums = torch.zeros(2 * c, dtype=torch.float64, device=x.device)
+        dgamma = dbeta = None
+        if gamma is not None:
+            call("ssg_bn_bwd_reduce", dy, y, x, dtype_code(dt), _rows(x), c, mean, inv_std, act, slope, sums)
+            dgamma = torch.empty(c, dtype=torch.float32, device=x.device)
+            dbeta = torch.empty(c, dtype=torch.float32, device=x.device)
+            call("ssg_bn_param_grads", sums, c, dgamma, dbeta)
+        dx = empty_nhwc(n, c, h, w, dt, x.device)
+        dres = empty_nhwc(n, c, h, w, dt, x.device) if has_res else None
+        call("ssg_bn_bwd_apply", dy, y, x, dx, dres, dtype_code(dt), _rows(x), c, mean, inv_std, gamma, sums, 1.0, act, slope, 0)
+        return dx, dgamma, dbeta, dres, None, None, None, None, None
+
+
+def batch_norm(x, gamma, beta, running_mean, running_var, training, momentum=0.1, eps=1e-5, residual=None,
+               act=ACT_NONE, slope=0.0, group=None, sync_quirk=False):
+    x = to_nhwc(x)
+    if residual is not None:
+        residual = to_nhwc(residual)
+    if training:
+        return _BatchNorm.apply(x, gamma, beta, residual, running_mean, running_var, momentum, eps, act, slope, group, sync_quirk)
+    return _BatchNormEval.apply(x, gamma, beta, residual, running_mean, running_var, eps, act, slope)
+
+
+# ----------------------------------------------------------------------------------------------
+# pooling / resampling / concat
+# ----------------------------------------------------------------------------------------------
+class _MaxPool(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x):
+        n, c, h, w = x.shape
+        y = empty_nhwc(n, c, h // 2, w // 2, x.dtype, x.device)
+        code = torch.empty((n, h // 2, w // 2, c), dtype=torch.uint8, device=x.device)
+        call("ssg_maxpool2x2_fwd", x, y, code, dtype_code(x.dtype), n, h, w, c)
+        ctx.save_for_backward(code)
+        ctx.hw = (h, w)
+        ctx.mark_non_differentiable(code)
+        return y, code
+
+    @staticmethod
+    def backward(ctx, dy, _dcode):
+        (code,) = ctx.saved_tensors
+        n, c, oh, ow = dy.shape
+        h, w = ctx.hw
+        dy = _as_storage(dy)
+        if (h, w) == (2 * oh, 2 * ow):
+            dx = empty_nhwc(n, c, h, w, dy.dtype, dy.device)
+        else:   # odd sizes: the last row/col never entered a window
+            dx = torch.zeros((n, h, w, c), dtype=dy.dtype, device=dy.device).permute(0, 3, 1, 2)
+            raise _lib.SsgError("max_pool2x2 backward needs even spatial sizes")
+        call("ssg_scatter2x2", dy, code, dx, dtype_code(dy.dtype), n, oh, ow, c)
+        return dx
+
+
+class _MaxUnpool(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, code):
+        n, c, h, w = x.shape
+        y = empty_nhwc(n, c, 2 * h, 2 * w, x.dtype, x.device)
+        call("ssg_scatter2x2", x, code, y, dtype_code(x.dtype), n, h, w, c)
+        ctx.save_for_backward(code)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        (code,) = ctx.saved_tensors
+        n, c, h2, w2 = dy.shape
+        dy = _as_storage(dy)
+        dx = empty_nhwc(n, c, h2 // 2, w2 // 2, dy.dtype, dy.device)
+        call("ssg_gather2x2", dy, code, dx, dtype_code(dy.dtype), n, h2 // 2, w2 // 2, c)
+        return dx, None
+
+
+class _Upsample2x(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x):
+        n, c, h, w = x.shape
+        y = empty_nhwc(n, c, 2 * h, 2 * w, x.dtype, x.device)
+        call("ssg_upsample2x_fwd", x, y, dtype_code(x.dtype), n, h, w, c)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        n, c, h2, w2 = dy.shape
+        dy = _as_storage(dy)
+        dx = empty_nhwc(n, c, h2 // 2, w2 // 2, dy.dtype, dy.device)
+        call("ssg_upsample2x_bwd", dy, dx, dtype_code(dy.dtype), n, h2 // 2, w2 // 2, c)
+        return dx
+
+
+class _Concat2(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, a, b):
+        n, ca, h, w = a.shape
+        cb = b.shape[1]
+        y = empty_nhwc(n, ca + cb, h, w, a.dtype, a.device)
+        call("ssg_concat2", a, ca, b, cb, y, dtype_code(a.dtype), _rows(a))
+        ctx.split = (ca, cb)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        ca, cb = ctx.split
+        n, _, h, w = dy.shape
+        dy = _as_storage(dy)
+        da = empty_nhwc(n, ca, h, w, dy.dtype, dy.device)
+        db = empty_nhwc(n, cb, h, w, dy.dtype, dy.device)
+        call("ssg_split2", dy, da, ca, db, cb, dtype_code(dy.dtype), _rows(dy))
+        return da, db
+
+
+def max_pool2x2(x):
+    return _MaxPool.apply(to_nhwc(x))
+
+
+def max_unpool2x2(x, code):
+    return _MaxUnpool.apply(to_nhwc(x), code)
+
+
+def upsample_bilinear2x(x):
+    return _Upsample2x.apply(to_nhwc(x))
+
+
+def concat_channels(a, b):
+    a = to_nhwc(a)
+    return _Concat2.apply(a, to_nhwc(b, a.dtype))
+
+
+# ----------------------------------------------------------------------------------------------
+# SPADE modulation, activations
+# ----------------------------------------------------------------------------------------------
+class _SpadeModulate(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, gb):
+        n, c, h, w = x.shape
+        y = empty_nhwc(n, c, h, w, x.dtype, x.device)
+        call("ssg_spade_modulate_fwd", x, gb, y, dtype_code(x.dtype), _rows(x), c)
+        ctx.save_for_backward(x, gb)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, gb = ctx.saved_tensors
+        n, c, h, w = x.shape
+        dy = _as_storage(dy, x.dtype)
+        dx = empty_nhwc(n, c, h, w, x.dtype, x.device)
+        dgb = empty_nhwc(n, 2 * c, h, w, x.dtype, x.device)
+        call("ssg_spade_modulate_bwd", dy, x, gb, dx, dgb, dtype_code(x.dtype), _rows(x), c)
+        return dx, dgb
+
+
+def spade_modulate(x, gb):
+    return _SpadeModulate.apply(to_nhwc(x), gb)
+
+
+class _Act(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, act, slope):
+        x = x.contiguous() if x.dim() != 4 else x
+        y = torch.empty_like(x)
+        call("ssg_act_fwd", x, y, dtype_code(x.dtype), x.numel(), act, slope)
+        ctx.save_for_backward(y)
+        ctx.cfg = (act, slope)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        (y,) = ctx.saved_tensors
+        act, slope = ctx.cfg
+        if dy.dim() == 4:
+            dy = _as_storage(dy, y.dtype)
+        else:
+            dy = dy.contiguous().to(y.dtype)
+        dx = torch.empty_like(y)
+        call("ssg_act_bwd", dy, y, dx, dtype_code(y.dtype), y.numel(), act, slope)
+        return dx, None, None
+
+
+def relu(x):
+    return _Act.apply(to_nhwc(x) if x.dim() == 4 else x, ACT_RELU, 0.0)
+
+
+def leaky_relu(x, slope=0.2):
+    return _Act.apply(to_nhwc(x) if x.dim() == 4 else x, ACT_LEAKY, slope)
+
+
+# ----------------------------------------------------------------------------------------------
+# discriminator head
+# ----------------------------------------------------------------------------------------------
+class _AvgPoolFlat(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, oh, ow):
+        n, c, h, w = x.shape
+        y = torch.empty((n, c * oh * ow), dtype=x.dtype, device=x.device)
+        call("ssg_adaptive_avgpool_flat_fwd", x, y, dtype_code(x.dtype), n, h, w, c, oh, ow)
+        ctx.cfg = (n, c, h, w, oh, ow)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        n, c, h, w, oh, ow = ctx.cfg
+        dy = dy.contiguous()
+        dx = empty_nhwc(n, c, h, w, dy.dtype, dy.device)
+        call("ssg_adaptive_avgpool_flat_bwd", dy, dx, dtype_code(dy.dtype), n, h, w, c, oh, ow)
+        return dx, None, None
+
+
+def adaptive_avg_pool_flat(x, oh, ow):
+    return _AvgPoolFlat.apply(to_nhwc(x), oh, ow)
+
+
+class _Linear(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, weight, bias, act, slope):
+        x = x.contiguous()
+        m, k = x.shape
+        nout = weight.shape[0]
+        y = torch.empty((m, nout), dtype=x.dtype, device=x.device)
+        call("ssg_linear_fwd", x, weight.contiguous(), bias, y, dtype_code(x.dtype), m, k, nout, act, slope, None)
+        ctx.save_for_backward(x, weight, y if act != ACT_NONE else None)
+        ctx.cfg = (act, slope, bias is not None)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, weight, y = ctx.saved_tensors
+        act, slope, has_bias = ctx.cfg
+        m, k = x.shape
+        nout = weight.shape[0]
+        dt = x.dtype
+        dy = dy.contiguous().to(dt)
+        if act != ACT_NONE:
+            dz = torch.empty_like(dy)
+            call("ssg_act_bwd", dy, y, dz, dtype_code(dt), dy.numel(), act, slope)
+            dy = dz
+        dx = dw = db = None
+        if ctx.needs_input_grad[0]:
+            dx32 = torch.empty((m, k), dtype=torch.float32, device=x.device)
+            call("ssg_linear_dgrad", dy, weight.contiguous(), dx32, dtype_code(dt), m, k, nout, None)
+            if dt == torch.float32:
+                dx = dx32
+            else:
+                dx = torch.empty((m, k), dtype=dt, device=x.device)
+                call("ssg_cast", dx32, _lib.SSG_F32, dx, dtype_code(dt), dx32.numel())
+        if ctx.needs_input_grad[1]:
+            dw = torch.empty_like(weight, dtype=torch.float32)
+            db = torch.empty(nout, dtype=torch.float32, device=x.device) if has_bias else None
+            call("ssg_linear_wgrad", x, dy, dw, db, dtype_code(dt), m, k, nout)
+        return dx, dw, db, None, None
+
+
+def linear(x, weight, bias=None, act=ACT_NONE, slope=0.0):
+    if x.dtype not in (torch.float32, torch.bfloat16):
+        x = x.float()
+    return _Linear.apply(x, weight, bias, act, slope)
+
+
+# ----------------------------------------------------------------------------------------------
+# losses
+# ----------------------------------------------------------------------------------------------
+class _SegLoss(torch.autograd.Function):
+    """(BCEDiceLoss, MSELoss) of fp32 NCHW logits against fp32 masks in one pass (losses.py:280-302)."""
+
+    @staticmethod
+    def forward(ctx, logits, target):
+        logits = logits.contiguous().float()
+        target = target.contiguous().float()
+        b = logits.shape[0]
+        per = logits.numel() // b
+        sums = torch.empty(b * 5, dtype=torch.float64, device=logits.device)
+        out = torch.empty(5, dtype=torch.float32, device=logits.device)
+        call("ssg_seg_loss_sums", logits, target, b, per, sums)
+        call("ssg_seg_loss_finalize", sums, b, per, out)
+        ctx.save_for_backward(logits, target, sums, out)
+        loss, mse, bce = out[0].clone(), out[3].clone(), out[1].clone()
+        ctx.mark_non_differentiable(out)
+        return loss, mse, bce, out
+
+    @staticmethod
+    def backward(ctx, g_loss, g_mse, g_bce, _g_out):
+        logits, target, sums, out = ctx.saved_tensors
+        b = logits.shape[0]
+        per = logits.numel() // b
+        g = torch.stack([g_loss.float().reshape(()), g_mse.float().reshape(()), g_bce.float().reshape(())]).contiguous()
+        dx = torch.empty_like(logits)
+        call("ssg_seg_loss_bwd", logits, target, sums, out, g, b, per, dx)
+        return dx, None
+
+
+def seg_losses(logits, target):
+    """Returns (BCEDiceLoss, MSELoss, StableBCELoss, detail[5]); detail = [loss, bce, dice, mse, nan_branch]."""
+    return _SegLoss.apply(to_nchw_f32(logits), target)
+
+
+class _BceLogitsConst(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, target_value):
+        x = x.contiguous().float()
+        out = torch.empty((), dtype=torch.float32, device=x.device)
+        call("ssg_bce_logits_fwd", x, float(target_value), x.numel(), out)
+        ctx.save_for_backward(x)
+        ctx.tv = float(target_value)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        (x,) = ctx.saved_tensors
+        dx = torch.empty_like(x)
+        call("ssg_bce_logits_bwd", x, ctx.tv, x.numel(), g.contiguous().float(), dx)
+        return dx, None
+
+
+def bce_with_logits_const(x, target_value):
+    return _BceLogitsConst.apply(x, target_value)
+
+
+class _NanScrub(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x):
+        x = x.contiguous()
+        y = torch.empty_like(x)
+        call("ssg_nan_scrub_fwd", x, y, x.numel())
+        ctx.save_for_backward(x)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        (x,) = ctx.saved_tensors
+        dx = torch.empty_like(x)
+        call("ssg_nan_scrub_bwd", dy.contiguous(), x, dx, x.numel())
+        return dx
+
+
+def nan_to_zero(x):
+    return _NanScrub.apply(to_nchw_f32(x))
+
+
+# ----------------------------------------------------------------------------------------------
+# spectral norm
+# ----------------------------------------------------------------------------------------------
+class _SpectralWeight(torch.autograd.Function):
+    """W_orig, u, v -> W_orig / sigma with one power iteration in training mode (spectral_norm.py:38-88).
+    u and v are updated IN PLACE (as the reference does) under no_grad."""
+
+    @staticmethod
+    def forward(ctx, w_orig, u, v, eps, do_power_iteration, n_iter):
+        rows = w_orig.shape[0]
+        cols = w_orig.numel() // rows
+        w = w_orig.detach().contiguous()
+        ws = torch.empty(rows + cols, dtype=torch.float32, device=w.device)
+        inv_sigma = torch.empty(2, dtype=torch.float32, device=w.device)
+        iters = n_iter if do_power_iteration else 1
+        for _ in range(iters):
+            call("ssg_spectral_sigma", w, u, v, rows, cols, eps, int(do_power_iteration), inv_sigma, ws)
+        out = torch.empty_like(w)
+        call("ssg_scale_by_dev", w, inv_sigma, out, w.numel())
+        ctx.save_for_backward(w, u.clone(), v.clone(), inv_sigma)
+        return out
+
+    @staticmethod
+    def backward(ctx, dw):
+        w, u, v, inv_sigma = ctx.saved_tensors
+        rows = w.shape[0]
+        cols = w.numel() // rows
+        dot = torch.empty(1, dtype=torch.float64, device=w.device)
+        out = torch.empty_like(w)
+        call("ssg_spectral_weight_bwd", dw.contiguous().float(), w, u, v, rows, cols, inv_sigma, dot, out)
+        return out, None, None, None, None, None
+
+
+def spectral_weight(w_orig, u, v, eps, do_power_iteration, n_iter=1):
+    return _SpectralWeight.apply(w_orig, u, v, eps, do_power_iteration, n_iter)

@@ -1,0 +1,87 @@
+"""One G+D iteration of the seg-GAN fine-tuning loop (reference: train_seg_gan.py:182-233), one
+process per GPU.
+
+`gan_train_step` is a line-by-line mirror of the reference loop body driving this package's modules
+(the same call sequence the reference makes, so it also works with `torch.optim.Adam` +
+`clip_gradient`).  Differences from the reference that do NOT change results:
+  * the discriminator's parameters do not accumulate gradients during the generator step — the
+    reference computes them and `optimizer_d.zero_grad()` throws them away (train_seg_gan.py:225);
+  * BCEDiceLoss and MSELoss are one fused pass;
+  * the IoU/Dice metrics can be skipped (`with_metrics=False`) — they force a host sync.
+Data parallelism: wrap G and D in `replicate.DataParallelWithCallback` (after
+`batchnorm.convert_model` for SyncBN); gradients are averaged over ranks when backward finishes.
+"""
+from collections import OrderedDict
+
+import torch
+
+from . import ops
+from .losses import BCEDiceAndContentLoss
+from .metrics import dice_coef, iou_score
+from .srgan_utils import clip_gradient
+
+ALPA = 1e-4      # train_seg_gan.py:172
+BETA = 1e-3      # train_seg_gan.py:173
+GRAD_CLIP = 0.8  # train_seg_gan.py:174
+
+
+def _set_requires_grad(module, flag, saved=None):
+    if flag is False:
+        saved = [(p, p.requires_grad) for p in module.parameters()]
+        for p, _ in saved:
+            p.requires_grad_(False)
+        return saved
+    for p, r in saved:
+        p.requires_grad_(r)
+    return None
+
+
+def gan_train_step(generator, discriminator, optimizer_g, optimizer_d, input, target, num_classes=3,
+                   with_metrics=True, grad_clip=GRAD_CLIP, alpa=ALPA, beta=BETA):
+    """input: N x Cin x H x W fp32 CUDA, target: N x num_classes x H x W fp32 {0,1} CUDA.
+    Returns an OrderedDict of 0-dim tensors / python scalars: loss, content, adv_g, adv_d, iou, dice."""
+    criterion = BCEDiceAndContentLoss()
+
+    # ---- generator update (train_seg_gan.py:188-215) ----
+    generator_output = generator(input)
+    generator_output = ops.nan_to_zero(generator_output)                       # :190
+    loss, content_loss = criterion(generator_output, target)                   # :194-195
+    iou = dice = None
+    if with_metrics:
+        out_m = generator_output[:, 1:num_classes].detach().contiguous()       # :191
+        tar_m = target[:, 1:num_classes].contiguous()                          # :192
+        iou = iou_score(out_m, tar_m)                                          # :197
+        dice = dice_coef(out_m, tar_m)                                         # :198
+    saved = _set_requires_grad(discriminator, False)
+    seg_discriminated = discriminator(generator_output)                        # :202
+    _set_requires_grad(discriminator, True, saved)
+    adversarial_loss = ops.bce_with_logits_const(seg_discriminated, 1.0)       # :204
+    perceptual_loss = loss + alpa * content_loss + beta * adversarial_loss     # :205
+    optimizer_g.zero_grad()                                                    # :207
+    perceptual_loss.backward()                                                 # :208
+    if grad_clip is not None:
+        clip_gradient(optimizer_g, grad_clip)                                  # :211-212
+    optimizer_g.step()                                                         # :215
+    adv_g = adversarial_loss.detach()
+
+    # ---- discriminator update (train_seg_gan.py:217-233) ----
+    hr_discriminated = discriminator(target)                                   # :217
+    sr_discriminated = discriminator(generator_output.detach())                # :218
+    adversarial_loss = ops.bce_with_logits_const(sr_discriminated, 0.0) + \
+        ops.bce_with_logits_const(hr_discriminated, 1.0)                       # :221-222
+    optimizer_d.zero_grad()                                                    # :225
+    adversarial_loss.backward()                                                # :226
+    if grad_clip is not None:
+        clip_gradient(optimizer_d, grad_clip)                                  # :229-230
+    optimizer_d.step()                                                         # :233
+    return OrderedDict([("loss", loss.detach()), ("content", content_loss.detach()), ("adv_g", adv_g),
+                        ("adv_d", adversarial_loss.detach()), ("iou", iou), ("dice", dice),
+                        ("logits", generator_output.detach())])
+
+
+def generator_fwd_bwd(generator, input, target):
+    """BASELINE config 1: generator forward + BCEDiceLoss + backward (train.py:85-108 without the optimiser)."""
+    out = generator(input)
+    loss = ops.seg_losses(out, target)[0]
+    loss.backward()
+    return out.detach(), loss.detach()

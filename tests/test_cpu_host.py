@@ -1,0 +1,161 @@
+"""CPU-side checks: the C-ABI library loads and exports everything the header declares, the product
+refuses to run without CUDA, host-side logic (pairwise-sum tree, SyncMaster rendezvous, data-parallel
+gradient averaging and SyncBN statistics exchange over gloo with world_size 2)."""
+import ctypes
+import os
+import re
+import socket
+import threading
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    from ssunet_gan_b200 import _lib
+    L = _lib.lib()
+    hdr = open(os.path.join(ROOT, "include", "ssunet_b200.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    declared = sorted(set(re.findall(r"\b(ssg_\w+)\s*\(", hdr)))
+    assert len(declared) >= 50
+    for name in declared:
+        assert hasattr(L, name), "missing export %s" % name
+    assert sorted(_lib.exported_symbols()) == declared
+    assert L.ssg_version() >= 100
+
+
+def test_product_has_no_cpu_path():
+    from ssunet_gan_b200 import _lib, ops
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(_lib.SsgError):
+        _lib.call("ssg_add", None, None, None, 0, 0)
+    with pytest.raises(_lib.SsgError):
+        ops.conv2d(torch.zeros(1, 3, 8, 8), torch.zeros(4, 3, 3, 3))
+
+
+def test_product_never_imports_oracle():
+    pkg = os.path.join(ROOT, "ssunet-gan_b200")
+    for dp, _, fs in os.walk(pkg):
+        for f in fs:
+            if f.endswith((".py", ".cu", ".cuh")):
+                src = open(os.path.join(dp, f)).read()
+                assert "ssunet_oracle" not in src and "oracle/" not in src and "/root/reference" not in src, f
+
+
+def test_pairwise_tree_host_helpers_match_numpy():
+    from ssunet_gan_b200 import _lib
+    L = _lib.lib()
+    rs = np.random.RandomState(0)
+    for n in (1, 5, 8, 127, 128, 129, 255, 256, 257, 1000, 4099, 65536, 100003, 786432):
+        a = (rs.rand(n).astype(np.float32) * 3).astype(np.float32)
+        cnt = L.ssg_pairwise_leaves_host(n, None, 0)
+        offs = np.empty(cnt + 1, dtype=np.int64)
+        assert L.ssg_pairwise_leaves_host(n, offs.ctypes.data_as(ctypes.c_void_p), cnt + 1) == cnt
+        assert offs[0] == 0 and offs[-1] == n and np.all(np.diff(offs) > 0) and np.all(np.diff(offs) <= 128)
+        leaf = np.array([a[offs[i]:offs[i + 1]].sum() for i in range(cnt)], dtype=np.float32)
+        got = L.ssg_pairwise_combine_host(leaf.ctypes.data_as(ctypes.c_void_p), n)
+        assert np.float32(got) == a.sum(), n
+
+
+def test_sync_master_rendezvous():
+    """comm.py semantics: one message per slave, callback on the master, reply to each, ACKs drained."""
+    from ssunet_gan_b200.comm import SyncMaster
+
+    def callback(msgs):
+        total = sum(m for _, m in msgs)
+        return [(ident, total + ident) for ident, _ in msgs]
+
+    master = SyncMaster(callback)
+    pipes = [master.register_slave(i) for i in (1, 2, 3)]
+    out = {}
+
+    def slave(p):
+        out[p.identifier] = p.run_slave(10 * p.identifier)
+
+    ts = [threading.Thread(target=slave, args=(p,)) for p in pipes]
+    [t.start() for t in ts]
+    out[0] = master.run_master(5)
+    [t.join() for t in ts]
+    assert out == {0: 65, 1: 66, 2: 67, 3: 68}
+    assert master.nr_slaves == 3
+    master.register_slave(1)      # new round re-initialises the registry
+    assert master.nr_slaves == 1
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, ret):
+    import sys
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        import ssunet_oracle as O
+        from ssunet_gan_b200 import batchnorm, replicate
+        torch.manual_seed(100 + rank)          # ranks start from DIFFERENT weights: the wrapper must broadcast rank 0's
+        net = torch.nn.Sequential(torch.nn.Linear(6, 4), batchnorm.SynchronizedBatchNorm1d(4), torch.nn.Linear(4, 2))
+        dp = replicate.DataParallelWithCallback(net)
+        w0 = net[0].weight.detach().clone()
+        gathered = [torch.zeros_like(w0) for _ in range(world)]
+        dist.all_gather(gathered, w0)
+        same = all(torch.equal(gathered[0], g) for g in gathered)
+        sbn = net[1]
+        par = (sbn._is_parallel, sbn._parallel_id, sbn._world)
+        # gradient averaging == gradient of the global-batch mean loss
+        g = torch.Generator().manual_seed(5)
+        xs = torch.randn(8, 6, generator=g)
+        lin = torch.nn.Linear(6, 3)
+        with torch.no_grad():
+            lin.weight.copy_(torch.randn(3, 6, generator=g)); lin.bias.zero_()
+        dpl = replicate.DataParallelWithCallback(lin)
+        shard = xs.chunk(world)[rank]
+        dpl(shard).pow(2).mean().backward()
+        full = torch.nn.Linear(6, 3)
+        with torch.no_grad():
+            full.weight.copy_(lin.weight); full.bias.zero_()
+        full(xs).pow(2).mean().backward()
+        grad_ok = torch.allclose(lin.weight.grad, full.weight.grad, atol=1e-6)
+        # SyncBN statistics exchange: all-reduced (sum, ssum) over ranks == single-device BN on the whole batch
+        xb = torch.randn(6, 8, 5, 7, generator=torch.Generator().manual_seed(9)) * 2 + 0.5
+        sd = {"bn.weight": torch.ones(8), "bn.bias": torch.zeros(8), "bn.running_mean": torch.zeros(8),
+              "bn.running_var": torch.ones(8), "bn.num_batches_tracked": torch.zeros((), dtype=torch.int64)}
+
+        def sync(s, ss, n):
+            t = torch.cat([s, ss, torch.tensor([float(n)])]).double()
+            dist.all_reduce(t)
+            return t[:8].float(), t[8:16].float(), int(t[16])
+
+        y = O.batch_norm(sd, "bn", xb.chunk(world)[rank], True, sync_stats=sync)
+        ref = torch.nn.functional.batch_norm(xb, None, None, None, None, True, 0.1, 1e-5).chunk(world)[rank]
+        bn_ok = torch.allclose(y, ref, atol=2e-5)
+        ret[rank] = (same, par, grad_ok, bn_ok)
+    finally:
+        dist.destroy_process_group()
+
+
+def test_data_parallel_host_logic_gloo_world2():
+    world = 2
+    port = _free_port()
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_worker, args=(world, port, ret), nprocs=world, join=True)
+    for rank in range(world):
+        same, par, grad_ok, bn_ok = ret[rank]
+        assert same, "parameters were not broadcast from rank 0"
+        assert par == (True, rank, world)
+        assert grad_ok, "gradient averaging does not reproduce the global-batch gradient"
+        assert bn_ok, "SyncBN statistics exchange does not reproduce full-batch BN"

@@ -1,0 +1,219 @@
+"""Module- and step-level parity on the GPU: this package's drop-in modules against (a) the golden
+fixtures produced by the unmodified reference and (b) the CPU oracle on the same seeded inputs.
+Tolerances (north_star): fp32 1e-4 relative, bf16 1e-2 relative on logits and losses."""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def rel(a, b):
+    a = torch.as_tensor(a).detach().double().cpu()
+    b = torch.as_tensor(b).detach().double().cpu()
+    return float((a - b).norm() / (b.norm() + 1e-30))
+
+
+def _csum(t):
+    t = t.detach().double().cpu()
+    return np.array([float(t.sum()), float(t.abs().sum()), float((t * t).sum())])
+
+
+@pytest.fixture(autouse=True)
+def _reset():
+    import ssunet_gan_b200 as ssg
+    yield
+    ssg.set_compute_dtype(torch.bfloat16)
+    ssg.set_conv_impl("auto")
+
+
+def _make_g(O, dtype, impl="auto"):
+    import ssunet_gan_b200 as ssg
+    from ssunet_gan_b200 import models_seg_gan
+    ssg.set_compute_dtype(dtype)
+    ssg.set_conv_impl(impl)
+    g = models_seg_gan.Generator({"arch": "UNet_R_SS_v2", "num_classes": 3, "input_channels": 3, "deep_supervision": False})
+    g.load_state_dict(O.portable_state_dict(O.unet_r_ss_v2_spec(3, 3, prefix="net.")))
+    return g.cuda()
+
+
+def _make_d(O, dtype, impl="auto"):
+    import ssunet_gan_b200 as ssg
+    from ssunet_gan_b200 import models_seg_gan
+    ssg.set_compute_dtype(dtype)
+    ssg.set_conv_impl(impl)
+    d = models_seg_gan.Discriminator(3)
+    d.load_state_dict(O.portable_state_dict(O.discriminator_spec(3)))
+    return d.cuda()
+
+
+def test_state_dict_layout_and_default_init(golden_dir):
+    """Same keys/shapes as the reference and bit-identical default initialisation under seed 41."""
+    from ssunet_gan_b200 import models_seg_gan
+    lay = json.load(open(os.path.join(golden_dir, "state_layout.json")))
+    torch.manual_seed(41)
+    g = models_seg_gan.Generator({"arch": "UNet_R_SS_v2", "num_classes": 3, "input_channels": 3, "deep_supervision": False})
+    d = models_seg_gan.Discriminator(3)
+    assert [[k, list(v.shape)] for k, v in g.state_dict().items()] == lay["generator"]
+    assert [[k, list(v.shape)] for k, v in d.state_dict().items()] == lay["discriminator"]
+    for k, v in g.state_dict().items():
+        if v.is_floating_point():
+            np.testing.assert_allclose(_csum(v), lay["init_seed41_generator"][k], rtol=1e-6)
+
+
+@pytest.mark.parametrize("dtype,impl,tol", [(torch.float32, "simt", 1e-4), (torch.bfloat16, "auto", 2e-2)])
+def test_generator_fwd_bwd_vs_reference_golden(golden_dir, dtype, impl, tol):
+    import ssunet_oracle as O
+    from ssunet_gan_b200 import losses, metrics
+    z = np.load(os.path.join(golden_dir, "generator_fwd_bwd_2x64.npz"))
+    g = _make_g(O, dtype, impl)
+    g.train()
+    x, t = O.synthetic_batch(2, 3, 64, 64, seed=1234)
+    out = g(x.cuda())
+    assert out.dtype == torch.float32 and out.is_contiguous() and tuple(out.shape) == (2, 3, 64, 64)
+    loss = losses.BCEDiceLoss()(out, t.cuda())
+    loss.backward()
+    assert rel(out, z["logits"]) < tol
+    assert abs(float(loss) - float(z["loss"])) < tol * abs(float(z["loss"]))
+    sd = g.state_dict()
+    assert rel(sd["net.conv0_0.bn1.running_mean"], z["bn_running_mean"]) < max(tol, 1e-4) * 5
+    assert rel(sd["net.conv2_1.bn2.running_var"], z["bn_running_var"]) < max(tol, 1e-4) * 5
+    assert int(sd["net.conv0_0.bn1.num_batches_tracked"]) == 1
+    grads = {k: p.grad for k, p in g.named_parameters()}
+    worst = 0.0
+    for k, c in zip(z["grad_keys"], z["grad_csum"]):
+        got = _csum(grads[str(k)])
+        worst = max(worst, abs(got[1] - c[1]) / (abs(c[1]) + 1e-12), abs(got[2] - c[2]) / (abs(c[2]) + 1e-12))
+    gtol = 2e-3 if dtype == torch.float32 else 8e-2
+    assert worst < gtol, worst
+    if dtype == torch.float32:
+        # metrics on identical masks: the thresholded prediction equals the reference's, so IoU is bit-equal
+        assert metrics.iou_score(out[:, 1:].contiguous(), t[:, 1:].cuda().contiguous()) == float(z["iou"])
+        assert abs(float(metrics.dice_coef(out[:, 1:].contiguous(), t[:, 1:].cuda().contiguous())) - float(z["dice"])) < 2e-6
+
+
+@pytest.mark.parametrize("dtype,impl,tol", [(torch.float32, "simt", 1e-4), (torch.bfloat16, "auto", 1e-2)])
+def test_generator_eval_vs_reference_golden(golden_dir, dtype, impl, tol):
+    import ssunet_oracle as O
+    z = np.load(os.path.join(golden_dir, "generator_eval_1x96.npz"))
+    g = _make_g(O, dtype, impl)
+    g.eval()
+    x, _ = O.synthetic_batch(1, 3, 96, 96, seed=77)
+    with torch.no_grad():
+        out = g(x.cuda())
+    assert rel(out, z["logits"]) < tol
+
+
+@pytest.mark.parametrize("dtype,impl,tol", [(torch.float32, "simt", 1e-4), (torch.bfloat16, "auto", 1e-2)])
+def test_discriminator_vs_reference_golden(golden_dir, dtype, impl, tol):
+    import ssunet_oracle as O
+    from ssunet_gan_b200 import ops
+    z = np.load(os.path.join(golden_dir, "discriminator_fwd_bwd_3x96.npz"))
+    d = _make_d(O, dtype, impl)
+    d.train()
+    x, _ = O.synthetic_batch(3, 3, 96, 96, seed=5)
+    xc = x.cuda().requires_grad_(True)
+    lo = d(xc)
+    assert tuple(lo.shape) == (3, 1)
+    l = ops.bce_with_logits_const(lo, 1.0)
+    l.backward()
+    assert rel(lo, z["logit"]) < tol * 3
+    assert abs(float(l) - float(z["loss"])) < tol * abs(float(z["loss"]))
+    assert rel(xc.grad, z["dx"]) < (2e-3 if dtype == torch.float32 else 0.12)
+    grads = {k: p.grad for k, p in d.named_parameters()}
+    worst = 0.0
+    for k, c in zip(z["grad_keys"], z["grad_csum"]):
+        got = _csum(grads[str(k)])
+        if c[1] < 1e-7:         # conv biases in front of BN: exactly-zero-gradient parameters
+            assert got[1] < 1e-4
+            continue
+        worst = max(worst, abs(got[1] - c[1]) / abs(c[1]))
+    assert worst < (2e-3 if dtype == torch.float32 else 0.1), worst
+
+
+@pytest.mark.parametrize("dtype,impl,tol", [(torch.float32, "simt", 1e-4), (torch.bfloat16, "auto", 1e-2)])
+def test_gan_step_vs_reference_golden(golden_dir, dtype, impl, tol):
+    """Two iterations of the literal loop body (train_seg_gan.py:188-233) against the reference run."""
+    import ssunet_oracle as O
+    from ssunet_gan_b200 import optim, train_step
+    z = np.load(os.path.join(golden_dir, "gan_step_2it_2x64.npz"))
+    g = _make_g(O, dtype, impl)
+    d = _make_d(O, dtype, impl)
+    g.train(); d.train()
+    og = optim.FusedClampAdam(g.parameters(), lr=2e-5)
+    od = optim.FusedClampAdam(d.parameters(), lr=2e-5)
+    for it in range(2):
+        x, t = O.synthetic_batch(2, 3, 64, 64, seed=1234 + it, blobby=(it == 1))
+        r = train_step.gan_train_step(g, d, og, od, x.cuda(), t.cuda())
+        want = z["it%d_scalars" % it]
+        got = [float(r["loss"]), float(r["content"]), float(r["adv_g"]), float(r["adv_d"])]
+        for a, b in zip(got, want[:4]):
+            assert abs(a - b) < tol * abs(b) * (1 if dtype == torch.float32 else 3), (it, got, want)
+        assert rel(r["logits"], z["it%d_logits" % it]) < tol * (1 if dtype == torch.float32 else 2)
+        if dtype == torch.float32:
+            assert abs(r["iou"] - want[4]) < 2e-4
+            assert abs(float(r["dice"]) - want[5]) < 1e-5
+    sdg, sdd = g.state_dict(), d.state_dict()
+    assert int(sdd["conv_blocks.1.conv_block.1.num_batches_tracked"]) == 6       # 3 D passes per step
+    # parameters moved by exactly two clamped Adam steps (|delta| <= 2*lr each)
+    import ssunet_oracle as O2
+    init_g = O2.portable_state_dict(O2.unet_r_ss_v2_spec(3, 3, prefix="net."))
+    k = "net.final.weight"
+    delta = (sdg[k].cpu() - init_g[k]).abs().max()
+    assert 0 < float(delta) <= 4.0001e-5
+    if dtype == torch.float32:
+        for key, c in zip(z["g_keys"], z["g_csum"]):
+            got = _csum(sdg[str(key)])
+            np.testing.assert_allclose(got[1:], c[1:], rtol=2e-4, atol=1e-4)
+        np.testing.assert_allclose(sdg[k].cpu().numpy(), z["final_weight"], rtol=0, atol=4.1e-5)
+
+
+def test_syncbn_module_single_process(golden_dir):
+    """SynchronizedBatchNorm2d outside parallel mode == BatchNorm2d; convert_model shares running stats."""
+    import ssunet_gan_b200 as ssg
+    from ssunet_gan_b200 import batchnorm, nn_layers
+    ssg.set_compute_dtype(torch.float32)
+    z = np.load(os.path.join(golden_dir, "syncbn_3shards.npz"))
+    x = torch.from_numpy(z["x"]).cuda()
+    bn = nn_layers.BatchNorm2d(8).cuda()
+    sbn = batchnorm.convert_model(torch.nn.Sequential(bn))[0]
+    assert isinstance(sbn, batchnorm.SynchronizedBatchNorm2d)
+    assert sbn.running_mean.data_ptr() == bn.running_mean.data_ptr()
+    import ssunet_oracle as O
+    with torch.no_grad():
+        sbn.weight.copy_(O.portable_tensor("sbn.weight", (8,))); sbn.bias.copy_(O.portable_tensor("sbn.bias", (8,)))
+    sbn.train()
+    # emulate the parallel path on one GPU: whole batch, sync-quirk arithmetic == reference _compute_mean_std
+    sbn._is_parallel = True
+    y = sbn(x)
+    assert rel(y, z["y"]) < 1e-5
+    assert rel(sbn.running_mean, z["running_mean"]) < 1e-5 and rel(sbn.running_var, z["running_var"]) < 1e-5
+    assert int(sbn.num_batches_tracked) == 0
+
+
+def test_spectral_discriminator_vs_oracle():
+    import ssunet_gan_b200 as ssg
+    import ssunet_oracle as O
+    from ssunet_gan_b200 import models_seg_gan, spectral_norm
+    ssg.set_compute_dtype(torch.float32)
+    ssg.set_conv_impl("simt")
+    d = models_seg_gan.Discriminator(3)
+    d.load_state_dict(O.portable_state_dict(O.discriminator_spec(3)))
+    torch.manual_seed(7)
+    spectral_norm.apply_spectral_norm_to_discriminator(d)
+    sd = {k: v.clone() for k, v in d.state_dict().items()}
+    d = d.cuda().train()
+    x, _ = O.synthetic_batch(2, 3, 64, 64, seed=9)
+    lo = d(x.cuda())
+    want = O.discriminator(sd, x, True, spectral=True)
+    assert rel(lo, want) < 2e-4
+    assert rel(d.state_dict()["fc1.weight_u"], sd["fc1.weight_u"]) < 1e-4
+
+
+def test_no_cpu_path():
+    from ssunet_gan_b200 import ops, _lib
+    with pytest.raises(_lib.SsgError):
+        ops.conv2d(torch.zeros(1, 3, 8, 8), torch.zeros(4, 3, 3, 3))
