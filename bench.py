@@ -1,0 +1,277 @@
+"""bench.py — G+D seg-GAN training step throughput (BASELINE.json metric) on N B200s of one node.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
+        bench.py --gpus N --steps K --warmup W
+
+A "step" is one full iteration of the reference loop body (train_seg_gan.py:188-233): generator
+forward, BCEDice + content + adversarial losses, generator backward + clamp + Adam, three
+discriminator forwards, discriminator backward + clamp + Adam.  Workload at N = 1: BASELINE.json
+configs[1] (batch 16 x 3 x 512 x 512, bf16); at N > 1: configs[2] (batch 8 per GPU, SyncBN +
+gradient all-reduce over NCCL), weak scaling.  Prints ONE JSON line on rank 0.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for p in (ROOT, os.path.join(ROOT, "oracle")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+METRIC = "G+D train imgs/s @512^2 (full seg-GAN step: U-Net G + D, BCE+Dice+content+adversarial, clamp+Adam)"
+UNIT = "img/s"
+G_FWD_GFLOP_512 = 417.25       # per 512^2 image
+D_FWD_GFLOP_512 = 49.4
+STEP_GFLOP_512 = 3 * G_FWD_GFLOP_512 + 8 * D_FWD_GFLOP_512     # 1646.9 required per image per step
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=0, help="per-GPU batch override (debug)")
+    ap.add_argument("--size", type=int, default=512, help="tile size override (debug; headline is 512)")
+    ap.add_argument("--conv", default="auto", choices=["auto", "simt"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-sample", default="1x256", help="cpu_baseline sample BxS (bounded)")
+    return ap.parse_args()
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.idx = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                                          "-lms", "200"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for ln in self.proc.stdout:
+            self.lines.append(ln.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=3)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [s.strip() for s in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(names, f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def cpu_reference_step(batch, size, steps=1, warmup=0):
+    """The reference's CPU implementation of the step (oracle port of train_seg_gan.py:188-233), all host threads."""
+    import functools
+    import torch
+    import ssunet_oracle as O
+    torch.set_num_threads(os.cpu_count() or 1)
+    sd_g = O.portable_state_dict(O.unet_r_ss_v2_spec(3, 3, prefix="net."))
+    sd_d = O.portable_state_dict(O.discriminator_spec(3))
+    og = O.AdamState(O.trainable_keys(sd_g), 2e-5)
+    od = O.AdamState(O.trainable_keys(sd_d), 2e-5)
+    orig = O.unet_r_ss_v2
+    O.unet_r_ss_v2 = functools.partial(orig, prefix="net.")
+    times = []
+    try:
+        for it in range(warmup + steps):
+            x, t = O.synthetic_batch(batch, 3, size, size, seed=1234 + it)
+            t0 = time.perf_counter()
+            O.gan_train_step(sd_g, sd_d, og, od, x, t)
+            if it >= warmup:
+                times.append(time.perf_counter() - t0)
+    finally:
+        O.unet_r_ss_v2 = orig
+    return times
+
+
+def run_reference(args):
+    """--impl reference: the reference path on the host CPU.  The reference is pure Python/PyTorch and is not
+    installable on the GPU box (no /root/reference there), so the oracle port is timed (kind = "port")."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import torch
+    b, s = [int(v) for v in args.cpu_sample.split("x")]
+    steps = max(1, min(args.steps, 2))
+    warm = 1 if args.warmup > 0 else 0
+    times = cpu_reference_step(b, s, steps=steps, warmup=warm)
+    sec = sum(times) / len(times)
+    # scale the bounded sample to the metric's unit: images of 512^2 per second (work is proportional to pixels)
+    scale = (s * s) / (512.0 * 512.0)
+    val = b * scale / sec
+    cores = os.cpu_count() or 1
+    sample = "full G+D step, batch %d x 3 x %d x %d fp32, %d timed step(s), pixel-scaled to 512^2" % (b, s, s, steps)
+    line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": steps, "warmup": warm,
+            "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic",
+            "config": {"workload": "seg-GAN G+D step, 16 x 3 x 512 x 512 per GPU (configs[1]); CPU arm runs a bounded sample", "sample": sample},
+            "cpu_baseline": {"value": val, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port", "sample": sample},
+            "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    import torch.distributed as dist
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    assert world == args.gpus or world == 1, "launch with torchrun --nproc-per-node N for --gpus N"
+
+    import ssunet_gan_b200 as ssg
+    from ssunet_gan_b200 import _lib, batchnorm, models_seg_gan, optim, replicate, train_step
+    import ssunet_oracle as O      # synthetic data + portable weights only (not on the timed path)
+
+    ssg.set_compute_dtype(torch.bfloat16)
+    ssg.set_conv_impl(args.conv)
+    size = args.size
+    batch = args.batch or (16 if world == 1 else 8)
+    torch.manual_seed(41)          # train_seg_gan.py:35-36; G then D
+    g = models_seg_gan.Generator({"arch": "UNet_R_SS_v2", "num_classes": 3, "input_channels": 3, "deep_supervision": False}).cuda().train()
+    d = models_seg_gan.Discriminator(3).cuda().train()
+    if world > 1:
+        g = replicate.DataParallelWithCallback(batchnorm.convert_model(g))
+        d = replicate.DataParallelWithCallback(batchnorm.convert_model(d))
+    og = optim.FusedClampAdam(g.parameters(), lr=2e-5)
+    od = optim.FusedClampAdam(d.parameters(), lr=2e-5)
+
+    # synthetic inputs: pinned host copies for the e2e leg, device copies for the kernel leg
+    n_sets = 2
+    host = []
+    for i in range(n_sets):
+        x, t = O.synthetic_batch(batch, 3, size, size, seed=1234 + rank + 97 * i)
+        host.append((x.pin_memory(), t.pin_memory()))
+    dev = [(x.cuda(), t.cuda()) for x, t in host]
+
+    def step_dev(i):
+        x, t = dev[i % n_sets]
+        return train_step.gan_train_step(g, d, og, od, x, t, with_metrics=False)
+
+    def step_e2e(i):
+        hx, ht = host[i % n_sets]
+        x = hx.cuda(non_blocking=True)
+        t = ht.cuda(non_blocking=True)
+        r = train_step.gan_train_step(g, d, og, od, x, t, with_metrics=False)
+        return float(r["loss"])        # D2H read of the step's result (syncs)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, k):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(k):
+            fn(i)
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            tt = torch.tensor([ms], device="cuda")
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            ms = float(tt)
+        return ms
+
+    for i in range(args.warmup):
+        step_dev(i)
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    _lib.profile_reset(["ssg_conv2d_fwd_tc", "ssg_conv2d_wgrad_tc"])
+    l0 = _lib.launch_count
+    ms = timed(step_dev, args.steps)
+    launches = (_lib.launch_count - l0)
+    prof = _lib.profile_collect()
+    ms_e2e = timed(step_e2e, args.steps)
+    clocks = sampler.stop() if rank == 0 else None
+
+    imgs = world * batch * args.steps
+    scale = (size * size) / (512.0 * 512.0)
+    value = imgs * scale / (ms / 1e3)
+    e2e = imgs * scale / (ms_e2e / 1e3)
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak_tf = peaks.get("bf16_tflops_sustained", 1400.0)
+    peak_src = "measured (MEASURED_PEAKS.json bf16_tflops_sustained)" if peaks else "fallback 1.4 PFLOP/s sustained (B200_PROFILING.md)"
+    roof = {"bound": "tensor", "kernel": "conv2d_tc (tcgen05 implicit GEMM, fwd+dgrad+wgrad launches)", "achieved": None,
+            "peak": peak_tf, "unit": "TFLOP/s", "frac": None, "traffic": None, "peak_source": peak_src}
+    if prof and prof.get("ms", 0) > 0:
+        ach = prof["flops"] / (prof["ms"] / 1e3) / 1e12
+        roof.update({"achieved": ach, "frac": ach / peak_tf, "launches": prof["n"], "kernel_ms_per_step": prof["ms"] / args.steps,
+                     "share_of_step": prof["ms"] / ms})
+    step_tf = STEP_GFLOP_512 * 1e9 * scale * world * batch * args.steps / (ms / 1e3) / 1e12
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
+            "data": "synthetic (randn tiles, Bernoulli(0.5) masks; seed-41 default init)",
+            "config": {"workload": "seg-GAN G+D step: UNet_R_SS_v2 (config_v1) + SRGAN discriminator, batch %d x 3 x %d x %d per GPU%s"
+                                   % (batch, size, size, "" if world == 1 else ", SyncBN + gradient all-reduce (NCCL)"),
+                       "global_batch": world * batch, "parallelism": "dp%d" % world, "conv_impl": args.conv,
+                       "l2_policy": "inputs+activations per step (GBs) exceed the 126 MB L2; no explicit flush"},
+            "e2e": {"value": e2e, "unit": UNIT, "ms_per_step": ms_e2e / args.steps,
+                    "h2d_bytes_per_step": int(2 * batch * 3 * size * size * 4), "d2h_bytes_per_step": 4},
+            "gpu_launches": launches, "step_tflops_required_work": step_tf, "roofline": roof, "clocks": clocks}
+    if not args.no_cpu_baseline and world == 1:
+        b, s = [int(v) for v in args.cpu_sample.split("x")]
+        t = cpu_reference_step(b, s, steps=1, warmup=0)
+        v = b * (s * s) / (512.0 * 512.0) / t[0]
+        line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
+                                "sample": "one full G+D step, batch %d x 3 x %d x %d fp32 (%.1f s), pixel-scaled to 512^2" % (b, s, s, t[0])}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -485,3 +485,57 @@ def xresidual_block(sd, x, training=True, stride=1):
     y = x1 * torch.exp(-(t * t))
     y = F.conv2d(y, sd["conv2.weight"], sd["conv2.bias"], stride, 1)
     return batch_norm(sd, "bn1", y, training) + x
+
+
+# --------------------------------------------------------------------------------------
+# bf16-storage emulation of the generator forward (what an ideal bf16 implementation computes)
+# --------------------------------------------------------------------------------------
+def _q(t):
+    return t.bfloat16().float()
+
+
+def unet_r_ss_v2_bf16_emulated(sd, x, prefix=""):
+    """archs.py:623-671 with every stored activation and every conv weight rounded to bf16 (fp32
+    accumulation, fp32 BN statistics).  Used to separate "bf16 storage noise amplified by the
+    network" from kernel errors: the bf16 CUDA path is compared against this."""
+    P = prefix
+
+    def conv(t, w, b=None, pad=1):
+        return _q(F.conv2d(t, _q(w), b, 1, pad))
+
+    def bn(p, t, res=None):
+        y = F.batch_norm(t, None, None, sd[p + ".weight"], sd[p + ".bias"], True, 0.1, 1e-5)
+        if res is not None:
+            y = y + res
+        return _q(F.relu(y))
+
+    def block(p, t):
+        r1 = bn(p + ".bn1", conv(t, sd[p + ".conv1.weight"]))
+        c2 = conv(r1, sd[p + ".conv2.weight"])
+        return bn(p + ".bn2", c2, conv(t, sd[p + ".shortcut.0.weight"], None, 0))
+
+    def spd(p, t):
+        seg = conv(t, sd[p + ".x2map.weight"], sd[p + ".x2map.bias"])
+        a = _q(F.relu(F.conv2d(seg, _q(sd[p + ".mlp_shared.0.weight"]), sd[p + ".mlp_shared.0.bias"], 1, 1)))
+        g = conv(a, sd[p + ".mlp_gamma.weight"], sd[p + ".mlp_gamma.bias"])
+        b = conv(a, sd[p + ".mlp_beta.weight"], sd[p + ".mlp_beta.bias"])
+        return _q(t * (1 + g) + b)
+
+    def stage(c, s, t):
+        return spd(P + s, block(P + c, t))
+
+    def up(t):
+        return _q(_up(t))
+
+    e0 = stage("conv0_0", "SPADE0_0", _q(x)); p0, _ = F.max_pool2d(e0, 2, 2, return_indices=True)
+    e1 = stage("conv1_0", "SPADE1_0", p0); p1, _ = F.max_pool2d(e1, 2, 2, return_indices=True)
+    e2 = stage("conv2_0", "SPADE2_0", p1); p2, i2 = F.max_pool2d(e2, 2, 2, return_indices=True)
+    e3 = stage("conv3_0", "SPADE3_0", p2); p3, i3 = F.max_pool2d(e3, 2, 2, return_indices=True)
+    e4 = stage("conv4_0", "SPADE4_0", p3); p4, i4 = F.max_pool2d(e4, 2, 2, return_indices=True)
+    e5 = conv(stage("conv5_0", "SPADE5_0", p4), sd[P + "conv_head5_0.weight"], None, 0)
+    d4 = conv(stage("conv4_1", "SPADE4_1", torch.cat([e4, F.max_unpool2d(e5, i4, 2, 2)], 1)), sd[P + "conv_head4_1.weight"], None, 0)
+    d3 = conv(stage("conv3_1", "SPADE3_1", torch.cat([e3, F.max_unpool2d(d4, i3, 2, 2)], 1)), sd[P + "conv_head3_1.weight"], None, 0)
+    d2 = stage("conv2_1", "SPADE2_1", torch.cat([e2, F.max_unpool2d(d3, i2, 2, 2)], 1))
+    d1 = stage("conv1_1", "SPADE1_1", torch.cat([e1, up(d2)], 1))
+    d0 = stage("conv0_1", "SPADE0_1", torch.cat([e0, up(d1)], 1))
+    return conv(d0, sd[P + "final.weight"], sd[P + "final.bias"], 0)

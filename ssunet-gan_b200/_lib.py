@@ -98,14 +98,41 @@ def stream_ptr():
 launch_count = 0   # number of C-ABI compute calls issued (bench.py reports it as gpu_launches)
 
 
-def call(name, *args):
+_prof = None
+
+
+def profile_reset(names):
+    """Start timing every call to the named entry points with CUDA events on the launching stream."""
+    global _prof
+    _prof = {"names": set(names), "events": [], "flops": 0.0}
+
+
+def profile_collect():
+    """Stop profiling; returns {"ms": total device time, "flops": algorithmic FLOPs, "n": launches}."""
+    global _prof
+    if _prof is None:
+        return None
+    torch.cuda.synchronize()
+    p, _prof = _prof, None
+    return {"ms": sum(a.elapsed_time(b) for a, b in p["events"]), "flops": p["flops"], "n": len(p["events"])}
+
+
+def call(name, *args, flops=0.0):
     """Invoke a C-ABI entry point on the current torch CUDA stream; tensors are passed as raw pointers."""
     global launch_count
     L = lib()
     if not torch.cuda.is_available():
         raise SsgError("%s: no CUDA device; ssunet-gan_b200 has no CPU path" % name)
     conv = [_ptr(a) for a in args]
+    timed = _prof is not None and name in _prof["names"]
+    if timed:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
     rc = getattr(L, name)(*conv, stream_ptr())
+    if timed:
+        e1.record()
+        _prof["events"].append((e0, e1))
+        _prof["flops"] += flops
     launch_count += 1
     if rc != 0:
         raise SsgError("%s failed (%d): %s" % (name, rc, L.ssg_last_error().decode()))

@@ -9,7 +9,7 @@ import torch.nn.functional as F
 
 pytestmark = pytest.mark.gpu
 
-TOL = {torch.float32: 1e-4, torch.bfloat16: 1.2e-2}
+TOL = {torch.float32: 1e-4, torch.bfloat16: 1e-2}
 
 
 def rel(a, b):
@@ -52,11 +52,17 @@ def test_conv2d_simt(cfg, dt):
     x = torch.randn(n, cin, h, w, generator=g)
     wt = torch.randn(cout, cin, k, k, generator=g) / math.sqrt(cin * k * k)
     b = torch.randn(cout, generator=g) if bias else None
+    if dt == torch.bfloat16:
+        # the kernel sees bf16-rounded operands; compare against the same rounded operands so that the
+        # LeakyReLU mask (non-smooth) is decided on identical pre-activations
+        x, wt = x.bfloat16().float(), wt.bfloat16().float()
     xr = x.clone().requires_grad_(True)
     wr = wt.clone().requires_grad_(True)
     br = b.clone().requires_grad_(True) if bias else None
     yr = F.leaky_relu(F.conv2d(xr, wr, br, stride, pad), 0.2)
     gy = torch.randn(yr.shape, generator=g)
+    if dt == torch.bfloat16:
+        gy = gy.bfloat16().float()
     yr.backward(gy)
     xc = x.cuda().requires_grad_(True)
     wc = wt.cuda().requires_grad_(True)
