@@ -68,6 +68,16 @@ int ssg_conv2d_dgrad_simt(const void* dy, const void* w, void* dx, int dtype, in
 int ssg_conv2d_wgrad_simt(const void* x, const void* dy, float* dw_oihw, int dtype, int n, int h, int w_, int cin,
                           int cout, int kh, int kw, int stride, int pad, ssg_stream_t s);
 
+/* ---- convolution, tcgen05 / TMEM / TMA implicit GEMM (bf16 NHWC, fp32 accumulate) ------------------- */
+/* Same-size convolution (1x1 pad 0 or 3x3 pad 1, stride 1) of the channel concatenation [x0 | x1]
+ * (x1 may be NULL with c1 == 0; torch.cat is never materialised, archs.py:651-667).  c0, c1 multiples of 64;
+ * w_packed: bf16 [taps][cout][c0+c1] (SSG_W_RSKC); y = act(conv + bias), bf16 [n,h,w,cout].
+ * The data gradient of such a convolution is the same call on the flipped/transposed weights
+ * (SSG_W_RSCK_FLIP read as [taps][cin][cout]) with dy as input.  Replaces the cuDNN implicit-GEMM calls behind
+ * archs.py:210,212,218,593-601 and models_seg_gan.py:38-39 (stride-1 blocks). */
+int ssg_conv2d_fwd_tc(const void* x0, int c0, const void* x1, int c1, const void* w_packed, const float* bias, void* y, int n,
+                      int h, int w, int cout, int ksize, int pad, int act, float slope, ssg_stream_t s);
+
 /* ---- per-channel statistics / batch norm -------------------------------------------------- */
 /* batchnorm.py:59-64 (_sum_ft of x and x**2): sums[0:C] = sum x, sums[C:2C] = sum x^2 (fp64,
  * overwritten).  With with_sq == 0 only sums[0:C] is produced (bias gradients). */

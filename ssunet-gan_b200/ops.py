@@ -202,7 +202,7 @@ class _Conv2d(torch.autograd.Function):
         dx = dw = db = None
         if ctx.needs_input_grad[0]:
             dx = empty_nhwc(n, cin, h, w, dt, x.device)
-            if use_tc and _tc_eligible(cout, cin, kh, stride, dt) and stride == 1:
+            if _tc_eligible(cout, cin, kh, stride, dt):
                 from . import conv_tc
                 conv_tc.dgrad(dy, weight, dx, stride, pad)
             else:
