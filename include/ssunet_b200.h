@@ -78,6 +78,12 @@ int ssg_conv2d_wgrad_simt(const void* x, const void* dy, float* dw_oihw, int dty
 int ssg_conv2d_fwd_tc(const void* x0, int c0, const void* x1, int c1, const void* w_packed, const float* bias, void* y, int n,
                       int h, int w, int cout, int ksize, int pad, int act, float slope, ssg_stream_t s);
 
+/* Weight gradient of the same convolution on tensor cores (both operands MN-major straight from the NHWC
+ * tensors, split-K over pixel tiles, fp32 atomics into dw): dw_oihw fp32 [cout][c0+c1][k][k] is overwritten.
+ * cout, c0, c1 multiples of 64. */
+int ssg_conv2d_wgrad_tc(const void* x0, int c0, const void* x1, int c1, const void* dy, float* dw_oihw, int n, int h, int w,
+                        int cout, int ksize, int pad, ssg_stream_t s);
+
 /* ---- per-channel statistics / batch norm -------------------------------------------------- */
 /* batchnorm.py:59-64 (_sum_ft of x and x**2): sums[0:C] = sum x, sums[C:2C] = sum x^2 (fp64,
  * overwritten).  With with_sq == 0 only sums[0:C] is produced (bias gradients). */

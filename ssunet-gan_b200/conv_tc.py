@@ -35,5 +35,13 @@ def dgrad(dy, weight, dx, stride, pad):
          flops=_flops(n, h, w, cin, cout, k))
 
 
-def wgrad(x, dy, dw, stride, pad):
-    return False
+def wgrad(x, dy, dw, stride, pad, x1=None):
+    """dW (OIHW fp32) on tensor cores; returns False when the shape is not eligible (caller falls back to SIMT)."""
+    n, c0, h, w = x.shape
+    c1 = x1.shape[1] if x1 is not None else 0
+    cout = dy.shape[1]
+    k = dw.shape[-1]
+    if stride != 1 or cout % 64 or c0 % 64 or c1 % 64 or k not in (1, 3) or 2 * pad != k - 1 or dy.dtype != torch.bfloat16:
+        return False
+    call("ssg_conv2d_wgrad_tc", x, c0, x1, c1, dy, dw, n, h, w, cout, k, pad, flops=_flops(n, h, w, c0 + c1, cout, k))
+    return True

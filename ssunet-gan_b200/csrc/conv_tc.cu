@@ -254,3 +254,223 @@ int ssg_conv2d_fwd_tc(const void* x0, int c0, const void* x1, int c1, const void
 }
 
 }  // extern "C"
+
+// =====================================================================================================
+// Weight gradient: dW[co][ci][r][s] = sum over pixels of dy[pix][co] * x[pix + (r,s) - pad][ci]
+// GEMM view per (tap, 64-channel chunk) "unit": D[M = 128 rows = 2 units x 64 ci][N = co tile] += A^T B with the
+// pixel index as the reduction dimension, i.e. BOTH operands are MN-major: the same {64 ch x 128 px} TMA boxes as
+// the forward kernel, read by tcgen05.mma with a_major = b_major = MN (no transposes anywhere).
+// A CTA owns G accumulators (G * N <= 512 TMEM columns) for one co tile and walks a strided subset of the pixel
+// tiles (split-K); partial sums are combined with fp32 red.global.add into the OIHW gradient.
+// =====================================================================================================
+namespace ssg {
+namespace tc {
+
+struct WgradParams {
+    float* dw;                  // OIHW fp32, pre-zeroed
+    int N, H, W;                // dy spatial dims (== x dims, stride 1)
+    int cout, cin;
+    int tw_log2, th_log2, tiles_x, tiles_y, m_tiles;
+    int taps, kw, pad;
+    int chunks0, chunks1;
+    int units;                  // taps * (chunks0 + chunks1)
+};
+
+template <int BN>   // co tile: 64 or 128
+struct WgradCfg {
+    static constexpr int G = 512 / BN;               // accumulators per CTA (unit pairs)
+    static constexpr int NJ = BN / 64;               // dy boxes per pixel tile
+    static constexpr int XS = 4;                     // x ring slots (each = one unit pair = 2 boxes)
+    static constexpr int BOX = BM * BK * 2;          // 16 KB
+    static constexpr int DY_BYTES = NJ * BOX;
+    static constexpr int X_OFFSET = 2 * DY_BYTES;
+    static constexpr int BAR_OFFSET = X_OFFSET + XS * 2 * BOX;
+    static constexpr int TOTAL = BAR_OFFSET + 256 + 1024;
+};
+
+template <int BN>
+__global__ void __launch_bounds__(NUM_THREADS) conv_tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmX0,
+                                                                     const __grid_constant__ CUtensorMap tmX1,
+                                                                     const __grid_constant__ CUtensorMap tmDY, const WgradParams p) {
+    using C = WgradCfg<BN>;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint64_t* dy_full = reinterpret_cast<uint64_t*>(smem + C::BAR_OFFSET);
+    uint64_t* dy_empty = dy_full + 2;
+    uint64_t* x_full = dy_empty + 2;
+    uint64_t* x_empty = x_full + C::XS;
+    uint64_t* acc_full = x_empty + C::XS;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_full + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int TW = 1 << p.tw_log2, TH = 1 << p.th_log2;
+    const int chunks = p.chunks0 + p.chunks1;
+    const int unit0 = blockIdx.x * 2 * C::G;
+    int n_units = p.units - unit0;
+    if (n_units > 2 * C::G) n_units = 2 * C::G;
+    const int pairs = (n_units + 1) >> 1;
+    const int co0 = blockIdx.y * BN;
+    const int n_iter = (p.m_tiles - (int)blockIdx.z + (int)gridDim.z - 1) / (int)gridDim.z;   // pixel tiles of this CTA
+
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < 2; ++i) { mbar_init(&dy_full[i], 1); mbar_init(&dy_empty[i], 1); }
+        for (int i = 0; i < C::XS; ++i) { mbar_init(&x_full[i], 1); mbar_init(&x_empty[i], 1); }
+        mbar_init(acc_full, 1);
+        fence_barrier_init();
+    }
+    if (warp == 2) tmem_alloc(tmem_slot, 512);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            int xc = 0;
+            for (int it = 0; it < n_iter; ++it) {
+                int tile = blockIdx.z + it * gridDim.z;
+                const int tx = tile % p.tiles_x; tile /= p.tiles_x;
+                const int ty = tile % p.tiles_y;
+                const int tn = tile / p.tiles_y;
+                const int w0 = tx * TW, h0 = ty * TH, img0 = tn * (BM >> (p.tw_log2 + p.th_log2));
+                const int b = it & 1;
+                mbar_wait(&dy_empty[b], ((it >> 1) & 1) ^ 1);
+                mbar_expect_tx(&dy_full[b], C::DY_BYTES);
+                for (int j = 0; j < C::NJ; ++j)
+                    tma_load_4d(smem + b * C::DY_BYTES + j * C::BOX, &tmDY, co0 + 64 * j, w0, h0, img0, &dy_full[b]);
+                for (int g = 0; g < pairs; ++g, ++xc) {
+                    const int slot = xc % C::XS;
+                    mbar_wait(&x_empty[slot], ((xc / C::XS) & 1) ^ 1);
+                    mbar_expect_tx(&x_full[slot], 2 * C::BOX);
+                    for (int e = 0; e < 2; ++e) {
+                        int u = unit0 + 2 * g + e;
+                        if (u >= p.units) u = unit0;                       // dummy half: rows are never stored
+                        const int tap = u / chunks, ch = u - tap * chunks;
+                        const int r = tap / p.kw, s = tap - r * p.kw;
+                        uint8_t* dst = smem + C::X_OFFSET + (slot * 2 + e) * C::BOX;
+                        if (ch < p.chunks0) tma_load_4d(dst, &tmX0, ch * BK, w0 + s - p.pad, h0 + r - p.pad, img0, &x_full[slot]);
+                        else tma_load_4d(dst, &tmX1, (ch - p.chunks0) * BK, w0 + s - p.pad, h0 + r - p.pad, img0, &x_full[slot]);
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            constexpr uint32_t idesc = make_idesc_bf16(BM, BN, 1, 1);     // both operands MN-major
+            int xc = 0;
+            for (int it = 0; it < n_iter; ++it) {
+                const int b = it & 1;
+                mbar_wait(&dy_full[b], (it >> 1) & 1);
+                tc_fence_after();
+                const uint32_t dy_addr = smem_u32(smem + b * C::DY_BYTES);
+                for (int g = 0; g < pairs; ++g, ++xc) {
+                    const int slot = xc % C::XS;
+                    mbar_wait(&x_full[slot], (xc / C::XS) & 1);
+                    tc_fence_after();
+                    const uint32_t x_addr = smem_u32(smem + C::X_OFFSET + slot * 2 * C::BOX);
+                    // MN-major SW128: LBO = distance between 64-element MN atoms (one box), SBO = 8 pixel rows
+                    const uint64_t da = make_smem_desc(x_addr, C::BOX, 1024, 2);
+                    const uint64_t db = make_smem_desc(dy_addr, C::BOX, 1024, 2);
+#pragma unroll
+                    for (int k = 0; k < BM / 16; ++k)    // 16 pixels per MMA: +2048 bytes (>>4 == 128)
+                        umma_bf16(tmem_base + (uint32_t)(g * BN), da + (uint64_t)(128 * k), db + (uint64_t)(128 * k), idesc, (it | k) != 0);
+                    umma_commit(&x_empty[slot]);
+                }
+                umma_commit(&dy_empty[b]);
+            }
+            umma_commit(acc_full);
+        }
+    } else {
+        const int q = warp & 3;
+        const int row = q * 32 + lane;                  // accumulator row: unit (row >> 6), ci (row & 63)
+        mbar_wait(acc_full, 0);
+        tc_fence_after();
+        const int kk = p.taps;                           // kh * kw
+        for (int g = 0; g < pairs; ++g) {
+            const int u = unit0 + 2 * g + (row >> 6);
+            const bool row_ok = u < p.units && n_iter > 0;
+            const int tap = u / chunks, ch = u - tap * chunks;
+            const int ci = ch * BK + (row & 63);
+#pragma unroll 1
+            for (int c0 = 0; c0 < BN; c0 += 16) {
+                uint32_t v[16];
+                tmem_ld_32x32b_x16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(g * BN + c0), v);
+                tmem_ld_wait();
+                if (!row_ok) continue;
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                    const int co = co0 + c0 + j;
+                    if (co < p.cout) atomicAdd(p.dw + ((long long)co * p.cin + ci) * kk + tap, __uint_as_float(v[j]));
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) tmem_dealloc(tmem_base, 512);
+}
+
+template <int BN>
+static int launch_wgrad(const CUtensorMap& x0, const CUtensorMap& x1, const CUtensorMap& dy, const WgradParams& p, cudaStream_t st) {
+    using C = WgradCfg<BN>;
+    static bool attr_set = false;
+    if (!attr_set) {
+        SSG_CHECK_CUDA(cudaFuncSetAttribute(conv_tc_wgrad_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::TOTAL));
+        attr_set = true;
+    }
+    const int groups = (p.units + 2 * C::G - 1) / (2 * C::G);
+    const int co_tiles = (p.cout + BN - 1) / BN;
+    int splits = (sm_count_cached() + groups * co_tiles - 1) / (groups * co_tiles);   // ~one CTA per SM (512 TMEM columns each)
+    if (splits > p.m_tiles) splits = p.m_tiles;
+    if (splits < 1) splits = 1;
+    dim3 grid((unsigned)groups, (unsigned)co_tiles, (unsigned)splits);
+    conv_tc_wgrad_kernel<BN><<<grid, NUM_THREADS, C::TOTAL, st>>>(x0, x1, dy, p);
+    SSG_CHECK_LAUNCH();
+    return SSG_OK;
+}
+
+}  // namespace tc
+}  // namespace ssg
+
+extern "C" int ssg_conv2d_wgrad_tc(const void* x0, int c0, const void* x1, int c1, const void* dy, float* dw_oihw, int n, int h, int w,
+                                   int cout, int ksize, int pad, ssg_stream_t s) {
+    using namespace ssg;
+    using namespace ssg::tc;
+    SSG_CHECK_ARG(n > 0 && h > 0 && w > 0 && cout > 0 && cout % 64 == 0 && c0 > 0 && c0 % 64 == 0 && c1 >= 0 && c1 % 64 == 0,
+                  "conv2d_wgrad_tc: channels must be multiples of 64 (c0=%d c1=%d cout=%d)", c0, c1, cout);
+    SSG_CHECK_ARG((ksize == 1 || ksize == 3) && 2 * pad == ksize - 1, "conv2d_wgrad_tc: only 1x1/p0 and 3x3/p1");
+    const int cin = c0 + c1, taps = ksize * ksize;
+    cudaStream_t st = (cudaStream_t)s;
+    SSG_CHECK_CUDA(cudaMemsetAsync(dw_oihw, 0, sizeof(float) * (size_t)cout * cin * taps, st));
+    int twl = ilog2_ceil(w); if (twl > 7) twl = 7;
+    int thl = ilog2_ceil(h); if (thl > 7 - twl) thl = 7 - twl;
+    const int TW = 1 << twl, TH = 1 << thl, NB = BM / (TW * TH);
+    WgradParams p;
+    p.dw = dw_oihw; p.N = n; p.H = h; p.W = w; p.cout = cout; p.cin = cin;
+    p.tw_log2 = twl; p.th_log2 = thl; p.tiles_x = (w + TW - 1) / TW; p.tiles_y = (h + TH - 1) / TH;
+    p.m_tiles = p.tiles_x * p.tiles_y * ((n + NB - 1) / NB);
+    p.taps = taps; p.kw = ksize; p.pad = pad; p.chunks0 = c0 / 64; p.chunks1 = c1 / 64; p.units = taps * (cin / 64);
+    CUtensorMap mx0, mx1, mdy;
+    uint32_t box[4] = {64, (uint32_t)TW, (uint32_t)TH, (uint32_t)NB};
+    {
+        uint64_t dims[4] = {(uint64_t)c0, (uint64_t)w, (uint64_t)h, (uint64_t)n};
+        uint64_t str[3] = {(uint64_t)c0 * 2, (uint64_t)w * c0 * 2, (uint64_t)h * w * c0 * 2};
+        int rc = encode_bf16_map(&mx0, x0, 4, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B);
+        if (rc) return rc;
+        mx1 = mx0;
+    }
+    if (c1 > 0) {
+        uint64_t dims[4] = {(uint64_t)c1, (uint64_t)w, (uint64_t)h, (uint64_t)n};
+        uint64_t str[3] = {(uint64_t)c1 * 2, (uint64_t)w * c1 * 2, (uint64_t)h * w * c1 * 2};
+        int rc = encode_bf16_map(&mx1, x1, 4, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B);
+        if (rc) return rc;
+    }
+    {
+        uint64_t dims[4] = {(uint64_t)cout, (uint64_t)w, (uint64_t)h, (uint64_t)n};
+        uint64_t str[3] = {(uint64_t)cout * 2, (uint64_t)w * cout * 2, (uint64_t)h * w * cout * 2};
+        int rc = encode_bf16_map(&mdy, dy, 4, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B);
+        if (rc) return rc;
+    }
+    if (cout % 128 == 0) return launch_wgrad<128>(mx0, mx1, mdy, p, st);
+    return launch_wgrad<64>(mx0, mx1, mdy, p, st);
+}

@@ -211,7 +211,7 @@ class _Conv2d(torch.autograd.Function):
         if ctx.needs_input_grad[1]:
             dw = torch.empty_like(weight, dtype=torch.float32)
             done = False
-            if use_tc:
+            if _CONV_IMPL != "simt" and dt == torch.bfloat16:
                 from . import conv_tc
                 done = conv_tc.wgrad(x, dy, dw, stride, pad)
             if not done:
