@@ -31,10 +31,12 @@ enum ssg_dtype { SSG_F32 = 0, SSG_BF16 = 1 };
 enum ssg_act { SSG_ACT_NONE = 0, SSG_ACT_RELU = 1, SSG_ACT_LEAKY = 2 };
 /* packed-weight layouts produced by ssg_pack_conv_weight */
 enum ssg_wlayout {
-    SSG_W_RSCK = 0, /* [kh][kw][cin][cout]  : forward operand of the SIMT kernels            */
+    SSG_W_RSCK = 0, /* [kh][kw][cin][cout]  : forward operand of the SIMT kernels,
+                                              dgrad (K-major in cout) operand of the tcgen05 kernels */
     SSG_W_RSKC = 1, /* [kh][kw][cout][cin]  : dgrad operand of the SIMT kernels,
                                               forward (K-major) operand of the tcgen05 kernels */
-    SSG_W_RSCK_FLIP = 2 /* [kh-1-r][kw-1-s][cin][cout]: tcgen05 dgrad (K-major in cout)       */
+    SSG_W_RSCK_FLIP = 2 /* [kh-1-r][kw-1-s][cin][cout]: flipped-tap variant (kept for callers that
+                                              express dgrad as a plain forward convolution)     */
 };
 
 int ssg_version(void);
@@ -69,20 +71,26 @@ int ssg_conv2d_wgrad_simt(const void* x, const void* dy, float* dw_oihw, int dty
                           int cout, int kh, int kw, int stride, int pad, ssg_stream_t s);
 
 /* ---- convolution, tcgen05 / TMEM / TMA implicit GEMM (bf16 NHWC, fp32 accumulate) ------------------- */
-/* Same-size convolution (1x1 pad 0 or 3x3 pad 1, stride 1) of the channel concatenation [x0 | x1]
+/* Convolution (1x1 or 3x3, stride 1 or 2, zero padding `pad`) of the channel concatenation [x0 | x1]
  * (x1 may be NULL with c1 == 0; torch.cat is never materialised, archs.py:651-667).  c0, c1 multiples of 64;
- * w_packed: bf16 [taps][cout][c0+c1] (SSG_W_RSKC); y = act(conv + bias), bf16 [n,h,w,cout].
- * The data gradient of such a convolution is the same call on the flipped/transposed weights
- * (SSG_W_RSCK_FLIP read as [taps][cin][cout]) with dy as input.  Replaces the cuDNN implicit-GEMM calls behind
- * archs.py:210,212,218,593-601 and models_seg_gan.py:38-39 (stride-1 blocks). */
+ * (h, w) are the INPUT spatial dims.  w_packed: bf16 [taps][cout][c0+c1] (SSG_W_RSKC);
+ * y = act(conv + bias), bf16 [n,oh,ow,cout].  The stride-2 gather is done by the TMA unit (element-strided
+ * tensor-map traversal).  Replaces the cuDNN implicit-GEMM calls behind archs.py:210,212,218,593-601 and
+ * models_seg_gan.py:38-39 (stride-1 and stride-2 blocks). */
 int ssg_conv2d_fwd_tc(const void* x0, int c0, const void* x1, int c1, const void* w_packed, const float* bias, void* y, int n,
-                      int h, int w, int cout, int ksize, int pad, int act, float slope, ssg_stream_t s);
+                      int h, int w, int cout, int ksize, int stride, int pad, int act, float slope, ssg_stream_t s);
+
+/* Data gradient of the same convolution: dx bf16 [n,h,w,cin] from dy bf16 [n,oh,ow,cout]; cout multiple of 64.
+ * w_packed: bf16 [taps][cin][cout] (SSG_W_RSCK).  Stride 2 is computed as four output-parity classes (each a
+ * small stride-1 convolution over dy with 1, 2, 2 and 4 taps) written interleaved into dx. */
+int ssg_conv2d_dgrad_tc(const void* dy, const void* w_packed, void* dx, int n, int h, int w, int cin, int cout, int ksize,
+                        int stride, int pad, ssg_stream_t s);
 
 /* Weight gradient of the same convolution on tensor cores (both operands MN-major straight from the NHWC
  * tensors, split-K over pixel tiles, fp32 atomics into dw): dw_oihw fp32 [cout][c0+c1][k][k] is overwritten.
- * cout, c0, c1 multiples of 64. */
+ * cout, c0, c1 multiples of 64; (h, w) are the INPUT spatial dims. */
 int ssg_conv2d_wgrad_tc(const void* x0, int c0, const void* x1, int c1, const void* dy, float* dw_oihw, int n, int h, int w,
-                        int cout, int ksize, int pad, ssg_stream_t s);
+                        int cout, int ksize, int stride, int pad, ssg_stream_t s);
 
 /* ---- per-channel statistics / batch norm -------------------------------------------------- */
 /* batchnorm.py:59-64 (_sum_ft of x and x**2): sums[0:C] = sum x, sums[C:2C] = sum x^2 (fp64,

@@ -2,16 +2,24 @@
 import torch
 
 from . import _lib
-from ._lib import W_RSCK_FLIP, W_RSKC, call
+from ._lib import W_RSCK, W_RSKC, call
 
 
 def eligible(cin, cout, k, stride):
-    """Shapes the tensor-core forward kernel takes: 64-channel input granularity, 1x1 / 3x3 same-size, stride 1."""
-    return cin % 64 == 0 and cin >= 64 and k in (1, 3) and stride == 1
+    """Shapes the tensor-core forward kernel takes: 64-channel input granularity, 1x1 / 3x3, stride 1 or 2."""
+    return cin % 64 == 0 and cin >= 64 and k in (1, 3) and stride in (1, 2)
 
 
-def _flops(n, h, w, cin, cout, k):
-    return 2.0 * n * h * w * cin * cout * k * k
+def dgrad_eligible(cin, cout, k, stride):
+    return cout % 64 == 0 and cout >= 64 and k in (1, 3) and (stride == 1 or (stride == 2 and k == 3))
+
+
+def _out_hw(h, w, k, stride, pad):
+    return (h + 2 * pad - k) // stride + 1, (w + 2 * pad - k) // stride + 1
+
+
+def _flops(n, oh, ow, cin, cout, k):
+    return 2.0 * n * oh * ow * cin * cout * k * k
 
 
 def forward(x, weight, bias, y, stride, pad, act, slope, x1=None):
@@ -19,20 +27,21 @@ def forward(x, weight, bias, y, stride, pad, act, slope, x1=None):
     n, c0, h, w = x.shape
     c1 = x1.shape[1] if x1 is not None else 0
     cout, cin, k, _ = weight.shape
-    assert cin == c0 + c1 and 2 * pad == k - 1 and stride == 1
+    assert cin == c0 + c1
+    oh, ow = _out_hw(h, w, k, stride, pad)
     wp = packed_weight(weight, W_RSKC, torch.bfloat16)
-    call("ssg_conv2d_fwd_tc", x, c0, x1, c1, wp, bias, y, n, h, w, cout, k, pad, act, slope, flops=_flops(n, h, w, cin, cout, k))
+    call("ssg_conv2d_fwd_tc", x, c0, x1, c1, wp, bias, y, n, h, w, cout, k, stride, pad, act, slope,
+         flops=_flops(n, oh, ow, cin, cout, k))
 
 
 def dgrad(dy, weight, dx, stride, pad):
-    """dx = conv(dy, flip(W)^T): the forward kernel with roles of cin / cout swapped."""
+    """dx (n, cin, h, w) from dy (n, cout, oh, ow); weights packed [tap][cin][cout] (K-major in cout)."""
     from .ops import packed_weight
-    n, cout, h, w = dy.shape
-    _, cin, k, _ = weight.shape
-    assert stride == 1 and 2 * pad == k - 1
-    wp = packed_weight(weight, W_RSCK_FLIP, torch.bfloat16)     # [tap'][cin][cout] == [taps][N][K]
-    call("ssg_conv2d_fwd_tc", dy, cout, None, 0, wp, None, dx, n, h, w, cin, k, k - 1 - pad, 0, 0.0,
-         flops=_flops(n, h, w, cin, cout, k))
+    n, cin, h, w = dx.shape
+    cout, _, k, _ = weight.shape
+    wp = packed_weight(weight, W_RSCK, torch.bfloat16)
+    call("ssg_conv2d_dgrad_tc", dy, wp, dx, n, h, w, cin, cout, k, stride, pad,
+         flops=_flops(n, dy.shape[2], dy.shape[3], cin, cout, k))
 
 
 def wgrad(x, dy, dw, stride, pad, x1=None):
@@ -41,7 +50,8 @@ def wgrad(x, dy, dw, stride, pad, x1=None):
     c1 = x1.shape[1] if x1 is not None else 0
     cout = dy.shape[1]
     k = dw.shape[-1]
-    if stride != 1 or cout % 64 or c0 % 64 or c1 % 64 or k not in (1, 3) or 2 * pad != k - 1 or dy.dtype != torch.bfloat16:
+    if stride not in (1, 2) or cout % 64 or c0 % 64 or c1 % 64 or k not in (1, 3) or dy.dtype != torch.bfloat16:
         return False
-    call("ssg_conv2d_wgrad_tc", x, c0, x1, c1, dy, dw, n, h, w, cout, k, pad, flops=_flops(n, h, w, c0 + c1, cout, k))
+    call("ssg_conv2d_wgrad_tc", x, c0, x1, c1, dy, dw, n, h, w, cout, k, stride, pad,
+         flops=_flops(n, dy.shape[2], dy.shape[3], c0 + c1, cout, k))
     return True

@@ -14,6 +14,7 @@
 #include "tc_common.cuh"
 #include <cudaTypedefs.h>
 #include <mutex>
+#include <string.h>
 
 namespace ssg {
 namespace tc {
@@ -23,17 +24,29 @@ constexpr int BK = 64;           // bf16 channels per k-block (128 bytes == swiz
 constexpr int A_BYTES = BM * BK * 2;
 constexpr int NUM_THREADS = 192;
 
+// One output-parity class of a (possibly strided / transposed) convolution: the taps that contribute to it, as
+// source-pixel offsets (added to in_mul * tile pixel) and the index of the weight tap they multiply.
+struct TapClass {
+    int ntaps;
+    int8_t dy[9], dx[9], wt[9];
+    int8_t add_y, add_x;         // destination pixel = out_mul * tile pixel + add
+    int8_t pad_[3];
+};
+
 struct ConvTcParams {
     bf16* y;
     const float* bias;
-    int N, H, W;                 // output (== input) batch / spatial dims
+    int N, H, W;                 // tile-space dims: the pixel grid the GEMM rows enumerate
+    int out_H, out_W;            // spatial dims of y
+    int out_mul;                 // 1; 2 for the data gradient of a stride-2 convolution (one class per parity)
+    int in_mul;                  // 1; 2 for a stride-2 forward (the tensor map traverses with the same stride)
     int cout;                    // real output channels; row stride of y
     int tw_log2, th_log2;        // tile = TW x TH x NB pixels (product 128)
     int tiles_x, tiles_y;
-    int taps, kw, pad;
     int chunks0, chunks1;        // 64-channel chunks taken from x0 / x1
     int act;
     float slope;
+    TapClass cls[4];             // blockIdx.z selects the class
 };
 
 template <int BN>
@@ -68,7 +81,8 @@ __global__ void __launch_bounds__(NUM_THREADS) conv_tc_fwd_kernel(const __grid_c
     const int w0 = tx * TW, h0 = ty * TH, img0 = tn * (BM >> (p.tw_log2 + p.th_log2));
     const int n0 = blockIdx.y * BN;
     const int chunks = p.chunks0 + p.chunks1;
-    const int num_kb = p.taps * chunks;
+    const TapClass& tcl = p.cls[blockIdx.z];
+    const int num_kb = tcl.ntaps * chunks;
 
     if (threadIdx.x == 0) {
         for (int i = 0; i < L::STAGES; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
@@ -91,12 +105,12 @@ __global__ void __launch_bounds__(NUM_THREADS) conv_tc_fwd_kernel(const __grid_c
                 mbar_wait(&empty_bar[stage], phase ^ 1);
                 mbar_expect_tx(&full_bar[stage], L::STAGE_BYTES);
                 const int tap = kb / chunks, ch = kb - tap * chunks;
-                const int r = tap / p.kw, s = tap - r * p.kw;
+                const int cx = p.in_mul * w0 + tcl.dx[tap], cy = p.in_mul * h0 + tcl.dy[tap];
                 uint8_t* sa = smem + stage * L::STAGE_BYTES;
                 uint8_t* sb = sa + A_BYTES;
-                if (ch < p.chunks0) tma_load_4d(sa, &tmA0, ch * BK, w0 + s - p.pad, h0 + r - p.pad, img0, &full_bar[stage]);
-                else tma_load_4d(sa, &tmA1, (ch - p.chunks0) * BK, w0 + s - p.pad, h0 + r - p.pad, img0, &full_bar[stage]);
-                tma_load_3d(sb, &tmB, ch * BK, n0, tap, &full_bar[stage]);
+                if (ch < p.chunks0) tma_load_4d(sa, &tmA0, ch * BK, cx, cy, img0, &full_bar[stage]);
+                else tma_load_4d(sa, &tmA1, (ch - p.chunks0) * BK, cx, cy, img0, &full_bar[stage]);
+                tma_load_3d(sb, &tmB, ch * BK, n0, tcl.wt[tap], &full_bar[stage]);
             }
         }
     } else if (warp == 1) {
@@ -122,9 +136,10 @@ __global__ void __launch_bounds__(NUM_THREADS) conv_tc_fwd_kernel(const __grid_c
         const int q = warp & 3;
         const int m = q * 32 + lane;                // accumulator row == pixel index inside the tile
         const int twi = m & (TW - 1), thi = (m >> p.tw_log2) & (TH - 1), nbi = m >> (p.tw_log2 + p.th_log2);
-        const int ox = w0 + twi, oy = h0 + thi, on = img0 + nbi;
-        const bool row_ok = ox < p.W && oy < p.H && on < p.N;
-        bf16* yrow = p.y + (((long long)on * p.H + oy) * p.W + ox) * p.cout + n0;
+        const int tx_ = w0 + twi, ty_ = h0 + thi, on = img0 + nbi;
+        const int ox = p.out_mul * tx_ + tcl.add_x, oy = p.out_mul * ty_ + tcl.add_y;
+        const bool row_ok = tx_ < p.W && ty_ < p.H && on < p.N && ox < p.out_W && oy < p.out_H;
+        bf16* yrow = p.y + (((long long)on * p.out_H + oy) * p.out_W + ox) * p.cout + n0;
         mbar_wait(tmem_full_bar, 0);
         tc_fence_after();
         const bool vec_ok = (p.cout % 8 == 0);
@@ -173,10 +188,11 @@ static PFN_cuTensorMapEncodeTiled_v12000 get_encode() {
 
 // bf16 tensor map; dims/box innermost first; strides in BYTES for dims 1..rank-1
 int encode_bf16_map(CUtensorMap* map, const void* ptr, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
-                    const uint32_t* box, CUtensorMapSwizzle swizzle) {
+                    const uint32_t* box, CUtensorMapSwizzle swizzle, const uint32_t* elem_strides = nullptr) {
     auto enc = get_encode();
     if (!enc) { set_error("cuTensorMapEncodeTiled entry point unavailable"); return SSG_ERR_CUDA; }
     uint32_t estr[5] = {1, 1, 1, 1, 1};
+    if (elem_strides) for (int i = 0; i < rank; ++i) estr[i] = elem_strides[i];
     CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(ptr), dims, strides_bytes, box, estr,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed with CUresult %d", (int)r); return SSG_ERR_CUDA; }
@@ -187,14 +203,14 @@ static int ilog2_ceil(int v) { int l = 0; while ((1 << l) < v) ++l; return l; }
 
 template <int BN>
 static int launch_fwd(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b, const ConvTcParams& p, int m_tiles,
-                      cudaStream_t st) {
+                      int n_classes, cudaStream_t st) {
     using L = SmemLayout<BN>;
     static bool attr_set = false;
     if (!attr_set) {
         SSG_CHECK_CUDA(cudaFuncSetAttribute(conv_tc_fwd_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
         attr_set = true;
     }
-    dim3 grid((unsigned)m_tiles, (unsigned)((p.cout + BN - 1) / BN));
+    dim3 grid((unsigned)m_tiles, (unsigned)((p.cout + BN - 1) / BN), (unsigned)n_classes);
     conv_tc_fwd_kernel<BN><<<grid, NUM_THREADS, L::TOTAL, st>>>(a0, a1, b, p);
     SSG_CHECK_LAUNCH();
     return SSG_OK;
@@ -205,52 +221,119 @@ static int launch_fwd(const CUtensorMap& a0, const CUtensorMap& a1, const CUtens
 using namespace ssg;
 using namespace ssg::tc;
 
-extern "C" {
+namespace ssg {
+namespace tc {
 
-int ssg_conv2d_fwd_tc(const void* x0, int c0, const void* x1, int c1, const void* w_packed, const float* bias, void* y, int n, int h,
-                      int w, int cout, int ksize, int pad, int act, float slope, ssg_stream_t s) {
-    SSG_CHECK_ARG(n > 0 && h > 0 && w > 0 && cout > 0 && c0 > 0 && c0 % 64 == 0 && c1 >= 0 && c1 % 64 == 0,
-                  "conv2d_fwd_tc: channels must be multiples of 64 (c0=%d c1=%d)", c0, c1);
-    SSG_CHECK_ARG((ksize == 1 || ksize == 3) && pad >= 0 && 2 * pad == ksize - 1, "conv2d_fwd_tc: only 1x1/p0 and 3x3/p1 (same-size) convolutions");
-    SSG_CHECK_ARG(x1 != nullptr || c1 == 0, "conv2d_fwd_tc: x1 missing");
-    const int cin = c0 + c1, taps = ksize * ksize;
-    int twl = ilog2_ceil(w); if (twl > 7) twl = 7;
-    int thl = ilog2_ceil(h); if (thl > 7 - twl) thl = 7 - twl;
+static void pick_tile(int h, int w, int& twl, int& thl) {
+    twl = ilog2_ceil(w); if (twl > 7) twl = 7;
+    thl = ilog2_ceil(h); if (thl > 7 - twl) thl = 7 - twl;
+}
+
+// NHWC activation map: box = {64 ch, TW, TH, NB} output pixels; with in_mul == 2 the box spans 2TW x 2TH source
+// pixels traversed with element stride 2 (the stride-2 convolution's gather).
+static int encode_act_map(CUtensorMap* m, const void* ptr, int c, int n, int h, int w, int twl, int thl, int in_mul) {
+    const int TW = 1 << twl, TH = 1 << thl, NB = BM / (TW * TH);
+    uint64_t dims[4] = {(uint64_t)c, (uint64_t)w, (uint64_t)h, (uint64_t)n};
+    uint64_t str[3] = {(uint64_t)c * 2, (uint64_t)w * c * 2, (uint64_t)h * w * c * 2};
+    uint32_t box[4] = {64, (uint32_t)(TW * in_mul), (uint32_t)(TH * in_mul), (uint32_t)NB};
+    uint32_t es[4] = {1, (uint32_t)in_mul, (uint32_t)in_mul, 1};
+    return encode_bf16_map(m, ptr, 4, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B, es);
+}
+
+// Shared driver of the forward / data-gradient launches.  (sh, sw): source spatial dims; (th_, tw_): tile-space dims;
+// (oh, ow): destination dims; gemm_n: destination channels; weights are [taps][gemm_n][c0 + c1] bf16.
+static int run_conv(const void* x0, int c0, const void* x1, int c1, const void* w_packed, int w_taps, const float* bias, void* y,
+                    int n, int sh, int sw, int th_, int tw_, int oh, int ow, int gemm_n, int in_mul, int out_mul,
+                    const TapClass* cls, int n_classes, int act, float slope, cudaStream_t st) {
+    int twl, thl;
+    pick_tile(th_, tw_, twl, thl);
     const int TW = 1 << twl, TH = 1 << thl, NB = BM / (TW * TH);
     ConvTcParams p;
-    p.y = (bf16*)y; p.bias = bias; p.N = n; p.H = h; p.W = w; p.cout = cout;
-    p.tw_log2 = twl; p.th_log2 = thl;
-    p.tiles_x = (w + TW - 1) / TW; p.tiles_y = (h + TH - 1) / TH;
+    memset(&p, 0, sizeof(p));
+    p.y = (bf16*)y; p.bias = bias; p.N = n; p.H = th_; p.W = tw_; p.out_H = oh; p.out_W = ow; p.out_mul = out_mul; p.in_mul = in_mul;
+    p.cout = gemm_n; p.tw_log2 = twl; p.th_log2 = thl;
+    p.tiles_x = (tw_ + TW - 1) / TW; p.tiles_y = (th_ + TH - 1) / TH;
+    p.chunks0 = c0 / 64; p.chunks1 = c1 / 64; p.act = act; p.slope = slope;
+    for (int i = 0; i < n_classes; ++i) p.cls[i] = cls[i];
     const int tiles_n = (n + NB - 1) / NB;
-    p.taps = taps; p.kw = ksize; p.pad = pad; p.chunks0 = c0 / 64; p.chunks1 = c1 / 64; p.act = act; p.slope = slope;
     CUtensorMap ma0, ma1, mb;
-    {
-        uint64_t dims[4] = {(uint64_t)c0, (uint64_t)w, (uint64_t)h, (uint64_t)n};
-        uint64_t str[3] = {(uint64_t)c0 * 2, (uint64_t)w * c0 * 2, (uint64_t)h * w * c0 * 2};
-        uint32_t box[4] = {64, (uint32_t)TW, (uint32_t)TH, (uint32_t)NB};
-        int rc = encode_bf16_map(&ma0, x0, 4, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B);
+    int rc = encode_act_map(&ma0, x0, c0, n, sh, sw, twl, thl, in_mul);
+    if (rc) return rc;
+    ma1 = ma0;
+    if (c1 > 0) {
+        rc = encode_act_map(&ma1, x1, c1, n, sh, sw, twl, thl, in_mul);
         if (rc) return rc;
-        ma1 = ma0;
-        if (c1 > 0) {
-            uint64_t dims1[4] = {(uint64_t)c1, (uint64_t)w, (uint64_t)h, (uint64_t)n};
-            uint64_t str1[3] = {(uint64_t)c1 * 2, (uint64_t)w * c1 * 2, (uint64_t)h * w * c1 * 2};
-            rc = encode_bf16_map(&ma1, x1, 4, dims1, str1, box, CU_TENSOR_MAP_SWIZZLE_128B);
-            if (rc) return rc;
-        }
     }
-    const int BN = cout >= 128 ? 128 : (cout > 16 ? 64 : 16);
+    const int cin = c0 + c1;
+    const int BN = gemm_n >= 128 ? 128 : (gemm_n > 16 ? 64 : 16);
     {
-        uint64_t dims[3] = {(uint64_t)cin, (uint64_t)cout, (uint64_t)taps};
-        uint64_t str[2] = {(uint64_t)cin * 2, (uint64_t)cout * cin * 2};
+        uint64_t dims[3] = {(uint64_t)cin, (uint64_t)gemm_n, (uint64_t)w_taps};
+        uint64_t str[2] = {(uint64_t)cin * 2, (uint64_t)gemm_n * cin * 2};
         uint32_t box[3] = {64, (uint32_t)BN, 1};
-        int rc = encode_bf16_map(&mb, w_packed, 3, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B);
+        rc = encode_bf16_map(&mb, w_packed, 3, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B);
         if (rc) return rc;
     }
     const int m_tiles = p.tiles_x * p.tiles_y * tiles_n;
-    cudaStream_t st = (cudaStream_t)s;
-    if (BN == 128) return launch_fwd<128>(ma0, ma1, mb, p, m_tiles, st);
-    if (BN == 64) return launch_fwd<64>(ma0, ma1, mb, p, m_tiles, st);
-    return launch_fwd<16>(ma0, ma1, mb, p, m_tiles, st);
+    if (BN == 128) return launch_fwd<128>(ma0, ma1, mb, p, m_tiles, n_classes, st);
+    if (BN == 64) return launch_fwd<64>(ma0, ma1, mb, p, m_tiles, n_classes, st);
+    return launch_fwd<16>(ma0, ma1, mb, p, m_tiles, n_classes, st);
+}
+
+}  // namespace tc
+}  // namespace ssg
+
+extern "C" {
+
+int ssg_conv2d_fwd_tc(const void* x0, int c0, const void* x1, int c1, const void* w_packed, const float* bias, void* y, int n, int h,
+                      int w, int cout, int ksize, int stride, int pad, int act, float slope, ssg_stream_t s) {
+    SSG_CHECK_ARG(n > 0 && h > 0 && w > 0 && cout > 0 && c0 > 0 && c0 % 64 == 0 && c1 >= 0 && c1 % 64 == 0,
+                  "conv2d_fwd_tc: channels must be multiples of 64 (c0=%d c1=%d)", c0, c1);
+    SSG_CHECK_ARG((ksize == 1 || ksize == 3) && pad >= 0 && pad < ksize && (stride == 1 || stride == 2),
+                  "conv2d_fwd_tc: kernel 1 or 3, stride 1 or 2 (k=%d stride=%d pad=%d)", ksize, stride, pad);
+    SSG_CHECK_ARG(x1 != nullptr || c1 == 0, "conv2d_fwd_tc: x1 missing");
+    const int oh = (h + 2 * pad - ksize) / stride + 1, ow = (w + 2 * pad - ksize) / stride + 1;
+    SSG_CHECK_ARG(oh > 0 && ow > 0, "conv2d_fwd_tc: empty output");
+    TapClass c;
+    memset(&c, 0, sizeof(c));
+    c.ntaps = ksize * ksize;
+    for (int r = 0; r < ksize; ++r)
+        for (int q = 0; q < ksize; ++q) {
+            const int t = r * ksize + q;
+            c.dy[t] = (int8_t)(r - pad); c.dx[t] = (int8_t)(q - pad); c.wt[t] = (int8_t)t;
+        }
+    return run_conv(x0, c0, x1, c1, w_packed, ksize * ksize, bias, y, n, h, w, oh, ow, oh, ow, cout, stride, 1, &c, 1, act, slope,
+                    (cudaStream_t)s);
+}
+
+int ssg_conv2d_dgrad_tc(const void* dy, const void* w_packed, void* dx, int n, int h, int w, int cin, int cout, int ksize, int stride,
+                        int pad, ssg_stream_t s) {
+    SSG_CHECK_ARG(n > 0 && h > 0 && w > 0 && cin > 0 && cout > 0 && cout % 64 == 0, "conv2d_dgrad_tc: cout must be a multiple of 64 (%d)", cout);
+    SSG_CHECK_ARG((ksize == 1 || ksize == 3) && pad >= 0 && pad < ksize && (stride == 1 || (stride == 2 && ksize == 3)),
+                  "conv2d_dgrad_tc: kernel 1 or 3 at stride 1, kernel 3 at stride 2 (k=%d stride=%d)", ksize, stride);
+    const int oh = (h + 2 * pad - ksize) / stride + 1, ow = (w + 2 * pad - ksize) / stride + 1;
+    SSG_CHECK_ARG(oh > 0 && ow > 0, "conv2d_dgrad_tc: empty dy");
+    TapClass c[4];
+    memset(c, 0, sizeof(c));
+    int ncls = 0;
+    // dx[i] = sum_r dy[(i + pad - r) / stride] W[r] over the taps where the division is exact: one class per parity of i
+    for (int py = 0; py < stride; ++py)
+        for (int px = 0; px < stride; ++px) {
+            TapClass& k = c[ncls++];
+            k.add_y = (int8_t)py; k.add_x = (int8_t)px;
+            for (int r = 0; r < ksize; ++r)
+                for (int q = 0; q < ksize; ++q) {
+                    const int ny = py + pad - r, nx = px + pad - q;
+                    if (((ny % stride) + stride) % stride != 0 || ((nx % stride) + stride) % stride != 0) continue;
+                    const int t = k.ntaps++;
+                    k.dy[t] = (int8_t)(ny >= 0 ? ny / stride : -((-ny) / stride));
+                    k.dx[t] = (int8_t)(nx >= 0 ? nx / stride : -((-nx) / stride));
+                    k.wt[t] = (int8_t)(r * ksize + q);
+                }
+            SSG_CHECK_ARG(k.ntaps > 0, "conv2d_dgrad_tc: empty parity class");
+        }
+    const int th_ = (h + stride - 1) / stride, tw_ = (w + stride - 1) / stride;
+    return run_conv(dy, cout, nullptr, 0, w_packed, ksize * ksize, nullptr, dx, n, oh, ow, th_, tw_, h, w, cin, 1, stride, c, ncls, 0, 0.f,
+                    (cudaStream_t)s);
 }
 
 }  // extern "C"
@@ -272,6 +355,7 @@ struct WgradParams {
     int cout, cin;
     int tw_log2, th_log2, tiles_x, tiles_y, m_tiles;
     int taps, kw, pad;
+    int in_mul;                 // convolution stride: x pixel = in_mul * dy pixel + tap - pad
     int chunks0, chunks1;
     int units;                  // taps * (chunks0 + chunks1)
 };
@@ -348,8 +432,9 @@ __global__ void __launch_bounds__(NUM_THREADS) conv_tc_wgrad_kernel(const __grid
                         const int tap = u / chunks, ch = u - tap * chunks;
                         const int r = tap / p.kw, s = tap - r * p.kw;
                         uint8_t* dst = smem + C::X_OFFSET + (slot * 2 + e) * C::BOX;
-                        if (ch < p.chunks0) tma_load_4d(dst, &tmX0, ch * BK, w0 + s - p.pad, h0 + r - p.pad, img0, &x_full[slot]);
-                        else tma_load_4d(dst, &tmX1, (ch - p.chunks0) * BK, w0 + s - p.pad, h0 + r - p.pad, img0, &x_full[slot]);
+                        const int cx = p.in_mul * w0 + s - p.pad, cy = p.in_mul * h0 + r - p.pad;
+                        if (ch < p.chunks0) tma_load_4d(dst, &tmX0, ch * BK, cx, cy, img0, &x_full[slot]);
+                        else tma_load_4d(dst, &tmX1, (ch - p.chunks0) * BK, cx, cy, img0, &x_full[slot]);
                     }
                 }
             }
@@ -433,44 +518,36 @@ static int launch_wgrad(const CUtensorMap& x0, const CUtensorMap& x1, const CUte
 }  // namespace ssg
 
 extern "C" int ssg_conv2d_wgrad_tc(const void* x0, int c0, const void* x1, int c1, const void* dy, float* dw_oihw, int n, int h, int w,
-                                   int cout, int ksize, int pad, ssg_stream_t s) {
+                                   int cout, int ksize, int stride, int pad, ssg_stream_t s) {
     using namespace ssg;
     using namespace ssg::tc;
     SSG_CHECK_ARG(n > 0 && h > 0 && w > 0 && cout > 0 && cout % 64 == 0 && c0 > 0 && c0 % 64 == 0 && c1 >= 0 && c1 % 64 == 0,
                   "conv2d_wgrad_tc: channels must be multiples of 64 (c0=%d c1=%d cout=%d)", c0, c1, cout);
-    SSG_CHECK_ARG((ksize == 1 || ksize == 3) && 2 * pad == ksize - 1, "conv2d_wgrad_tc: only 1x1/p0 and 3x3/p1");
+    SSG_CHECK_ARG((ksize == 1 || ksize == 3) && pad >= 0 && pad < ksize && (stride == 1 || stride == 2),
+                  "conv2d_wgrad_tc: kernel 1 or 3, stride 1 or 2");
+    const int oh = (h + 2 * pad - ksize) / stride + 1, ow = (w + 2 * pad - ksize) / stride + 1;
+    SSG_CHECK_ARG(oh > 0 && ow > 0, "conv2d_wgrad_tc: empty dy");
     const int cin = c0 + c1, taps = ksize * ksize;
     cudaStream_t st = (cudaStream_t)s;
     SSG_CHECK_CUDA(cudaMemsetAsync(dw_oihw, 0, sizeof(float) * (size_t)cout * cin * taps, st));
-    int twl = ilog2_ceil(w); if (twl > 7) twl = 7;
-    int thl = ilog2_ceil(h); if (thl > 7 - twl) thl = 7 - twl;
+    int twl, thl;
+    pick_tile(oh, ow, twl, thl);          // pixel tiles enumerate dy; x is gathered at stride * pixel + tap - pad
     const int TW = 1 << twl, TH = 1 << thl, NB = BM / (TW * TH);
     WgradParams p;
-    p.dw = dw_oihw; p.N = n; p.H = h; p.W = w; p.cout = cout; p.cin = cin;
-    p.tw_log2 = twl; p.th_log2 = thl; p.tiles_x = (w + TW - 1) / TW; p.tiles_y = (h + TH - 1) / TH;
+    p.dw = dw_oihw; p.N = n; p.H = oh; p.W = ow; p.cout = cout; p.cin = cin; p.in_mul = stride;
+    p.tw_log2 = twl; p.th_log2 = thl; p.tiles_x = (ow + TW - 1) / TW; p.tiles_y = (oh + TH - 1) / TH;
     p.m_tiles = p.tiles_x * p.tiles_y * ((n + NB - 1) / NB);
     p.taps = taps; p.kw = ksize; p.pad = pad; p.chunks0 = c0 / 64; p.chunks1 = c1 / 64; p.units = taps * (cin / 64);
     CUtensorMap mx0, mx1, mdy;
-    uint32_t box[4] = {64, (uint32_t)TW, (uint32_t)TH, (uint32_t)NB};
-    {
-        uint64_t dims[4] = {(uint64_t)c0, (uint64_t)w, (uint64_t)h, (uint64_t)n};
-        uint64_t str[3] = {(uint64_t)c0 * 2, (uint64_t)w * c0 * 2, (uint64_t)h * w * c0 * 2};
-        int rc = encode_bf16_map(&mx0, x0, 4, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B);
-        if (rc) return rc;
-        mx1 = mx0;
-    }
+    int rc = encode_act_map(&mx0, x0, c0, n, h, w, twl, thl, stride);
+    if (rc) return rc;
+    mx1 = mx0;
     if (c1 > 0) {
-        uint64_t dims[4] = {(uint64_t)c1, (uint64_t)w, (uint64_t)h, (uint64_t)n};
-        uint64_t str[3] = {(uint64_t)c1 * 2, (uint64_t)w * c1 * 2, (uint64_t)h * w * c1 * 2};
-        int rc = encode_bf16_map(&mx1, x1, 4, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B);
+        rc = encode_act_map(&mx1, x1, c1, n, h, w, twl, thl, stride);
         if (rc) return rc;
     }
-    {
-        uint64_t dims[4] = {(uint64_t)cout, (uint64_t)w, (uint64_t)h, (uint64_t)n};
-        uint64_t str[3] = {(uint64_t)cout * 2, (uint64_t)w * cout * 2, (uint64_t)h * w * cout * 2};
-        int rc = encode_bf16_map(&mdy, dy, 4, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B);
-        if (rc) return rc;
-    }
+    rc = encode_act_map(&mdy, dy, cout, n, oh, ow, twl, thl, 1);
+    if (rc) return rc;
     if (cout % 128 == 0) return launch_wgrad<128>(mx0, mx1, mdy, p, st);
     return launch_wgrad<64>(mx0, mx1, mdy, p, st);
 }

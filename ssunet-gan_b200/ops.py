@@ -202,8 +202,8 @@ class _Conv2d(torch.autograd.Function):
         dx = dw = db = None
         if ctx.needs_input_grad[0]:
             dx = empty_nhwc(n, cin, h, w, dt, x.device)
-            if _tc_eligible(cout, cin, kh, stride, dt):
-                from . import conv_tc
+            from . import conv_tc
+            if _CONV_IMPL != "simt" and dt == torch.bfloat16 and conv_tc.dgrad_eligible(cin, cout, kh, stride):
                 conv_tc.dgrad(dy, weight, dx, stride, pad)
             else:
                 wp = packed_weight(weight, W_RSKC, dt)

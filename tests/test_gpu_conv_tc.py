@@ -26,6 +26,14 @@ CASES = [
     (1, 64, 64, 70, 130, 3),      # W > 128: two column tiles, ragged
     (1, 64, 768, 16, 16, 1),
     (2, 512, 64, 12, 12, 3),      # long K loop (72 k-blocks): pipeline wrap-around
+    # stride 2 (discriminator blocks 1,3,5,7: models_seg_gan.py:267-273): element-strided TMA gather forward /
+    # wgrad, parity-class data gradient
+    (2, 64, 64, 16, 16, 3, 2),
+    (1, 128, 128, 24, 20, 3, 2),  # ragged tiles
+    (3, 64, 128, 6, 10, 3, 2),    # several images per tile
+    (1, 256, 64, 34, 18, 3, 2),
+    (2, 64, 64, 15, 13, 3, 2),    # odd spatial dims: last row / column handled by the parity classes
+    (1, 64, 64, 140, 132, 3, 2),  # > 64 output columns: two column tiles
 ]
 
 
@@ -33,7 +41,8 @@ CASES = [
 def test_conv_tc_forward_backward(cfg):
     import ssunet_gan_b200 as ssg
     from ssunet_gan_b200 import ops
-    n, cin, cout, h, w, k = cfg
+    n, cin, cout, h, w, k = cfg[:6]
+    stride = cfg[6] if len(cfg) > 6 else 1
     ssg.set_compute_dtype(torch.bfloat16)
     ssg.set_conv_impl("auto")
     g = torch.Generator().manual_seed(cin * 7 + cout + h)
@@ -41,11 +50,11 @@ def test_conv_tc_forward_backward(cfg):
     wt = (torch.randn(cout, cin, k, k, generator=g) / math.sqrt(cin * k * k)).bfloat16().float()
     b = torch.randn(cout, generator=g)
     xr, wr, br = x.clone().requires_grad_(True), wt.clone().requires_grad_(True), b.clone().requires_grad_(True)
-    yr = F.leaky_relu(F.conv2d(xr, wr, br, 1, k // 2), 0.2)
+    yr = F.leaky_relu(F.conv2d(xr, wr, br, stride, k // 2), 0.2)
     gy = torch.randn(yr.shape, generator=g).bfloat16().float()
     yr.backward(gy)
     xc, wc, bc = x.cuda().requires_grad_(True), wt.cuda().requires_grad_(True), b.cuda().requires_grad_(True)
-    y = ops.conv2d(xc, wc, bc, 1, k // 2, ops.ACT_LEAKY, 0.2)
+    y = ops.conv2d(xc, wc, bc, stride, k // 2, ops.ACT_LEAKY, 0.2)
     y.backward(gy.cuda().bfloat16())
     assert rel(y.float(), yr) < 6e-3
     assert rel(xc.grad, xr.grad) < 8e-3       # tcgen05 dgrad (cout % 64 == 0) or SIMT dgrad
@@ -53,7 +62,7 @@ def test_conv_tc_forward_backward(cfg):
     assert rel(bc.grad, br.grad) < 8e-3
     # cross-check against the CUDA-core kernel on the device
     ssg.set_conv_impl("simt")
-    y2 = ops.conv2d(x.cuda(), wt.cuda(), b.cuda(), 1, k // 2, ops.ACT_LEAKY, 0.2)
+    y2 = ops.conv2d(x.cuda(), wt.cuda(), b.cuda(), stride, k // 2, ops.ACT_LEAKY, 0.2)
     assert rel(y.float(), y2.float()) < 6e-3
 
 
