@@ -48,6 +48,11 @@ int ssg_device_info(int* sm_count, int* cc_major, int* cc_minor);
 /* module boundary: reference tensors are NCHW fp32 (dataset.py:126-142, archs.py:623). */
 int ssg_nchw_to_nhwc(const float* src, void* dst, int dtype, int n, int c, int h, int w, ssg_stream_t s);
 int ssg_nhwc_to_nchw(const void* src, int dtype, float* dst, int n, int c, int h, int w, ssg_stream_t s);
+/* Same with channel-padded NHWC storage (c_dst / c_src >= c; padding channels are zero / ignored).  The tensor-core
+ * kernels need the NHWC pixel pitch to be a multiple of 16 bytes (TMA), so 3-channel images and SPADE's 3 / h-channel
+ * maps (normalization.py:93-98) are stored with their channel count rounded up to a multiple of 8. */
+int ssg_nchw_to_nhwc_pad(const float* src, void* dst, int dtype, int n, int c, int c_dst, int h, int w, ssg_stream_t s);
+int ssg_nhwc_to_nchw_pad(const void* src, int dtype, float* dst, int n, int c, int c_src, int h, int w, ssg_stream_t s);
 /* dtype cast of a flat buffer (fp32 <-> bf16), n elements */
 int ssg_cast(const void* src, int src_dtype, void* dst, int dst_dtype, long long n, ssg_stream_t s);
 /* torch.cat([a, b], 1) (archs.py:651,656,661,664,667) and its adjoint; rows = N*H*W */
@@ -57,6 +62,9 @@ int ssg_split2(const void* in, void* a, int ca, void* b, int cb, int dtype, long
  * multiplies every element (spectral norm's 1/sigma, spectral_norm.py:86-87). */
 int ssg_pack_conv_weight(const float* w_oihw, void* dst, int dtype, int layout, int cout, int cin, int kh, int kw,
                          const float* inv_scale_dev, ssg_stream_t s);
+/* Same, zero-padded to [.. cout_p ..][.. cin_p ..] channel extents (operands of channel-padded activations). */
+int ssg_pack_conv_weight_pad(const float* w_oihw, void* dst, int dtype, int layout, int cout, int cin, int kh, int kw, int cout_p,
+                             int cin_p, const float* inv_scale_dev, ssg_stream_t s);
 
 /* ---- convolution, CUDA-core implicit GEMM (any shape; the only path for tiny channel counts) */
 /* nn.Conv2d forward (archs.py:210,212,218; normalization.py:93-98; models_seg_gan.py:38-39).
@@ -71,26 +79,30 @@ int ssg_conv2d_wgrad_simt(const void* x, const void* dy, float* dw_oihw, int dty
                           int cout, int kh, int kw, int stride, int pad, ssg_stream_t s);
 
 /* ---- convolution, tcgen05 / TMEM / TMA implicit GEMM (bf16 NHWC, fp32 accumulate) ------------------- */
-/* Convolution (1x1 or 3x3, stride 1 or 2, zero padding `pad`) of the channel concatenation [x0 | x1]
- * (x1 may be NULL with c1 == 0; torch.cat is never materialised, archs.py:651-667).  c0, c1 multiples of 64;
- * (h, w) are the INPUT spatial dims.  w_packed: bf16 [taps][cout][c0+c1] (SSG_W_RSKC);
- * y = act(conv + bias), bf16 [n,oh,ow,cout].  The stride-2 gather is done by the TMA unit (element-strided
- * tensor-map traversal).  Replaces the cuDNN implicit-GEMM calls behind archs.py:210,212,218,593-601 and
- * models_seg_gan.py:38-39 (stride-1 and stride-2 blocks). */
-int ssg_conv2d_fwd_tc(const void* x0, int c0, const void* x1, int c1, const void* w_packed, const float* bias, void* y, int n,
-                      int h, int w, int cout, int ksize, int stride, int pad, int act, float slope, ssg_stream_t s);
+/* Channel counts passed to these three calls are the STORED (possibly zero-padded) channel counts of the NHWC
+ * tensors; they must be multiples of 8 (16-byte pixel pitch for TMA).  K-blocks are 64 channels wide; a ragged last
+ * block (e.g. the 8-channel stems and SPADE's 8..48-channel maps) is zero-filled by the TMA unit.
+ *
+ * Convolution (1x1 or 3x3, stride 1 or 2, zero padding `pad`) of the channel concatenation [x0 | x1]
+ * (x1 may be NULL with c1 == 0; torch.cat is never materialised, archs.py:651-667; c0 % 64 == 0 when x1 is given).
+ * (h, w) are the INPUT spatial dims.  w_packed: bf16 [taps][cout][c0+c1] (SSG_W_RSKC, zero rows/columns for
+ * padding channels); bias: bias_n fp32 entries or NULL; y = act(conv + bias), bf16 [n,oh,ow,cout].  The stride-2
+ * gather is done by the TMA unit (element-strided tensor-map traversal).  Replaces the cuDNN implicit-GEMM calls
+ * behind archs.py:210,212,218,593-601,615, normalization.py:93-98 and models_seg_gan.py:38-39. */
+int ssg_conv2d_fwd_tc(const void* x0, int c0, const void* x1, int c1, const void* w_packed, const float* bias, int bias_n, void* y,
+                      int n, int h, int w, int cout, int ksize, int stride, int pad, int act, float slope, ssg_stream_t s);
 
-/* Data gradient of the same convolution: dx bf16 [n,h,w,cin] from dy bf16 [n,oh,ow,cout]; cout multiple of 64.
+/* Data gradient of the same convolution: dx bf16 [n,h,w,cin] from dy bf16 [n,oh,ow,cout].
  * w_packed: bf16 [taps][cin][cout] (SSG_W_RSCK).  Stride 2 is computed as four output-parity classes (each a
  * small stride-1 convolution over dy with 1, 2, 2 and 4 taps) written interleaved into dx. */
 int ssg_conv2d_dgrad_tc(const void* dy, const void* w_packed, void* dx, int n, int h, int w, int cin, int cout, int ksize,
                         int stride, int pad, ssg_stream_t s);
 
 /* Weight gradient of the same convolution on tensor cores (both operands MN-major straight from the NHWC
- * tensors, split-K over pixel tiles, fp32 atomics into dw): dw_oihw fp32 [cout][c0+c1][k][k] is overwritten.
- * cout, c0, c1 multiples of 64; (h, w) are the INPUT spatial dims. */
-int ssg_conv2d_wgrad_tc(const void* x0, int c0, const void* x1, int c1, const void* dy, float* dw_oihw, int n, int h, int w,
-                        int cout, int ksize, int stride, int pad, ssg_stream_t s);
+ * tensors, split-K over pixel tiles, fp32 atomics into dw): dw_oihw fp32 [cout_real][cin_real][k][k] is
+ * overwritten (padding channels of x / dy are ignored).  (h, w) are the INPUT spatial dims. */
+int ssg_conv2d_wgrad_tc(const void* x0, int c0, const void* x1, int c1, const void* dy, int cout, float* dw_oihw, int cout_real,
+                        int cin_real, int n, int h, int w, int ksize, int stride, int pad, ssg_stream_t s);
 
 /* ---- per-channel statistics / batch norm -------------------------------------------------- */
 /* batchnorm.py:59-64 (_sum_ft of x and x**2): sums[0:C] = sum x, sums[C:2C] = sum x^2 (fp64,

@@ -108,7 +108,7 @@ class UNet_R_SS_v2(nn.Module):
         self.final.bias.data.fill_(0)
 
     def forward(self, input):
-        x = ops.to_nhwc(input)
+        x = ops.to_nhwc(input, pad_channels=True)
         enc_0 = self.conv0_0(x)
         enc_0 = self.SPADE0_0(enc_0, enc_0)
         p0, _ = self.pool(enc_0)
@@ -139,4 +139,5 @@ class UNet_R_SS_v2(nn.Module):
         dec_1 = self.SPADE1_1(dec_1, dec_1)
         dec_0 = self.conv0_1(ops.concat_channels(enc_0, self.up(dec_1)))
         dec_0 = self.SPADE0_1(dec_0, dec_0)
-        return ops.to_nchw_f32(self.final(dec_0))
+        nc = self.final.out_channels
+        return ops.to_nchw_f32(self.final(dec_0, cout_store=ops.thin_pad(nc)), channels=nc)

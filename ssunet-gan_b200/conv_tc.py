@@ -5,13 +5,10 @@ from . import _lib
 from ._lib import W_RSCK, W_RSKC, call
 
 
-def eligible(cin, cout, k, stride):
-    """Shapes the tensor-core forward kernel takes: 64-channel input granularity, 1x1 / 3x3, stride 1 or 2."""
-    return cin % 64 == 0 and cin >= 64 and k in (1, 3) and stride in (1, 2)
-
-
-def dgrad_eligible(cin, cout, k, stride):
-    return cout % 64 == 0 and cout >= 64 and k in (1, 3) and (stride == 1 or (stride == 2 and k == 3))
+def eligible(cin_s, cout_s, k, stride):
+    """Shapes the tensor-core kernels take: stored channel counts multiples of 8 (16-byte NHWC pixel pitch for TMA),
+    1x1 / 3x3, stride 1 or 2 (1x1 only at stride 1)."""
+    return cin_s % 8 == 0 and cout_s % 8 == 0 and (k == 3 or (k == 1 and stride == 1)) and stride in (1, 2)
 
 
 def _out_hw(h, w, k, stride, pad):
@@ -23,35 +20,34 @@ def _flops(n, oh, ow, cin, cout, k):
 
 
 def forward(x, weight, bias, y, stride, pad, act, slope, x1=None):
+    """y = act(conv([x | x1], weight) + bias); x / x1 / y may be channel-padded (ops.thin_pad)."""
     from .ops import packed_weight
     n, c0, h, w = x.shape
     c1 = x1.shape[1] if x1 is not None else 0
     cout, cin, k, _ = weight.shape
-    assert cin == c0 + c1
+    assert cin <= c0 + c1 and cout <= y.shape[1]
     oh, ow = _out_hw(h, w, k, stride, pad)
-    wp = packed_weight(weight, W_RSKC, torch.bfloat16)
-    call("ssg_conv2d_fwd_tc", x, c0, x1, c1, wp, bias, y, n, h, w, cout, k, stride, pad, act, slope,
-         flops=_flops(n, oh, ow, cin, cout, k))
+    wp = packed_weight(weight, W_RSKC, torch.bfloat16, cout_p=y.shape[1], cin_p=c0 + c1)
+    call("ssg_conv2d_fwd_tc", x, c0, x1, c1, wp, bias, cout if bias is not None else 0, y, n, h, w, y.shape[1], k, stride, pad, act,
+         slope, flops=_flops(n, oh, ow, cin, cout, k))
 
 
 def dgrad(dy, weight, dx, stride, pad):
-    """dx (n, cin, h, w) from dy (n, cout, oh, ow); weights packed [tap][cin][cout] (K-major in cout)."""
+    """dx (n, cin_s, h, w) from dy (n, cout_s, oh, ow); weights packed [tap][cin_s][cout_s] (K-major in cout)."""
     from .ops import packed_weight
-    n, cin, h, w = dx.shape
-    cout, _, k, _ = weight.shape
-    wp = packed_weight(weight, W_RSCK, torch.bfloat16)
-    call("ssg_conv2d_dgrad_tc", dy, wp, dx, n, h, w, cin, cout, k, stride, pad,
+    n, cin_s, h, w = dx.shape
+    cout, cin, k, _ = weight.shape
+    cout_s = dy.shape[1]
+    wp = packed_weight(weight, W_RSCK, torch.bfloat16, cout_p=cout_s, cin_p=cin_s)
+    call("ssg_conv2d_dgrad_tc", dy, wp, dx, n, h, w, cin_s, cout_s, k, stride, pad,
          flops=_flops(n, dy.shape[2], dy.shape[3], cin, cout, k))
 
 
 def wgrad(x, dy, dw, stride, pad, x1=None):
-    """dW (OIHW fp32) on tensor cores; returns False when the shape is not eligible (caller falls back to SIMT)."""
+    """dW (OIHW fp32, real channel extents) on tensor cores from (possibly channel-padded) x and dy."""
     n, c0, h, w = x.shape
     c1 = x1.shape[1] if x1 is not None else 0
-    cout = dy.shape[1]
-    k = dw.shape[-1]
-    if stride not in (1, 2) or cout % 64 or c0 % 64 or c1 % 64 or k not in (1, 3) or dy.dtype != torch.bfloat16:
-        return False
-    call("ssg_conv2d_wgrad_tc", x, c0, x1, c1, dy, dw, n, h, w, cout, k, stride, pad,
-         flops=_flops(n, dy.shape[2], dy.shape[3], c0 + c1, cout, k))
+    cout, cin, k, _ = dw.shape
+    call("ssg_conv2d_wgrad_tc", x, c0, x1, c1, dy, dy.shape[1], dw, cout, cin, n, h, w, k, stride, pad,
+         flops=_flops(n, dy.shape[2], dy.shape[3], cin, cout, k))
     return True

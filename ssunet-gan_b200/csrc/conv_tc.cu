@@ -40,7 +40,8 @@ struct ConvTcParams {
     int out_H, out_W;            // spatial dims of y
     int out_mul;                 // 1; 2 for the data gradient of a stride-2 convolution (one class per parity)
     int in_mul;                  // 1; 2 for a stride-2 forward (the tensor map traverses with the same stride)
-    int cout;                    // real output channels; row stride of y
+    int cout;                    // output channels as stored (row stride of y)
+    int bias_n;                  // number of valid bias entries (real channels; padding channels get none)
     int tw_log2, th_log2;        // tile = TW x TH x NB pixels (product 128)
     int tiles_x, tiles_y;
     int chunks0, chunks1;        // 64-channel chunks taken from x0 / x1
@@ -154,13 +155,16 @@ __global__ void __launch_bounds__(NUM_THREADS) conv_tc_fwd_kernel(const __grid_c
             for (int j = 0; j < 16; ++j) {
                 const int n = n0 + c0 + j;
                 float t = __uint_as_float(v[j]);
-                if (p.bias != nullptr && n < p.cout) t += p.bias[n];
+                if (p.bias != nullptr && n < p.bias_n) t += p.bias[n];
                 f[j] = apply_act(t, p.act, p.slope);
             }
             if (vec_ok && n0 + c0 + 16 <= p.cout) {
                 Vec<bf16> o;
                 o.set(f); o.store(yrow + c0);
                 o.set(f + 8); o.store(yrow + c0 + 8);
+            } else if (vec_ok && n0 + c0 + 8 <= p.cout) {
+                Vec<bf16> o;
+                o.set(f); o.store(yrow + c0);
             } else {
 #pragma unroll
                 for (int j = 0; j < 16; ++j)
@@ -242,18 +246,18 @@ static int encode_act_map(CUtensorMap* m, const void* ptr, int c, int n, int h, 
 
 // Shared driver of the forward / data-gradient launches.  (sh, sw): source spatial dims; (th_, tw_): tile-space dims;
 // (oh, ow): destination dims; gemm_n: destination channels; weights are [taps][gemm_n][c0 + c1] bf16.
-static int run_conv(const void* x0, int c0, const void* x1, int c1, const void* w_packed, int w_taps, const float* bias, void* y,
-                    int n, int sh, int sw, int th_, int tw_, int oh, int ow, int gemm_n, int in_mul, int out_mul,
+static int run_conv(const void* x0, int c0, const void* x1, int c1, const void* w_packed, int w_taps, const float* bias, int bias_n,
+                    void* y, int n, int sh, int sw, int th_, int tw_, int oh, int ow, int gemm_n, int in_mul, int out_mul,
                     const TapClass* cls, int n_classes, int act, float slope, cudaStream_t st) {
     int twl, thl;
     pick_tile(th_, tw_, twl, thl);
     const int TW = 1 << twl, TH = 1 << thl, NB = BM / (TW * TH);
     ConvTcParams p;
     memset(&p, 0, sizeof(p));
-    p.y = (bf16*)y; p.bias = bias; p.N = n; p.H = th_; p.W = tw_; p.out_H = oh; p.out_W = ow; p.out_mul = out_mul; p.in_mul = in_mul;
+    p.y = (bf16*)y; p.bias = bias; p.bias_n = bias_n; p.N = n; p.H = th_; p.W = tw_; p.out_H = oh; p.out_W = ow; p.out_mul = out_mul; p.in_mul = in_mul;
     p.cout = gemm_n; p.tw_log2 = twl; p.th_log2 = thl;
     p.tiles_x = (tw_ + TW - 1) / TW; p.tiles_y = (th_ + TH - 1) / TH;
-    p.chunks0 = c0 / 64; p.chunks1 = c1 / 64; p.act = act; p.slope = slope;
+    p.chunks0 = (c0 + 63) / 64; p.chunks1 = (c1 + 63) / 64; p.act = act; p.slope = slope;
     for (int i = 0; i < n_classes; ++i) p.cls[i] = cls[i];
     const int tiles_n = (n + NB - 1) / NB;
     CUtensorMap ma0, ma1, mb;
@@ -284,10 +288,12 @@ static int run_conv(const void* x0, int c0, const void* x1, int c1, const void* 
 
 extern "C" {
 
-int ssg_conv2d_fwd_tc(const void* x0, int c0, const void* x1, int c1, const void* w_packed, const float* bias, void* y, int n, int h,
-                      int w, int cout, int ksize, int stride, int pad, int act, float slope, ssg_stream_t s) {
-    SSG_CHECK_ARG(n > 0 && h > 0 && w > 0 && cout > 0 && c0 > 0 && c0 % 64 == 0 && c1 >= 0 && c1 % 64 == 0,
-                  "conv2d_fwd_tc: channels must be multiples of 64 (c0=%d c1=%d)", c0, c1);
+int ssg_conv2d_fwd_tc(const void* x0, int c0, const void* x1, int c1, const void* w_packed, const float* bias, int bias_n, void* y,
+                      int n, int h, int w, int cout, int ksize, int stride, int pad, int act, float slope, ssg_stream_t s) {
+    SSG_CHECK_ARG(n > 0 && h > 0 && w > 0 && cout > 0 && cout % 8 == 0 && c0 > 0 && c0 % 8 == 0 && c1 >= 0 && c1 % 8 == 0 &&
+                      (c1 == 0 || c0 % 64 == 0),
+                  "conv2d_fwd_tc: stored channel counts must be multiples of 8, c0 of 64 when x1 is given (c0=%d c1=%d cout=%d)", c0, c1,
+                  cout);
     SSG_CHECK_ARG((ksize == 1 || ksize == 3) && pad >= 0 && pad < ksize && (stride == 1 || stride == 2),
                   "conv2d_fwd_tc: kernel 1 or 3, stride 1 or 2 (k=%d stride=%d pad=%d)", ksize, stride, pad);
     SSG_CHECK_ARG(x1 != nullptr || c1 == 0, "conv2d_fwd_tc: x1 missing");
@@ -301,13 +307,14 @@ int ssg_conv2d_fwd_tc(const void* x0, int c0, const void* x1, int c1, const void
             const int t = r * ksize + q;
             c.dy[t] = (int8_t)(r - pad); c.dx[t] = (int8_t)(q - pad); c.wt[t] = (int8_t)t;
         }
-    return run_conv(x0, c0, x1, c1, w_packed, ksize * ksize, bias, y, n, h, w, oh, ow, oh, ow, cout, stride, 1, &c, 1, act, slope,
+    return run_conv(x0, c0, x1, c1, w_packed, ksize * ksize, bias, bias_n, y, n, h, w, oh, ow, oh, ow, cout, stride, 1, &c, 1, act, slope,
                     (cudaStream_t)s);
 }
 
 int ssg_conv2d_dgrad_tc(const void* dy, const void* w_packed, void* dx, int n, int h, int w, int cin, int cout, int ksize, int stride,
                         int pad, ssg_stream_t s) {
-    SSG_CHECK_ARG(n > 0 && h > 0 && w > 0 && cin > 0 && cout > 0 && cout % 64 == 0, "conv2d_dgrad_tc: cout must be a multiple of 64 (%d)", cout);
+    SSG_CHECK_ARG(n > 0 && h > 0 && w > 0 && cin > 0 && cout > 0 && cout % 8 == 0 && cin % 8 == 0,
+                  "conv2d_dgrad_tc: stored channel counts must be multiples of 8 (cin=%d cout=%d)", cin, cout);
     SSG_CHECK_ARG((ksize == 1 || ksize == 3) && pad >= 0 && pad < ksize && (stride == 1 || (stride == 2 && ksize == 3)),
                   "conv2d_dgrad_tc: kernel 1 or 3 at stride 1, kernel 3 at stride 2 (k=%d stride=%d)", ksize, stride);
     const int oh = (h + 2 * pad - ksize) / stride + 1, ow = (w + 2 * pad - ksize) / stride + 1;
@@ -332,7 +339,7 @@ int ssg_conv2d_dgrad_tc(const void* dy, const void* w_packed, void* dx, int n, i
             SSG_CHECK_ARG(k.ntaps > 0, "conv2d_dgrad_tc: empty parity class");
         }
     const int th_ = (h + stride - 1) / stride, tw_ = (w + stride - 1) / stride;
-    return run_conv(dy, cout, nullptr, 0, w_packed, ksize * ksize, nullptr, dx, n, oh, ow, th_, tw_, h, w, cin, 1, stride, c, ncls, 0, 0.f,
+    return run_conv(dy, cout, nullptr, 0, w_packed, ksize * ksize, nullptr, 0, dx, n, oh, ow, th_, tw_, h, w, cin, 1, stride, c, ncls, 0, 0.f,
                     (cudaStream_t)s);
 }
 
@@ -352,7 +359,7 @@ namespace tc {
 struct WgradParams {
     float* dw;                  // OIHW fp32, pre-zeroed
     int N, H, W;                // dy spatial dims (== x dims, stride 1)
-    int cout, cin;
+    int cout, cin;              // REAL channel counts: extents of dw (stored tensors may be channel-padded)
     int tw_log2, th_log2, tiles_x, tiles_y, m_tiles;
     int taps, kw, pad;
     int in_mul;                 // convolution stride: x pixel = in_mul * dy pixel + tap - pad
@@ -473,9 +480,9 @@ __global__ void __launch_bounds__(NUM_THREADS) conv_tc_wgrad_kernel(const __grid
         const int kk = p.taps;                           // kh * kw
         for (int g = 0; g < pairs; ++g) {
             const int u = unit0 + 2 * g + (row >> 6);
-            const bool row_ok = u < p.units && n_iter > 0;
             const int tap = u / chunks, ch = u - tap * chunks;
             const int ci = ch * BK + (row & 63);
+            const bool row_ok = u < p.units && n_iter > 0 && ci < p.cin;
 #pragma unroll 1
             for (int c0 = 0; c0 < BN; c0 += 16) {
                 uint32_t v[16];
@@ -517,27 +524,28 @@ static int launch_wgrad(const CUtensorMap& x0, const CUtensorMap& x1, const CUte
 }  // namespace tc
 }  // namespace ssg
 
-extern "C" int ssg_conv2d_wgrad_tc(const void* x0, int c0, const void* x1, int c1, const void* dy, float* dw_oihw, int n, int h, int w,
-                                   int cout, int ksize, int stride, int pad, ssg_stream_t s) {
+extern "C" int ssg_conv2d_wgrad_tc(const void* x0, int c0, const void* x1, int c1, const void* dy, int cout, float* dw_oihw,
+                                   int cout_real, int cin_real, int n, int h, int w, int ksize, int stride, int pad, ssg_stream_t s) {
     using namespace ssg;
     using namespace ssg::tc;
-    SSG_CHECK_ARG(n > 0 && h > 0 && w > 0 && cout > 0 && cout % 64 == 0 && c0 > 0 && c0 % 64 == 0 && c1 >= 0 && c1 % 64 == 0,
-                  "conv2d_wgrad_tc: channels must be multiples of 64 (c0=%d c1=%d cout=%d)", c0, c1, cout);
+    SSG_CHECK_ARG(n > 0 && h > 0 && w > 0 && cout > 0 && cout % 8 == 0 && c0 > 0 && c0 % 8 == 0 && c1 >= 0 && c1 % 8 == 0 &&
+                      (c1 == 0 || c0 % 64 == 0) && cout_real > 0 && cout_real <= cout && cin_real > 0 && cin_real <= c0 + c1,
+                  "conv2d_wgrad_tc: stored channel counts must be multiples of 8 (c0=%d c1=%d cout=%d)", c0, c1, cout);
     SSG_CHECK_ARG((ksize == 1 || ksize == 3) && pad >= 0 && pad < ksize && (stride == 1 || stride == 2),
                   "conv2d_wgrad_tc: kernel 1 or 3, stride 1 or 2");
     const int oh = (h + 2 * pad - ksize) / stride + 1, ow = (w + 2 * pad - ksize) / stride + 1;
     SSG_CHECK_ARG(oh > 0 && ow > 0, "conv2d_wgrad_tc: empty dy");
-    const int cin = c0 + c1, taps = ksize * ksize;
+    const int taps = ksize * ksize;
     cudaStream_t st = (cudaStream_t)s;
-    SSG_CHECK_CUDA(cudaMemsetAsync(dw_oihw, 0, sizeof(float) * (size_t)cout * cin * taps, st));
+    SSG_CHECK_CUDA(cudaMemsetAsync(dw_oihw, 0, sizeof(float) * (size_t)cout_real * cin_real * taps, st));
     int twl, thl;
     pick_tile(oh, ow, twl, thl);          // pixel tiles enumerate dy; x is gathered at stride * pixel + tap - pad
     const int TW = 1 << twl, TH = 1 << thl, NB = BM / (TW * TH);
     WgradParams p;
-    p.dw = dw_oihw; p.N = n; p.H = oh; p.W = ow; p.cout = cout; p.cin = cin; p.in_mul = stride;
+    p.dw = dw_oihw; p.N = n; p.H = oh; p.W = ow; p.cout = cout_real; p.cin = cin_real; p.in_mul = stride;
     p.tw_log2 = twl; p.th_log2 = thl; p.tiles_x = (ow + TW - 1) / TW; p.tiles_y = (oh + TH - 1) / TH;
     p.m_tiles = p.tiles_x * p.tiles_y * ((n + NB - 1) / NB);
-    p.taps = taps; p.kw = ksize; p.pad = pad; p.chunks0 = c0 / 64; p.chunks1 = c1 / 64; p.units = taps * (cin / 64);
+    p.taps = taps; p.kw = ksize; p.pad = pad; p.chunks0 = (c0 + 63) / 64; p.chunks1 = (c1 + 63) / 64; p.units = taps * (p.chunks0 + p.chunks1);
     CUtensorMap mx0, mx1, mdy;
     int rc = encode_act_map(&mx0, x0, c0, n, h, w, twl, thl, stride);
     if (rc) return rc;
@@ -548,6 +556,6 @@ extern "C" int ssg_conv2d_wgrad_tc(const void* x0, int c0, const void* x1, int c
     }
     rc = encode_act_map(&mdy, dy, cout, n, oh, ow, twl, thl, 1);
     if (rc) return rc;
-    if (cout % 128 == 0) return launch_wgrad<128>(mx0, mx1, mdy, p, st);
+    if (cout_real > 64) return launch_wgrad<128>(mx0, mx1, mdy, p, st);
     return launch_wgrad<64>(mx0, mx1, mdy, p, st);
 }

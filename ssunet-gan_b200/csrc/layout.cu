@@ -5,13 +5,14 @@ namespace ssg {
 
 // [n][C][HW] (float) -> [n][HW][C] (T): 32x32 smem tile transpose, coalesced on both sides.
 template <typename T>
-__global__ void nchw_to_nhwc_kernel(const float* __restrict__ src, T* __restrict__ dst, int C, long long HW) {
+__global__ void nchw_to_nhwc_kernel(const float* __restrict__ src, T* __restrict__ dst, int C, int CD, long long HW) {
+    // CD >= C: destination channel count (storage padding); channels [C, CD) are written as zeros
     __shared__ float tile[32][33];
     const int n = blockIdx.z;
     const long long p0 = (long long)blockIdx.x * 32;
     const int c0 = blockIdx.y * 32;
     const float* s = src + (long long)n * C * HW;
-    T* d = dst + (long long)n * C * HW;
+    T* d = dst + (long long)n * CD * HW;
     for (int i = threadIdx.y; i < 32; i += blockDim.y) {
         int c = c0 + i;
         long long p = p0 + threadIdx.x;
@@ -21,22 +22,23 @@ __global__ void nchw_to_nhwc_kernel(const float* __restrict__ src, T* __restrict
     for (int i = threadIdx.y; i < 32; i += blockDim.y) {
         long long p = p0 + i;
         int c = c0 + threadIdx.x;
-        if (c < C && p < HW) d[p * C + c] = from_f<T>(tile[threadIdx.x][i]);
+        if (c < CD && p < HW) d[p * CD + c] = from_f<T>(tile[threadIdx.x][i]);
     }
 }
 
 template <typename T>
-__global__ void nhwc_to_nchw_kernel(const T* __restrict__ src, float* __restrict__ dst, int C, long long HW) {
+__global__ void nhwc_to_nchw_kernel(const T* __restrict__ src, float* __restrict__ dst, int C, int CS, long long HW) {
+    // CS >= C: source channel count (storage padding); only the first C channels are copied
     __shared__ float tile[32][33];
     const int n = blockIdx.z;
     const long long p0 = (long long)blockIdx.x * 32;
     const int c0 = blockIdx.y * 32;
-    const T* s = src + (long long)n * C * HW;
+    const T* s = src + (long long)n * CS * HW;
     float* d = dst + (long long)n * C * HW;
     for (int i = threadIdx.y; i < 32; i += blockDim.y) {
         long long p = p0 + i;
         int c = c0 + threadIdx.x;
-        tile[i][threadIdx.x] = (c < C && p < HW) ? to_f(s[p * C + c]) : 0.f;
+        tile[i][threadIdx.x] = (c < C && p < HW) ? to_f(s[p * CS + c]) : 0.f;
     }
     __syncthreads();
     for (int i = threadIdx.y; i < 32; i += blockDim.y) {
@@ -89,20 +91,21 @@ __global__ void concat2_scalar_kernel(T* __restrict__ a, int ca, T* __restrict__
 // OIHW fp32 -> packed layouts.  One thread per destination element.
 template <typename T>
 __global__ void pack_weight_kernel(const float* __restrict__ w, T* __restrict__ dst, int layout, int cout, int cin, int kh,
-                                   int kw, const float* __restrict__ inv_scale) {
-    const long long total = (long long)cout * cin * kh * kw;
+                                   int kw, const float* __restrict__ inv_scale, int cout_p, int cin_p) {
+    // destination dims are the padded channel counts (cout_p >= cout, cin_p >= cin); padding is zero
+    const long long total = (long long)cout_p * cin_p * kh * kw;
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= total) return;
     const float sc = inv_scale ? inv_scale[0] : 1.f;
     int r, s, c, k;
     long long t = i;
     if (layout == SSG_W_RSKC) {  // [r][s][k][c]
-        c = (int)(t % cin); t /= cin; k = (int)(t % cout); t /= cout; s = (int)(t % kw); r = (int)(t / kw);
+        c = (int)(t % cin_p); t /= cin_p; k = (int)(t % cout_p); t /= cout_p; s = (int)(t % kw); r = (int)(t / kw);
     } else {                     // [r][s][c][k] (optionally flipped taps)
-        k = (int)(t % cout); t /= cout; c = (int)(t % cin); t /= cin; s = (int)(t % kw); r = (int)(t / kw);
+        k = (int)(t % cout_p); t /= cout_p; c = (int)(t % cin_p); t /= cin_p; s = (int)(t % kw); r = (int)(t / kw);
         if (layout == SSG_W_RSCK_FLIP) { r = kh - 1 - r; s = kw - 1 - s; }
     }
-    dst[i] = from_f<T>(w[(((long long)k * cin + c) * kh + r) * kw + s] * sc);
+    dst[i] = (k < cout && c < cin) ? from_f<T>(w[(((long long)k * cin + c) * kh + r) * kw + s] * sc) : from_f<T>(0.f);
 }
 
 }  // namespace ssg
@@ -127,22 +130,28 @@ static int concat_impl(void* a, int ca, void* b, int cb, void* cat, int dtype, l
 
 extern "C" {
 
-int ssg_nchw_to_nhwc(const float* src, void* dst, int dtype, int n, int c, int h, int w, ssg_stream_t s) {
-    SSG_CHECK_ARG(n > 0 && c > 0 && h > 0 && w > 0 && n <= 65535, "nchw_to_nhwc: bad shape");
+int ssg_nchw_to_nhwc_pad(const float* src, void* dst, int dtype, int n, int c, int c_dst, int h, int w, ssg_stream_t s) {
+    SSG_CHECK_ARG(n > 0 && c > 0 && c_dst >= c && h > 0 && w > 0 && n <= 65535, "nchw_to_nhwc: bad shape");
     long long hw = (long long)h * w;
-    dim3 grid((unsigned)((hw + 31) / 32), (unsigned)((c + 31) / 32), (unsigned)n), block(32, 8);
-    SSG_DISPATCH_DTYPE(dtype, nchw_to_nhwc_kernel<T><<<grid, block, 0, (cudaStream_t)s>>>(src, (T*)dst, c, hw));
+    dim3 grid((unsigned)((hw + 31) / 32), (unsigned)((c_dst + 31) / 32), (unsigned)n), block(32, 8);
+    SSG_DISPATCH_DTYPE(dtype, nchw_to_nhwc_kernel<T><<<grid, block, 0, (cudaStream_t)s>>>(src, (T*)dst, c, c_dst, hw));
     SSG_CHECK_LAUNCH();
     return SSG_OK;
 }
+int ssg_nchw_to_nhwc(const float* src, void* dst, int dtype, int n, int c, int h, int w, ssg_stream_t s) {
+    return ssg_nchw_to_nhwc_pad(src, dst, dtype, n, c, c, h, w, s);
+}
 
-int ssg_nhwc_to_nchw(const void* src, int dtype, float* dst, int n, int c, int h, int w, ssg_stream_t s) {
-    SSG_CHECK_ARG(n > 0 && c > 0 && h > 0 && w > 0 && n <= 65535, "nhwc_to_nchw: bad shape");
+int ssg_nhwc_to_nchw_pad(const void* src, int dtype, float* dst, int n, int c, int c_src, int h, int w, ssg_stream_t s) {
+    SSG_CHECK_ARG(n > 0 && c > 0 && c_src >= c && h > 0 && w > 0 && n <= 65535, "nhwc_to_nchw: bad shape");
     long long hw = (long long)h * w;
     dim3 grid((unsigned)((hw + 31) / 32), (unsigned)((c + 31) / 32), (unsigned)n), block(32, 8);
-    SSG_DISPATCH_DTYPE(dtype, nhwc_to_nchw_kernel<T><<<grid, block, 0, (cudaStream_t)s>>>((const T*)src, dst, c, hw));
+    SSG_DISPATCH_DTYPE(dtype, nhwc_to_nchw_kernel<T><<<grid, block, 0, (cudaStream_t)s>>>((const T*)src, dst, c, c_src, hw));
     SSG_CHECK_LAUNCH();
     return SSG_OK;
+}
+int ssg_nhwc_to_nchw(const void* src, int dtype, float* dst, int n, int c, int h, int w, ssg_stream_t s) {
+    return ssg_nhwc_to_nchw_pad(src, dtype, dst, n, c, c, h, w, s);
 }
 
 int ssg_cast(const void* src, int sd, void* dst, int dd, long long n, ssg_stream_t s) {
@@ -165,14 +174,20 @@ int ssg_split2(const void* in, void* a, int ca, void* b, int cb, int dtype, long
     return concat_impl<true>(a, ca, b, cb, (void*)in, dtype, rows, s);
 }
 
-int ssg_pack_conv_weight(const float* w, void* dst, int dtype, int layout, int cout, int cin, int kh, int kw,
-                         const float* inv_scale_dev, ssg_stream_t s) {
-    SSG_CHECK_ARG(cout > 0 && cin > 0 && kh > 0 && kw > 0 && layout >= 0 && layout <= 2, "pack_conv_weight: bad args");
-    long long total = (long long)cout * cin * kh * kw;
+int ssg_pack_conv_weight_pad(const float* w, void* dst, int dtype, int layout, int cout, int cin, int kh, int kw, int cout_p,
+                             int cin_p, const float* inv_scale_dev, ssg_stream_t s) {
+    SSG_CHECK_ARG(cout > 0 && cin > 0 && kh > 0 && kw > 0 && layout >= 0 && layout <= 2 && cout_p >= cout && cin_p >= cin,
+                  "pack_conv_weight: bad args");
+    long long total = (long long)cout_p * cin_p * kh * kw;
     unsigned g = (unsigned)((total + 255) / 256);
-    SSG_DISPATCH_DTYPE(dtype, pack_weight_kernel<T><<<g, 256, 0, (cudaStream_t)s>>>(w, (T*)dst, layout, cout, cin, kh, kw, inv_scale_dev));
+    SSG_DISPATCH_DTYPE(dtype, pack_weight_kernel<T><<<g, 256, 0, (cudaStream_t)s>>>(w, (T*)dst, layout, cout, cin, kh, kw, inv_scale_dev,
+                                                                                    cout_p, cin_p));
     SSG_CHECK_LAUNCH();
     return SSG_OK;
+}
+int ssg_pack_conv_weight(const float* w, void* dst, int dtype, int layout, int cout, int cin, int kh, int kw,
+                         const float* inv_scale_dev, ssg_stream_t s) {
+    return ssg_pack_conv_weight_pad(w, dst, dtype, layout, cout, cin, kh, kw, cout, cin, inv_scale_dev, s);
 }
 
 }  // extern "C"

@@ -86,7 +86,7 @@ class Discriminator(nn.Module):
         self.fc2 = Linear(1024, 1)
 
     def forward(self, imgs):
-        out = ops.to_nhwc(imgs)
+        out = ops.to_nhwc(imgs, pad_channels=True)
         for blk in self.conv_blocks:
             out = blk(out)
         flat = ops.adaptive_avg_pool_flat(out, 6, 6)

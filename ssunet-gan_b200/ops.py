@@ -34,6 +34,18 @@ def set_conv_impl(name):
     _CONV_IMPL = name
 
 
+def tc_mode():
+    """True when convolutions run on the tcgen05 kernels (bf16 storage, conv_impl "auto")."""
+    return _CONV_IMPL != "simt" and _COMPUTE_DTYPE == torch.bfloat16
+
+
+def thin_pad(c):
+    """Stored channel count of a thin activation (3-channel images / logits, SPADE's 3- and h-channel maps): rounded up
+    to a multiple of 8 in tensor-core mode so the NHWC pixel pitch is a multiple of 16 bytes (TMA); the padding channels
+    hold zeros and meet zero weight rows/columns.  Unchanged in the fp32 / SIMT parity mode."""
+    return (c + 7) // 8 * 8 if tc_mode() else c
+
+
 def bump_weight_epoch():
     global _WEIGHT_EPOCH
     _WEIGHT_EPOCH += 1
@@ -56,63 +68,68 @@ def _rows(x):
 
 
 class _ToNHWC(torch.autograd.Function):
-    """NCHW fp32 contiguous -> NHWC compute dtype (module entry); backward is the inverse."""
+    """NCHW fp32 contiguous -> NHWC compute dtype with `c_store` >= C stored channels (module entry); backward is the
+    inverse (padding channels dropped)."""
 
     @staticmethod
-    def forward(ctx, x, dtype):
+    def forward(ctx, x, dtype, c_store):
         x = x.contiguous()
         if x.dtype != torch.float32:
             x = x.float()
         n, c, h, w = x.shape
-        y = empty_nhwc(n, c, h, w, dtype, x.device)
-        call("ssg_nchw_to_nhwc", x, y, dtype_code(dtype), n, c, h, w)
+        ctx.c = c
+        y = empty_nhwc(n, c_store, h, w, dtype, x.device)
+        call("ssg_nchw_to_nhwc_pad", x, y, dtype_code(dtype), n, c, c_store, h, w)
         return y
 
     @staticmethod
     def backward(ctx, dy):
-        n, c, h, w = dy.shape
+        n, cs, h, w = dy.shape
         dy = _as_storage(dy)
-        dx = torch.empty((n, c, h, w), dtype=torch.float32, device=dy.device)
-        call("ssg_nhwc_to_nchw", dy, dtype_code(dy.dtype), dx, n, c, h, w)
-        return dx, None
+        dx = torch.empty((n, ctx.c, h, w), dtype=torch.float32, device=dy.device)
+        call("ssg_nhwc_to_nchw_pad", dy, dtype_code(dy.dtype), dx, n, ctx.c, cs, h, w)
+        return dx, None, None
 
 
 class _ToNCHW(torch.autograd.Function):
-    """NHWC compute dtype -> NCHW fp32 contiguous (module exit)."""
+    """NHWC compute dtype (first `c` of the stored channels) -> NCHW fp32 contiguous (module exit)."""
 
     @staticmethod
-    def forward(ctx, x):
-        n, c, h, w = x.shape
-        ctx.dt = x.dtype
+    def forward(ctx, x, c):
+        n, cs, h, w = x.shape
+        ctx.dt, ctx.cs = x.dtype, cs
         y = torch.empty((n, c, h, w), dtype=torch.float32, device=x.device)
-        call("ssg_nhwc_to_nchw", x, dtype_code(x.dtype), y, n, c, h, w)
+        call("ssg_nhwc_to_nchw_pad", x, dtype_code(x.dtype), y, n, c, cs, h, w)
         return y
 
     @staticmethod
     def backward(ctx, dy):
         dy = dy.contiguous().float()
         n, c, h, w = dy.shape
-        dx = empty_nhwc(n, c, h, w, ctx.dt, dy.device)
-        call("ssg_nchw_to_nhwc", dy, dx, dtype_code(ctx.dt), n, c, h, w)
-        return dx
+        dx = empty_nhwc(n, ctx.cs, h, w, ctx.dt, dy.device)
+        call("ssg_nchw_to_nhwc_pad", dy, dx, dtype_code(ctx.dt), n, c, ctx.cs, h, w)
+        return dx, None
 
 
-def to_nhwc(x, dtype=None):
-    """Accept whatever the caller has (reference API: NCHW fp32) and return NHWC storage in compute dtype."""
+def to_nhwc(x, dtype=None, pad_channels=False):
+    """Accept whatever the caller has (reference API: NCHW fp32) and return NHWC storage in compute dtype.
+    pad_channels: store thin inputs with `thin_pad(C)` channels (zeros beyond C)."""
     dtype = dtype or _COMPUTE_DTYPE
     if not x.is_cuda:
         raise _lib.SsgError("ssunet-gan_b200 ops need CUDA tensors (there is no CPU path)")
     if x.dtype == dtype and is_nhwc(x):
         return x
     if is_nhwc(x) and x.dtype != dtype:       # NHWC but other dtype: go through NCHW fp32 (rare, boundary only)
-        x = _ToNCHW.apply(x)
-    return _ToNHWC.apply(x, dtype)
+        x = _ToNCHW.apply(x, x.shape[1])
+    return _ToNHWC.apply(x, dtype, thin_pad(x.shape[1]) if pad_channels else x.shape[1])
 
 
-def to_nchw_f32(x):
-    if x.dtype == torch.float32 and x.is_contiguous():
+def to_nchw_f32(x, channels=None):
+    """NCHW fp32 contiguous view of the first `channels` stored channels (all by default)."""
+    c = channels or x.shape[1]
+    if x.dtype == torch.float32 and x.is_contiguous() and c == x.shape[1]:
         return x
-    return _ToNCHW.apply(to_nhwc(x, x.dtype if x.dtype in (torch.float32, torch.bfloat16) else None))
+    return _ToNCHW.apply(to_nhwc(x, x.dtype if x.dtype in (torch.float32, torch.bfloat16) else None), c)
 
 
 def _as_storage(t, dtype=None):
@@ -129,9 +146,12 @@ def _as_storage(t, dtype=None):
 # ----------------------------------------------------------------------------------------------
 # packed weights
 # ----------------------------------------------------------------------------------------------
-def packed_weight(w, layout, dtype, inv_scale=None):
-    """OIHW fp32 parameter -> kernel operand, cached on the tensor until it changes."""
-    key = (layout, dtype)
+def packed_weight(w, layout, dtype, inv_scale=None, cout_p=None, cin_p=None):
+    """OIHW fp32 parameter -> kernel operand (optionally zero-padded to cout_p x cin_p channels), cached on the tensor
+    until it changes."""
+    cout_p = cout_p or w.shape[0]
+    cin_p = cin_p or w.shape[1]
+    key = (layout, dtype, cout_p, cin_p)
     token = (w._version, _WEIGHT_EPOCH, w.data_ptr())
     cache = getattr(w, "_ssg_pack", None)
     if cache is None:
@@ -144,8 +164,8 @@ def packed_weight(w, layout, dtype, inv_scale=None):
     if hit is not None and hit[0] == token and inv_scale is None:
         return hit[1]
     cout, cin, kh, kw = w.shape
-    out = torch.empty(w.numel(), dtype=dtype, device=w.device)
-    call("ssg_pack_conv_weight", w.detach(), out, dtype_code(dtype), layout, cout, cin, kh, kw, inv_scale)
+    out = torch.empty(cout_p * cin_p * kh * kw, dtype=dtype, device=w.device)
+    call("ssg_pack_conv_weight_pad", w.detach(), out, dtype_code(dtype), layout, cout, cin, kh, kw, cout_p, cin_p, inv_scale)
     if inv_scale is None:
         cache[key] = (token, out)
     return out
@@ -158,29 +178,35 @@ def _conv_out_hw(h, w, k, stride, pad):
     return (h + 2 * pad - k) // stride + 1, (w + 2 * pad - k) // stride + 1
 
 
-def _tc_eligible(cin, cout, k, stride, dtype):
+def _tc_eligible(cin_s, cout_s, k, stride, dtype):
+    """cin_s / cout_s: STORED channel counts of the input / output activations."""
     if _CONV_IMPL == "simt" or dtype != torch.bfloat16:
         return False
     from . import conv_tc
-    return conv_tc.eligible(cin, cout, k, stride)
+    return conv_tc.eligible(cin_s, cout_s, k, stride)
 
 
 class _Conv2d(torch.autograd.Function):
-    """nn.Conv2d (square kernel, symmetric padding, groups=1) with optional fused bias + activation."""
+    """nn.Conv2d (square kernel, symmetric padding, groups=1) with optional fused bias + activation.
+    x may be stored with more channels than the weight has inputs, and the output may be stored with `cout_store`
+    >= Cout channels (thin_pad): the extra channels are zeros."""
 
     @staticmethod
-    def forward(ctx, x, weight, bias, stride, pad, act, slope):
-        n, cin, h, w = x.shape
-        cout, cin_w, kh, kw = weight.shape
-        assert cin == cin_w and kh == kw, "conv2d: shape mismatch %s vs %s" % (tuple(x.shape), tuple(weight.shape))
+    def forward(ctx, x, weight, bias, stride, pad, act, slope, cout_store):
+        n, cin_s, h, w = x.shape
+        cout, cin, kh, kw = weight.shape
+        cout_s = cout_store or cout
+        assert cin_s >= cin and cout_s >= cout and kh == kw, "conv2d: shape mismatch %s vs %s" % (tuple(x.shape), tuple(weight.shape))
         oh, ow = _conv_out_hw(h, w, kh, stride, pad)
         dt = x.dtype
-        y = empty_nhwc(n, cout, oh, ow, dt, x.device)
-        use_tc = _tc_eligible(cin, cout, kh, stride, dt)
+        y = empty_nhwc(n, cout_s, oh, ow, dt, x.device)
+        use_tc = _tc_eligible(cin_s, cout_s, kh, stride, dt)
         if use_tc:
             from . import conv_tc
             conv_tc.forward(x, weight, bias, y, stride, pad, act, slope)
         else:
+            if cin_s != cin or cout_s != cout:
+                raise _lib.SsgError("conv2d: channel-padded activations need the tensor-core path (bf16, conv_impl auto)")
             wp = packed_weight(weight, W_RSCK, dt)
             call("ssg_conv2d_fwd_simt", x, wp, bias, y, dtype_code(dt), n, h, w, cin, cout, kh, kw, stride, pad, act, slope)
         ctx.save_for_backward(x, weight, y if act != ACT_NONE else None)
@@ -191,8 +217,9 @@ class _Conv2d(torch.autograd.Function):
     def backward(ctx, dy):
         x, weight, y = ctx.saved_tensors
         stride, pad, act, slope, has_bias, use_tc = ctx.cfg
-        n, cin, h, w = x.shape
-        cout, _, kh, kw = weight.shape
+        n, cin_s, h, w = x.shape
+        cout, cin, kh, kw = weight.shape
+        cout_s = dy.shape[1]
         dt = x.dtype
         dy = _as_storage(dy, dt)
         if act != ACT_NONE:
@@ -200,31 +227,30 @@ class _Conv2d(torch.autograd.Function):
             call("ssg_act_bwd", dy, y, dz, dtype_code(dt), dy.numel(), act, slope)
             dy = dz
         dx = dw = db = None
-        if ctx.needs_input_grad[0]:
-            dx = empty_nhwc(n, cin, h, w, dt, x.device)
+        if use_tc:
             from . import conv_tc
-            if _CONV_IMPL != "simt" and dt == torch.bfloat16 and conv_tc.dgrad_eligible(cin, cout, kh, stride):
+        if ctx.needs_input_grad[0]:
+            dx = empty_nhwc(n, cin_s, h, w, dt, x.device)
+            if use_tc:
                 conv_tc.dgrad(dy, weight, dx, stride, pad)
             else:
                 wp = packed_weight(weight, W_RSKC, dt)
                 call("ssg_conv2d_dgrad_simt", dy, wp, dx, dtype_code(dt), n, h, w, cin, cout, kh, kw, stride, pad)
         if ctx.needs_input_grad[1]:
             dw = torch.empty_like(weight, dtype=torch.float32)
-            done = False
-            if _CONV_IMPL != "simt" and dt == torch.bfloat16:
-                from . import conv_tc
-                done = conv_tc.wgrad(x, dy, dw, stride, pad)
-            if not done:
+            if use_tc:
+                conv_tc.wgrad(x, dy, dw, stride, pad)
+            else:
                 call("ssg_conv2d_wgrad_simt", x, dy, dw, dtype_code(dt), n, h, w, cin, cout, kh, kw, stride, pad)
         if has_bias and ctx.needs_input_grad[2]:
-            sums = torch.empty(2 * cout, dtype=torch.float64, device=x.device)
-            call("ssg_channel_stats", dy, dtype_code(dt), _rows(dy), cout, sums, 0)
+            sums = torch.empty(2 * cout_s, dtype=torch.float64, device=x.device)
+            call("ssg_channel_stats", dy, dtype_code(dt), _rows(dy), cout_s, sums, 0)
             db = sums[:cout].float()
-        return dx, dw, db, None, None, None, None
+        return dx, dw, db, None, None, None, None, None
 
 
-def conv2d(x, weight, bias=None, stride=1, pad=0, act=ACT_NONE, slope=0.0):
-    return _Conv2d.apply(to_nhwc(x), weight, bias, stride, pad, act, slope)
+def conv2d(x, weight, bias=None, stride=1, pad=0, act=ACT_NONE, slope=0.0, cout_store=None):
+    return _Conv2d.apply(to_nhwc(x), weight, bias, stride, pad, act, slope, cout_store)
 
 
 # ----------------------------------------------------------------------------------------------

@@ -77,3 +77,49 @@ def test_conv_tc_virtual_concat():
     y = ops.empty_nhwc(2, 64, 20, 20, torch.bfloat16)
     conv_tc.forward(ac, wt.cuda(), None, y, 1, 1, 0, 0.0, x1=bc)
     assert rel(y.float(), yr) < 6e-3
+
+
+THIN = [
+    # n, cin, cout, h, w, k, stride   -- thin (channel-padded) operands: image stems, SPADE maps, logits head
+    (2, 3, 64, 20, 24, 3, 1),     # archs.py:576 conv0_0.conv1 / models_seg_gan.py:267 block 0
+    (2, 3, 64, 20, 24, 1, 1),     # BasicBlock shortcut on the image
+    (1, 64, 3, 16, 16, 3, 1),     # SPADE.x2map (normalization.py:94)
+    (2, 3, 4, 12, 12, 3, 1),      # SPADE.mlp_shared, both sides thin
+    (1, 4, 128, 18, 10, 3, 1),    # SPADE gamma|beta at level 0
+    (1, 24, 768, 8, 8, 3, 1),     # level 3
+    (2, 48, 192, 6, 6, 3, 1),
+    (1, 64, 3, 33, 17, 1, 1),     # final 1x1 head (archs.py:615)
+    (2, 3, 64, 16, 16, 3, 2),
+]
+
+
+@pytest.mark.parametrize("cfg", THIN)
+def test_conv_tc_thin_channels(cfg):
+    """Thin tensors are stored with their channel count rounded up to 8 (zeros) and run through the same tcgen05 kernels;
+    results and all three gradients must match the unpadded convolution."""
+    import ssunet_gan_b200 as ssg
+    from ssunet_gan_b200 import ops
+    n, cin, cout, h, w, k, stride = cfg
+    ssg.set_compute_dtype(torch.bfloat16)
+    ssg.set_conv_impl("auto")
+    g = torch.Generator().manual_seed(cin * 13 + cout + h)
+    x = torch.randn(n, cin, h, w, generator=g).bfloat16().float()
+    wt = (torch.randn(cout, cin, k, k, generator=g) / math.sqrt(cin * k * k)).bfloat16().float()
+    b = torch.randn(cout, generator=g)
+    xr, wr, br = x.clone().requires_grad_(True), wt.clone().requires_grad_(True), b.clone().requires_grad_(True)
+    yr = F.relu(F.conv2d(xr, wr, br, stride, k // 2))
+    gy = torch.randn(yr.shape, generator=g).bfloat16().float()
+    yr.backward(gy)
+    xc, wc, bc = x.cuda().requires_grad_(True), wt.cuda().requires_grad_(True), b.cuda().requires_grad_(True)
+    xs = ops.to_nhwc(xc, pad_channels=True)
+    assert xs.shape[1] == ops.thin_pad(cin) and xs.shape[1] % 8 == 0
+    ys = ops.conv2d(xs, wc, bc, stride, k // 2, ops.ACT_RELU, 0.0, cout_store=ops.thin_pad(cout))
+    assert ys.shape[1] == ops.thin_pad(cout)
+    if ys.shape[1] > cout:
+        assert float(ys[:, cout:].float().abs().max()) == 0.0          # padding channels stay zero
+    y = ops.to_nchw_f32(ys, channels=cout)
+    y.backward(gy.cuda())
+    assert rel(y, yr) < 6e-3
+    assert rel(xc.grad, xr.grad) < 8e-3
+    assert rel(wc.grad, wr.grad) < 8e-3
+    assert rel(bc.grad, br.grad) < 8e-3
