@@ -14,6 +14,7 @@
 #include "tc_common.cuh"
 #include <cudaTypedefs.h>
 #include <mutex>
+#include <stdlib.h>
 #include <string.h>
 
 namespace ssg {
@@ -191,8 +192,19 @@ static PFN_cuTensorMapEncodeTiled_v12000 get_encode() {
 }
 
 // bf16 tensor map; dims/box innermost first; strides in BYTES for dims 1..rank-1
+int run_conv_halo(const void* x0, int c0, const void* x1, int c1, const void* w_packed, int w_taps, const float* bias, int bias_n,
+                  void* y, int n, int h, int w, int gemm_n, int ksize, const int8_t* hy, const int8_t* hx, const int8_t* wt, int ntaps,
+                  int act, float slope, cudaStream_t st);
 int encode_bf16_map(CUtensorMap* map, const void* ptr, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
-                    const uint32_t* box, CUtensorMapSwizzle swizzle, const uint32_t* elem_strides = nullptr) {
+                    const uint32_t* box, CUtensorMapSwizzle swizzle, const uint32_t* elem_strides);
+
+static bool use_halo_kernel() {
+    static const bool v1 = getenv("SSG_CONV_V1") != nullptr;    // debugging / A-B switch: force the per-tap kernel
+    return !v1;
+}
+
+int encode_bf16_map(CUtensorMap* map, const void* ptr, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                    const uint32_t* box, CUtensorMapSwizzle swizzle, const uint32_t* elem_strides) {
     auto enc = get_encode();
     if (!enc) { set_error("cuTensorMapEncodeTiled entry point unavailable"); return SSG_ERR_CUDA; }
     uint32_t estr[5] = {1, 1, 1, 1, 1};
@@ -274,7 +286,7 @@ static int run_conv(const void* x0, int c0, const void* x1, int c1, const void* 
         uint64_t dims[3] = {(uint64_t)cin, (uint64_t)gemm_n, (uint64_t)w_taps};
         uint64_t str[2] = {(uint64_t)cin * 2, (uint64_t)gemm_n * cin * 2};
         uint32_t box[3] = {64, (uint32_t)BN, 1};
-        rc = encode_bf16_map(&mb, w_packed, 3, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B);
+        rc = encode_bf16_map(&mb, w_packed, 3, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B, nullptr);
         if (rc) return rc;
     }
     const int m_tiles = p.tiles_x * p.tiles_y * tiles_n;
@@ -307,6 +319,12 @@ int ssg_conv2d_fwd_tc(const void* x0, int c0, const void* x1, int c1, const void
             const int t = r * ksize + q;
             c.dy[t] = (int8_t)(r - pad); c.dx[t] = (int8_t)(q - pad); c.wt[t] = (int8_t)t;
         }
+    if (stride == 1 && 2 * pad == ksize - 1 && use_halo_kernel()) {
+        int8_t hy[9], hx[9];
+        for (int t = 0; t < c.ntaps; ++t) { hy[t] = (int8_t)(t / ksize); hx[t] = (int8_t)(t % ksize); }
+        return run_conv_halo(x0, c0, x1, c1, w_packed, ksize * ksize, bias, bias_n, y, n, h, w, cout, ksize, hy, hx, c.wt, c.ntaps, act, slope,
+                             (cudaStream_t)s);
+    }
     return run_conv(x0, c0, x1, c1, w_packed, ksize * ksize, bias, bias_n, y, n, h, w, oh, ow, oh, ow, cout, stride, 1, &c, 1, act, slope,
                     (cudaStream_t)s);
 }
@@ -319,6 +337,15 @@ int ssg_conv2d_dgrad_tc(const void* dy, const void* w_packed, void* dx, int n, i
                   "conv2d_dgrad_tc: kernel 1 or 3 at stride 1, kernel 3 at stride 2 (k=%d stride=%d)", ksize, stride);
     const int oh = (h + 2 * pad - ksize) / stride + 1, ow = (w + 2 * pad - ksize) / stride + 1;
     SSG_CHECK_ARG(oh > 0 && ow > 0, "conv2d_dgrad_tc: empty dy");
+    if (stride == 1 && 2 * pad == ksize - 1 && use_halo_kernel()) {
+        // dx[i] = sum_r dy[i + pad - r] W[r]: halo origin i0 - pad, tap r reads halo row (k - 1 - r)
+        int8_t hy[9], hx[9], wt[9];
+        for (int t = 0; t < ksize * ksize; ++t) {
+            hy[t] = (int8_t)(ksize - 1 - t / ksize); hx[t] = (int8_t)(ksize - 1 - t % ksize); wt[t] = (int8_t)t;
+        }
+        return run_conv_halo(dy, cout, nullptr, 0, w_packed, ksize * ksize, nullptr, 0, dx, n, h, w, cin, ksize, hy, hx, wt, ksize * ksize, 0, 0.f,
+                             (cudaStream_t)s);
+    }
     TapClass c[4];
     memset(c, 0, sizeof(c));
     int ncls = 0;

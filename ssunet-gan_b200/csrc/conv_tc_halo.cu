@@ -1,0 +1,334 @@
+// Halo-tile tcgen05 implicit-GEMM convolution (stride 1, 1x1 / 3x3 same-size, bf16 NHWC, fp32 accumulate in TMEM).
+//
+// The plain kernel (conv_tc.cu) re-reads a shifted 128-pixel A tile for every filter tap: 16 KB of A + BN*128 B of
+// weights per 64-channel k-block, i.e. >= 96 B/clk/SM at full tensor rate while the L2 delivers ~42 B/clk/SM.  This
+// kernel cuts the operand traffic per MMA cycle three ways:
+//   * ONE halo tile per (M-tile, 64-channel chunk): an 18 x 10 pixel TMA box (zero-filled outside the image) feeds all
+//     nine taps.  Tap (r, s) is the same shared memory seen through a UMMA descriptor whose start address is advanced
+//     by (r * 10 + s) pixels and whose stride-byte-offset is the halo pitch (10 * 128 B): the SWIZZLE_128B pattern is a
+//     function of absolute smem address bits, so any 128-byte row may start a K-major operand (verified on B200 with
+//     scratch/halo_test.cu).  A traffic drops 9 * 128 / 180 = 6.4x.
+//   * MT M-tiles (16 x 8 pixels each) per CTA share every weight tile: B traffic per MMA cycle drops MT x.
+//   * persistent CTAs (one per SM) walk (M super-tile, N tile) work items with the N tile fastest, so CTAs running
+//     together read the same activations from L2; the 2 x MT x BN = 512 TMEM columns hold two accumulator sets, so the
+//     epilogue of one work item overlaps the MMAs of the next.
+// Warp roles (256 threads): warp 0 = A (halo) TMA producer, warp 1 = B (weights) TMA producer, warp 2 = MMA issuer +
+// TMEM owner, warp 3 idle, warps 4..7 = epilogue (TMEM -> registers -> bias / activation -> bf16 -> global).
+#include "tc_common.cuh"
+#include <cudaTypedefs.h>
+#include <stdlib.h>
+#include <string.h>
+
+namespace ssg {
+namespace tc {
+
+int encode_bf16_map(CUtensorMap* map, const void* ptr, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                    const uint32_t* box, CUtensorMapSwizzle swizzle, const uint32_t* elem_strides);
+
+constexpr int H_TH = 16, H_TW = 8;              // M-tile: 16 rows x 8 columns = 128 pixels = UMMA M
+constexpr int H_THREADS = 256;
+constexpr int H_A_TILE_STRIDE = 23552;          // 18 * 10 * 128 B = 23040 rounded up to 1024
+
+struct HaloParams {
+    bf16* y;
+    const float* bias;
+    int bias_n;
+    int N, H, W;                 // image dims (output == input: stride 1, same-size)
+    int cout;                    // stored output channels (row stride of y)
+    int tiles_x, tiles_y;        // M-tiles per image
+    int m_tiles;                 // N * tiles_y * tiles_x
+    int n_tiles;                 // ceil(cout / BN)
+    int total_items;             // ceil(m_tiles / MT) * n_tiles
+    int chunks0, chunks1;        // 64-channel chunks from x0 / x1 (virtual concat)
+    int ntaps;
+    int8_t hy[9], hx[9], wt[9];  // tap -> (halo row, halo column) offset and weight tap index
+    int halo_c, halo_r;          // halo box dims in pixels: (8 + k - 1) x (16 + k - 1)
+    int org;                     // halo origin = tile origin - org
+    int act;
+    float slope;
+};
+
+template <int MT, int BN, int ACCS>     // ACCS accumulator sets (2: epilogue overlaps the next item's MMAs)
+struct HaloCfg {
+    static constexpr int OUT_BYTES = 4 * 4096 + 4 * 512;   // epilogue staging: one 32-pixel x 64-channel bf16 box per warp
+                                                           // + one BN-float bias row per warp
+    static constexpr int BUDGET = 227 * 1024 - 256 - 1024 - OUT_BYTES;
+    static constexpr int B_BYTES = BN * 128;
+    static constexpr int A_STAGE_BYTES = MT * H_A_TILE_STRIDE;
+    static constexpr int A_STAGES = (3 * A_STAGE_BYTES + 4 * B_BYTES <= BUDGET) ? 3 : 2;
+    static constexpr int B_SLOTS_RAW = (BUDGET - A_STAGES * A_STAGE_BYTES) / B_BYTES;
+    static constexpr int B_SLOTS = B_SLOTS_RAW > 6 ? 6 : B_SLOTS_RAW;
+    static constexpr int B_OFFSET = A_STAGES * A_STAGE_BYTES;
+    static constexpr int OUT_OFFSET = B_OFFSET + B_SLOTS * B_BYTES;
+    static constexpr int BAR_OFFSET = OUT_OFFSET + OUT_BYTES;
+    static constexpr int TOTAL = BAR_OFFSET + 256 + 1024;
+    static constexpr int ACC_COLS = MT * BN;           // TMEM columns of one accumulator set
+    static_assert(ACCS * ACC_COLS <= 512, "accumulator sets must fit in TMEM");
+    static_assert(B_SLOTS >= 2, "weight ring too small");
+    static_assert(TOTAL <= 227 * 1024, "shared memory budget");
+};
+
+template <int MT, int BN, int ACCS>
+__global__ void __launch_bounds__(H_THREADS, 1) conv_tc_halo_kernel(const __grid_constant__ CUtensorMap tmA0,
+                                                                     const __grid_constant__ CUtensorMap tmA1,
+                                                                     const __grid_constant__ CUtensorMap tmB,
+                                                                     const __grid_constant__ CUtensorMap tmY, const HaloParams p) {
+    using C = HaloCfg<MT, BN, ACCS>;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint64_t* a_full = reinterpret_cast<uint64_t*>(smem + C::BAR_OFFSET);
+    uint64_t* a_empty = a_full + C::A_STAGES;
+    uint64_t* b_full = a_empty + C::A_STAGES;
+    uint64_t* b_empty = b_full + C::B_SLOTS;
+    uint64_t* acc_full = b_empty + C::B_SLOTS;
+    uint64_t* acc_empty = acc_full + ACCS;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + ACCS);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int chunks = p.chunks0 + p.chunks1;
+    const int tiles_per_img = p.tiles_x * p.tiles_y;
+
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < C::A_STAGES; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); }
+        for (int i = 0; i < C::B_SLOTS; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); }
+        for (int i = 0; i < ACCS; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 128); }
+        fence_barrier_init();
+    }
+    if (warp == 2) tmem_alloc(tmem_slot, 512);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ---- A producer: one halo tile per (M-tile, chunk) ----
+        if (lane == 0) {
+            tma_prefetch_desc(&tmA0);
+            const uint32_t a_bytes = (uint32_t)(MT * p.halo_c * p.halo_r * 128);
+            int ac = 0;
+            for (int item = blockIdx.x; item < p.total_items; item += gridDim.x) {
+                const int super = item / p.n_tiles;
+                for (int ch = 0; ch < chunks; ++ch, ++ac) {
+                    const int st = ac % C::A_STAGES;
+                    mbar_wait(&a_empty[st], ((ac / C::A_STAGES) & 1) ^ 1);
+                    mbar_expect_tx(&a_full[st], a_bytes);
+#pragma unroll
+                    for (int mt = 0; mt < MT; ++mt) {
+                        const int t = super * MT + mt;          // tiles past m_tiles have img >= N: the box is zero-filled
+                        const int img = t / tiles_per_img, rem = t - img * tiles_per_img;
+                        const int ty = rem / p.tiles_x, tx = rem - ty * p.tiles_x;
+                        uint8_t* dst = smem + st * C::A_STAGE_BYTES + mt * H_A_TILE_STRIDE;
+                        if (ch < p.chunks0) tma_load_4d(dst, &tmA0, ch * 64, tx * H_TW - p.org, ty * H_TH - p.org, img, &a_full[st]);
+                        else tma_load_4d(dst, &tmA1, (ch - p.chunks0) * 64, tx * H_TW - p.org, ty * H_TH - p.org, img, &a_full[st]);
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ---- B producer: one weight tile per (chunk, tap) ----
+        if (lane == 0) {
+            tma_prefetch_desc(&tmB);
+            int bc = 0;
+            for (int item = blockIdx.x; item < p.total_items; item += gridDim.x) {
+                const int n0 = (item % p.n_tiles) * BN;
+                for (int ch = 0; ch < chunks; ++ch)
+                    for (int tap = 0; tap < p.ntaps; ++tap, ++bc) {
+                        const int sl = bc % C::B_SLOTS;
+                        mbar_wait(&b_empty[sl], ((bc / C::B_SLOTS) & 1) ^ 1);
+                        mbar_expect_tx(&b_full[sl], C::B_BYTES);
+                        tma_load_3d(smem + C::B_OFFSET + sl * C::B_BYTES, &tmB, ch * 64, n0, p.wt[tap], &b_full[sl]);
+                    }
+            }
+        }
+    } else if (warp == 2) {
+        // ---- MMA issuer ----
+        if (lane == 0) {
+            constexpr uint32_t idesc = make_idesc_bf16(128, BN, 0, 0);
+            const uint32_t sbo = (uint32_t)p.halo_c * 128;
+            int ac = 0, bc = 0, it = 0;
+            for (int item = blockIdx.x; item < p.total_items; item += gridDim.x, ++it) {
+                const int acc = it % ACCS;
+                mbar_wait(&acc_empty[acc], ((it / ACCS) & 1) ^ 1);
+                tc_fence_after();
+                const uint32_t d_base = tmem_base + (uint32_t)(acc * C::ACC_COLS);
+                for (int ch = 0; ch < chunks; ++ch, ++ac) {
+                    const int st = ac % C::A_STAGES;
+                    mbar_wait(&a_full[st], (ac / C::A_STAGES) & 1);
+                    tc_fence_after();
+                    const uint32_t a_stage = smem_u32(smem + st * C::A_STAGE_BYTES);
+                    for (int tap = 0; tap < p.ntaps; ++tap, ++bc) {
+                        const int sl = bc % C::B_SLOTS;
+                        mbar_wait(&b_full[sl], (bc / C::B_SLOTS) & 1);
+                        tc_fence_after();
+                        const uint64_t db = make_desc_kmajor_sw128(smem_u32(smem + C::B_OFFSET + sl * C::B_BYTES));
+                        const uint32_t a_off = (uint32_t)(p.hy[tap] * p.halo_c + p.hx[tap]) * 128;
+#pragma unroll
+                        for (int mt = 0; mt < MT; ++mt) {
+                            const uint64_t da = make_smem_desc(a_stage + mt * H_A_TILE_STRIDE + a_off, 16, sbo, 2);
+#pragma unroll
+                            for (int k = 0; k < 4; ++k)
+                                umma_bf16(d_base + (uint32_t)(mt * BN), da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc,
+                                          (ch | tap | k) != 0);
+                        }
+                        umma_commit(&b_empty[sl]);
+                    }
+                    umma_commit(&a_empty[st]);
+                }
+                umma_commit(&acc_full[acc]);
+            }
+        }
+    } else if (warp >= 4) {
+        // ---- epilogue: warp q owns TMEM lanes [32q, 32q + 32) = tile rows 4q .. 4q + 3 (a {64 ch, 8, 4, 1} box of y).
+        // TMEM -> registers -> bias / activation -> bf16 -> swizzled smem staging -> ONE TMA store per (tile, 64 channels):
+        // full-line coalesced writes, clipped to the image / channel bounds by the TMA unit.
+        const int q = warp & 3;
+        uint8_t* stage = smem + C::OUT_OFFSET + q * 4096;
+        float* bias_s = reinterpret_cast<float*>(smem + C::OUT_OFFSET + 4 * 4096 + q * 512);
+        uint8_t* my_row = stage + lane * 128;
+        const int sw = lane & 7;
+        const bool has_bias = p.bias != nullptr;
+        // act(v) = max(v, v * neg): neg = 1 (identity), 0 (ReLU) or the LeakyReLU slope -- branch-free in the hot loop
+        const float neg = p.act == SSG_ACT_RELU ? 0.f : (p.act == SSG_ACT_LEAKY ? p.slope : 1.f);
+        int it = 0, bias_n0 = -1;
+        for (int item = blockIdx.x; item < p.total_items; item += gridDim.x, ++it) {
+            const int acc = it % ACCS;
+            const int super = item / p.n_tiles;
+            const int n0 = (item - super * p.n_tiles) * BN;
+            if (has_bias && n0 != bias_n0) {                        // stage this N tile's bias row (zeros past bias_n)
+                __syncwarp();
+#pragma unroll
+                for (int e = lane; e < BN; e += 32) bias_s[e] = (n0 + e < p.bias_n) ? __ldg(p.bias + n0 + e) : 0.f;
+                __syncwarp();
+                bias_n0 = n0;
+            }
+            mbar_wait(&acc_full[acc], (it / ACCS) & 1);
+            tc_fence_after();
+#pragma unroll 1
+            for (int mt = 0; mt < MT; ++mt) {
+                const int t = super * MT + mt;
+                if (t >= p.m_tiles) break;
+                const int img = t / tiles_per_img, rem = t - img * tiles_per_img;
+                const int ty = rem / p.tiles_x, tx = rem - ty * p.tiles_x;
+                const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * C::ACC_COLS + mt * BN);
+#pragma unroll 1
+                for (int h0 = 0; h0 < BN; h0 += 64) {
+                    if (n0 + h0 >= p.cout) break;
+                    uint32_t v[64];
+                    tmem_ld_32x32b_x32(t_addr + (uint32_t)h0, v);
+                    tmem_ld_32x32b_x32(t_addr + (uint32_t)(h0 + 32), v + 32);
+                    tmem_ld_wait();
+                    if (has_bias) {
+#pragma unroll
+                        for (int e = 0; e < 64; e += 4) {
+                            const float4 b4 = *reinterpret_cast<const float4*>(bias_s + h0 + e);
+                            v[e] = __float_as_uint(__uint_as_float(v[e]) + b4.x);
+                            v[e + 1] = __float_as_uint(__uint_as_float(v[e + 1]) + b4.y);
+                            v[e + 2] = __float_as_uint(__uint_as_float(v[e + 2]) + b4.z);
+                            v[e + 3] = __float_as_uint(__uint_as_float(v[e + 3]) + b4.w);
+                        }
+                    }
+                    if (lane == 0) tma_store_wait_read();          // the previous store has finished reading the staging box
+                    __syncwarp();
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {                   // 8 channels = one 16-byte chunk
+                        uint32_t w4[4];
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            float a = __uint_as_float(v[j * 8 + 2 * e]), b = __uint_as_float(v[j * 8 + 2 * e + 1]);
+                            a = fmaxf(a, a * neg);
+                            b = fmaxf(b, b * neg);
+                            const __nv_bfloat162 hh = __floats2bfloat162_rn(a, b);
+                            w4[e] = *reinterpret_cast<const uint32_t*>(&hh);
+                        }
+                        *reinterpret_cast<uint4*>(my_row + ((j ^ sw) << 4)) = make_uint4(w4[0], w4[1], w4[2], w4[3]);
+                    }
+                    fence_proxy_async();
+                    __syncwarp();
+                    if (lane == 0) {
+                        tma_store_4d(&tmY, stage, n0 + h0, tx * H_TW, ty * H_TH + 4 * q, img);
+                        tma_store_commit();
+                    }
+                }
+            }
+            tc_fence_before();
+            mbar_arrive(&acc_empty[acc]);
+        }
+        if (lane == 0) tma_store_wait_all();
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) tmem_dealloc(tmem_base, 512);
+}
+
+template <int MT, int BN, int ACCS>
+static int launch_halo(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b, const CUtensorMap& ym, HaloParams& p,
+                       cudaStream_t st) {
+    using C = HaloCfg<MT, BN, ACCS>;
+    static bool attr_set = false;
+    if (!attr_set) {
+        SSG_CHECK_CUDA(cudaFuncSetAttribute(conv_tc_halo_kernel<MT, BN, ACCS>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::TOTAL));
+        attr_set = true;
+    }
+    p.n_tiles = (p.cout + BN - 1) / BN;
+    p.total_items = ((p.m_tiles + MT - 1) / MT) * p.n_tiles;
+    int grid = sm_count_cached();
+    if (grid > p.total_items) grid = p.total_items;
+    conv_tc_halo_kernel<MT, BN, ACCS><<<grid, H_THREADS, C::TOTAL, st>>>(a0, a1, b, ym, p);
+    SSG_CHECK_LAUNCH();
+    return SSG_OK;
+}
+
+// Same-size stride-1 convolution / data gradient.  taps: (hy, hx, wt) per tap in halo coordinates.
+int run_conv_halo(const void* x0, int c0, const void* x1, int c1, const void* w_packed, int w_taps, const float* bias, int bias_n,
+                  void* y, int n, int h, int w, int gemm_n, int ksize, const int8_t* hy, const int8_t* hx, const int8_t* wt, int ntaps,
+                  int act, float slope, cudaStream_t st) {
+    HaloParams p;
+    memset(&p, 0, sizeof(p));
+    p.y = (bf16*)y; p.bias = bias; p.bias_n = bias_n; p.N = n; p.H = h; p.W = w; p.cout = gemm_n;
+    p.tiles_x = (w + H_TW - 1) / H_TW; p.tiles_y = (h + H_TH - 1) / H_TH; p.m_tiles = n * p.tiles_x * p.tiles_y;
+    p.chunks0 = (c0 + 63) / 64; p.chunks1 = (c1 + 63) / 64;
+    p.ntaps = ntaps;
+    for (int i = 0; i < ntaps; ++i) { p.hy[i] = hy[i]; p.hx[i] = hx[i]; p.wt[i] = wt[i]; }
+    p.halo_c = H_TW + ksize - 1; p.halo_r = H_TH + ksize - 1; p.org = (ksize - 1) / 2;
+    p.act = act; p.slope = slope;
+    CUtensorMap ma0, ma1, mb;
+    auto enc_act = [&](CUtensorMap* m, const void* ptr, int c) {
+        uint64_t dims[4] = {(uint64_t)c, (uint64_t)w, (uint64_t)h, (uint64_t)n};
+        uint64_t str[3] = {(uint64_t)c * 2, (uint64_t)w * c * 2, (uint64_t)h * w * c * 2};
+        uint32_t box[4] = {64, (uint32_t)p.halo_c, (uint32_t)p.halo_r, 1};
+        return encode_bf16_map(m, ptr, 4, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B, nullptr);
+    };
+    int rc = enc_act(&ma0, x0, c0);
+    if (rc) return rc;
+    ma1 = ma0;
+    if (c1 > 0) {
+        rc = enc_act(&ma1, x1, c1);
+        if (rc) return rc;
+    }
+    const int cin = c0 + c1;
+    // tile shape: SSG_HALO_SHAPE = "464" (4 M-tiles x BN 64) or "2128" (2 M-tiles x BN 128), two accumulator sets each; default by Cout
+    static const char* shape_env = getenv("SSG_HALO_SHAPE");
+    int shape = gemm_n > 64 ? 2128 : 464;
+    if (shape_env && gemm_n > 64) shape = atoi(shape_env);
+    const bool wide = shape != 464;
+    {
+        uint64_t dims[3] = {(uint64_t)cin, (uint64_t)gemm_n, (uint64_t)w_taps};
+        uint64_t str[2] = {(uint64_t)cin * 2, (uint64_t)gemm_n * cin * 2};
+        uint32_t box[3] = {64, (uint32_t)(wide ? 128 : 64), 1};
+        rc = encode_bf16_map(&mb, w_packed, 3, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B, nullptr);
+        if (rc) return rc;
+    }
+    CUtensorMap my;
+    {
+        uint64_t dims[4] = {(uint64_t)gemm_n, (uint64_t)w, (uint64_t)h, (uint64_t)n};
+        uint64_t str[3] = {(uint64_t)gemm_n * 2, (uint64_t)w * gemm_n * 2, (uint64_t)h * w * gemm_n * 2};
+        uint32_t box[4] = {64, H_TW, 4, 1};
+        rc = encode_bf16_map(&my, y, 4, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B, nullptr);
+        if (rc) return rc;
+    }
+    if (shape == 2128) return launch_halo<2, 128, 2>(ma0, ma1, mb, my, p, st);
+    return launch_halo<4, 64, 2>(ma0, ma1, mb, my, p, st);
+}
+
+}  // namespace tc
+}  // namespace ssg
