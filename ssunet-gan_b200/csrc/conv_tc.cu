@@ -145,20 +145,26 @@ __global__ void __launch_bounds__(NUM_THREADS) conv_tc_fwd_kernel(const __grid_c
         mbar_wait(tmem_full_bar, 0);
         tc_fence_after();
         const bool vec_ok = (p.cout % 8 == 0);
+        const bool has_bias = p.bias != nullptr;
+        // act(v) = max(v, v * neg): neg = 1 (identity), 0 (ReLU) or the LeakyReLU slope -- branch-free
+        const float neg = p.act == SSG_ACT_RELU ? 0.f : (p.act == SSG_ACT_LEAKY ? p.slope : 1.f);
 #pragma unroll 1
         for (int c0 = 0; c0 < BN; c0 += 16) {
+            if (n0 + c0 >= p.cout) break;
             uint32_t v[16];
             tmem_ld_32x32b_x16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
             tmem_ld_wait();
             if (!row_ok) continue;
             float f[16];
 #pragma unroll
-            for (int j = 0; j < 16; ++j) {
-                const int n = n0 + c0 + j;
-                float t = __uint_as_float(v[j]);
-                if (p.bias != nullptr && n < p.bias_n) t += p.bias[n];
-                f[j] = apply_act(t, p.act, p.slope);
+            for (int j = 0; j < 16; ++j) f[j] = __uint_as_float(v[j]);
+            if (has_bias) {
+#pragma unroll
+                for (int j = 0; j < 16; ++j)
+                    if (n0 + c0 + j < p.bias_n) f[j] += __ldg(p.bias + n0 + c0 + j);
             }
+#pragma unroll
+            for (int j = 0; j < 16; ++j) f[j] = fmaxf(f[j], f[j] * neg);
             if (vec_ok && n0 + c0 + 16 <= p.cout) {
                 Vec<bf16> o;
                 o.set(f); o.store(yrow + c0);
@@ -195,6 +201,8 @@ static PFN_cuTensorMapEncodeTiled_v12000 get_encode() {
 int run_conv_halo(const void* x0, int c0, const void* x1, int c1, const void* w_packed, int w_taps, const float* bias, int bias_n,
                   void* y, int n, int h, int w, int gemm_n, int ksize, const int8_t* hy, const int8_t* hx, const int8_t* wt, int ntaps,
                   int act, float slope, cudaStream_t st);
+int run_wgrad_halo(const void* x0, int c0, const void* x1, int c1, const void* dy, int cout_s, float* dw, int cout_real, int cin_real,
+                   int n, int h, int w, cudaStream_t st);
 int encode_bf16_map(CUtensorMap* map, const void* ptr, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
                     const uint32_t* box, CUtensorMapSwizzle swizzle, const uint32_t* elem_strides);
 
@@ -565,6 +573,8 @@ extern "C" int ssg_conv2d_wgrad_tc(const void* x0, int c0, const void* x1, int c
     const int taps = ksize * ksize;
     cudaStream_t st = (cudaStream_t)s;
     SSG_CHECK_CUDA(cudaMemsetAsync(dw_oihw, 0, sizeof(float) * (size_t)cout_real * cin_real * taps, st));
+    if (ksize == 3 && stride == 1 && pad == 1 && use_halo_kernel())
+        return run_wgrad_halo(x0, c0, x1, c1, dy, cout, dw_oihw, cout_real, cin_real, n, h, w, st);
     int twl, thl;
     pick_tile(oh, ow, twl, thl);          // pixel tiles enumerate dy; x is gathered at stride * pixel + tap - pad
     const int TW = 1 << twl, TH = 1 << thl, NB = BM / (TW * TH);

@@ -332,3 +332,186 @@ int run_conv_halo(const void* x0, int c0, const void* x1, int c1, const void* w_
 
 }  // namespace tc
 }  // namespace ssg
+
+// =====================================================================================================
+// Halo-tile weight gradient (3x3, stride 1, same-size): dW[co][ci][r][s] = sum_px dy[px][co] * x[px + (r,s) - pad][ci].
+// GEMM view: D[M = 128 = two taps x 64 ci][N = 64 co] += A^T B with the pixel index as K, both operands MN-major
+// straight from the NHWC TMA boxes.  A CTA owns ONE 64-channel chunk of x, ONE 64-wide co tile and all nine taps
+// (five tap pairs -> five 128 x 64 fp32 accumulators = 320 TMEM columns) and walks a strided subset of the 16 x 8
+// pixel tiles (split-K).  Per pixel tile it loads ONE 18 x 10 halo box of x (23 KB) and one dy box (16 KB): the nine
+// shifted views of x are UMMA descriptors into the same halo tile (start address advanced by (r * 10 + s) pixels,
+// stride-byte-offset = halo pitch), the second tap of a pair is reached through the leading-byte-offset.  The plain
+// kernel loads 9 x 16 KB of x per 64-channel chunk instead (4.4 x more operand bytes per MMA cycle).
+// =====================================================================================================
+namespace ssg {
+namespace tc {
+
+struct HaloWgradParams {
+    float* dw;                   // OIHW fp32 [cout][cin][3][3], pre-zeroed
+    int N, H, W;
+    int cout, cin;               // real channel extents of dw
+    int tiles_x, tiles_y, m_tiles;
+    int chunks0, chunks1;
+};
+
+constexpr int HW_XS = 4, HW_DS = 4;                    // ring slots
+constexpr int HW_DY_BYTES = 128 * 128;
+constexpr int HW_X_OFFSET = 0;
+constexpr int HW_DY_OFFSET = HW_XS * H_A_TILE_STRIDE;
+constexpr int HW_BAR_OFFSET = HW_DY_OFFSET + HW_DS * HW_DY_BYTES;
+constexpr int HW_TOTAL = HW_BAR_OFFSET + 256 + 1024;
+
+__global__ void __launch_bounds__(H_THREADS, 1) conv_tc_halo_wgrad_kernel(const __grid_constant__ CUtensorMap tmX0,
+                                                                           const __grid_constant__ CUtensorMap tmX1,
+                                                                           const __grid_constant__ CUtensorMap tmDY,
+                                                                           const HaloWgradParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint64_t* x_full = reinterpret_cast<uint64_t*>(smem + HW_BAR_OFFSET);
+    uint64_t* x_empty = x_full + HW_XS;
+    uint64_t* dy_full = x_empty + HW_XS;
+    uint64_t* dy_empty = dy_full + HW_DS;
+    uint64_t* acc_full = dy_empty + HW_DS;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_full + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int chunk = blockIdx.x, co0 = blockIdx.y * 64;
+    const int tiles_per_img = p.tiles_x * p.tiles_y;
+    const int n_iter = (p.m_tiles - (int)blockIdx.z + (int)gridDim.z - 1) / (int)gridDim.z;
+
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < HW_XS; ++i) { mbar_init(&x_full[i], 1); mbar_init(&x_empty[i], 1); }
+        for (int i = 0; i < HW_DS; ++i) { mbar_init(&dy_full[i], 1); mbar_init(&dy_empty[i], 1); }
+        mbar_init(acc_full, 1);
+        fence_barrier_init();
+    }
+    if (warp == 2) tmem_alloc(tmem_slot, 512);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            for (int it = 0; it < n_iter; ++it) {
+                const int t = blockIdx.z + it * gridDim.z;
+                const int img = t / tiles_per_img, rem = t - img * tiles_per_img;
+                const int ty = rem / p.tiles_x, tx = rem - ty * p.tiles_x;
+                const int sl = it % HW_XS;
+                mbar_wait(&x_empty[sl], ((it / HW_XS) & 1) ^ 1);
+                mbar_expect_tx(&x_full[sl], 18 * 10 * 128);
+                uint8_t* dst = smem + HW_X_OFFSET + sl * H_A_TILE_STRIDE;
+                if (chunk < p.chunks0) tma_load_4d(dst, &tmX0, chunk * 64, tx * H_TW - 1, ty * H_TH - 1, img, &x_full[sl]);
+                else tma_load_4d(dst, &tmX1, (chunk - p.chunks0) * 64, tx * H_TW - 1, ty * H_TH - 1, img, &x_full[sl]);
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            for (int it = 0; it < n_iter; ++it) {
+                const int t = blockIdx.z + it * gridDim.z;
+                const int img = t / tiles_per_img, rem = t - img * tiles_per_img;
+                const int ty = rem / p.tiles_x, tx = rem - ty * p.tiles_x;
+                const int sl = it % HW_DS;
+                mbar_wait(&dy_empty[sl], ((it / HW_DS) & 1) ^ 1);
+                mbar_expect_tx(&dy_full[sl], HW_DY_BYTES);
+                tma_load_4d(smem + HW_DY_OFFSET + sl * HW_DY_BYTES, &tmDY, co0, tx * H_TW, ty * H_TH, img, &dy_full[sl]);
+            }
+        }
+    } else if (warp == 2) {
+        if (lane == 0) {
+            constexpr uint32_t idesc = make_idesc_bf16(128, 64, 1, 1);     // both operands MN-major
+            for (int it = 0; it < n_iter; ++it) {
+                const int xs = it % HW_XS, ds = it % HW_DS;
+                mbar_wait(&x_full[xs], (it / HW_XS) & 1);
+                mbar_wait(&dy_full[ds], (it / HW_DS) & 1);
+                tc_fence_after();
+                const uint32_t x_addr = smem_u32(smem + HW_X_OFFSET + xs * H_A_TILE_STRIDE);
+                const uint32_t dy_addr = smem_u32(smem + HW_DY_OFFSET + ds * HW_DY_BYTES);
+                const uint64_t db = make_smem_desc(dy_addr, 1024, 1024, 2);
+#pragma unroll
+                for (int g = 0; g < 5; ++g) {
+                    // taps 2g and 2g+1 (tap 8 is paired with a dummy second half whose rows are never stored)
+                    const int ta = 2 * g, tb = g < 4 ? 2 * g + 1 : 8;
+                    const int off_a = ((ta / 3) * 10 + ta % 3) * 128, off_b = ((tb / 3) * 10 + tb % 3) * 128;
+                    const uint32_t lbo = g < 4 ? (uint32_t)(off_b - off_a) : 128u;
+                    const uint64_t da = make_smem_desc(x_addr + off_a, lbo, 1280, 2);
+#pragma unroll
+                    for (int k = 0; k < 8; ++k)      // 16 pixels = two tile rows per MMA: x advances 2 halo rows, dy 2 box rows
+                        umma_bf16(tmem_base + (uint32_t)(g * 64), da + (uint64_t)(160 * k), db + (uint64_t)(128 * k), idesc, (it | k) != 0);
+                }
+                umma_commit(&x_empty[xs]);
+                umma_commit(&dy_empty[ds]);
+            }
+            umma_commit(acc_full);
+        }
+    } else if (warp >= 4) {
+        const int q = warp & 3;
+        const int row = q * 32 + lane;                  // accumulator row: tap half (row >> 6), ci (row & 63)
+        const int ci = chunk * 64 + (row & 63);
+        mbar_wait(acc_full, 0);
+        tc_fence_after();
+        if (n_iter > 0) {
+#pragma unroll 1
+            for (int g = 0; g < 5; ++g) {
+                const int tap = 2 * g + (row >> 6);
+                const bool row_ok = tap < 9 && ci < p.cin;
+#pragma unroll 1
+                for (int c0 = 0; c0 < 64; c0 += 32) {
+                    uint32_t v[32];
+                    tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(g * 64 + c0), v);
+                    tmem_ld_wait();
+                    if (!row_ok) continue;
+                    float* dst = p.dw + ((long long)(co0 + c0) * p.cin + ci) * 9 + tap;
+#pragma unroll
+                    for (int j = 0; j < 32; ++j)
+                        if (co0 + c0 + j < p.cout) atomicAdd(dst + (long long)j * p.cin * 9, __uint_as_float(v[j]));
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) tmem_dealloc(tmem_base, 512);
+}
+
+// x0 | x1: stored channel counts c0 / c1 (multiples of 8); dy: stored channels cout_s.  dw must be zeroed by the caller.
+int run_wgrad_halo(const void* x0, int c0, const void* x1, int c1, const void* dy, int cout_s, float* dw, int cout_real, int cin_real,
+                   int n, int h, int w, cudaStream_t st) {
+    HaloWgradParams p;
+    memset(&p, 0, sizeof(p));
+    p.dw = dw; p.N = n; p.H = h; p.W = w; p.cout = cout_real; p.cin = cin_real;
+    p.tiles_x = (w + H_TW - 1) / H_TW; p.tiles_y = (h + H_TH - 1) / H_TH; p.m_tiles = n * p.tiles_x * p.tiles_y;
+    p.chunks0 = (c0 + 63) / 64; p.chunks1 = (c1 + 63) / 64;
+    CUtensorMap mx0, mx1, mdy;
+    auto enc = [&](CUtensorMap* m, const void* ptr, int c, int bw, int bh) {
+        uint64_t dims[4] = {(uint64_t)c, (uint64_t)w, (uint64_t)h, (uint64_t)n};
+        uint64_t str[3] = {(uint64_t)c * 2, (uint64_t)w * c * 2, (uint64_t)h * w * c * 2};
+        uint32_t box[4] = {64, (uint32_t)bw, (uint32_t)bh, 1};
+        return encode_bf16_map(m, ptr, 4, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B, nullptr);
+    };
+    int rc = enc(&mx0, x0, c0, 10, 18);
+    if (rc) return rc;
+    mx1 = mx0;
+    if (c1 > 0) {
+        rc = enc(&mx1, x1, c1, 10, 18);
+        if (rc) return rc;
+    }
+    rc = enc(&mdy, dy, cout_s, H_TW, H_TH);
+    if (rc) return rc;
+    static bool attr_set = false;
+    if (!attr_set) {
+        SSG_CHECK_CUDA(cudaFuncSetAttribute(conv_tc_halo_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, HW_TOTAL));
+        attr_set = true;
+    }
+    const int chunks = p.chunks0 + p.chunks1, co_tiles = (cout_real + 63) / 64;
+    int splits = (2 * sm_count_cached() + chunks * co_tiles - 1) / (chunks * co_tiles);      // ~two waves of CTAs
+    if (splits > p.m_tiles) splits = p.m_tiles;
+    if (splits < 1) splits = 1;
+    dim3 grid((unsigned)chunks, (unsigned)co_tiles, (unsigned)splits);
+    conv_tc_halo_wgrad_kernel<<<grid, H_THREADS, HW_TOTAL, st>>>(mx0, mx1, mdy, p);
+    SSG_CHECK_LAUNCH();
+    return SSG_OK;
+}
+
+}  // namespace tc
+}  // namespace ssg

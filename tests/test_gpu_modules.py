@@ -167,7 +167,8 @@ def test_gan_step_vs_reference_golden(golden_dir, dtype, impl, tol):
         ltol = (1e-4 if it == 0 else 1e-2) if dtype == torch.float32 else 0.12
         assert rel(r["logits"], z["it%d_logits" % it]) < ltol
         if dtype == torch.float32:
-            assert abs(r["iou"] - want[4]) < 2e-4
+            # IoU counts thresholded pixels: after one sign-like Adam step a few of the 16 384 pixels may flip
+            assert abs(r["iou"] - want[4]) < (2e-4 if it == 0 else 1e-3)
             assert abs(float(r["dice"]) - want[5]) < 1e-5
     sdg, sdd = g.state_dict(), d.state_dict()
     assert int(sdd["conv_blocks.1.conv_block.1.num_batches_tracked"]) == 6       # 3 D passes per step
