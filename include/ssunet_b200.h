@@ -88,9 +88,15 @@ int ssg_conv2d_wgrad_simt(const void* x, const void* dy, float* dw_oihw, int dty
  * (h, w) are the INPUT spatial dims.  w_packed: bf16 [taps][cout][c0+c1] (SSG_W_RSKC, zero rows/columns for
  * padding channels); bias: bias_n fp32 entries or NULL; y = act(conv + bias), bf16 [n,oh,ow,cout].  The stride-2
  * gather is done by the TMA unit (element-strided tensor-map traversal).  Replaces the cuDNN implicit-GEMM calls
- * behind archs.py:210,212,218,593-601,615, normalization.py:93-98 and models_seg_gan.py:38-39. */
+ * behind archs.py:210,212,218,593-601,615, normalization.py:93-98 and models_seg_gan.py:38-39.
+ * stats (optional, NULL otherwise): fp64 [2][cout], overwritten with the per-channel sum and sum of squares of the
+ * stored output -- the BatchNorm statistics of batchnorm.py:59-64 as a by-product of the epilogue (only for the
+ * shapes ssg_conv2d_fwd_tc_has_stats() accepts: stride 1, same-size). */
 int ssg_conv2d_fwd_tc(const void* x0, int c0, const void* x1, int c1, const void* w_packed, const float* bias, int bias_n, void* y,
-                      int n, int h, int w, int cout, int ksize, int stride, int pad, int act, float slope, ssg_stream_t s);
+                      int n, int h, int w, int cout, int ksize, int stride, int pad, int act, float slope, double* stats,
+                      ssg_stream_t s);
+/* 1 if ssg_conv2d_fwd_tc can produce `stats` for this geometry (host query, returns 0/1, never fails) */
+int ssg_conv2d_fwd_tc_has_stats(int ksize, int stride, int pad);
 
 /* Data gradient of the same convolution: dx bf16 [n,h,w,cin] from dy bf16 [n,oh,ow,cout].
  * w_packed: bf16 [taps][cin][cout] (SSG_W_RSCK).  Stride 2 is computed as four output-parity classes (each a

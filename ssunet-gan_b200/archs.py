@@ -38,10 +38,11 @@ class BasicBlock(nn.Module):
 
     def forward(self, x):
         x = ops.to_nhwc(x)
-        out = self.bn1(self.conv1(x), act=ACT_RELU)
-        out = self.conv2(out)
+        y1, s1 = self.conv1(x, want_stats=self.training)  # BN statistics are reduced in the conv epilogue when possible
+        out = self.bn1(y1, act=ACT_RELU, sums=s1)
+        y2, s2 = self.conv2(out, want_stats=self.training)
         sc = self.shortcut[0](x) if len(self.shortcut) else x
-        return self.bn2(out, residual=sc, act=ACT_RELU)
+        return self.bn2(y2, residual=sc, act=ACT_RELU, sums=s2)
 
 
 class _Pool(nn.Module):

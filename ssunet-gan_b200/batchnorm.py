@@ -49,7 +49,7 @@ class _SynchronizedBatchNorm(_BatchNorm):
     def _to4d(self, x):
         return x
 
-    def forward(self, input, residual=None, act=ACT_NONE, slope=0.0):
+    def forward(self, input, residual=None, act=ACT_NONE, slope=0.0, sums=None):
         self._check_input_dim(input)
         shape = input.shape
         x = self._to4d(input)
@@ -58,7 +58,7 @@ class _SynchronizedBatchNorm(_BatchNorm):
             self.num_batches_tracked.add_(1)          # F.batch_norm path (batchnorm.py:52-55)
         y = ops.batch_norm(x, self.weight, self.bias, self.running_mean, self.running_var, self.training,
                            self.momentum, self.eps, residual, act, slope,
-                           self._group if parallel else None, sync_quirk=parallel)
+                           self._group if parallel else None, sync_quirk=parallel, sums=sums)
         if y.shape != shape:
             y = ops.to_nchw_f32(y).reshape(shape)
         return y

@@ -19,8 +19,14 @@ def _flops(n, oh, ow, cin, cout, k):
     return 2.0 * n * oh * ow * cin * cout * k * k
 
 
-def forward(x, weight, bias, y, stride, pad, act, slope, x1=None):
-    """y = act(conv([x | x1], weight) + bias); x / x1 / y may be channel-padded (ops.thin_pad)."""
+def has_stats(k, stride, pad):
+    """True when the forward kernel can emit BatchNorm sum / sum-of-squares as a by-product of its epilogue."""
+    return bool(_lib.lib().ssg_conv2d_fwd_tc_has_stats(int(k), int(stride), int(pad)))
+
+
+def forward(x, weight, bias, y, stride, pad, act, slope, x1=None, stats=None):
+    """y = act(conv([x | x1], weight) + bias); x / x1 / y may be channel-padded (ops.thin_pad).
+    stats: optional fp64 [2 * Cout_stored] tensor that receives per-channel sum(y), sum(y^2)."""
     from .ops import packed_weight
     n, c0, h, w = x.shape
     c1 = x1.shape[1] if x1 is not None else 0
@@ -29,7 +35,7 @@ def forward(x, weight, bias, y, stride, pad, act, slope, x1=None):
     oh, ow = _out_hw(h, w, k, stride, pad)
     wp = packed_weight(weight, W_RSKC, torch.bfloat16, cout_p=y.shape[1], cin_p=c0 + c1)
     call("ssg_conv2d_fwd_tc", x, c0, x1, c1, wp, bias, cout if bias is not None else 0, y, n, h, w, y.shape[1], k, stride, pad, act,
-         slope, flops=_flops(n, oh, ow, cin, cout, k))
+         slope, stats, flops=_flops(n, oh, ow, cin, cout, k))
 
 
 def dgrad(dy, weight, dx, stride, pad):

@@ -38,7 +38,44 @@ __global__ void __launch_bounds__(BN_THREADS) channel_reduce_vec_kernel(
 #pragma unroll
                 for (int i = 0; i < V; ++i) { mu[i] = mean[v * V + i]; is[i] = inv_std[v * V + i]; }
             }
-            for (long long r = r_begin + rsub; r < r_end; r += rpb) {
+            // U rows per trip with all loads issued before the first use: U independent 16-byte requests per operand
+            // in flight per thread (a single dependent load per trip left this kernel latency-bound at < 20 % of HBM)
+            constexpr int U = 4;
+            long long r = r_begin + rsub;
+            for (; r + (long long)(U - 1) * rpb < r_end; r += (long long)U * rpb) {
+                Vec<T> va[U], vx[U], vy[U];
+#pragma unroll
+                for (int u = 0; u < U; ++u) va[u].load(a + (r + (long long)u * rpb) * C + (long long)v * V);
+                if (MODE == 1) {
+#pragma unroll
+                    for (int u = 0; u < U; ++u) vx[u].load(xin + (r + (long long)u * rpb) * C + (long long)v * V);
+                    if (act != SSG_ACT_NONE) {
+#pragma unroll
+                        for (int u = 0; u < U; ++u) vy[u].load(yout + (r + (long long)u * rpb) * C + (long long)v * V);
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    float fa[V]; va[u].get(fa);
+                    if (MODE == 0) {
+#pragma unroll
+                        for (int i = 0; i < V; ++i) { acc0[i] += fa[i]; acc1[i] = fmaf(fa[i], fa[i], acc1[i]); }
+                    } else {
+                        float fx[V]; vx[u].get(fx);
+                        if (act != SSG_ACT_NONE) {
+                            float fy[V]; vy[u].get(fy);
+#pragma unroll
+                            for (int i = 0; i < V; ++i) fa[i] *= act_grad_from_out(fy[i], act, slope);
+                        }
+#pragma unroll
+                        for (int i = 0; i < V; ++i) {
+                            acc0[i] += fa[i];
+                            acc1[i] = fmaf(fa[i], (fx[i] - mu[i]) * is[i], acc1[i]);
+                        }
+                    }
+                }
+            }
+            for (; r < r_end; r += rpb) {
                 const long long off = r * C + (long long)v * V;
                 Vec<T> va; va.load(a + off);
                 float fa[V]; va.get(fa);

@@ -200,7 +200,7 @@ static PFN_cuTensorMapEncodeTiled_v12000 get_encode() {
 // bf16 tensor map; dims/box innermost first; strides in BYTES for dims 1..rank-1
 int run_conv_halo(const void* x0, int c0, const void* x1, int c1, const void* w_packed, int w_taps, const float* bias, int bias_n,
                   void* y, int n, int h, int w, int gemm_n, int ksize, const int8_t* hy, const int8_t* hx, const int8_t* wt, int ntaps,
-                  int act, float slope, cudaStream_t st);
+                  int act, float slope, double* stats, cudaStream_t st);
 int run_wgrad_halo(const void* x0, int c0, const void* x1, int c1, const void* dy, int cout_s, float* dw, int cout_real, int cin_real,
                    int n, int h, int w, cudaStream_t st);
 int encode_bf16_map(CUtensorMap* map, const void* ptr, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
@@ -309,7 +309,8 @@ static int run_conv(const void* x0, int c0, const void* x1, int c1, const void* 
 extern "C" {
 
 int ssg_conv2d_fwd_tc(const void* x0, int c0, const void* x1, int c1, const void* w_packed, const float* bias, int bias_n, void* y,
-                      int n, int h, int w, int cout, int ksize, int stride, int pad, int act, float slope, ssg_stream_t s) {
+                      int n, int h, int w, int cout, int ksize, int stride, int pad, int act, float slope, double* stats,
+                      ssg_stream_t s) {
     SSG_CHECK_ARG(n > 0 && h > 0 && w > 0 && cout > 0 && cout % 8 == 0 && c0 > 0 && c0 % 8 == 0 && c1 >= 0 && c1 % 8 == 0 &&
                       (c1 == 0 || c0 % 64 == 0),
                   "conv2d_fwd_tc: stored channel counts must be multiples of 8, c0 of 64 when x1 is given (c0=%d c1=%d cout=%d)", c0, c1,
@@ -331,10 +332,15 @@ int ssg_conv2d_fwd_tc(const void* x0, int c0, const void* x1, int c1, const void
         int8_t hy[9], hx[9];
         for (int t = 0; t < c.ntaps; ++t) { hy[t] = (int8_t)(t / ksize); hx[t] = (int8_t)(t % ksize); }
         return run_conv_halo(x0, c0, x1, c1, w_packed, ksize * ksize, bias, bias_n, y, n, h, w, cout, ksize, hy, hx, c.wt, c.ntaps, act, slope,
-                             (cudaStream_t)s);
+                             stats, (cudaStream_t)s);
     }
+    SSG_CHECK_ARG(stats == nullptr, "conv2d_fwd_tc: fused statistics need a stride-1 same-size convolution (query ssg_conv2d_fwd_tc_has_stats)");
     return run_conv(x0, c0, x1, c1, w_packed, ksize * ksize, bias, bias_n, y, n, h, w, oh, ow, oh, ow, cout, stride, 1, &c, 1, act, slope,
                     (cudaStream_t)s);
+}
+
+int ssg_conv2d_fwd_tc_has_stats(int ksize, int stride, int pad) {
+    return (stride == 1 && 2 * pad == ksize - 1 && (ksize == 1 || ksize == 3) && use_halo_kernel()) ? 1 : 0;
 }
 
 int ssg_conv2d_dgrad_tc(const void* dy, const void* w_packed, void* dx, int n, int h, int w, int cin, int cout, int ksize, int stride,
@@ -352,7 +358,7 @@ int ssg_conv2d_dgrad_tc(const void* dy, const void* w_packed, void* dx, int n, i
             hy[t] = (int8_t)(ksize - 1 - t / ksize); hx[t] = (int8_t)(ksize - 1 - t % ksize); wt[t] = (int8_t)t;
         }
         return run_conv_halo(dy, cout, nullptr, 0, w_packed, ksize * ksize, nullptr, 0, dx, n, h, w, cin, ksize, hy, hx, wt, ksize * ksize, 0, 0.f,
-                             (cudaStream_t)s);
+                             nullptr, (cudaStream_t)s);
     }
     TapClass c[4];
     memset(c, 0, sizeof(c));

@@ -46,6 +46,7 @@ struct HaloParams {
     int org;                     // halo origin = tile origin - org
     int act;
     float slope;
+    double* stats;               // optional [2][cout] fp64 (pre-zeroed): per-channel sum / sum of squares of the stored y
 };
 
 template <int MT, int BN, int ACCS>     // ACCS accumulator sets (2: epilogue overlaps the next item's MMAs)
@@ -189,6 +190,23 @@ __global__ void __launch_bounds__(H_THREADS, 1) conv_tc_halo_kernel(const __grid
         const bool has_bias = p.bias != nullptr;
         // act(v) = max(v, v * neg): neg = 1 (identity), 0 (ReLU) or the LeakyReLU slope -- branch-free in the hot loop
         const float neg = p.act == SSG_ACT_RELU ? 0.f : (p.act == SSG_ACT_LEAKY ? p.slope : 1.f);
+        // BatchNorm statistics of the output (batchnorm.py:59-64) as a by-product: lane l keeps fp32 partial sums of
+        // channels 2l, 2l+1 of each 64-channel half over every row this warp stores; flushed with fp64 atomics when the
+        // N tile changes.  The values summed are the bf16-rounded ones the normalisation will read back.
+        const bool want_stats = p.stats != nullptr;
+        float st[BN / 64][4];
+#pragma unroll
+        for (int i = 0; i < BN / 64; ++i) st[i][0] = st[i][1] = st[i][2] = st[i][3] = 0.f;
+        int stats_n0 = -1;
+        auto flush_stats = [&]() {
+#pragma unroll
+            for (int i = 0; i < BN / 64; ++i) {
+                const int c = stats_n0 + i * 64 + 2 * lane;
+                if (c < p.cout) { atomicAdd(p.stats + c, (double)st[i][0]); atomicAdd(p.stats + p.cout + c, (double)st[i][2]); }
+                if (c + 1 < p.cout) { atomicAdd(p.stats + c + 1, (double)st[i][1]); atomicAdd(p.stats + p.cout + c + 1, (double)st[i][3]); }
+                st[i][0] = st[i][1] = st[i][2] = st[i][3] = 0.f;
+            }
+        };
         int it = 0, bias_n0 = -1;
         for (int item = blockIdx.x; item < p.total_items; item += gridDim.x, ++it) {
             const int acc = it % ACCS;
@@ -201,6 +219,10 @@ __global__ void __launch_bounds__(H_THREADS, 1) conv_tc_halo_kernel(const __grid
                 __syncwarp();
                 bias_n0 = n0;
             }
+            if (want_stats && n0 != stats_n0) {
+                if (stats_n0 >= 0) flush_stats();
+                stats_n0 = n0;
+            }
             mbar_wait(&acc_full[acc], (it / ACCS) & 1);
             tc_fence_after();
 #pragma unroll 1
@@ -210,7 +232,7 @@ __global__ void __launch_bounds__(H_THREADS, 1) conv_tc_halo_kernel(const __grid
                 const int img = t / tiles_per_img, rem = t - img * tiles_per_img;
                 const int ty = rem / p.tiles_x, tx = rem - ty * p.tiles_x;
                 const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * C::ACC_COLS + mt * BN);
-#pragma unroll 1
+#pragma unroll
                 for (int h0 = 0; h0 < BN; h0 += 64) {
                     if (n0 + h0 >= p.cout) break;
                     uint32_t v[64];
@@ -248,11 +270,27 @@ __global__ void __launch_bounds__(H_THREADS, 1) conv_tc_halo_kernel(const __grid
                         tma_store_4d(&tmY, stage, n0 + h0, tx * H_TW, ty * H_TH + 4 * q, img);
                         tma_store_commit();
                     }
+                    if (want_stats) {
+                        const uint32_t valid = __ballot_sync(0xffffffffu, (ty * H_TH + 4 * q + (lane >> 3) < p.H) && (tx * H_TW + (lane & 7) < p.W));
+                        float a0 = 0.f, a1 = 0.f, q0 = 0.f, q1 = 0.f;
+                        const uint8_t* col = stage + ((lane & 3) << 2);
+#pragma unroll
+                        for (int r = 0; r < 32; ++r) {
+                            if ((valid >> r) & 1u) {                 // warp-uniform: rows outside the image are skipped
+                                const uint32_t w2 = *reinterpret_cast<const uint32_t*>(col + r * 128 + (((lane >> 2) ^ (r & 7)) << 4));
+                                const float a = __uint_as_float(w2 << 16), b = __uint_as_float(w2 & 0xffff0000u);
+                                a0 += a; a1 += b;
+                                q0 = fmaf(a, a, q0); q1 = fmaf(b, b, q1);
+                            }
+                        }
+                        st[h0 / 64][0] += a0; st[h0 / 64][1] += a1; st[h0 / 64][2] += q0; st[h0 / 64][3] += q1;
+                    }
                 }
             }
             tc_fence_before();
             mbar_arrive(&acc_empty[acc]);
         }
+        if (want_stats && stats_n0 >= 0) flush_stats();
         if (lane == 0) tma_store_wait_all();
     }
     tc_fence_before();
@@ -281,9 +319,11 @@ static int launch_halo(const CUtensorMap& a0, const CUtensorMap& a1, const CUten
 // Same-size stride-1 convolution / data gradient.  taps: (hy, hx, wt) per tap in halo coordinates.
 int run_conv_halo(const void* x0, int c0, const void* x1, int c1, const void* w_packed, int w_taps, const float* bias, int bias_n,
                   void* y, int n, int h, int w, int gemm_n, int ksize, const int8_t* hy, const int8_t* hx, const int8_t* wt, int ntaps,
-                  int act, float slope, cudaStream_t st) {
+                  int act, float slope, double* stats, cudaStream_t st) {
     HaloParams p;
     memset(&p, 0, sizeof(p));
+    p.stats = stats;
+    if (stats) SSG_CHECK_CUDA(cudaMemsetAsync(stats, 0, sizeof(double) * 2 * (size_t)gemm_n, st));
     p.y = (bf16*)y; p.bias = bias; p.bias_n = bias_n; p.N = n; p.H = h; p.W = w; p.cout = gemm_n;
     p.tiles_x = (w + H_TW - 1) / H_TW; p.tiles_y = (h + H_TH - 1) / H_TH; p.m_tiles = n * p.tiles_x * p.tiles_y;
     p.chunks0 = (c0 + 63) / 64; p.chunks1 = (c1 + 63) / 64;

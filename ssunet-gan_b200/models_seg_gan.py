@@ -41,7 +41,8 @@ class ConvolutionalBlock(nn.Module):
             raise NotImplementedError("only None / LeakyReLU activations are on the seg-GAN path")
         conv = self.conv_block[0]
         if self._has_bn:
-            return self.conv_block[1](conv(input), act=self._act, slope=0.2)
+            y, sums = conv(input, want_stats=self.training)
+            return self.conv_block[1](y, act=self._act, slope=0.2, sums=sums)
         return conv(input, act=self._act, slope=0.2)
 
 

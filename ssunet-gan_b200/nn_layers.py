@@ -10,11 +10,11 @@ from ._lib import ACT_LEAKY, ACT_NONE, ACT_RELU  # noqa: F401
 class Conv2d(nn.Conv2d):
     """nn.Conv2d drop-in (square kernel, symmetric zero padding, dilation 1, groups 1)."""
 
-    def forward(self, x, act=ACT_NONE, slope=0.0, cout_store=None):
+    def forward(self, x, act=ACT_NONE, slope=0.0, cout_store=None, want_stats=None):
         assert self.groups == 1 and self.dilation == (1, 1) and self.padding_mode == "zeros"
         assert self.kernel_size[0] == self.kernel_size[1] and self.stride[0] == self.stride[1]
         assert self.padding[0] == self.padding[1]
-        return ops.conv2d(x, self.weight, self.bias, self.stride[0], self.padding[0], act, slope, cout_store)
+        return ops.conv2d(x, self.weight, self.bias, self.stride[0], self.padding[0], act, slope, cout_store, want_stats)
 
 
 class Linear(nn.Linear):
@@ -29,7 +29,7 @@ class BatchNorm2d(nn.BatchNorm2d):
     sync_group = None      # set by convert_model / SynchronizedBatchNorm2d
     sync_quirk = False
 
-    def forward(self, x, residual=None, act=ACT_NONE, slope=0.0):
+    def forward(self, x, residual=None, act=ACT_NONE, slope=0.0, sums=None):
         training = self.training or (self.running_mean is None)
         if training and self.track_running_stats and self.num_batches_tracked is not None and not self.sync_quirk:
             self.num_batches_tracked.add_(1)
@@ -38,7 +38,7 @@ class BatchNorm2d(nn.BatchNorm2d):
             momentum = 1.0 / float(self.num_batches_tracked) if training else 0.0
         return ops.batch_norm(x, self.weight, self.bias, self.running_mean if self.track_running_stats else None,
                               self.running_var if self.track_running_stats else None, training, momentum, self.eps,
-                              residual, act, slope, self.sync_group, self.sync_quirk)
+                              residual, act, slope, self.sync_group, self.sync_quirk, sums)
 
 
 class ReLU(nn.Module):

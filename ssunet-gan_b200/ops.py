@@ -192,7 +192,7 @@ class _Conv2d(torch.autograd.Function):
     >= Cout channels (thin_pad): the extra channels are zeros."""
 
     @staticmethod
-    def forward(ctx, x, weight, bias, stride, pad, act, slope, cout_store):
+    def forward(ctx, x, weight, bias, stride, pad, act, slope, cout_store, want_stats):
         n, cin_s, h, w = x.shape
         cout, cin, kh, kw = weight.shape
         cout_s = cout_store or cout
@@ -201,9 +201,13 @@ class _Conv2d(torch.autograd.Function):
         dt = x.dtype
         y = empty_nhwc(n, cout_s, oh, ow, dt, x.device)
         use_tc = _tc_eligible(cin_s, cout_s, kh, stride, dt)
+        sums = None
         if use_tc:
             from . import conv_tc
-            conv_tc.forward(x, weight, bias, y, stride, pad, act, slope)
+            if want_stats and conv_tc.has_stats(kh, stride, pad):
+                # BatchNorm's sum / sum-of-squares (batchnorm.py:59-64) come out of the conv epilogue: no extra pass over y
+                sums = torch.empty(2 * cout_s, dtype=torch.float64, device=x.device)
+            conv_tc.forward(x, weight, bias, y, stride, pad, act, slope, stats=sums)
         else:
             if cin_s != cin or cout_s != cout:
                 raise _lib.SsgError("conv2d: channel-padded activations need the tensor-core path (bf16, conv_impl auto)")
@@ -211,10 +215,12 @@ class _Conv2d(torch.autograd.Function):
             call("ssg_conv2d_fwd_simt", x, wp, bias, y, dtype_code(dt), n, h, w, cin, cout, kh, kw, stride, pad, act, slope)
         ctx.save_for_backward(x, weight, y if act != ACT_NONE else None)
         ctx.cfg = (stride, pad, act, slope, bias is not None, use_tc)
-        return y
+        if sums is not None:
+            ctx.mark_non_differentiable(sums)
+        return y, sums
 
     @staticmethod
-    def backward(ctx, dy):
+    def backward(ctx, dy, _dsums=None):
         x, weight, y = ctx.saved_tensors
         stride, pad, act, slope, has_bias, use_tc = ctx.cfg
         n, cin_s, h, w = x.shape
@@ -246,11 +252,15 @@ class _Conv2d(torch.autograd.Function):
             sums = torch.empty(2 * cout_s, dtype=torch.float64, device=x.device)
             call("ssg_channel_stats", dy, dtype_code(dt), _rows(dy), cout_s, sums, 0)
             db = sums[:cout].float()
-        return dx, dw, db, None, None, None, None, None
+        return dx, dw, db, None, None, None, None, None, None
 
 
-def conv2d(x, weight, bias=None, stride=1, pad=0, act=ACT_NONE, slope=0.0, cout_store=None):
-    return _Conv2d.apply(to_nhwc(x), weight, bias, stride, pad, act, slope, cout_store)
+def conv2d(x, weight, bias=None, stride=1, pad=0, act=ACT_NONE, slope=0.0, cout_store=None, want_stats=None):
+    """want_stats (True / False; None = plain call returning y): return `(y, sums)` where sums is the fp64
+    [sum y | sum y^2] per-channel statistics of the output when requested and the kernel can produce them in its epilogue
+    (else None)."""
+    y, sums = _Conv2d.apply(to_nhwc(x), weight, bias, stride, pad, act, slope, cout_store, bool(want_stats))
+    return (y, sums) if want_stats is not None else y
 
 
 # ----------------------------------------------------------------------------------------------
@@ -268,13 +278,16 @@ class _BatchNorm(torch.autograd.Function):
     ``group`` spans more than one rank.  ``sync_quirk`` selects batchnorm.py:127's clamp(eps)."""
 
     @staticmethod
-    def forward(ctx, x, gamma, beta, residual, running_mean, running_var, momentum, eps, act, slope, group, sync_quirk):
+    def forward(ctx, x, gamma, beta, residual, running_mean, running_var, momentum, eps, act, slope, group, sync_quirk, sums):
         n, c, h, w = x.shape
         dt = x.dtype
         rows = _rows(x)
         dev = x.device
-        sums = torch.empty(2 * c, dtype=torch.float64, device=dev)
-        call("ssg_channel_stats", x, dtype_code(dt), rows, c, sums, 1)
+        if sums is None:          # otherwise the producing convolution already reduced them in its epilogue
+            sums = torch.empty(2 * c, dtype=torch.float64, device=dev)
+            call("ssg_channel_stats", x, dtype_code(dt), rows, c, sums, 1)
+        elif group is not None:
+            sums = sums.clone()   # the all-reduce below is in place
         world = _all_reduce_sum(sums, group)
         count = float(rows * world)
         mean = torch.empty(c, dtype=torch.float32, device=dev)
@@ -306,7 +319,7 @@ class _BatchNorm(torch.autograd.Function):
         dx = empty_nhwc(n, c, h, w, dt, x.device)
         dres = empty_nhwc(n, c, h, w, dt, x.device) if has_res else None
         call("ssg_bn_bwd_apply", dy, y, x, dx, dres, dtype_code(dt), rows, c, mean, inv_std, gamma, sums, count, act, slope, 1)
-        return dx, dgamma, dbeta, dres, None, None, None, None, None, None, None, None
+        return dx, dgamma, dbeta, dres, None, None, None, None, None, None, None, None, None
 
 
 class _BatchNormEval(torch.autograd.Function):
@@ -344,12 +357,14 @@ class _BatchNormEval(torch.autograd.Function):
 
 
 def batch_norm(x, gamma, beta, running_mean, running_var, training, momentum=0.1, eps=1e-5, residual=None,
-               act=ACT_NONE, slope=0.0, group=None, sync_quirk=False):
+               act=ACT_NONE, slope=0.0, group=None, sync_quirk=False, sums=None):
+    """sums: optional fp64 [sum x | sum x^2] already reduced by the producer of x (conv2d(..., want_stats=True))."""
     x = to_nhwc(x)
     if residual is not None:
         residual = to_nhwc(residual)
     if training:
-        return _BatchNorm.apply(x, gamma, beta, residual, running_mean, running_var, momentum, eps, act, slope, group, sync_quirk)
+        return _BatchNorm.apply(x, gamma, beta, residual, running_mean, running_var, momentum, eps, act, slope, group, sync_quirk,
+                                sums)
     return _BatchNormEval.apply(x, gamma, beta, residual, running_mean, running_var, eps, act, slope)
 
 

@@ -123,3 +123,27 @@ def test_conv_tc_thin_channels(cfg):
     assert rel(xc.grad, xr.grad) < 8e-3
     assert rel(wc.grad, wr.grad) < 8e-3
     assert rel(bc.grad, br.grad) < 8e-3
+
+
+@pytest.mark.parametrize("cfg", [(2, 64, 64, 40, 24, 3), (1, 128, 192, 19, 13, 3), (3, 64, 128, 8, 8, 1), (1, 192, 64, 33, 9, 3)])
+def test_conv_epilogue_bn_statistics(cfg):
+    """The per-channel sum / sum-of-squares the conv epilogue emits (batchnorm.py:59-64 as a by-product) equal the
+    standalone reduction kernel's result on the stored bf16 output, including ragged tiles (masked rows)."""
+    import ssunet_gan_b200 as ssg
+    from ssunet_gan_b200 import ops
+    from ssunet_gan_b200._lib import call, dtype_code
+    n, cin, cout, h, w, k = cfg
+    ssg.set_compute_dtype(torch.bfloat16)
+    ssg.set_conv_impl("auto")
+    g = torch.Generator().manual_seed(7 * cin + cout)
+    x = torch.randn(n, cin, h, w, generator=g).cuda()
+    wt = (torch.randn(cout, cin, k, k, generator=g) / math.sqrt(cin * k * k)).cuda()
+    y, sums = ops.conv2d(x, wt, None, 1, k // 2, want_stats=True)
+    assert sums is not None and sums.dtype == torch.float64 and sums.numel() == 2 * cout
+    ref = torch.empty(2 * cout, dtype=torch.float64, device="cuda")
+    call("ssg_channel_stats", y, dtype_code(y.dtype), n * h * w, cout, ref, 1)
+    yf = y.float()
+    want = torch.cat([yf.sum((0, 2, 3)), (yf * yf).sum((0, 2, 3))]).double()
+    assert rel(ref, want) < 1e-5
+    assert rel(sums, want) < 1e-5
+    assert float((sums[cout:] - want[cout:]).abs().max() / want[cout:].abs().max()) < 1e-4

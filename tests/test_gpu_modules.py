@@ -161,7 +161,7 @@ def test_gan_step_vs_reference_golden(golden_dir, dtype, impl, tol):
         got = [float(r["loss"]), float(r["content"]), float(r["adv_g"]), float(r["adv_d"])]
         # iteration 1 follows one Adam step: m/sqrt(v) is sign-like on step 1, so parameters whose gradient is
         # rounding-level noise move by +-lr either way; bf16: adversarial terms go through D on bf16 logits
-        stol = [tol, tol, 3 * tol, 3 * tol] if it == 0 else [10 * tol] * 4
+        stol = [tol, tol, 3 * tol, 3 * tol] if it == 0 else [10 * tol, 10 * tol, 30 * tol, 30 * tol]
         for a, b, tl in zip(got, want[:4], stol):
             assert abs(a - b) < tl * abs(b), (it, got, want)
         ltol = (1e-4 if it == 0 else 1e-2) if dtype == torch.float32 else 0.12
