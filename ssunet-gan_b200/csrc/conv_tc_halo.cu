@@ -194,13 +194,14 @@ __global__ void __launch_bounds__(H_THREADS, 1) conv_tc_halo_kernel(const __grid
         // channels 2l, 2l+1 of each 64-channel half over every row this warp stores; flushed with fp64 atomics when the
         // N tile changes.  The values summed are the bf16-rounded ones the normalisation will read back.
         const bool want_stats = p.stats != nullptr;
-        float st[BN / 64][4];
+        constexpr int NH = (BN + 63) / 64;                     // 64-channel halves of the N tile
+        float st[NH][4];
 #pragma unroll
-        for (int i = 0; i < BN / 64; ++i) st[i][0] = st[i][1] = st[i][2] = st[i][3] = 0.f;
+        for (int i = 0; i < NH; ++i) st[i][0] = st[i][1] = st[i][2] = st[i][3] = 0.f;
         int stats_n0 = -1;
         auto flush_stats = [&]() {
 #pragma unroll
-            for (int i = 0; i < BN / 64; ++i) {
+            for (int i = 0; i < NH; ++i) {
                 const int c = stats_n0 + i * 64 + 2 * lane;
                 if (c < p.cout) { atomicAdd(p.stats + c, (double)st[i][0]); atomicAdd(p.stats + p.cout + c, (double)st[i][2]); }
                 if (c + 1 < p.cout) { atomicAdd(p.stats + c + 1, (double)st[i][1]); atomicAdd(p.stats + p.cout + c + 1, (double)st[i][3]); }
@@ -348,13 +349,14 @@ int run_conv_halo(const void* x0, int c0, const void* x1, int c1, const void* w_
     const int cin = c0 + c1;
     // tile shape: SSG_HALO_SHAPE = "464" (4 M-tiles x BN 64) or "2128" (2 M-tiles x BN 128), two accumulator sets each; default by Cout
     static const char* shape_env = getenv("SSG_HALO_SHAPE");
-    int shape = gemm_n > 64 ? 2128 : 464;
+    int shape = gemm_n > 64 ? 2128 : (gemm_n <= 16 ? 416 : 464);      // thin outputs (SPADE maps, logits): N = 16 MMAs
     if (shape_env && gemm_n > 64) shape = atoi(shape_env);
-    const bool wide = shape != 464;
+    const bool wide = shape == 2128;
+    const int bn = wide ? 128 : (shape == 416 ? 16 : 64);
     {
         uint64_t dims[3] = {(uint64_t)cin, (uint64_t)gemm_n, (uint64_t)w_taps};
         uint64_t str[2] = {(uint64_t)cin * 2, (uint64_t)gemm_n * cin * 2};
-        uint32_t box[3] = {64, (uint32_t)(wide ? 128 : 64), 1};
+        uint32_t box[3] = {64, (uint32_t)bn, 1};
         rc = encode_bf16_map(&mb, w_packed, 3, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B, nullptr);
         if (rc) return rc;
     }
@@ -367,6 +369,7 @@ int run_conv_halo(const void* x0, int c0, const void* x1, int c1, const void* w_
         if (rc) return rc;
     }
     if (shape == 2128) return launch_halo<2, 128, 2>(ma0, ma1, mb, my, p, st);
+    if (shape == 416) return launch_halo<4, 16, 2>(ma0, ma1, mb, my, p, st);
     return launch_halo<4, 64, 2>(ma0, ma1, mb, my, p, st);
 }
 

@@ -48,6 +48,44 @@ __global__ void nhwc_to_nchw_kernel(const T* __restrict__ src, float* __restrict
     }
 }
 
+// Thin tensors (C <= 8 source channels: images, masks, logits): one thread per pixel, C coalesced plane reads and one
+// 16-byte (CD == 8, bf16) or element-wise store.  The 32 x 32 tile transpose above wastes 29/32 of its lanes here.
+template <typename T, int CD>
+__global__ void __launch_bounds__(256) nchw_to_nhwc_thin_kernel(const float* __restrict__ src, T* __restrict__ dst, int C, long long HW) {
+    const int n = blockIdx.y;
+    const float* s = src + (long long)n * C * HW;
+    T* d = dst + (long long)n * CD * HW;
+    for (long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x; p < HW; p += (long long)gridDim.x * blockDim.x) {
+        float f[CD];
+#pragma unroll
+        for (int c = 0; c < CD; ++c) f[c] = c < C ? s[(long long)c * HW + p] : 0.f;
+        if (CD == Vec<T>::N) {
+            Vec<T> v; v.set(f); v.store(d + p * CD);
+        } else {
+#pragma unroll
+            for (int c = 0; c < CD; ++c) d[p * CD + c] = from_f<T>(f[c]);
+        }
+    }
+}
+template <typename T, int CS>
+__global__ void __launch_bounds__(256) nhwc_to_nchw_thin_kernel(const T* __restrict__ src, float* __restrict__ dst, int C, long long HW) {
+    const int n = blockIdx.y;
+    const T* s = src + (long long)n * CS * HW;
+    float* d = dst + (long long)n * C * HW;
+    for (long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x; p < HW; p += (long long)gridDim.x * blockDim.x) {
+        float f[CS];
+        if (CS == Vec<T>::N) {
+            Vec<T> v; v.load(s + p * CS); v.get(f);
+        } else {
+#pragma unroll
+            for (int c = 0; c < CS; ++c) f[c] = to_f(s[p * CS + c]);
+        }
+#pragma unroll
+        for (int c = 0; c < CS; ++c)
+            if (c < C) d[(long long)c * HW + p] = f[c];
+    }
+}
+
 template <typename S, typename D>
 __global__ void cast_kernel(const S* __restrict__ src, D* __restrict__ dst, long long n) {
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -133,6 +171,12 @@ extern "C" {
 int ssg_nchw_to_nhwc_pad(const float* src, void* dst, int dtype, int n, int c, int c_dst, int h, int w, ssg_stream_t s) {
     SSG_CHECK_ARG(n > 0 && c > 0 && c_dst >= c && h > 0 && w > 0 && n <= 65535, "nchw_to_nhwc: bad shape");
     long long hw = (long long)h * w;
+    if (c_dst == 8 && dtype == SSG_BF16) {
+        dim3 tg((unsigned)((hw + 1023) / 1024), (unsigned)n);
+        nchw_to_nhwc_thin_kernel<bf16, 8><<<tg, 256, 0, (cudaStream_t)s>>>(src, (bf16*)dst, c, hw);
+        SSG_CHECK_LAUNCH();
+        return SSG_OK;
+    }
     dim3 grid((unsigned)((hw + 31) / 32), (unsigned)((c_dst + 31) / 32), (unsigned)n), block(32, 8);
     SSG_DISPATCH_DTYPE(dtype, nchw_to_nhwc_kernel<T><<<grid, block, 0, (cudaStream_t)s>>>(src, (T*)dst, c, c_dst, hw));
     SSG_CHECK_LAUNCH();
@@ -145,6 +189,12 @@ int ssg_nchw_to_nhwc(const float* src, void* dst, int dtype, int n, int c, int h
 int ssg_nhwc_to_nchw_pad(const void* src, int dtype, float* dst, int n, int c, int c_src, int h, int w, ssg_stream_t s) {
     SSG_CHECK_ARG(n > 0 && c > 0 && c_src >= c && h > 0 && w > 0 && n <= 65535, "nhwc_to_nchw: bad shape");
     long long hw = (long long)h * w;
+    if (c_src == 8 && dtype == SSG_BF16) {
+        dim3 tg((unsigned)((hw + 1023) / 1024), (unsigned)n);
+        nhwc_to_nchw_thin_kernel<bf16, 8><<<tg, 256, 0, (cudaStream_t)s>>>((const bf16*)src, dst, c, hw);
+        SSG_CHECK_LAUNCH();
+        return SSG_OK;
+    }
     dim3 grid((unsigned)((hw + 31) / 32), (unsigned)((c + 31) / 32), (unsigned)n), block(32, 8);
     SSG_DISPATCH_DTYPE(dtype, nhwc_to_nchw_kernel<T><<<grid, block, 0, (cudaStream_t)s>>>((const T*)src, dst, c, c_src, hw));
     SSG_CHECK_LAUNCH();
