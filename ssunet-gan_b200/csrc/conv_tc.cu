@@ -199,8 +199,7 @@ static PFN_cuTensorMapEncodeTiled_v12000 get_encode() {
 
 // bf16 tensor map; dims/box innermost first; strides in BYTES for dims 1..rank-1
 int run_conv_halo(const void* x0, int c0, const void* x1, int c1, const void* w_packed, int w_taps, const float* bias, int bias_n,
-                  void* y, int n, int h, int w, int gemm_n, int ksize, const int8_t* hy, const int8_t* hx, const int8_t* wt, int ntaps,
-                  int act, float slope, double* stats, cudaStream_t st);
+                  void* y, int n, int h, int w, int gemm_n, int ksize, int flip, int act, float slope, double* stats, cudaStream_t st);
 int run_wgrad_halo(const void* x0, int c0, const void* x1, int c1, const void* dy, int cout_s, float* dw, int cout_real, int cin_real,
                    int n, int h, int w, cudaStream_t st);
 int encode_bf16_map(CUtensorMap* map, const void* ptr, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
@@ -328,12 +327,9 @@ int ssg_conv2d_fwd_tc(const void* x0, int c0, const void* x1, int c1, const void
             const int t = r * ksize + q;
             c.dy[t] = (int8_t)(r - pad); c.dx[t] = (int8_t)(q - pad); c.wt[t] = (int8_t)t;
         }
-    if (stride == 1 && 2 * pad == ksize - 1 && use_halo_kernel()) {
-        int8_t hy[9], hx[9];
-        for (int t = 0; t < c.ntaps; ++t) { hy[t] = (int8_t)(t / ksize); hx[t] = (int8_t)(t % ksize); }
-        return run_conv_halo(x0, c0, x1, c1, w_packed, ksize * ksize, bias, bias_n, y, n, h, w, cout, ksize, hy, hx, c.wt, c.ntaps, act, slope,
-                             stats, (cudaStream_t)s);
-    }
+    if (stride == 1 && 2 * pad == ksize - 1 && use_halo_kernel())
+        return run_conv_halo(x0, c0, x1, c1, w_packed, ksize * ksize, bias, bias_n, y, n, h, w, cout, ksize, 0, act, slope, stats,
+                             (cudaStream_t)s);
     SSG_CHECK_ARG(stats == nullptr, "conv2d_fwd_tc: fused statistics need a stride-1 same-size convolution (query ssg_conv2d_fwd_tc_has_stats)");
     return run_conv(x0, c0, x1, c1, w_packed, ksize * ksize, bias, bias_n, y, n, h, w, oh, ow, oh, ow, cout, stride, 1, &c, 1, act, slope,
                     (cudaStream_t)s);
@@ -351,15 +347,10 @@ int ssg_conv2d_dgrad_tc(const void* dy, const void* w_packed, void* dx, int n, i
                   "conv2d_dgrad_tc: kernel 1 or 3 at stride 1, kernel 3 at stride 2 (k=%d stride=%d)", ksize, stride);
     const int oh = (h + 2 * pad - ksize) / stride + 1, ow = (w + 2 * pad - ksize) / stride + 1;
     SSG_CHECK_ARG(oh > 0 && ow > 0, "conv2d_dgrad_tc: empty dy");
-    if (stride == 1 && 2 * pad == ksize - 1 && use_halo_kernel()) {
+    if (stride == 1 && 2 * pad == ksize - 1 && use_halo_kernel())
         // dx[i] = sum_r dy[i + pad - r] W[r]: halo origin i0 - pad, tap r reads halo row (k - 1 - r)
-        int8_t hy[9], hx[9], wt[9];
-        for (int t = 0; t < ksize * ksize; ++t) {
-            hy[t] = (int8_t)(ksize - 1 - t / ksize); hx[t] = (int8_t)(ksize - 1 - t % ksize); wt[t] = (int8_t)t;
-        }
-        return run_conv_halo(dy, cout, nullptr, 0, w_packed, ksize * ksize, nullptr, 0, dx, n, h, w, cin, ksize, hy, hx, wt, ksize * ksize, 0, 0.f,
-                             nullptr, (cudaStream_t)s);
-    }
+        return run_conv_halo(dy, cout, nullptr, 0, w_packed, ksize * ksize, nullptr, 0, dx, n, h, w, cin, ksize, 1, 0, 0.f, nullptr,
+                             (cudaStream_t)s);
     TapClass c[4];
     memset(c, 0, sizeof(c));
     int ncls = 0;

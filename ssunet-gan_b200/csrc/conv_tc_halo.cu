@@ -40,8 +40,8 @@ struct HaloParams {
     int n_tiles;                 // ceil(cout / BN)
     int total_items;             // ceil(m_tiles / MT) * n_tiles
     int chunks0, chunks1;        // 64-channel chunks from x0 / x1 (virtual concat)
-    int ntaps;
-    int8_t hy[9], hx[9], wt[9];  // tap -> (halo row, halo column) offset and weight tap index
+    int ntaps, ksize;
+    int flip;                    // 0: tap t reads halo (t / k, t % k) (forward); 1: (k-1 - t / k, k-1 - t % k) (data gradient)
     int halo_c, halo_r;          // halo box dims in pixels: (8 + k - 1) x (16 + k - 1)
     int org;                     // halo origin = tile origin - org
     int act;
@@ -99,7 +99,7 @@ __global__ void __launch_bounds__(H_THREADS, 1) conv_tc_halo_kernel(const __grid
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    const uint32_t tmem_base = *tmem_slot;
+    const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);     // warp-uniform (uniform datapath in the MMA warp)
 
     if (warp == 0) {
         // ---- A producer: one halo tile per (M-tile, chunk) ----
@@ -137,15 +137,17 @@ __global__ void __launch_bounds__(H_THREADS, 1) conv_tc_halo_kernel(const __grid
                         const int sl = bc % C::B_SLOTS;
                         mbar_wait(&b_empty[sl], ((bc / C::B_SLOTS) & 1) ^ 1);
                         mbar_expect_tx(&b_full[sl], C::B_BYTES);
-                        tma_load_3d(smem + C::B_OFFSET + sl * C::B_BYTES, &tmB, ch * 64, n0, p.wt[tap], &b_full[sl]);
+                        tma_load_3d(smem + C::B_OFFSET + sl * C::B_BYTES, &tmB, ch * 64, n0, tap, &b_full[sl]);
                     }
             }
         }
     } else if (warp == 2) {
-        // ---- MMA issuer ----
-        if (lane == 0) {
+        // ---- MMA issuer: the WHOLE warp walks the (warp-uniform) loop so that barrier addresses, descriptors and TMEM
+        // addresses live on the uniform datapath; lane 0 alone issues tcgen05.mma / tcgen05.commit ----
+        {
             constexpr uint32_t idesc = make_idesc_bf16(128, BN, 0, 0);
-            const uint32_t sbo = (uint32_t)p.halo_c * 128;
+            const bool leader = elect_one();
+            const uint32_t a_hi = desc_hi((uint32_t)p.halo_c * 128, 2), b_hi = desc_hi(1024, 2);
             int ac = 0, bc = 0, it = 0;
             for (int item = blockIdx.x; item < p.total_items; item += gridDim.x, ++it) {
                 const int acc = it % ACCS;
@@ -155,27 +157,38 @@ __global__ void __launch_bounds__(H_THREADS, 1) conv_tc_halo_kernel(const __grid
                 for (int ch = 0; ch < chunks; ++ch, ++ac) {
                     const int st = ac % C::A_STAGES;
                     mbar_wait(&a_full[st], (ac / C::A_STAGES) & 1);
-                    tc_fence_after();
-                    const uint32_t a_stage = smem_u32(smem + st * C::A_STAGE_BYTES);
+                    const uint32_t a_lo0 = desc_lo(smem_u32(smem + st * C::A_STAGE_BYTES), 16);
+                    // taps in weight order t = r * k + s; the halo offset advances by one pixel per s and one halo row per r
+                    // (mirrored for the data gradient) -- no division or table lookup on the issue path
+                    const int step_s = p.flip ? -8 : 8, step_r = (p.flip ? -1 : 1) * (p.halo_c - p.ksize) * 8;
+                    uint32_t a_lo = a_lo0 + (p.flip ? (uint32_t)((p.ksize - 1) * p.halo_c + p.ksize - 1) * 8 : 0u);   // 8 x 16 B per pixel
+                    int tq = 0;
                     for (int tap = 0; tap < p.ntaps; ++tap, ++bc) {
                         const int sl = bc % C::B_SLOTS;
                         mbar_wait(&b_full[sl], (bc / C::B_SLOTS) & 1);
                         tc_fence_after();
-                        const uint64_t db = make_desc_kmajor_sw128(smem_u32(smem + C::B_OFFSET + sl * C::B_BYTES));
-                        const uint32_t a_off = (uint32_t)(p.hy[tap] * p.halo_c + p.hx[tap]) * 128;
+                        const uint32_t b_lo = desc_lo(smem_u32(smem + C::B_OFFSET + sl * C::B_BYTES), 16);
+                        const uint32_t keep = (uint32_t)(ch | tap);                                         // 0: first k-block of the item
+                        if (leader) {
+                            // k outer, M-tile inner: consecutive MMAs accumulate into DIFFERENT TMEM accumulators
 #pragma unroll
-                        for (int mt = 0; mt < MT; ++mt) {
-                            const uint64_t da = make_smem_desc(a_stage + mt * H_A_TILE_STRIDE + a_off, 16, sbo, 2);
+                            for (int k = 0; k < 4; ++k) {
 #pragma unroll
-                            for (int k = 0; k < 4; ++k)
-                                umma_bf16(d_base + (uint32_t)(mt * BN), da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc,
-                                          (ch | tap | k) != 0);
+                                for (int mt = 0; mt < MT; ++mt)
+                                    umma_bf16_lohi(d_base + (uint32_t)(mt * BN), a_lo + (uint32_t)(mt * (H_A_TILE_STRIDE / 16) + 2 * k), a_hi,
+                                                   b_lo + (uint32_t)(2 * k), b_hi, idesc, k == 0 ? keep : 1u);
+                            }
+                            umma_commit(&b_empty[sl]);
                         }
-                        umma_commit(&b_empty[sl]);
+                        __syncwarp();
+                        a_lo += (uint32_t)step_s;
+                        if (++tq == p.ksize) { tq = 0; a_lo += (uint32_t)step_r; }
                     }
-                    umma_commit(&a_empty[st]);
+                    if (leader) umma_commit(&a_empty[st]);
+                    __syncwarp();
                 }
-                umma_commit(&acc_full[acc]);
+                if (leader) umma_commit(&acc_full[acc]);
+                __syncwarp();
             }
         }
     } else if (warp >= 4) {
@@ -317,10 +330,9 @@ static int launch_halo(const CUtensorMap& a0, const CUtensorMap& a1, const CUten
     return SSG_OK;
 }
 
-// Same-size stride-1 convolution / data gradient.  taps: (hy, hx, wt) per tap in halo coordinates.
+// Same-size stride-1 convolution (flip = 0) / data gradient (flip = 1: tap t reads the mirrored halo offset).
 int run_conv_halo(const void* x0, int c0, const void* x1, int c1, const void* w_packed, int w_taps, const float* bias, int bias_n,
-                  void* y, int n, int h, int w, int gemm_n, int ksize, const int8_t* hy, const int8_t* hx, const int8_t* wt, int ntaps,
-                  int act, float slope, double* stats, cudaStream_t st) {
+                  void* y, int n, int h, int w, int gemm_n, int ksize, int flip, int act, float slope, double* stats, cudaStream_t st) {
     HaloParams p;
     memset(&p, 0, sizeof(p));
     p.stats = stats;
@@ -328,8 +340,7 @@ int run_conv_halo(const void* x0, int c0, const void* x1, int c1, const void* w_
     p.y = (bf16*)y; p.bias = bias; p.bias_n = bias_n; p.N = n; p.H = h; p.W = w; p.cout = gemm_n;
     p.tiles_x = (w + H_TW - 1) / H_TW; p.tiles_y = (h + H_TH - 1) / H_TH; p.m_tiles = n * p.tiles_x * p.tiles_y;
     p.chunks0 = (c0 + 63) / 64; p.chunks1 = (c1 + 63) / 64;
-    p.ntaps = ntaps;
-    for (int i = 0; i < ntaps; ++i) { p.hy[i] = hy[i]; p.hx[i] = hx[i]; p.wt[i] = wt[i]; }
+    p.ntaps = ksize * ksize; p.ksize = ksize; p.flip = flip;
     p.halo_c = H_TW + ksize - 1; p.halo_r = H_TH + ksize - 1; p.org = (ksize - 1) / 2;
     p.act = act; p.slope = slope;
     CUtensorMap ma0, ma1, mb;
@@ -432,7 +443,7 @@ __global__ void __launch_bounds__(H_THREADS, 1) conv_tc_halo_wgrad_kernel(const 
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    const uint32_t tmem_base = *tmem_slot;
+    const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
 
     if (warp == 0) {
         if (lane == 0) {
@@ -461,32 +472,39 @@ __global__ void __launch_bounds__(H_THREADS, 1) conv_tc_halo_wgrad_kernel(const 
             }
         }
     } else if (warp == 2) {
-        if (lane == 0) {
-            constexpr uint32_t idesc = make_idesc_bf16(128, 64, 1, 1);     // both operands MN-major
-            for (int it = 0; it < n_iter; ++it) {
-                const int xs = it % HW_XS, ds = it % HW_DS;
-                mbar_wait(&x_full[xs], (it / HW_XS) & 1);
-                mbar_wait(&dy_full[ds], (it / HW_DS) & 1);
-                tc_fence_after();
-                const uint32_t x_addr = smem_u32(smem + HW_X_OFFSET + xs * H_A_TILE_STRIDE);
-                const uint32_t dy_addr = smem_u32(smem + HW_DY_OFFSET + ds * HW_DY_BYTES);
-                const uint64_t db = make_smem_desc(dy_addr, 1024, 1024, 2);
+        // whole warp walks the loop (uniform datapath); lane 0 issues the MMAs and commits
+        constexpr uint32_t idesc = make_idesc_bf16(128, 64, 1, 1);     // both operands MN-major
+        const bool leader = elect_one();
+        const uint32_t x_hi = desc_hi(1280, 2), dy_hi = desc_hi(1024, 2);
+        for (int it = 0; it < n_iter; ++it) {
+            const int xs = it % HW_XS, ds = it % HW_DS;
+            mbar_wait(&x_full[xs], (it / HW_XS) & 1);
+            mbar_wait(&dy_full[ds], (it / HW_DS) & 1);
+            tc_fence_after();
+            const uint32_t x_addr = smem_u32(smem + HW_X_OFFSET + xs * H_A_TILE_STRIDE);
+            const uint32_t dy_lo = desc_lo(smem_u32(smem + HW_DY_OFFSET + ds * HW_DY_BYTES), 1024);
+            const uint32_t keep = (uint32_t)it;
+            if (leader) {
+                // k outer, tap pair inner: consecutive MMAs accumulate into different TMEM accumulators.
+                // Pair g = taps 2g and 2g+1 (tap 8 is paired with a dummy second half whose rows are never stored).
 #pragma unroll
-                for (int g = 0; g < 5; ++g) {
-                    // taps 2g and 2g+1 (tap 8 is paired with a dummy second half whose rows are never stored)
-                    const int ta = 2 * g, tb = g < 4 ? 2 * g + 1 : 8;
-                    const int off_a = ((ta / 3) * 10 + ta % 3) * 128, off_b = ((tb / 3) * 10 + tb % 3) * 128;
-                    const uint32_t lbo = g < 4 ? (uint32_t)(off_b - off_a) : 128u;
-                    const uint64_t da = make_smem_desc(x_addr + off_a, lbo, 1280, 2);
+                for (int k = 0; k < 8; ++k) {        // 16 pixels = two tile rows per MMA: x advances 2 halo rows, dy 2 box rows
 #pragma unroll
-                    for (int k = 0; k < 8; ++k)      // 16 pixels = two tile rows per MMA: x advances 2 halo rows, dy 2 box rows
-                        umma_bf16(tmem_base + (uint32_t)(g * 64), da + (uint64_t)(160 * k), db + (uint64_t)(128 * k), idesc, (it | k) != 0);
+                    for (int g = 0; g < 5; ++g) {
+                        const int ta = 2 * g, tb = g < 4 ? 2 * g + 1 : 8;
+                        const int off_a = ((ta / 3) * 10 + ta % 3) * 128, off_b = ((tb / 3) * 10 + tb % 3) * 128;
+                        const uint32_t lbo = g < 4 ? (uint32_t)(off_b - off_a) : 128u;
+                        umma_bf16_lohi(tmem_base + (uint32_t)(g * 64), desc_lo(x_addr + off_a, lbo) + (uint32_t)(160 * k), x_hi,
+                                       dy_lo + (uint32_t)(128 * k), dy_hi, idesc, k == 0 ? keep : 1u);
+                    }
                 }
                 umma_commit(&x_empty[xs]);
                 umma_commit(&dy_empty[ds]);
             }
-            umma_commit(acc_full);
+            __syncwarp();
         }
+        if (leader) umma_commit(acc_full);
+        __syncwarp();
     } else if (warp >= 4) {
         const int q = warp & 3;
         const int row = q * 32 + lane;                  // accumulator row: tap half (row >> 6), ci (row & 63)
