@@ -95,7 +95,7 @@ __global__ void __launch_bounds__(NUM_THREADS) conv_tc_fwd_kernel(const __grid_c
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    const uint32_t tmem_base = *tmem_slot;
+    const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
 
     if (warp == 0) {
         if (lane == 0) {
@@ -116,23 +116,28 @@ __global__ void __launch_bounds__(NUM_THREADS) conv_tc_fwd_kernel(const __grid_c
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
-            constexpr uint32_t idesc = make_idesc_bf16(BM, BN, 0, 0);
-            for (int kb = 0; kb < num_kb; ++kb) {
-                const int stage = kb % L::STAGES;
-                const uint32_t phase = (kb / L::STAGES) & 1;
-                mbar_wait(&full_bar[stage], phase);
-                tc_fence_after();
-                const uint32_t sa = smem_u32(smem + stage * L::STAGE_BYTES);
-                const uint64_t da = make_desc_kmajor_sw128(sa);
-                const uint64_t db = make_desc_kmajor_sw128(sa + A_BYTES);
+        // whole warp walks the (uniform) loop; the elected lane issues tcgen05.mma / commit (uniform-datapath issue sequence)
+        constexpr uint32_t idesc = make_idesc_bf16(BM, BN, 0, 0);
+        const bool leader = elect_one();
+        const uint32_t hi = desc_hi(1024, 2);
+        for (int kb = 0; kb < num_kb; ++kb) {
+            const int stage = kb % L::STAGES;
+            const uint32_t phase = (kb / L::STAGES) & 1;
+            mbar_wait(&full_bar[stage], phase);
+            tc_fence_after();
+            const uint32_t sa = smem_u32(smem + stage * L::STAGE_BYTES);
+            const uint32_t a_lo = desc_lo(sa, 16), b_lo = desc_lo(sa + A_BYTES, 16);
+            if (leader) {
+                umma_bf16_lohi(tmem_base, a_lo, hi, b_lo, hi, idesc, (uint32_t)kb);
 #pragma unroll
-                for (int k = 0; k < BK / 16; ++k)   // +32 bytes (>>4 == 2) per 16-element K step inside the swizzle atom
-                    umma_bf16(tmem_base, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (kb | k) != 0);
+                for (int k = 1; k < BK / 16; ++k)   // +32 bytes (>>4 == 2) per 16-element K step inside the swizzle atom
+                    umma_bf16_lohi(tmem_base, a_lo + (uint32_t)(2 * k), hi, b_lo + (uint32_t)(2 * k), hi, idesc, 1u);
                 umma_commit(&empty_bar[stage]);     // frees the smem slot once these MMAs have read it
             }
-            umma_commit(tmem_full_bar);             // accumulator complete
+            __syncwarp();
         }
+        if (leader) umma_commit(tmem_full_bar);     // accumulator complete
+        __syncwarp();
     } else {
         // ---- epilogue: warp w may touch TMEM lanes [32*(w%4), 32*(w%4)+32) ----
         const int q = warp & 3;
@@ -445,7 +450,7 @@ __global__ void __launch_bounds__(NUM_THREADS) conv_tc_wgrad_kernel(const __grid
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    const uint32_t tmem_base = *tmem_slot;
+    const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
 
     if (warp == 0) {
         if (lane == 0) {
@@ -479,31 +484,36 @@ __global__ void __launch_bounds__(NUM_THREADS) conv_tc_wgrad_kernel(const __grid
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
-            constexpr uint32_t idesc = make_idesc_bf16(BM, BN, 1, 1);     // both operands MN-major
-            int xc = 0;
-            for (int it = 0; it < n_iter; ++it) {
-                const int b = it & 1;
-                mbar_wait(&dy_full[b], (it >> 1) & 1);
+        // whole warp walks the (uniform) loop; the elected lane issues (see conv_tc_fwd_kernel)
+        constexpr uint32_t idesc = make_idesc_bf16(BM, BN, 1, 1);     // both operands MN-major
+        const bool leader = elect_one();
+        // MN-major SW128: LBO = distance between 64-element MN atoms (one box), SBO = 8 pixel rows
+        const uint32_t hi = desc_hi(1024, 2);
+        int xc = 0;
+        for (int it = 0; it < n_iter; ++it) {
+            const int b = it & 1;
+            mbar_wait(&dy_full[b], (it >> 1) & 1);
+            tc_fence_after();
+            const uint32_t dy_lo = desc_lo(smem_u32(smem + b * C::DY_BYTES), C::BOX);
+            for (int g = 0; g < pairs; ++g, ++xc) {
+                const int slot = xc % C::XS;
+                mbar_wait(&x_full[slot], (xc / C::XS) & 1);
                 tc_fence_after();
-                const uint32_t dy_addr = smem_u32(smem + b * C::DY_BYTES);
-                for (int g = 0; g < pairs; ++g, ++xc) {
-                    const int slot = xc % C::XS;
-                    mbar_wait(&x_full[slot], (xc / C::XS) & 1);
-                    tc_fence_after();
-                    const uint32_t x_addr = smem_u32(smem + C::X_OFFSET + slot * 2 * C::BOX);
-                    // MN-major SW128: LBO = distance between 64-element MN atoms (one box), SBO = 8 pixel rows
-                    const uint64_t da = make_smem_desc(x_addr, C::BOX, 1024, 2);
-                    const uint64_t db = make_smem_desc(dy_addr, C::BOX, 1024, 2);
+                const uint32_t x_lo = desc_lo(smem_u32(smem + C::X_OFFSET + slot * 2 * C::BOX), C::BOX);
+                if (leader) {
+                    umma_bf16_lohi(tmem_base + (uint32_t)(g * BN), x_lo, hi, dy_lo, hi, idesc, (uint32_t)it);
 #pragma unroll
-                    for (int k = 0; k < BM / 16; ++k)    // 16 pixels per MMA: +2048 bytes (>>4 == 128)
-                        umma_bf16(tmem_base + (uint32_t)(g * BN), da + (uint64_t)(128 * k), db + (uint64_t)(128 * k), idesc, (it | k) != 0);
+                    for (int k = 1; k < BM / 16; ++k)    // 16 pixels per MMA: +2048 bytes (>>4 == 128)
+                        umma_bf16_lohi(tmem_base + (uint32_t)(g * BN), x_lo + (uint32_t)(128 * k), hi, dy_lo + (uint32_t)(128 * k), hi, idesc, 1u);
                     umma_commit(&x_empty[slot]);
                 }
-                umma_commit(&dy_empty[b]);
+                __syncwarp();
             }
-            umma_commit(acc_full);
+            if (leader) umma_commit(&dy_empty[b]);
+            __syncwarp();
         }
+        if (leader) umma_commit(acc_full);
+        __syncwarp();
     } else {
         const int q = warp & 3;
         const int row = q * 32 + lane;                  // accumulator row: unit (row >> 6), ci (row & 63)

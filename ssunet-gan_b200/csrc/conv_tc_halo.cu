@@ -487,16 +487,21 @@ __global__ void __launch_bounds__(H_THREADS, 1) conv_tc_halo_wgrad_kernel(const 
             if (leader) {
                 // k outer, tap pair inner: consecutive MMAs accumulate into different TMEM accumulators.
                 // Pair g = taps 2g and 2g+1 (tap 8 is paired with a dummy second half whose rows are never stored).
-#pragma unroll
+                uint32_t xk = desc_lo(x_addr, 0), dk = dy_lo;
+#pragma unroll 1
                 for (int k = 0; k < 8; ++k) {        // 16 pixels = two tile rows per MMA: x advances 2 halo rows, dy 2 box rows
+                    const uint32_t en = k == 0 ? keep : 1u;
 #pragma unroll
                     for (int g = 0; g < 5; ++g) {
+                        constexpr int dummy = 0;
                         const int ta = 2 * g, tb = g < 4 ? 2 * g + 1 : 8;
                         const int off_a = ((ta / 3) * 10 + ta % 3) * 128, off_b = ((tb / 3) * 10 + tb % 3) * 128;
                         const uint32_t lbo = g < 4 ? (uint32_t)(off_b - off_a) : 128u;
-                        umma_bf16_lohi(tmem_base + (uint32_t)(g * 64), desc_lo(x_addr + off_a, lbo) + (uint32_t)(160 * k), x_hi,
-                                       dy_lo + (uint32_t)(128 * k), dy_hi, idesc, k == 0 ? keep : 1u);
+                        // start-address field += off_a / 16; LBO field (bits 16..29) = lbo / 16: both compile-time constants
+                        umma_bf16_lohi(tmem_base + (uint32_t)(g * 64), xk + (uint32_t)((off_a >> 4) | ((lbo >> 4) << 16)) + dummy, x_hi, dk, dy_hi,
+                                       idesc, en);
                     }
+                    xk += 160; dk += 128;
                 }
                 umma_commit(&x_empty[xs]);
                 umma_commit(&dy_empty[ds]);

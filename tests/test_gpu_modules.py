@@ -169,7 +169,7 @@ def test_gan_step_vs_reference_golden(golden_dir, dtype, impl, tol):
         if dtype == torch.float32:
             # IoU counts thresholded pixels: after one sign-like Adam step a few of the 16 384 pixels may flip
             assert abs(r["iou"] - want[4]) < (2e-4 if it == 0 else 1e-3)
-            assert abs(float(r["dice"]) - want[5]) < 1e-5
+            assert abs(float(r["dice"]) - want[5]) < (1e-5 if it == 0 else 1e-4)    # same reason: parameters moved by +-lr
     sdg, sdd = g.state_dict(), d.state_dict()
     assert int(sdd["conv_blocks.1.conv_block.1.num_batches_tracked"]) == 6       # 3 D passes per step
     # parameters moved by exactly two clamped Adam steps (|delta| <= 2*lr each)
