@@ -210,6 +210,12 @@ int ssg_clamp_(float* g, long long n, float clip, ssg_stream_t s);
 int ssg_clamp_adam(float* p, float* g, float* m, float* v, long long n, float lr, float beta1, float beta2, float eps,
                    float bias_corr1, float bias_corr2, float clip, float grad_scale, ssg_stream_t s);
 
+/* Same update with the step count t kept on the device (float, incremented by the call before use; bias corrections
+ * 1 - beta^t are computed in the kernel): the launch carries no per-step host scalar, so a whole training step can be
+ * captured in a CUDA graph and replayed. */
+int ssg_clamp_adam_dev(float* p, float* g, float* m, float* v, long long n, float lr, float beta1, float beta2, float eps,
+                       float* step_dev, float clip, float grad_scale, ssg_stream_t s);
+
 /* ---- spectral norm (spectral_norm.py:38-88) ---------------------------------------------------- */
 /* One power iteration on W [rows, cols] fp32: v = normalize(W^T u); u = normalize(W v); sigma = u.(W v).
  * u, v updated in place when do_power_iteration != 0.  inv_sigma: device float[2] = {1/sigma, sigma}.

@@ -124,7 +124,7 @@ def call(name, *args, flops=0.0):
     if not torch.cuda.is_available():
         raise SsgError("%s: no CUDA device; ssunet-gan_b200 has no CPU path" % name)
     conv = [_ptr(a) for a in args]
-    timed = _prof is not None and name in _prof["names"]
+    timed = _prof is not None and name in _prof["names"] and not torch.cuda.is_current_stream_capturing()
     if timed:
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()

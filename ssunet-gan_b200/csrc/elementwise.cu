@@ -116,6 +116,27 @@ __global__ void __launch_bounds__(256) clamp_adam_kernel(float* __restrict__ p, 
         p[i] = p[i] - step * (mi / denom);
     }
 }
+// Graph-capturable variant: the step count lives on the device (a captured launch cannot carry per-step host scalars).
+__global__ void step_inc_kernel(float* step) { step[0] += 1.f; }
+__global__ void __launch_bounds__(256) clamp_adam_dev_kernel(float* __restrict__ p, float* __restrict__ g, float* __restrict__ m,
+                                                              float* __restrict__ v, long long n, float lr, float b1, float b2,
+                                                              float eps, const float* __restrict__ step_dev, float clip, float gscale) {
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    const float t = step_dev[0];
+    const float bc1 = 1.f - powf(b1, t), bc2_sqrt = sqrtf(1.f - powf(b2, t));
+    const float step = lr / bc1;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        float gi = g[i] * gscale;
+        if (clip > 0.f) gi = fminf(fmaxf(gi, -clip), clip);
+        g[i] = gi;
+        const float mi = b1 * m[i] + (1.f - b1) * gi;
+        const float vi = b2 * v[i] + (1.f - b2) * gi * gi;
+        m[i] = mi;
+        v[i] = vi;
+        const float denom = sqrtf(vi) / bc2_sqrt + eps;
+        p[i] = p[i] - step * (mi / denom);
+    }
+}
 __global__ void scale_by_dev_kernel(const float* __restrict__ w, const float* __restrict__ sc, float* __restrict__ o, long long n) {
     const float s = sc[0];
     const long long stride = (long long)gridDim.x * blockDim.x;
@@ -186,6 +207,15 @@ int ssg_clamp_adam(float* p, float* g, float* m, float* v, long long n, float lr
     if (n <= 0) return SSG_OK;
     clamp_adam_kernel<<<grid_for(n, 1024), 256, 0, (cudaStream_t)s>>>(p, g, m, v, n, lr, beta1, beta2, eps, bias_corr1,
                                                                       sqrtf(bias_corr2), clip, grad_scale);
+    SSG_CHECK_LAUNCH();
+    return SSG_OK;
+}
+int ssg_clamp_adam_dev(float* p, float* g, float* m, float* v, long long n, float lr, float beta1, float beta2, float eps,
+                       float* step_dev, float clip, float grad_scale, ssg_stream_t s) {
+    if (n <= 0) return SSG_OK;
+    SSG_CHECK_ARG(step_dev != nullptr, "clamp_adam_dev: step counter missing");
+    step_inc_kernel<<<1, 1, 0, (cudaStream_t)s>>>(step_dev);
+    clamp_adam_dev_kernel<<<grid_for(n, 1024), 256, 0, (cudaStream_t)s>>>(p, g, m, v, n, lr, beta1, beta2, eps, step_dev, clip, grad_scale);
     SSG_CHECK_LAUNCH();
     return SSG_OK;
 }

@@ -48,7 +48,15 @@ class FusedClampAdam(torch.optim.Optimizer):
                 p.grad = g
                 off += k
         self._params = params
+        self._step_dev = None          # device-resident step count (capturable mode, see make_capturable)
         ops.bump_weight_epoch()
+
+    def make_capturable(self):
+        """Keep the Adam step count on the device so `step()` can be captured in a CUDA graph and replayed
+        (train_step.GraphedGanStep)."""
+        if self._step_dev is None:
+            self._step_dev = torch.full((1,), float(self._step), dtype=torch.float32, device=self.flat_p.device)
+        return self
 
     def defer_clip(self, grad_clip):
         self._pending_clip = grad_clip
@@ -82,7 +90,11 @@ class FusedClampAdam(torch.optim.Optimizer):
         self._step += 1
         clip = self._pending_clip if self._pending_clip is not None else self._clip
         self._pending_clip = None
-        call("ssg_clamp_adam", self.flat_p, self.flat_g, self.flat_m, self.flat_v, self.flat_p.numel(), float(group["lr"]),
-             float(b1), float(b2), float(group["eps"]), 1.0 - b1 ** self._step, 1.0 - b2 ** self._step,
-             float(clip) if clip is not None else 0.0, float(grad_scale))
+        if self._step_dev is not None:
+            call("ssg_clamp_adam_dev", self.flat_p, self.flat_g, self.flat_m, self.flat_v, self.flat_p.numel(), float(group["lr"]),
+                 float(b1), float(b2), float(group["eps"]), self._step_dev, float(clip) if clip is not None else 0.0, float(grad_scale))
+        else:
+            call("ssg_clamp_adam", self.flat_p, self.flat_g, self.flat_m, self.flat_v, self.flat_p.numel(), float(group["lr"]),
+                 float(b1), float(b2), float(group["eps"]), 1.0 - b1 ** self._step, 1.0 - b2 ** self._step,
+                 float(clip) if clip is not None else 0.0, float(grad_scale))
         ops.bump_weight_epoch()

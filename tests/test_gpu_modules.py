@@ -251,3 +251,38 @@ def test_no_cpu_path():
     from ssunet_gan_b200 import ops, _lib
     with pytest.raises(_lib.SsgError):
         ops.conv2d(torch.zeros(1, 3, 8, 8), torch.zeros(4, 3, 3, 3))
+
+
+def test_graphed_step_matches_eager():
+    """The CUDA-graph replay of the captured G+D iteration (train_step.GraphedGanStep) tracks the eager step: same
+    losses and parameters after several iterations on fresh batches (differences: fp32 atomics order in wgrad only)."""
+    import copy
+    import ssunet_oracle as O
+    import ssunet_gan_b200 as ssg
+    from ssunet_gan_b200 import optim, train_step
+    ssg.set_compute_dtype(torch.bfloat16)
+    ssg.set_conv_impl("auto")
+    g1, d1 = _make_g(O, torch.bfloat16, "auto"), _make_d(O, torch.bfloat16, "auto")
+    g2, d2 = copy.deepcopy(g1), copy.deepcopy(d1)
+    for m in (g1, d1, g2, d2):
+        m.train()
+    o1 = (optim.FusedClampAdam(g1.parameters(), lr=2e-5), optim.FusedClampAdam(d1.parameters(), lr=2e-5))
+    o2 = (optim.FusedClampAdam(g2.parameters(), lr=2e-5), optim.FusedClampAdam(d2.parameters(), lr=2e-5))
+    graphed = train_step.GraphedGanStep(g2, d2, o2[0], o2[1], (2, 3, 64, 64), warmup=2)
+    # the graphed copy ran warm-up + capture iterations on its static (zero) inputs: replay the same history eagerly
+    x0 = torch.zeros(2, 3, 64, 64, device="cuda")
+    t0 = torch.zeros(2, 3, 64, 64, device="cuda"); t0[:, 0] = 1.0
+    for _ in range(2):
+        train_step.gan_train_step(g1, d1, o1[0], o1[1], x0, t0, with_metrics=False)
+    # (capture itself does not execute kernels)
+    for it in range(3):
+        x, t = O.synthetic_batch(2, 3, 64, 64, seed=77 + it)
+        r1 = train_step.gan_train_step(g1, d1, o1[0], o1[1], x.cuda(), t.cuda(), with_metrics=False)
+        r2 = graphed(x.cuda(), t.cuda())
+        for k in ("loss", "content", "adv_g", "adv_d"):
+            a, b = float(r1[k]), float(r2[k])
+            assert abs(a - b) < 2e-2 * abs(a) + 1e-4, (it, k, a, b)
+    p1 = torch.cat([p.detach().reshape(-1) for p in g1.parameters()])
+    p2 = torch.cat([p.detach().reshape(-1) for p in g2.parameters()])
+    assert float((p1 - p2).abs().max()) <= 5 * 2e-5 * 2 + 1e-7       # a handful of sign-like Adam steps of lr each
+    assert int(d2.state_dict()["conv_blocks.1.conv_block.1.num_batches_tracked"]) == int(d1.state_dict()["conv_blocks.1.conv_block.1.num_batches_tracked"])
