@@ -228,6 +228,47 @@ int ssg_spectral_weight_bwd(const float* dw_sn, const float* w_orig, const float
 /* out = w * inv_sigma[0] */
 int ssg_scale_by_dev(const float* w, const float* inv_sigma, float* out, long long n, ssg_stream_t s);
 
+/* ---- EfficientNet encoder / xResidualBlock: depthwise, squeeze-excite, swish (HBM-bound) ------------------------- */
+/* Depthwise convolution (groups == C) of efficientnet_pytorch/model.py:52-55 (Conv2dStaticSamePadding, utils.py:118-141)
+ * and xresidualblock.py:17.  w: the parameter itself, fp32 [C][1][k][k]; bias fp32 [C] or NULL.  TF-style "same" padding
+ * is asymmetric: (pad_t, pad_l) zero rows/columns lead the input, the trailing padding is whatever the given output
+ * size (oh, ow) implies.  C must be a multiple of 8 (bf16) / 4 (fp32); k <= 11; stride 1 or 2. */
+int ssg_dwconv2d_fwd(const void* x, const float* w, const float* bias, void* y, int dtype, int n, int h, int w_, int c, int k, int stride,
+                     int pad_t, int pad_l, int oh, int ow, ssg_stream_t s);
+/* dx [n,h,w_,c] from dy [n,oh,ow,c] */
+int ssg_dwconv2d_dgrad(const void* dy, const float* w, void* dx, int dtype, int n, int h, int w_, int c, int k, int stride, int pad_t,
+                       int pad_l, int oh, int ow, ssg_stream_t s);
+/* dw fp32 [C][1][k][k], overwritten */
+int ssg_dwconv2d_wgrad(const void* x, const void* dy, float* dw, int dtype, int n, int h, int w_, int c, int k, int stride, int pad_t,
+                       int pad_l, int oh, int ow, ssg_stream_t s);
+/* Per-sample, per-channel plane sums: sums[n][c] = sum_hw a[n,:,:,c] * (b ? b[n,:,:,c] : 1), fp32, overwritten.
+ * b == NULL: F.adaptive_avg_pool2d(x, 1) * HW (model.py:80); with b: the gate gradient sum_hw dy * x. */
+int ssg_plane_sums(const void* a, const void* b, float* sums, int dtype, int n, int hw, int c, ssg_stream_t s);
+/* Squeeze-excite gate MLP on the pooled vector (model.py:80-82): pooled = pooled_sum / hw;
+ * s_pre = W1 pooled + b1 (w1 fp32 [sq][c]); gate = sigmoid(W2 swish(s_pre) + b2) (w2 fp32 [c][sq]).
+ * Outputs pooled [n][c], s_pre [n][sq], gate [n][c] (fp32; kept for the backward). */
+int ssg_se_gate_fwd(const float* pooled_sum, int n, int hw, int c, int sq, const float* w1, const float* b1, const float* w2,
+                    const float* b2, float* pooled, float* s_pre, float* gate, ssg_stream_t s);
+/* dgate [n][c] -> dpooled [n][c] (dL/dx contribution per pixel, i.e. already divided by hw) and the MLP parameter
+ * gradients dw1/db1/dw2/db2 (overwritten, summed over samples). */
+int ssg_se_gate_bwd(const float* dgate, const float* gate, const float* s_pre, const float* pooled, const float* w1, const float* w2,
+                    int n, int hw, int c, int sq, float* dpooled, float* dw1, float* db1, float* dw2, float* db2, ssg_stream_t s);
+/* y[n,p,c] = a[n,p,c] * mul[n][c] + (add ? add[n][c] : 0): torch.sigmoid(x_squeezed) * x (model.py:82), drop_connect's
+ * per-sample scale (utils.py:83-93), and the SE input gradient dy * gate + dpooled. */
+int ssg_plane_scale(const void* a, const float* mul, const float* add, void* y, int dtype, int n, int hw, int c, ssg_stream_t s);
+/* MemoryEfficientSwish (utils.py:36-53): y = x * sigmoid(x); dx = dy * (sig * (1 + x * (1 - sig))) */
+int ssg_swish_fwd(const void* x, void* y, int dtype, long long n, ssg_stream_t s);
+int ssg_swish_bwd(const void* dy, const void* x, void* dx, int dtype, long long n, ssg_stream_t s);
+/* xresidualblock.py:4-6,19-23: y = x1 * exp(-z*z) and its gradients */
+int ssg_gauss_gate_fwd(const void* x1, const void* z, void* y, int dtype, long long n, ssg_stream_t s);
+int ssg_gauss_gate_bwd(const void* dy, const void* x1, const void* z, void* dx1, void* dz, int dtype, long long n, ssg_stream_t s);
+/* nn.ZeroPad2d (utils.py:133-136): y[n,oy,ox,:] = x[n,oy-pad_t,ox-pad_l,:] or 0; negative pads crop (the adjoint). */
+int ssg_pad2d(const void* x, void* y, int dtype, int n, int h, int w, int c, int pad_t, int pad_l, int oh, int ow, ssg_stream_t s);
+/* F.interpolate(size=(oh,ow), mode='bilinear', align_corners=False) (archs.py:459) on NHWC storage; the adjoint
+ * accumulates into an fp32 buffer dx32 [n,h,w,c] (overwritten). */
+int ssg_resize_bilinear_fwd(const void* x, void* y, int dtype, int n, int h, int w, int c, int oh, int ow, ssg_stream_t s);
+int ssg_resize_bilinear_bwd(const void* dy, float* dx32, int dtype, int n, int h, int w, int c, int oh, int ow, ssg_stream_t s);
+
 #ifdef __cplusplus
 }
 #endif

@@ -199,5 +199,68 @@ def main():
         print("  %-40s %8d bytes" % (fn, os.path.getsize(os.path.join(OUT, fn))))
 
 
+def efficientnet_golden():
+    """EfficientNet encoder rows of SURVEY.md §8a: one MBConv block of each flavour, b0 extract_features, AttentiveCNN(b2)."""
+    import archs  # noqa
+    from efficientnet_pytorch import EfficientNet
+    from efficientnet_pytorch.model import MBConvBlock
+    from efficientnet_pytorch.utils import BlockArgs, get_model_params
+
+    def grads(mod, keys):
+        named = dict(mod.named_parameters())
+        return {"grad:" + k: csum(named[k].grad) for k in keys}
+
+    out = {}
+    # --- single blocks (b0 global params, static padding from image_size 224) on 2 x C x 18 x 18 / 17 x 17 inputs
+    _, gp = get_model_params("efficientnet-b0", None)
+    cases = {"e1_k3_s1": dict(k=3, cin=32, cout=16, expand=1, stride=1, sq=8, hw=18),
+             "e6_k5_s2": dict(k=5, cin=24, cout=40, expand=6, stride=2, sq=6, hw=17),
+             "e6_k3_s1_skip": dict(k=3, cin=24, cout=24, expand=6, stride=1, sq=6, hw=18)}
+    for name, b in cases.items():
+        ba = BlockArgs(kernel_size=b["k"], num_repeat=1, input_filters=b["cin"], output_filters=b["cout"], expand_ratio=b["expand"],
+                       id_skip=True, stride=1 if "skip" in name else [b["stride"]], se_ratio=0.25)   # model.py:178: repeats carry int 1
+        m = MBConvBlock(ba, gp)
+        sd = O.portable_state_dict(O.mbconv_spec("blk", b))
+        m.load_state_dict({k[len("blk."):]: v for k, v in sd.items()})
+        m.train()
+        x = torch.randn(2, b["cin"], b["hw"], b["hw"], generator=torch.Generator().manual_seed(21)).requires_grad_(True)
+        y = m(x)
+        g = torch.randn(y.shape, generator=torch.Generator().manual_seed(22))
+        (y * g).sum().backward()
+        out["mb_%s:y" % name] = y.detach().numpy()
+        out["mb_%s:dx" % name] = x.grad.numpy()
+        for k, v in m.named_parameters():
+            out["mb_%s:grad:%s" % (name, k)] = v.grad.numpy()
+        out["mb_%s:bn1.running_var" % name] = m._bn1.running_var.numpy().copy()
+    # --- b0 extract_features, train (drop_connect off) and eval, 2 x 3 x 64 x 64
+    net = EfficientNet.from_name("efficientnet-b0", override_params={"drop_connect_rate": 0.0})
+    net.load_state_dict(O.portable_state_dict(O.efficientnet_spec("efficientnet-b0")))
+    x = torch.randn(2, 3, 64, 64, generator=torch.Generator().manual_seed(23))
+    net.train()
+    f = net.extract_features(x)
+    f.square().mean().backward()
+    out["b0:features_train"] = f.detach().numpy()
+    for k in ("_conv_stem.weight", "_blocks.0._depthwise_conv.weight", "_blocks.3._se_reduce.weight", "_blocks.3._se_expand.bias",
+              "_blocks.5._project_conv.weight", "_blocks.15._bn2.weight", "_conv_head.weight"):
+        out["b0:csum_grad:" + k] = csum(dict(net.named_parameters())[k].grad)
+    net.eval()
+    with torch.no_grad():
+        out["b0:features_eval"] = net.extract_features(x).numpy()
+        out["b0:logits_eval"] = net(x).numpy()
+    # --- AttentiveCNN on efficientnet-b2 (eval; from_name because phase_train=True needs the pretrained file)
+    att = archs.AttentiveCNN({"eff_flag": True, "phase_train": False, "eff_model_name": "efficientnet-b2"})
+    att.load_state_dict(O.portable_state_dict(O.attentive_cnn_spec("efficientnet-b2")))
+    att.eval()
+    img = torch.randn(1, 3, 96, 80, generator=torch.Generator().manual_seed(24))
+    with torch.no_grad():
+        out["att_b2:y_eval"] = att(img).numpy()
+    np.savez_compressed(os.path.join(OUT, "efficientnet.npz"), **out)
+    print("efficientnet.npz: %d bytes, %d arrays" % (os.path.getsize(os.path.join(OUT, "efficientnet.npz")), len(out)))
+
+
 if __name__ == "__main__":
-    main()
+    if len(sys.argv) > 1 and sys.argv[1] == "efficientnet":
+        efficientnet_golden()
+    else:
+        main()
+        efficientnet_golden()

@@ -488,6 +488,119 @@ def xresidual_block(sd, x, training=True, stride=1):
 
 
 # --------------------------------------------------------------------------------------
+# EfficientNet encoder (efficientnet_pytorch/model.py, utils.py) and AttentiveCNN (archs.py:409-466)
+# --------------------------------------------------------------------------------------
+_EFF_COEFFS = {  # utils.py:153-169: width, depth, resolution
+    "efficientnet-b0": (1.0, 1.0, 224), "efficientnet-b1": (1.0, 1.1, 240), "efficientnet-b2": (1.1, 1.2, 260),
+    "efficientnet-b3": (1.2, 1.4, 300), "efficientnet-b4": (1.4, 1.8, 380), "efficientnet-b5": (1.6, 2.2, 456),
+}
+# utils.py:258-263 as (kernel, repeats, in, out, expand, stride); every stage has se_ratio 0.25 and id_skip
+_EFF_STAGES = [(3, 1, 32, 16, 1, 1), (3, 2, 16, 24, 6, 2), (5, 2, 24, 40, 6, 2), (3, 3, 40, 80, 6, 2),
+               (5, 3, 80, 112, 6, 1), (5, 4, 112, 192, 6, 2), (3, 1, 192, 320, 6, 1)]
+EFF_BN_EPS, EFF_BN_MOMENTUM = 1e-3, 0.01      # utils.py:268-269 (momentum = 1 - 0.99, model.py:31)
+
+
+def _eff_round_filters(f, width, divisor=8):
+    """utils.py:56-68."""
+    f = f * width
+    nf = max(divisor, int(f + divisor / 2) // divisor * divisor)
+    if nf < 0.9 * f:
+        nf += divisor
+    return int(nf)
+
+
+def efficientnet_blocks(model_name):
+    """Per-block dicts in network order (model.py:167-182) plus (stem_out, head_out, image_size)."""
+    width, depth, res = _EFF_COEFFS[model_name]
+    blocks = []
+    for k, r, i, o, e, s in _EFF_STAGES:
+        i, o = _eff_round_filters(i, width), _eff_round_filters(o, width)
+        r = int(math.ceil(depth * r))
+        for j in range(r):
+            blocks.append(dict(k=k, cin=i if j == 0 else o, cout=o, expand=e, stride=s if j == 0 else 1,
+                               sq=max(1, int((i if j == 0 else o) * 0.25))))
+    return blocks, _eff_round_filters(32, width), _eff_round_filters(1280, width), res
+
+
+def mbconv_spec(p, b):
+    """Keys of one MBConvBlock in registration order (model.py:44-62)."""
+    mid = b["cin"] * b["expand"]
+    k = []
+    if b["expand"] != 1:
+        k += [(p + "._expand_conv.weight", (mid, b["cin"], 1, 1))] + _bn_keys(p + "._bn0", mid)
+    k += [(p + "._depthwise_conv.weight", (mid, 1, b["k"], b["k"]))] + _bn_keys(p + "._bn1", mid)
+    k += [(p + "._se_reduce.weight", (b["sq"], mid, 1, 1)), (p + "._se_reduce.bias", (b["sq"],)),
+          (p + "._se_expand.weight", (mid, b["sq"], 1, 1)), (p + "._se_expand.bias", (mid,))]
+    k += [(p + "._project_conv.weight", (b["cout"], mid, 1, 1))] + _bn_keys(p + "._bn2", b["cout"])
+    return k
+
+
+def efficientnet_spec(model_name, prefix="", num_classes=1000):
+    blocks, stem, head, _ = efficientnet_blocks(model_name)
+    k = [(prefix + "_conv_stem.weight", (stem, 3, 3, 3))] + _bn_keys(prefix + "_bn0", stem)
+    for i, b in enumerate(blocks):
+        k += mbconv_spec(prefix + "_blocks.%d" % i, b)
+    k += [(prefix + "_conv_head.weight", (head, blocks[-1]["cout"], 1, 1))] + _bn_keys(prefix + "_bn1", head)
+    k += [(prefix + "_fc.weight", (num_classes, head)), (prefix + "_fc.bias", (num_classes,))]
+    return k
+
+
+def _static_same_conv(x, w, b, stride, image_size, groups=1):
+    """Conv2dStaticSamePadding (utils.py:127-146): the pad comes from the nominal image size, not from x."""
+    kk = w.shape[-1]
+    o = math.ceil(image_size / stride)
+    pad = max((o - 1) * stride + (kk - 1) + 1 - image_size, 0)
+    if pad > 0:
+        x = F.pad(x, [pad // 2, pad - pad // 2, pad // 2, pad - pad // 2])
+    return F.conv2d(x, w, b, stride, 0, 1, groups)
+
+
+def _swish(x):
+    return x * torch.sigmoid(x)
+
+
+def mbconv_block(sd, p, x, b, image_size, training=True):
+    """model.py:64-94 without drop_connect (rate 0 / eval)."""
+    def bn(name, t):
+        return batch_norm(sd, p + name, t, training, EFF_BN_EPS, EFF_BN_MOMENTUM)
+
+    inp = x
+    if b["expand"] != 1:
+        x = _swish(bn("._bn0", _static_same_conv(x, sd[p + "._expand_conv.weight"], None, 1, image_size)))
+    x = _swish(bn("._bn1", _static_same_conv(x, sd[p + "._depthwise_conv.weight"], None, b["stride"], image_size, x.shape[1])))
+    sq = F.adaptive_avg_pool2d(x, 1)
+    sq = F.conv2d(_swish(F.conv2d(sq, sd[p + "._se_reduce.weight"], sd[p + "._se_reduce.bias"])),
+                  sd[p + "._se_expand.weight"], sd[p + "._se_expand.bias"])
+    x = torch.sigmoid(sq) * x
+    x = bn("._bn2", F.conv2d(x, sd[p + "._project_conv.weight"]))
+    if b["stride"] == 1 and b["cin"] == b["cout"]:
+        x = x + inp
+    return x
+
+
+def efficientnet_features(sd, x, model_name, training=True, prefix=""):
+    """EfficientNet.extract_features (model.py:202-218), drop_connect off."""
+    blocks, _, _, res = efficientnet_blocks(model_name)
+    x = _swish(batch_norm(sd, prefix + "_bn0", _static_same_conv(x, sd[prefix + "_conv_stem.weight"], None, 2, res), training,
+                          EFF_BN_EPS, EFF_BN_MOMENTUM))
+    for i, b in enumerate(blocks):
+        x = mbconv_block(sd, prefix + "_blocks.%d" % i, x, b, res, training)
+    x = F.conv2d(x, sd[prefix + "_conv_head.weight"])
+    return _swish(batch_norm(sd, prefix + "_bn1", x, training, EFF_BN_EPS, EFF_BN_MOMENTUM))
+
+
+def attentive_cnn_spec(model_name="efficientnet-b2", f_channel=1408):
+    return efficientnet_spec(model_name, prefix="eff_conv.") + [("conv_a.weight", (1024, f_channel, 1, 1))]
+
+
+def attentive_cnn(sd, images, model_name="efficientnet-b2", training=True):
+    """archs.py:454-466."""
+    res = _EFF_COEFFS[model_name][2]
+    r = F.interpolate(images, size=(res, res), mode="bilinear")
+    return F.conv2d(efficientnet_features(sd, r, model_name, training, prefix="eff_conv."), sd["conv_a.weight"])
+
+
+# --------------------------------------------------------------------------------------
 # bf16-storage emulation of the generator forward (what an ideal bf16 implementation computes)
 # --------------------------------------------------------------------------------------
 def _q(t):

@@ -13,6 +13,9 @@ from ._lib import ACT_NONE, ACT_RELU
 from .nn_layers import BatchNorm2d, Conv2d
 from .normalization import SPADE
 
+from .efficientnet_pytorch import EfficientNet
+from .xresidualblock import xResidualBlock  # noqa: F401
+
 __all__ = ["UNet_R_SS_v2"]
 
 
@@ -43,6 +46,38 @@ class BasicBlock(nn.Module):
         y2, s2 = self.conv2(out, want_stats=self.training)
         sc = self.shortcut[0](x) if len(self.shortcut) else x
         return self.bn2(y2, residual=sc, act=ACT_RELU, sums=s2)
+
+
+class AttentiveCNN(nn.Module):
+    """EfficientNet feature extractor + 1x1 projection to 1024 channels (archs.py:409-466, `eff_flag` branch):
+    bilinear resize to the encoder's native resolution -> `extract_features` -> `conv_a`.  Returns NCHW fp32."""
+
+    _F_CHANNEL = {"efficientnet-b2": 1408, "efficientnet-b3": 1536, "efficientnet-b4": 1792, "efficientnet-b5": 2048}
+
+    def __init__(self, model_info):
+        super().__init__()
+        self.f_channel = 1408
+        eff_net_flag = model_info["eff_flag"]
+        if eff_net_flag is not True:
+            raise ops._lib.SsgError("AttentiveCNN: only the EfficientNet backbone (eff_flag=True) is on this package's path; "
+                                    "the ResNet-101 branch (archs.py:436-443) needs torchvision's pretrained download")
+        model_name = model_info["eff_model_name"]
+        print("==> Building model.. : ", model_name)
+        if model_info["phase_train"] is True:
+            model = EfficientNet.from_pretrained(model_name, "../pretrained/normal/")
+        else:
+            model = EfficientNet.from_name(model_name)
+        self.f_channel = self._F_CHANNEL.get(model_name, self.f_channel)
+        self.eff_conv = model
+        self.input_img_size = EfficientNet.get_image_size(model_name)
+        self.eff_channel = 1024
+        self.conv_a = Conv2d(self.f_channel, self.eff_channel, kernel_size=1, bias=False)
+        self.eff_net_flag = eff_net_flag
+
+    def forward(self, images):
+        s = self.input_img_size
+        resized = ops.resize_bilinear(ops.to_nhwc(images), s, s)
+        return ops.to_nchw_f32(self.conv_a(self.eff_conv.extract_features(resized)))
 
 
 class _Pool(nn.Module):

@@ -716,3 +716,242 @@ class _SpectralWeight(torch.autograd.Function):
 
 def spectral_weight(w_orig, u, v, eps, do_power_iteration, n_iter=1):
     return _SpectralWeight.apply(w_orig, u, v, eps, do_power_iteration, n_iter)
+
+
+# ----------------------------------------------------------------------------------------------
+# EfficientNet encoder / xResidualBlock operators (csrc/mbconv.cu)
+# ----------------------------------------------------------------------------------------------
+class _DepthwiseConv2d(torch.autograd.Function):
+    """groups == C convolution with explicit leading padding (pad_t, pad_l) and output size (TF "same" padding is
+    asymmetric, utils.py:118-141)."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, stride, pad_t, pad_l, oh, ow):
+        n, c, h, w = x.shape
+        k = weight.shape[-1]
+        assert weight.shape[0] == c and weight.shape[1] == 1 and weight.shape[2] == k
+        y = empty_nhwc(n, c, oh, ow, x.dtype, x.device)
+        wd = weight.detach().contiguous()
+        call("ssg_dwconv2d_fwd", x, wd, bias, y, dtype_code(x.dtype), n, h, w, c, k, stride, pad_t, pad_l, oh, ow)
+        ctx.save_for_backward(x, weight)
+        ctx.cfg = (stride, pad_t, pad_l, oh, ow, bias is not None)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, weight = ctx.saved_tensors
+        stride, pad_t, pad_l, oh, ow, has_bias = ctx.cfg
+        n, c, h, w = x.shape
+        k = weight.shape[-1]
+        dt = x.dtype
+        dy = _as_storage(dy, dt)
+        dx = dw = db = None
+        if ctx.needs_input_grad[0]:
+            dx = empty_nhwc(n, c, h, w, dt, x.device)
+            call("ssg_dwconv2d_dgrad", dy, weight.detach().contiguous(), dx, dtype_code(dt), n, h, w, c, k, stride, pad_t, pad_l, oh, ow)
+        if ctx.needs_input_grad[1]:
+            dw = torch.empty_like(weight, dtype=torch.float32)
+            call("ssg_dwconv2d_wgrad", x, dy, dw, dtype_code(dt), n, h, w, c, k, stride, pad_t, pad_l, oh, ow)
+        if has_bias and ctx.needs_input_grad[2]:
+            sums = torch.empty(2 * c, dtype=torch.float64, device=x.device)
+            call("ssg_channel_stats", dy, dtype_code(dt), _rows(dy), c, sums, 0)
+            db = sums[:c].float()
+        return dx, dw, db, None, None, None, None, None
+
+
+def depthwise_conv2d(x, weight, bias=None, stride=1, pad_t=0, pad_l=0, out_hw=None):
+    x = to_nhwc(x)
+    k = weight.shape[-1]
+    if out_hw is None:          # symmetric padding
+        out_hw = _conv_out_hw(x.shape[2], x.shape[3], k, stride, pad_t)
+    return _DepthwiseConv2d.apply(x, weight, bias, stride, pad_t, pad_l, out_hw[0], out_hw[1])
+
+
+class _SqueezeExcite(torch.autograd.Function):
+    """x * sigmoid(W2 swish(W1 mean_hw(x) + b1) + b2)   (model.py:78-82).  Three launches each way: plane sums, the gate
+    MLP (one block per sample), the scale pass; the avg-pool gradient is folded into the scale pass of the backward."""
+
+    @staticmethod
+    def forward(ctx, x, w1, b1, w2, b2):
+        n, c, h, w = x.shape
+        sq = w1.shape[0]
+        dev = x.device
+        psum = torch.empty((n, c), dtype=torch.float32, device=dev)
+        call("ssg_plane_sums", x, None, psum, dtype_code(x.dtype), n, h * w, c)
+        pooled = torch.empty((n, c), dtype=torch.float32, device=dev)
+        s_pre = torch.empty((n, sq), dtype=torch.float32, device=dev)
+        gate = torch.empty((n, c), dtype=torch.float32, device=dev)
+        w1d, w2d = w1.detach().reshape(sq, c).contiguous(), w2.detach().reshape(c, sq).contiguous()
+        call("ssg_se_gate_fwd", psum, n, h * w, c, sq, w1d, b1.detach(), w2d, b2.detach(), pooled, s_pre, gate)
+        y = empty_nhwc(n, c, h, w, x.dtype, dev)
+        call("ssg_plane_scale", x, gate, None, y, dtype_code(x.dtype), n, h * w, c)
+        ctx.save_for_backward(x, w1, w2, pooled, s_pre, gate)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, w1, w2, pooled, s_pre, gate = ctx.saved_tensors
+        n, c, h, w = x.shape
+        sq = w1.shape[0]
+        dev = x.device
+        dy = _as_storage(dy, x.dtype)
+        dgate = torch.empty((n, c), dtype=torch.float32, device=dev)
+        call("ssg_plane_sums", dy, x, dgate, dtype_code(x.dtype), n, h * w, c)
+        dpooled = torch.empty((n, c), dtype=torch.float32, device=dev)
+        dw1 = torch.empty_like(w1, dtype=torch.float32)
+        dw2 = torch.empty_like(w2, dtype=torch.float32)
+        db1 = torch.empty(sq, dtype=torch.float32, device=dev)
+        db2 = torch.empty(c, dtype=torch.float32, device=dev)
+        call("ssg_se_gate_bwd", dgate, gate, s_pre, pooled, w1.detach().reshape(sq, c).contiguous(),
+             w2.detach().reshape(c, sq).contiguous(), n, h * w, c, sq, dpooled, dw1, db1, dw2, db2)
+        dx = empty_nhwc(n, c, h, w, x.dtype, dev)
+        call("ssg_plane_scale", dy, gate, dpooled, dx, dtype_code(x.dtype), n, h * w, c)
+        return dx, dw1, db1, dw2, db2
+
+
+def squeeze_excite(x, w_reduce, b_reduce, w_expand, b_expand):
+    return _SqueezeExcite.apply(to_nhwc(x), w_reduce, b_reduce, w_expand, b_expand)
+
+
+class _PlaneScale(torch.autograd.Function):
+    """y[n] = x[n] * scale[n] with a per-sample fp32 scale that needs no gradient (drop_connect, utils.py:83-93)."""
+
+    @staticmethod
+    def forward(ctx, x, scale_nc):
+        n, c, h, w = x.shape
+        y = empty_nhwc(n, c, h, w, x.dtype, x.device)
+        call("ssg_plane_scale", x, scale_nc, None, y, dtype_code(x.dtype), n, h * w, c)
+        ctx.save_for_backward(scale_nc)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        (scale_nc,) = ctx.saved_tensors
+        n, c, h, w = dy.shape
+        dy = _as_storage(dy)
+        dx = empty_nhwc(n, c, h, w, dy.dtype, dy.device)
+        call("ssg_plane_scale", dy, scale_nc, None, dx, dtype_code(dy.dtype), n, h * w, c)
+        return dx, None
+
+
+def sample_scale(x, scale_n):
+    """x * scale_n[:, None, None, None] (scale_n: fp32 [N], constant)."""
+    x = to_nhwc(x)
+    return _PlaneScale.apply(x, scale_n.float().reshape(-1, 1).expand(-1, x.shape[1]).contiguous())
+
+
+class _Swish(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x):
+        y = torch.empty_like(x)
+        call("ssg_swish_fwd", x, y, dtype_code(x.dtype), x.numel())
+        ctx.save_for_backward(x)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        (x,) = ctx.saved_tensors
+        dy = _as_storage(dy, x.dtype) if x.dim() == 4 else dy.contiguous().to(x.dtype)
+        dx = torch.empty_like(x)
+        call("ssg_swish_bwd", dy, x, dx, dtype_code(x.dtype), x.numel())
+        return dx
+
+
+def swish(x):
+    return _Swish.apply(to_nhwc(x) if x.dim() == 4 else x.contiguous())
+
+
+class _GaussGate(torch.autograd.Function):
+    """x1 * exp(-z^2)   (xresidualblock.py:4-6,19-23)."""
+
+    @staticmethod
+    def forward(ctx, x1, z):
+        y = torch.empty_like(x1)
+        call("ssg_gauss_gate_fwd", x1, z, y, dtype_code(x1.dtype), x1.numel())
+        ctx.save_for_backward(x1, z)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x1, z = ctx.saved_tensors
+        dy = _as_storage(dy, x1.dtype)
+        dx1, dz = torch.empty_like(x1), torch.empty_like(z)
+        call("ssg_gauss_gate_bwd", dy, x1, z, dx1, dz, dtype_code(x1.dtype), x1.numel())
+        return dx1, dz
+
+
+def gauss_gate(x1, z):
+    x1 = to_nhwc(x1)
+    return _GaussGate.apply(x1, to_nhwc(z, x1.dtype))
+
+
+class _Pad2d(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, pad_l, pad_r, pad_t, pad_b):
+        n, c, h, w = x.shape
+        oh, ow = h + pad_t + pad_b, w + pad_l + pad_r
+        y = empty_nhwc(n, c, oh, ow, x.dtype, x.device)
+        call("ssg_pad2d", x, y, dtype_code(x.dtype), n, h, w, c, pad_t, pad_l, oh, ow)
+        ctx.cfg = (h, w, pad_t, pad_l)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        h, w, pad_t, pad_l = ctx.cfg
+        n, c, oh, ow = dy.shape
+        dy = _as_storage(dy)
+        dx = empty_nhwc(n, c, h, w, dy.dtype, dy.device)
+        call("ssg_pad2d", dy, dx, dtype_code(dy.dtype), n, oh, ow, c, -pad_t, -pad_l, h, w)
+        return dx, None, None, None, None
+
+
+def zero_pad2d(x, pad_l, pad_r, pad_t, pad_b):
+    if not (pad_l or pad_r or pad_t or pad_b):
+        return x
+    return _Pad2d.apply(to_nhwc(x), pad_l, pad_r, pad_t, pad_b)
+
+
+class _ResizeBilinear(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, oh, ow):
+        n, c, h, w = x.shape
+        y = empty_nhwc(n, c, oh, ow, x.dtype, x.device)
+        call("ssg_resize_bilinear_fwd", x, y, dtype_code(x.dtype), n, h, w, c, oh, ow)
+        ctx.cfg = (h, w)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        h, w = ctx.cfg
+        n, c, oh, ow = dy.shape
+        dy = _as_storage(dy)
+        dx32 = torch.empty((n, h, w, c), dtype=torch.float32, device=dy.device)
+        call("ssg_resize_bilinear_bwd", dy, dx32, dtype_code(dy.dtype), n, h, w, c, oh, ow)
+        if dy.dtype == torch.float32:
+            return dx32.permute(0, 3, 1, 2), None, None
+        dx = empty_nhwc(n, c, h, w, dy.dtype, dy.device)
+        call("ssg_cast", dx32, _lib.SSG_F32, dx, dtype_code(dy.dtype), dx32.numel())
+        return dx, None, None
+
+
+def resize_bilinear(x, oh, ow):
+    """F.interpolate(x, size=(oh, ow), mode='bilinear') (align_corners=False), archs.py:459."""
+    return _ResizeBilinear.apply(to_nhwc(x), oh, ow)
+
+
+class _Add(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, a, b):
+        y = torch.empty_like(a)
+        call("ssg_add", a, b, y, dtype_code(a.dtype), a.numel())
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        return dy, dy
+
+
+def add(a, b):
+    """a + b on same-shape NHWC activations (the MBConv / xResidualBlock identity skips)."""
+    a = to_nhwc(a)
+    return _Add.apply(a, to_nhwc(b, a.dtype))

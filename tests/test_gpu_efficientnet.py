@@ -1,0 +1,294 @@
+"""EfficientNet-encoder rows of SURVEY.md §8a on the GPU: the depthwise / squeeze-excite / swish kernels of
+csrc/mbconv.cu against CPU fp32 arithmetic, and the drop-in modules (MBConvBlock, EfficientNet.extract_features,
+AttentiveCNN, xResidualBlock) against the fixtures written by the unmodified reference and the CPU oracle.
+Tolerances (north_star): fp32 1e-4 relative, bf16 1e-2 relative."""
+import os
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+
+def rel(a, b):
+    a = torch.as_tensor(a).detach().double().cpu()
+    b = torch.as_tensor(b).detach().double().cpu()
+    return float((a - b).norm() / (b.norm() + 1e-30))
+
+
+@pytest.fixture(autouse=True)
+def _reset():
+    import ssunet_gan_b200 as ssg
+    yield
+    ssg.set_compute_dtype(torch.bfloat16)
+    ssg.set_conv_impl("auto")
+
+
+def _tol(dt):
+    return 1e-4 if dt == torch.float32 else 1e-2
+
+
+DW_CASES = [  # n, c, h, w, k, stride, pad_total_h, pad_total_w, bias
+    (2, 32, 18, 18, 3, 1, 2, 2, False),      # b0 stage 1
+    (2, 144, 17, 17, 5, 2, 3, 3, False),     # k5 s2, asymmetric (1, 2) pad, odd size
+    (1, 96, 33, 29, 3, 2, 1, 1, False),      # k3 s2, pad only on the bottom/right
+    (2, 16, 20, 20, 9, 1, 8, 8, True),       # xResidualBlock's 9x9 with bias
+    (3, 40, 7, 5, 5, 1, 4, 4, False),        # feature map smaller than the halo
+    (1, 2112, 9, 9, 3, 1, 2, 2, False),      # widest b2 layer: many channel chunks
+]
+
+
+@pytest.mark.parametrize("dt", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("case", DW_CASES)
+def test_depthwise_conv(case, dt):
+    import ssunet_gan_b200 as ssg
+    from ssunet_gan_b200 import ops
+    ssg.set_compute_dtype(dt)
+    n, c, h, w, k, s, ph, pw, has_bias = case
+    g = torch.Generator().manual_seed(5)
+    x = torch.randn(n, c, h, w, generator=g).to(dt).float()
+    wt = torch.randn(c, 1, k, k, generator=g) / k
+    b = torch.randn(c, generator=g) if has_bias else None
+    pt, pl = ph // 2, pw // 2
+    xr = x.clone().requires_grad_(True)
+    wr = wt.clone().requires_grad_(True)
+    br = b.clone().requires_grad_(True) if has_bias else None
+    yr = F.conv2d(F.pad(xr, [pl, pw - pl, pt, ph - pt]), wr, br, s, 0, 1, c)
+    gy = torch.randn(yr.shape, generator=g).to(dt).float()
+    yr.backward(gy)
+
+    xd = x.cuda().requires_grad_(True)
+    wd = wt.cuda().requires_grad_(True)
+    bd = b.cuda().requires_grad_(True) if has_bias else None
+    xs = ops.to_nhwc(xd, dt)
+    y = ops.depthwise_conv2d(xs, wd, bd, s, pt, pl, (yr.shape[2], yr.shape[3]))
+    assert tuple(y.shape) == tuple(yr.shape)
+    ops.to_nchw_f32(y).backward(gy.cuda())
+    tol = _tol(dt)
+    assert rel(y.float(), yr) < tol
+    assert rel(xd.grad, xr.grad) < tol
+    assert rel(wd.grad, wr.grad) < tol
+    if has_bias:
+        assert rel(bd.grad, br.grad) < tol
+
+
+@pytest.mark.parametrize("dt", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("shape", [(2, 96, 9, 9, 4), (3, 144, 17, 13, 6), (1, 2112, 8, 8, 88), (2, 32, 65, 65, 8)])
+def test_squeeze_excite(shape, dt):
+    import ssunet_gan_b200 as ssg
+    from ssunet_gan_b200 import ops
+    ssg.set_compute_dtype(dt)
+    n, c, h, w, sq = shape
+    g = torch.Generator().manual_seed(6)
+    x = torch.randn(n, c, h, w, generator=g).to(dt).float()
+    w1 = torch.randn(sq, c, 1, 1, generator=g) / c ** 0.5
+    b1 = torch.randn(sq, generator=g) * 0.1
+    w2 = torch.randn(c, sq, 1, 1, generator=g) / sq ** 0.5
+    b2 = torch.randn(c, generator=g) * 0.1
+    ref = [t.clone().requires_grad_(True) for t in (x, w1, b1, w2, b2)]
+    p = F.adaptive_avg_pool2d(ref[0], 1)
+    e = F.conv2d(F.conv2d(p, ref[1], ref[2]) * torch.sigmoid(F.conv2d(p, ref[1], ref[2])), ref[3], ref[4])
+    yr = torch.sigmoid(e) * ref[0]
+    gy = torch.randn(yr.shape, generator=g).to(dt).float()
+    yr.backward(gy)
+    dev = [t.cuda().requires_grad_(True) for t in (x, w1, b1, w2, b2)]
+    y = ops.squeeze_excite(ops.to_nhwc(dev[0], dt), *dev[1:])
+    ops.to_nchw_f32(y).backward(gy.cuda())
+    tol = _tol(dt)
+    assert rel(y.float(), yr) < tol
+    for a, b_ in zip(dev, ref):
+        assert rel(a.grad, b_.grad) < (tol if dt == torch.float32 else 2e-2), (a.shape,)
+
+
+@pytest.mark.parametrize("dt", [torch.float32, torch.bfloat16])
+def test_swish_gauss_pad_resize(dt):
+    import ssunet_gan_b200 as ssg
+    from ssunet_gan_b200 import ops
+    ssg.set_compute_dtype(dt)
+    g = torch.Generator().manual_seed(7)
+    tol = _tol(dt)
+    x = (3 * torch.randn(2, 24, 11, 13, generator=g)).to(dt).float()
+    z = torch.randn(2, 24, 11, 13, generator=g).to(dt).float()
+    gy = torch.randn(2, 24, 11, 13, generator=g).to(dt).float()
+    # swish
+    xr = x.clone().requires_grad_(True)
+    (xr * torch.sigmoid(xr)).backward(gy)
+    xd = x.cuda().requires_grad_(True)
+    y = ops.swish(ops.to_nhwc(xd, dt))
+    ops.to_nchw_f32(y).backward(gy.cuda())
+    assert rel(y.float(), x * torch.sigmoid(x)) < tol and rel(xd.grad, xr.grad) < tol
+    # gaussian gate
+    xr, zr = x.clone().requires_grad_(True), z.clone().requires_grad_(True)
+    (xr * torch.exp(-zr * zr)).backward(gy)
+    xd, zd = x.cuda().requires_grad_(True), z.cuda().requires_grad_(True)
+    y = ops.gauss_gate(ops.to_nhwc(xd, dt), ops.to_nhwc(zd, dt))
+    ops.to_nchw_f32(y).backward(gy.cuda())
+    assert rel(y.float(), x * torch.exp(-z * z)) < tol and rel(xd.grad, xr.grad) < tol and rel(zd.grad, zr.grad) < tol
+    # zero pad (asymmetric) and its adjoint
+    xr = x.clone().requires_grad_(True)
+    yr = F.pad(xr, [0, 1, 1, 2])
+    g2 = torch.randn(yr.shape, generator=g).to(dt).float()
+    yr.backward(g2)
+    xd = x.cuda().requires_grad_(True)
+    y = ops.zero_pad2d(ops.to_nhwc(xd, dt), 0, 1, 1, 2)
+    ops.to_nchw_f32(y).backward(g2.cuda())
+    assert torch.equal(y.float().cpu(), yr.detach()) and rel(xd.grad, xr.grad) < 1e-6
+    # bilinear resize (align_corners=False), up- and down-scaling
+    for oh, ow in ((26, 26), (7, 9), (11, 13)):
+        xr = x.clone().requires_grad_(True)
+        yr = F.interpolate(xr, size=(oh, ow), mode="bilinear")
+        g3 = torch.randn(yr.shape, generator=g).to(dt).float()
+        yr.backward(g3)
+        xd = x.cuda().requires_grad_(True)
+        y = ops.resize_bilinear(ops.to_nhwc(xd, dt), oh, ow)
+        ops.to_nchw_f32(y).backward(g3.cuda())
+        assert rel(y.float(), yr) < tol and rel(xd.grad, xr.grad) < tol
+
+
+MB_CASES = {"e1_k3_s1": dict(k=3, cin=32, cout=16, expand=1, stride=1, sq=8, hw=18),
+            "e6_k5_s2": dict(k=5, cin=24, cout=40, expand=6, stride=2, sq=6, hw=17),
+            "e6_k3_s1_skip": dict(k=3, cin=24, cout=24, expand=6, stride=1, sq=6, hw=18)}
+
+
+@pytest.mark.parametrize("dt", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("name", list(MB_CASES))
+def test_mbconv_block_matches_reference(golden_dir, name, dt):
+    """MBConvBlock(block_args, global_params) fwd + bwd against the unmodified reference's outputs and gradients."""
+    import ssunet_oracle as O
+    import ssunet_gan_b200 as ssg
+    from ssunet_gan_b200 import ops
+    from ssunet_gan_b200.efficientnet_pytorch import MBConvBlock, BlockArgs, get_model_params
+    ssg.set_compute_dtype(dt)
+    z = np.load(os.path.join(golden_dir, "efficientnet.npz"))
+    b = MB_CASES[name]
+    _, gp = get_model_params("efficientnet-b0", None)
+    ba = BlockArgs(kernel_size=b["k"], num_repeat=1, input_filters=b["cin"], output_filters=b["cout"], expand_ratio=b["expand"],
+                   id_skip=True, stride=1 if "skip" in name else [b["stride"]], se_ratio=0.25)
+    m = MBConvBlock(ba, gp)
+    sd = O.portable_state_dict(O.mbconv_spec("blk", b))
+    m.load_state_dict({k[len("blk."):]: v for k, v in sd.items()})          # strict: same keys and shapes as the reference
+    m.cuda().train()
+    x = torch.randn(2, b["cin"], b["hw"], b["hw"], generator=torch.Generator().manual_seed(21)).cuda().requires_grad_(True)
+    y = ops.to_nchw_f32(m(x))
+    g = torch.randn(y.shape, generator=torch.Generator().manual_seed(22)).cuda()
+    (y * g).sum().backward()
+    tol = _tol(dt)
+    assert rel(y, z["mb_%s:y" % name]) < tol
+    gtol = 2e-4 if dt == torch.float32 else 3e-2        # gradients pass through three batch-norm backward reductions
+    assert rel(x.grad, z["mb_%s:dx" % name]) < gtol
+    for k, v in m.named_parameters():
+        ref = z["mb_%s:grad:%s" % (name, k)]
+        if np.linalg.norm(ref) < 1e-6 * max(1.0, np.sqrt(ref.size)):      # biases in front of a BN: exactly-zero gradients
+            assert float(v.grad.abs().max()) < 1e-2
+            continue
+        assert rel(v.grad, ref) < gtol, k
+    if dt == torch.float32:
+        assert rel(m._bn1.running_var, z["mb_%s:bn1.running_var" % name]) < 1e-5
+
+
+def _b0(O, dt, impl="auto"):
+    import ssunet_gan_b200 as ssg
+    from ssunet_gan_b200.efficientnet_pytorch import EfficientNet
+    ssg.set_compute_dtype(dt)
+    ssg.set_conv_impl(impl)
+    net = EfficientNet.from_name("efficientnet-b0", override_params={"drop_connect_rate": 0.0})
+    spec = O.efficientnet_spec("efficientnet-b0")
+    assert [(k, tuple(v.shape)) for k, v in net.state_dict().items()] == [(k, tuple(s)) for k, s in spec]
+    net.load_state_dict(O.portable_state_dict(spec))
+    return net.cuda()
+
+
+def test_efficientnet_b0_fp32_matches_reference(golden_dir):
+    import ssunet_oracle as O
+    from ssunet_gan_b200 import ops
+    z = np.load(os.path.join(golden_dir, "efficientnet.npz"))
+    net = _b0(O, torch.float32)
+    x = torch.randn(2, 3, 64, 64, generator=torch.Generator().manual_seed(23)).cuda()
+    net.train()
+    f = ops.to_nchw_f32(net.extract_features(x))
+    f.square().mean().backward()
+    assert rel(f, z["b0:features_train"]) < 1e-3          # 2 x 2 feature maps: BN over 8 values amplifies fp32 ordering noise
+    named = dict(net.named_parameters())
+    for key in z.files:
+        if key.startswith("b0:csum_grad:"):
+            gsum = named[key[len("b0:csum_grad:"):]].grad.double().cpu()
+            ref = z[key]
+            assert abs(float(gsum.abs().sum()) - ref[1]) < 2e-2 * ref[1] + 1e-9, key
+    net.eval()
+    with torch.no_grad():
+        f = ops.to_nchw_f32(net.extract_features(x))
+        logits = net(x)
+    assert rel(f, z["b0:features_eval"]) < 1e-4
+    assert rel(logits, z["b0:logits_eval"]) < 1e-4
+
+
+def test_efficientnet_b0_bf16_eval(golden_dir):
+    import ssunet_oracle as O
+    from ssunet_gan_b200 import ops
+    z = np.load(os.path.join(golden_dir, "efficientnet.npz"))
+    net = _b0(O, torch.bfloat16)
+    # reproduce the fixture's running statistics (one training pass), then compare the eval features
+    x = torch.randn(2, 3, 64, 64, generator=torch.Generator().manual_seed(23)).cuda()
+    net.train()
+    net.extract_features(x)
+    net.eval()
+    with torch.no_grad():
+        f = ops.to_nchw_f32(net.extract_features(x))
+    assert rel(f, z["b0:features_eval"]) < 3e-2           # 80 bf16-stored layers deep; per-layer error stays < 1e-2 (block tests)
+
+
+@pytest.mark.parametrize("dt", [torch.float32, torch.bfloat16])
+def test_attentive_cnn_b2(golden_dir, dt):
+    import ssunet_oracle as O
+    import ssunet_gan_b200 as ssg
+    from ssunet_gan_b200 import archs
+    ssg.set_compute_dtype(dt)
+    z = np.load(os.path.join(golden_dir, "efficientnet.npz"))
+    att = archs.AttentiveCNN({"eff_flag": True, "phase_train": False, "eff_model_name": "efficientnet-b2"})
+    spec = O.attentive_cnn_spec("efficientnet-b2")
+    assert [k for k, _ in spec] == list(att.state_dict().keys())
+    att.load_state_dict(O.portable_state_dict(spec))
+    att.cuda().eval()
+    img = torch.randn(1, 3, 96, 80, generator=torch.Generator().manual_seed(24)).cuda()
+    with torch.no_grad():
+        y = att(img)
+    assert tuple(y.shape) == (1, 1024, 8, 8) and y.dtype == torch.float32
+    assert rel(y, z["att_b2:y_eval"]) < (1e-4 if dt == torch.float32 else 3e-2)
+
+
+@pytest.mark.parametrize("dt", [torch.float32, torch.bfloat16])
+def test_xresidual_block(golden_dir, dt):
+    import ssunet_oracle as O
+    import ssunet_gan_b200 as ssg
+    from ssunet_gan_b200 import ops
+    from ssunet_gan_b200.xresidualblock import xResidualBlock
+    ssg.set_compute_dtype(dt)
+    z = np.load(os.path.join(golden_dir, "xresidual_2x16x20.npz"))
+    m = xResidualBlock(16, 16, 3, 1)
+    m.load_state_dict(O.portable_state_dict(O.xresidual_block_spec(16, 16)))
+    m.cuda().train()
+    xin = torch.randn(2, 16, 20, 20, generator=torch.Generator().manual_seed(8))
+    xd = xin.cuda().requires_grad_(True)
+    y = ops.to_nchw_f32(m(xd))
+    assert rel(y, z["y"]) < _tol(dt)
+    # gradients against the oracle
+    sd = O.portable_state_dict(O.xresidual_block_spec(16, 16))
+    O._leafify(sd)
+    xr = xin.clone().requires_grad_(True)
+    yr = O.xresidual_block(sd, xr, True)
+    g = torch.randn(yr.shape, generator=torch.Generator().manual_seed(9))
+    keys = O.trainable_keys(sd)
+    grads = torch.autograd.grad((yr * g).sum(), [xr] + [sd[k] for k in keys])
+    (y * g.cuda()).sum().backward()
+    gtol = 2e-4 if dt == torch.float32 else 5e-2          # bf16: the gradient crosses exp(-z^2) and three BN reductions
+    assert rel(xd.grad, grads[0]) < gtol
+    named = dict(m.named_parameters())
+    for k, gr in zip(keys, grads[1:]):
+        if k in ("md.module.2.bias", "conv2.bias"):       # a bias in front of a BN: the exact gradient is 0, both sides hold rounding noise
+            assert float(named[k].grad.abs().max()) < (1e-3 if dt == torch.float32 else 0.5)
+            continue
+        # bf16: BN affine / bias gradients are per-channel sums of 800 signed terms that largely cancel, so the bf16 storage
+        # noise of the summands is not small relative to the result; fp32 mode pins the arithmetic at 2e-4
+        assert rel(named[k].grad, gr) < (gtol if (dt == torch.float32 or gr.dim() > 1) else 0.35), k

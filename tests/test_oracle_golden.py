@@ -194,3 +194,47 @@ def test_xresidual_matches_reference(golden_dir):
     x = torch.randn(2, 16, 20, 20, generator=torch.Generator().manual_seed(8))
     y = O.xresidual_block(sd, x, True)
     _close(y.numpy(), z["y"], rtol=1e-4, atol=1e-5)
+
+
+# ---- EfficientNet encoder rows: oracle restatement vs the unmodified reference -------------------------
+MB_CASES = {"e1_k3_s1": dict(k=3, cin=32, cout=16, expand=1, stride=1, sq=8, hw=18),
+            "e6_k5_s2": dict(k=5, cin=24, cout=40, expand=6, stride=2, sq=6, hw=17),
+            "e6_k3_s1_skip": dict(k=3, cin=24, cout=24, expand=6, stride=1, sq=6, hw=18)}
+
+
+def test_mbconv_blocks_match_reference(golden_dir):
+    z = np.load(os.path.join(golden_dir, "efficientnet.npz"))
+    for name, b in MB_CASES.items():
+        sd = O.portable_state_dict(O.mbconv_spec("blk", b))
+        O._leafify(sd)
+        x = torch.randn(2, b["cin"], b["hw"], b["hw"], generator=torch.Generator().manual_seed(21)).requires_grad_(True)
+        y = O.mbconv_block(sd, "blk", x, b, 224, True)
+        g = torch.randn(y.shape, generator=torch.Generator().manual_seed(22))
+        keys = [k for k in O.trainable_keys(sd)]
+        grads = torch.autograd.grad((y * g).sum(), [x] + [sd[k] for k in keys])
+        _close(y.detach().numpy(), z["mb_%s:y" % name], rtol=1e-4, atol=1e-5)
+        _close(grads[0].numpy(), z["mb_%s:dx" % name], rtol=1e-3, atol=1e-5)
+        for k, gk in zip(keys, grads[1:]):
+            _close(gk.numpy(), z["mb_%s:grad:%s" % (name, k[len("blk."):])], rtol=2e-3, atol=2e-5)
+        _close(sd["blk._bn1.running_var"].numpy(), z["mb_%s:bn1.running_var" % name], rtol=1e-5)
+
+
+def test_efficientnet_b0_features_match_reference(golden_dir):
+    z = np.load(os.path.join(golden_dir, "efficientnet.npz"))
+    x = torch.randn(2, 3, 64, 64, generator=torch.Generator().manual_seed(23))
+    sd = O.portable_state_dict(O.efficientnet_spec("efficientnet-b0"))
+    assert len(sd) == 360                                   # reference EfficientNet-b0 state_dict size
+    f = O.efficientnet_features(sd, x, "efficientnet-b0", True)
+    _close(f.numpy(), z["b0:features_train"], rtol=2e-3, atol=1e-5)
+    # the fixture's eval pass ran after the training pass: running statistics carry one momentum-0.01 update
+    f = O.efficientnet_features(sd, x, "efficientnet-b0", False)
+    _close(f.numpy(), z["b0:features_eval"], rtol=1e-3, atol=1e-5)
+
+
+def test_attentive_cnn_b2_matches_reference(golden_dir):
+    z = np.load(os.path.join(golden_dir, "efficientnet.npz"))
+    img = torch.randn(1, 3, 96, 80, generator=torch.Generator().manual_seed(24))
+    sd = O.portable_state_dict(O.attentive_cnn_spec("efficientnet-b2"))
+    y = O.attentive_cnn(sd, img, "efficientnet-b2", False)
+    assert tuple(y.shape) == (1, 1024, 8, 8)          # 260 -> 130 -> 65 -> 32 -> 16 -> 8 (static pads from the nominal size)
+    _close(y.numpy(), z["att_b2:y_eval"], rtol=1e-3, atol=1e-5)
