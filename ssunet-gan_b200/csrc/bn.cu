@@ -301,6 +301,151 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const T* __restrict__
     }
 }
 
+// Row-strided variants for C % V == 0 and C / V <= 256: a thread keeps ONE channel vector for its whole life, so the
+// per-channel coefficients live in registers (no shared-memory table, no per-element div/mod), and U rows are loaded
+// before the first use (U independent 16-byte requests per operand in flight per thread).
+//   forward : y  = act(sc * x + sh + residual)
+//   backward: dz = dy * act'(y);  dx = A * dz + B * x + K  with A = gamma*inv_std, B = -A*inv_std*m1, K = A*(mean*inv_std*m1 - m0)
+template <typename T>
+__global__ void __launch_bounds__(256) bn_apply_rows_kernel(const T* __restrict__ x, const T* __restrict__ res, T* __restrict__ y,
+                                                             long long rows, int C, const float* __restrict__ mean,
+                                                             const float* __restrict__ inv_std, const float* __restrict__ gamma,
+                                                             const float* __restrict__ beta, int act, float slope) {
+    constexpr int V = Vec<T>::N;
+    constexpr int U = 4;
+    const int lanes = C / V, rpb = 256 / lanes;
+    const int lane = threadIdx.x % lanes, rsub = threadIdx.x / lanes;
+    if (rsub >= rpb) return;
+    float sc[V], sh[V];
+#pragma unroll
+    for (int k = 0; k < V; ++k) {
+        const int c = lane * V + k;
+        const float s = inv_std[c] * (gamma ? gamma[c] : 1.f);
+        sc[k] = s;
+        sh[k] = (beta ? beta[c] : 0.f) - mean[c] * s;
+    }
+    const long long rstride = (long long)gridDim.x * rpb;
+    const long long col = (long long)lane * V;
+    long long r = (long long)blockIdx.x * rpb + rsub;
+    for (; r + (U - 1) * rstride < rows; r += U * rstride) {
+        Vec<T> vx[U], vr[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) vx[u].load(x + (r + u * rstride) * C + col);
+        if (res) {
+#pragma unroll
+            for (int u = 0; u < U; ++u) vr[u].load(res + (r + u * rstride) * C + col);
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            float f[V], fr[V];
+            vx[u].get(f);
+            if (res) vr[u].get(fr);
+#pragma unroll
+            for (int k = 0; k < V; ++k) {
+                float v = fmaf(f[k], sc[k], sh[k]);
+                if (res) v += fr[k];
+                f[k] = apply_act(v, act, slope);
+            }
+            Vec<T> vo; vo.set(f); vo.store(y + (r + u * rstride) * C + col);
+        }
+    }
+    for (; r < rows; r += rstride) {
+        Vec<T> vx; vx.load(x + r * C + col);
+        float f[V], fr[V];
+        vx.get(f);
+        if (res) { Vec<T> vr; vr.load(res + r * C + col); vr.get(fr); }
+#pragma unroll
+        for (int k = 0; k < V; ++k) {
+            float v = fmaf(f[k], sc[k], sh[k]);
+            if (res) v += fr[k];
+            f[k] = apply_act(v, act, slope);
+        }
+        Vec<T> vo; vo.set(f); vo.store(y + r * C + col);
+    }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) bn_bwd_apply_rows_kernel(const T* __restrict__ dy, const T* __restrict__ yout,
+                                                                 const T* __restrict__ x, T* __restrict__ dx, T* __restrict__ dres,
+                                                                 long long rows, int C, const float* __restrict__ mean,
+                                                                 const float* __restrict__ inv_std, const float* __restrict__ gamma,
+                                                                 const double* __restrict__ sums, double count, int act, float slope,
+                                                                 int training) {
+    constexpr int V = Vec<T>::N;
+    constexpr int U = 4;
+    const int lanes = C / V, rpb = 256 / lanes;
+    const int lane = threadIdx.x % lanes, rsub = threadIdx.x / lanes;
+    if (rsub >= rpb) return;
+    float ka[V], kb[V], kc[V];
+#pragma unroll
+    for (int k = 0; k < V; ++k) {
+        const int c = lane * V + k;
+        const float is = inv_std[c], a = is * (gamma ? gamma[c] : 1.f);
+        const float m0 = training ? (float)(sums[c] / count) : 0.f;
+        const float m1 = training ? (float)(sums[C + c] / count) : 0.f;
+        ka[k] = a;
+        kb[k] = -a * is * m1;
+        kc[k] = a * (mean[c] * is * m1 - m0);
+    }
+    const bool has_act = act != SSG_ACT_NONE;
+    const long long rstride = (long long)gridDim.x * rpb;
+    const long long col = (long long)lane * V;
+    long long r = (long long)blockIdx.x * rpb + rsub;
+    for (; r + (U - 1) * rstride < rows; r += U * rstride) {
+        Vec<T> vd[U], vx[U], vy[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) vd[u].load(dy + (r + u * rstride) * C + col);
+#pragma unroll
+        for (int u = 0; u < U; ++u) vx[u].load(x + (r + u * rstride) * C + col);
+        if (has_act) {
+#pragma unroll
+            for (int u = 0; u < U; ++u) vy[u].load(yout + (r + u * rstride) * C + col);
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            float d[V], fx[V];
+            vd[u].get(d);
+            vx[u].get(fx);
+            if (has_act) {
+                float fy[V]; vy[u].get(fy);
+#pragma unroll
+                for (int k = 0; k < V; ++k) d[k] *= act_grad_from_out(fy[k], act, slope);
+            }
+            const long long off = (r + u * rstride) * C + col;
+            if (dres) { Vec<T> vr; vr.set(d); vr.store(dres + off); }
+#pragma unroll
+            for (int k = 0; k < V; ++k) d[k] = fmaf(ka[k], d[k], fmaf(kb[k], fx[k], kc[k]));
+            Vec<T> vo; vo.set(d); vo.store(dx + off);
+        }
+    }
+    for (; r < rows; r += rstride) {
+        const long long off = r * C + col;
+        Vec<T> vd; vd.load(dy + off);
+        Vec<T> vx; vx.load(x + off);
+        float d[V], fx[V];
+        vd.get(d);
+        vx.get(fx);
+        if (has_act) {
+            Vec<T> vy; vy.load(yout + off);
+            float fy[V]; vy.get(fy);
+#pragma unroll
+            for (int k = 0; k < V; ++k) d[k] *= act_grad_from_out(fy[k], act, slope);
+        }
+        if (dres) { Vec<T> vr; vr.set(d); vr.store(dres + off); }
+#pragma unroll
+        for (int k = 0; k < V; ++k) d[k] = fmaf(ka[k], d[k], fmaf(kb[k], fx[k], kc[k]));
+        Vec<T> vo; vo.set(d); vo.store(dx + off);
+    }
+}
+
+// grid for the row-strided kernels: enough blocks for ~8 resident per SM, never more blocks than row groups
+static inline unsigned rows_grid(long long rows, int rpb) {
+    long long b = (rows + rpb - 1) / rpb;
+    long long cap = (long long)sm_count_cached() * 8;
+    if (b > cap) b = cap;
+    return (unsigned)(b < 1 ? 1 : b);
+}
+
 __global__ void bn_param_grads_kernel(const double* sums, int C, float* dgamma, float* dbeta) {
     int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= C) return;
@@ -340,7 +485,10 @@ int ssg_bn_apply(const void* x, const void* residual, void* y, int dtype, long l
     size_t smem = sizeof(float) * 2 * c;
     SSG_DISPATCH_DTYPE(dtype, {
         constexpr int V = Vec<T>::N;
-        if (c % V == 0) {
+        if (c % V == 0 && c / V <= 256) {
+            const int rpb = 256 / (c / V);
+            bn_apply_rows_kernel<T><<<rows_grid(rows, rpb), 256, 0, (cudaStream_t)s>>>((const T*)x, (const T*)residual, (T*)y, rows, c, mean, inv_std, gamma, beta, act, slope);
+        } else if (c % V == 0) {
             unsigned g = grid_for(rows * (c / V), 256 * 2);
             bn_apply_kernel<T, true><<<g, 256, smem, (cudaStream_t)s>>>((const T*)x, (const T*)residual, (T*)y, rows, c, mean, inv_std, gamma, beta, act, slope);
         } else {
@@ -368,7 +516,10 @@ int ssg_bn_bwd_apply(const void* dy, const void* y, const void* x, void* dx, voi
     size_t smem = sizeof(float) * 5 * c;
     SSG_DISPATCH_DTYPE(dtype, {
         constexpr int V = Vec<T>::N;
-        if (c % V == 0) {
+        if (c % V == 0 && c / V <= 256) {
+            const int rpb = 256 / (c / V);
+            bn_bwd_apply_rows_kernel<T><<<rows_grid(rows, rpb), 256, 0, (cudaStream_t)s>>>((const T*)dy, (const T*)y, (const T*)x, (T*)dx, (T*)dres, rows, c, mean, inv_std, gamma, sums, count, act, slope, training);
+        } else if (c % V == 0) {
             unsigned g = grid_for(rows * (c / V), 256 * 2);
             bn_bwd_apply_kernel<T, true><<<g, 256, smem, (cudaStream_t)s>>>((const T*)dy, (const T*)y, (const T*)x, (T*)dx, (T*)dres, rows, c, mean, inv_std, gamma, sums, count, act, slope, training);
         } else {

@@ -43,6 +43,8 @@ struct HaloParams {
     int n_major;                 // item order: 0 = N tile fastest (CTAs running together share activations in L2);
                                  // 1 = M super-tile fastest (a CTA keeps one N tile's weights resident, RES mode)
     int chunks0, chunks1;        // 64-channel chunks from x0 / x1 (virtual concat)
+    int k_last;                  // 16-channel K steps (1..4) that hold live channels in the LAST chunk: thin inputs
+                                 // (8..48 stored channels) issue 1..3 MMAs per tap instead of 4 over TMA zero fill
     int ntaps, ksize;
     int flip;                    // 0: tap t reads halo (t / k, t % k) (forward); 1: (k-1 - t / k, k-1 - t % k) (data gradient)
     int halo_c, halo_r;          // halo box dims in pixels: (8 + k - 1) x (16 + k - 1)
@@ -179,6 +181,7 @@ __global__ void __launch_bounds__(H_THREADS, 1) conv_tc_halo_kernel(const __grid
                 const uint32_t d_base = tmem_base + (uint32_t)(acc * C::ACC_COLS);
                 for (int ch = 0; ch < chunks; ++ch, ++ac) {
                     const int st = ac % C::A_STAGES;
+                    const int ksteps = ch == chunks - 1 ? p.k_last : 4;
                     mbar_wait(&a_full[st], (ac / C::A_STAGES) & 1);
                     const uint32_t a_lo0 = desc_lo(smem_u32(smem + st * C::A_STAGE_BYTES), 16);
                     // taps in weight order t = r * k + s; the halo offset advances by one pixel per s and one halo row per r
@@ -196,10 +199,12 @@ __global__ void __launch_bounds__(H_THREADS, 1) conv_tc_halo_kernel(const __grid
                             // k outer, M-tile inner: consecutive MMAs accumulate into DIFFERENT TMEM accumulators
 #pragma unroll
                             for (int k = 0; k < 4; ++k) {
+                                if (k < ksteps) {
 #pragma unroll
-                                for (int mt = 0; mt < MT; ++mt)
-                                    umma_bf16_lohi(d_base + (uint32_t)(mt * BN), a_lo + (uint32_t)(mt * (H_A_TILE_STRIDE / 16) + 2 * k), a_hi,
-                                                   b_lo + (uint32_t)(2 * k), b_hi, idesc, k == 0 ? keep : 1u);
+                                    for (int mt = 0; mt < MT; ++mt)
+                                        umma_bf16_lohi(d_base + (uint32_t)(mt * BN), a_lo + (uint32_t)(mt * (H_A_TILE_STRIDE / 16) + 2 * k), a_hi,
+                                                       b_lo + (uint32_t)(2 * k), b_hi, idesc, k == 0 ? keep : 1u);
+                                }
                             }
                             if (!RES) umma_commit(&b_empty[sl]);
                         }
@@ -371,6 +376,10 @@ int run_conv_halo(const void* x0, int c0, const void* x1, int c1, const void* w_
     p.y = (bf16*)y; p.bias = bias; p.bias_n = bias_n; p.N = n; p.H = h; p.W = w; p.cout = gemm_n;
     p.tiles_x = (w + H_TW - 1) / H_TW; p.tiles_y = (h + H_TH - 1) / H_TH; p.m_tiles = n * p.tiles_x * p.tiles_y;
     p.chunks0 = (c0 + 63) / 64; p.chunks1 = (c1 + 63) / 64;
+    {
+        const int last = c1 > 0 ? c1 - 64 * (p.chunks1 - 1) : c0 - 64 * (p.chunks0 - 1);     // live channels of the last chunk
+        p.k_last = (last + 15) / 16;
+    }
     p.ntaps = ksize * ksize; p.ksize = ksize; p.flip = flip;
     p.halo_c = H_TW + ksize - 1; p.halo_r = H_TH + ksize - 1; p.org = (ksize - 1) / 2;
     p.act = act; p.slope = slope;

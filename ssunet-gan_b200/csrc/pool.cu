@@ -105,90 +105,102 @@ __device__ __forceinline__ void src_index(int o, float scale, int in_size, int& 
     l1 = s - (float)i0;
 }
 
+// One block row per output row (blockIdx.y = n*oh + oy): the vertical stencil is computed once per thread and all
+// index arithmetic is 32-bit (the earlier flat-index version spent its time in 64-bit div/mod).
 template <typename T, bool VEC>
 __global__ void __launch_bounds__(256) upsample2x_fwd_kernel(const T* __restrict__ x, T* __restrict__ y, int n, int h, int w, int c) {
     constexpr int V = VEC ? Vec<T>::N : 1;
     const int oh = 2 * h, ow = 2 * w, vpr = c / V;
     const float sy = oh > 1 ? (float)(h - 1) / (float)(oh - 1) : 0.f;
     const float sx = ow > 1 ? (float)(w - 1) / (float)(ow - 1) : 0.f;
-    const long long total = (long long)n * oh * ow * vpr;
-    const long long stride = (long long)gridDim.x * blockDim.x;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
-        const int cv = (int)(i % vpr);
-        long long p = i / vpr;
-        const int ox = (int)(p % ow); p /= ow;
-        const int oy = (int)(p % oh);
-        const int nn = (int)(p / oh);
-        int y0, y1, x0, x1; float ly, lx;
+    const int row_vecs = ow * vpr;
+    for (int row = blockIdx.y; row < n * oh; row += gridDim.y) {
+        const int nn = row / oh, oy = row - nn * oh;
+        int y0, y1; float ly;
         src_index(oy, sy, h, y0, y1, ly);
-        src_index(ox, sx, w, x0, x1, lx);
-        const float hy = 1.f - ly, hx = 1.f - lx;
-        const T* b = x + (long long)nn * h * w * c + (long long)cv * V;
-        float f00[V], f01[V], f10[V], f11[V], o[V];
-        if (VEC) {
-            Vec<T> v;
-            v.load(b + ((long long)y0 * w + x0) * c); v.get(f00);
-            v.load(b + ((long long)y0 * w + x1) * c); v.get(f01);
-            v.load(b + ((long long)y1 * w + x0) * c); v.get(f10);
-            v.load(b + ((long long)y1 * w + x1) * c); v.get(f11);
-        } else {
-            f00[0] = to_f(b[((long long)y0 * w + x0) * c]); f01[0] = to_f(b[((long long)y0 * w + x1) * c]);
-            f10[0] = to_f(b[((long long)y1 * w + x0) * c]); f11[0] = to_f(b[((long long)y1 * w + x1) * c]);
-        }
+        const float hy = 1.f - ly;
+        const T* r0 = x + ((long long)nn * h + y0) * w * c;
+        const T* r1 = x + ((long long)nn * h + y1) * w * c;
+        T* yo = y + (long long)row * ow * c;
+        for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < row_vecs; i += gridDim.x * blockDim.x) {
+            const int ox = i / vpr, cv = i - ox * vpr;
+            int x0, x1; float lx;
+            src_index(ox, sx, w, x0, x1, lx);
+            const float hx = 1.f - lx;
+            const int o0 = x0 * c + cv * V, o1 = x1 * c + cv * V;
+            float f00[V], f01[V], f10[V], f11[V], o[V];
+            if (VEC) {
+                Vec<T> v00, v01, v10, v11;
+                v00.load(r0 + o0); v01.load(r0 + o1); v10.load(r1 + o0); v11.load(r1 + o1);
+                v00.get(f00); v01.get(f01); v10.get(f10); v11.get(f11);
+            } else {
+                f00[0] = to_f(r0[o0]); f01[0] = to_f(r0[o1]); f10[0] = to_f(r1[o0]); f11[0] = to_f(r1[o1]);
+            }
 #pragma unroll
-        for (int k = 0; k < V; ++k) o[k] = hy * (hx * f00[k] + lx * f01[k]) + ly * (hx * f10[k] + lx * f11[k]);
-        if (VEC) { Vec<T> v; v.set(o); v.store(y + i * V); } else { y[i] = from_f<T>(o[0]); }
+            for (int k = 0; k < V; ++k) o[k] = hy * (hx * f00[k] + lx * f01[k]) + ly * (hx * f10[k] + lx * f11[k]);
+            if (VEC) { Vec<T> v; v.set(o); v.store(yo + (long long)i * V); } else { yo[i] = from_f<T>(o[0]); }
+        }
     }
 }
 
-// Adjoint in gather form: every input pixel scans the (few) output rows/cols whose stencil touches it,
-// recomputing the forward's index arithmetic exactly.
+// weights with which input index `i` receives from the candidate outputs lo .. lo+7 (scale < 0.5: every output whose
+// stencil touches i lies in [2i-3, 2i+4]); recomputes the forward's index arithmetic exactly.
+__device__ __forceinline__ void adjoint_weights(int i, int in_size, int out_size, float scale, int& lo, float (&wt)[8]) {
+    lo = 2 * i - 3;
+    if (in_size == 1) lo = 0;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const int o = lo + j;
+        float wv = 0.f;
+        if (o >= 0 && o < out_size) {
+            int i0, i1; float l;
+            src_index(o, scale, in_size, i0, i1, l);
+            if (i0 == i) wv += 1.f - l;
+            if (i1 == i) wv += l;
+        }
+        wt[j] = wv;
+    }
+}
+
+// Adjoint in gather form, one block row per input row: the stencil is separable, so a thread evaluates 8 + 8 candidate
+// weights (not 64) and loads only the outputs whose weight product is non-zero.
 template <typename T, bool VEC>
 __global__ void __launch_bounds__(256) upsample2x_bwd_kernel(const T* __restrict__ dy, T* __restrict__ dx, int n, int h, int w, int c) {
     constexpr int V = VEC ? Vec<T>::N : 1;
     const int oh = 2 * h, ow = 2 * w, vpr = c / V;
     const float sy = oh > 1 ? (float)(h - 1) / (float)(oh - 1) : 0.f;
     const float sx = ow > 1 ? (float)(w - 1) / (float)(ow - 1) : 0.f;
-    const long long total = (long long)n * h * w * vpr;
-    const long long stride = (long long)gridDim.x * blockDim.x;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
-        const int cv = (int)(i % vpr);
-        long long p = i / vpr;
-        const int ix = (int)(p % w); p /= w;
-        const int iy = (int)(p % h);
-        const int nn = (int)(p / h);
-        // candidate outputs: those with floor(scale*o) in {i-1, i}; scale < 0.5 so o is within [2i-3, 2i+4]
-        int oy_lo = 2 * iy - 3, oy_hi = 2 * iy + 4, ox_lo = 2 * ix - 3, ox_hi = 2 * ix + 4;
-        if (h == 1) { oy_lo = 0; oy_hi = oh - 1; }
-        if (w == 1) { ox_lo = 0; ox_hi = ow - 1; }
-        oy_lo = oy_lo < 0 ? 0 : oy_lo; ox_lo = ox_lo < 0 ? 0 : ox_lo;
-        oy_hi = oy_hi > oh - 1 ? oh - 1 : oy_hi; ox_hi = ox_hi > ow - 1 ? ow - 1 : ox_hi;
-        float acc[V];
+    const int row_vecs = w * vpr;
+    for (int row = blockIdx.y; row < n * h; row += gridDim.y) {
+        const int nn = row / h, iy = row - nn * h;
+        int oy_lo; float wy[8];
+        adjoint_weights(iy, h, oh, sy, oy_lo, wy);
+        const T* b = dy + (long long)nn * oh * ow * c;
+        T* xo = dx + (long long)row * w * c;
+        for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < row_vecs; i += gridDim.x * blockDim.x) {
+            const int ix = i / vpr, cv = i - ix * vpr;
+            int ox_lo; float wx[8];
+            adjoint_weights(ix, w, ow, sx, ox_lo, wx);
+            float acc[V];
 #pragma unroll
-        for (int k = 0; k < V; ++k) acc[k] = 0.f;
-        const T* b = dy + (long long)nn * oh * ow * c + (long long)cv * V;
-        for (int oy = oy_lo; oy <= oy_hi; ++oy) {
-            int y0, y1; float ly;
-            src_index(oy, sy, h, y0, y1, ly);
-            float wy = 0.f;
-            if (y0 == iy) wy += 1.f - ly;
-            if (y1 == iy) wy += ly;
-            if (wy == 0.f) continue;
-            for (int ox = ox_lo; ox <= ox_hi; ++ox) {
-                int x0, x1; float lx;
-                src_index(ox, sx, w, x0, x1, lx);
-                float wx = 0.f;
-                if (x0 == ix) wx += 1.f - lx;
-                if (x1 == ix) wx += lx;
-                if (wx == 0.f) continue;
-                float f[V];
-                if (VEC) { Vec<T> v; v.load(b + ((long long)oy * ow + ox) * c); v.get(f); }
-                else { f[0] = to_f(b[((long long)oy * ow + ox) * c]); }
+            for (int k = 0; k < V; ++k) acc[k] = 0.f;
 #pragma unroll
-                for (int k = 0; k < V; ++k) acc[k] = fmaf(wy * wx, f[k], acc[k]);
+            for (int jy = 0; jy < 8; ++jy) {
+                if (wy[jy] == 0.f) continue;
+                const T* rp = b + (long long)(oy_lo + jy) * ow * c + cv * V;
+#pragma unroll
+                for (int jx = 0; jx < 8; ++jx) {
+                    const float wgt = wy[jy] * wx[jx];
+                    if (wgt == 0.f) continue;
+                    float f[V];
+                    if (VEC) { Vec<T> v; v.load(rp + (long long)(ox_lo + jx) * c); v.get(f); }
+                    else { f[0] = to_f(rp[(long long)(ox_lo + jx) * c]); }
+#pragma unroll
+                    for (int k = 0; k < V; ++k) acc[k] = fmaf(wgt, f[k], acc[k]);
+                }
             }
+            if (VEC) { Vec<T> v; v.set(acc); v.store(xo + (long long)i * V); } else { xo[i] = from_f<T>(acc[0]); }
         }
-        if (VEC) { Vec<T> v; v.set(acc); v.store(dx + i * V); } else { dx[i] = from_f<T>(acc[0]); }
     }
 }
 
@@ -261,6 +273,19 @@ using namespace ssg;
     SSG_CHECK_LAUNCH();                                                                                 \
     return SSG_OK
 
+// 2-D launch for the row-structured kernels: grid.x covers one row's vectors, grid.y the rows (capped at 65535)
+#define SSG_ROW_LAUNCH(kernel, row_pixels, n_rows, ...)                                                 \
+    SSG_DISPATCH_DTYPE(dtype, {                                                                         \
+        constexpr int V = Vec<T>::N;                                                                    \
+        const bool vec = c % V == 0;                                                                    \
+        const long long per_row = (long long)(row_pixels) * (vec ? c / V : c);                          \
+        dim3 g((unsigned)((per_row + 255) / 256 > 64 ? 64 : (per_row + 255) / 256), (unsigned)((n_rows) > 65535 ? 65535 : (n_rows))); \
+        if (vec) kernel<T, true><<<g, 256, 0, (cudaStream_t)s>>>(__VA_ARGS__);                          \
+        else kernel<T, false><<<g, 256, 0, (cudaStream_t)s>>>(__VA_ARGS__);                             \
+    });                                                                                                 \
+    SSG_CHECK_LAUNCH();                                                                                 \
+    return SSG_OK
+
 extern "C" {
 
 int ssg_maxpool2x2_fwd(const void* x, void* y, uint8_t* code, int dtype, int n, int h, int w, int c, ssg_stream_t s) {
@@ -280,11 +305,11 @@ int ssg_gather2x2(const void* src, const uint8_t* code, void* dst, int dtype, in
 }
 int ssg_upsample2x_fwd(const void* x, void* y, int dtype, int n, int h, int w, int c, ssg_stream_t s) {
     SSG_CHECK_ARG(n > 0 && h > 0 && w > 0 && c > 0, "upsample2x: bad shape");
-    SSG_VEC_LAUNCH(upsample2x_fwd_kernel, (long long)n * 4 * h * w * c, (const T*)x, (T*)y, n, h, w, c);
+    SSG_ROW_LAUNCH(upsample2x_fwd_kernel, 2 * w, n * 2 * h, (const T*)x, (T*)y, n, h, w, c);
 }
 int ssg_upsample2x_bwd(const void* dy, void* dx, int dtype, int n, int h, int w, int c, ssg_stream_t s) {
     SSG_CHECK_ARG(n > 0 && h > 0 && w > 0 && c > 0, "upsample2x: bad shape");
-    SSG_VEC_LAUNCH(upsample2x_bwd_kernel, (long long)n * h * w * c, (const T*)dy, (T*)dx, n, h, w, c);
+    SSG_ROW_LAUNCH(upsample2x_bwd_kernel, w, n * h, (const T*)dy, (T*)dx, n, h, w, c);
 }
 int ssg_adaptive_avgpool_flat_fwd(const void* x, void* y, int dtype, int n, int h, int w, int c, int oh, int ow, ssg_stream_t s) {
     SSG_CHECK_ARG(n > 0 && h > 0 && w > 0 && c > 0 && oh > 0 && ow > 0, "adaptive_avgpool: bad shape");
