@@ -41,7 +41,8 @@ def parse():
     ap.add_argument("--conv", default="auto", choices=["auto", "simt"])
     ap.add_argument("--eager", action="store_true", help="launch every kernel from Python instead of replaying the captured CUDA graph")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--cpu-sample", default="1x256", help="cpu_baseline sample BxS (bounded)")
+    ap.add_argument("--infer-batch", type=int, default=64, help="BASELINE configs[4] leg: eval-mode segmentation batch (0 = skip)")
+    ap.add_argument("--cpu-sample", default="4x512", help="cpu_baseline sample BxS (bounded)")
     return ap.parse_args()
 
 
@@ -276,6 +277,48 @@ def main():
     prof = _lib.profile_collect()
     ms_prof = e0.elapsed_time(e1)
 
+    # SyncBN stat-reduce latency (BASELINE.json metric): the [sum x | sum x^2] fp64 all-reduce of one BN layer over NVLink,
+    # timed alone on the compute stream (CUDA events, 50 back-to-back reduces after 10 warm-ups), smallest and largest layer
+    stat_reduce_us = None
+    if world > 1:
+        stat_reduce_us = {}
+        for c in (64, 768):
+            buf = torch.zeros(2 * c, dtype=torch.float64, device="cuda")
+            for _ in range(10):
+                dist.all_reduce(buf)
+            barrier()
+            a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a0.record()
+            for _ in range(50):
+                dist.all_reduce(buf)
+            a1.record()
+            torch.cuda.synchronize()
+            tt = torch.tensor([a0.elapsed_time(a1) / 50 * 1e3], device="cuda")
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            stat_reduce_us["C=%d (%d B)" % (c, 16 * c)] = round(float(tt), 2)
+
+    # BASELINE configs[4] (extra key, not the headline): inference-only segmentation, eval-mode BN, logits -> IoU / Dice
+    # through metrics.py's kernels (host round trip for the two scalars included), batch 64 x 3 x size^2 resident in HBM
+    infer = None
+    if world == 1 and args.infer_batch > 0:
+        from ssunet_gan_b200 import metrics
+        g.eval()
+        ib = args.infer_batch
+        xi = torch.randn(ib, 3, size, size, device="cuda")
+        ti = (torch.rand(ib, 3, size, size, device="cuda") > 0.5).float()
+
+        def infer_step(_i):
+            with torch.no_grad():
+                lo = g(xi)
+                return metrics.iou_score(lo[:, 1:].contiguous(), ti[:, 1:].contiguous())
+
+        for i in range(2):
+            infer_step(i)
+        ms_inf = timed(infer_step, 3)
+        infer = {"value": ib * 3 / (ms_inf / 1e3), "unit": "img/s", "batch": ib, "ms_per_batch": ms_inf / 3,
+                 "what": "Generator.eval() forward + iou_score, batch %d x 3 x %d x %d bf16" % (ib, size, size)}
+        g.train()
+
     imgs = world * batch * args.steps
     scale = (size * size) / (512.0 * 512.0)
     value = imgs * scale / (ms / 1e3)
@@ -313,6 +356,10 @@ def main():
             "e2e": {"value": e2e, "unit": UNIT, "ms_per_step": ms_e2e / args.steps,
                     "h2d_bytes_per_step": int(2 * batch * 3 * size * size * 4), "d2h_bytes_per_step": 4},
             "gpu_launches": launches, "step_tflops_required_work": step_tf, "roofline": roof, "clocks": clocks}
+    if stat_reduce_us is not None:
+        line["syncbn_stat_reduce_us"] = stat_reduce_us
+    if infer is not None:
+        line["inference"] = infer
     if not args.no_cpu_baseline and world == 1:
         b, s = [int(v) for v in args.cpu_sample.split("x")]
         t = cpu_reference_step(b, s, steps=1, warmup=0)

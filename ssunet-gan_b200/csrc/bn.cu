@@ -2,6 +2,7 @@
 // HBM-bound: every kernel streams its operands once with 16-byte vector accesses; per-thread
 // fp32 partials -> shared-memory fp32 -> one fp64 atomic per channel per block.
 #include "common.cuh"
+#include <stdlib.h>
 
 namespace ssg {
 
@@ -439,6 +440,10 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_rows_kernel(const T* __restr
 }
 
 // grid for the row-strided kernels: enough blocks for ~8 resident per SM, never more blocks than row groups
+static inline bool bn_rows_enabled() {
+    static const bool off = getenv("SSG_BN_GENERIC") != nullptr;       // debugging aid: force the table-driven kernels
+    return !off;
+}
 static inline unsigned rows_grid(long long rows, int rpb) {
     long long b = (rows + rpb - 1) / rpb;
     long long cap = (long long)sm_count_cached() * 8;
@@ -485,7 +490,7 @@ int ssg_bn_apply(const void* x, const void* residual, void* y, int dtype, long l
     size_t smem = sizeof(float) * 2 * c;
     SSG_DISPATCH_DTYPE(dtype, {
         constexpr int V = Vec<T>::N;
-        if (c % V == 0 && c / V <= 256) {
+        if (c % V == 0 && c / V <= 256 && bn_rows_enabled()) {
             const int rpb = 256 / (c / V);
             bn_apply_rows_kernel<T><<<rows_grid(rows, rpb), 256, 0, (cudaStream_t)s>>>((const T*)x, (const T*)residual, (T*)y, rows, c, mean, inv_std, gamma, beta, act, slope);
         } else if (c % V == 0) {
@@ -516,7 +521,7 @@ int ssg_bn_bwd_apply(const void* dy, const void* y, const void* x, void* dx, voi
     size_t smem = sizeof(float) * 5 * c;
     SSG_DISPATCH_DTYPE(dtype, {
         constexpr int V = Vec<T>::N;
-        if (c % V == 0 && c / V <= 256) {
+        if (c % V == 0 && c / V <= 256 && bn_rows_enabled()) {
             const int rpb = 256 / (c / V);
             bn_bwd_apply_rows_kernel<T><<<rows_grid(rows, rpb), 256, 0, (cudaStream_t)s>>>((const T*)dy, (const T*)y, (const T*)x, (T*)dx, (T*)dres, rows, c, mean, inv_std, gamma, sums, count, act, slope, training);
         } else if (c % V == 0) {

@@ -167,14 +167,20 @@ __global__ void __launch_bounds__(H_THREADS, 1) conv_tc_halo_kernel(const __grid
         // addresses live on the uniform datapath; lane 0 alone issues tcgen05.mma / tcgen05.commit ----
         {
             constexpr uint32_t idesc = make_idesc_bf16(128, BN, 0, 0);
-            const bool leader = elect_one();
+            const uint32_t leader = elect_one() ? 1u : 0u;
             const uint32_t a_hi = desc_hi((uint32_t)p.halo_c * 128, 2), b_hi = desc_hi(1024, 2);
+            const uint32_t b_lo_base = desc_lo(smem_u32(smem + C::B_OFFSET), 16);
+            // taps in weight order t = r * k + s; the halo offset advances by one pixel per s and one halo row per r
+            // (mirrored for the data gradient) -- no division or table lookup on the issue path
+            const int step_s = p.flip ? -8 : 8, step_r = (p.flip ? -1 : 1) * (p.halo_c - p.ksize) * 8;
+            const uint32_t a_first = p.flip ? (uint32_t)((p.ksize - 1) * p.halo_c + p.ksize - 1) * 8 : 0u;        // 8 x 16 B per pixel
             int ac = 0, bc = 0, it = 0, cur_n0 = -1, reloads = 0;
             for (int item = blockIdx.x; item < p.total_items; item += gridDim.x, ++it) {
                 const int acc = it % ACCS;
+                bool fresh_b = !RES;            // RES: the resident weight tiles are awaited once, by the first item that uses them
                 if (RES) {
                     const int n0 = (p.n_major ? item / p.supers : item % p.n_tiles) * BN;
-                    if (n0 != cur_n0) { cur_n0 = n0; ++reloads; }
+                    if (n0 != cur_n0) { cur_n0 = n0; ++reloads; fresh_b = true; }
                 }
                 mbar_wait(&acc_empty[acc], ((it / ACCS) & 1) ^ 1);
                 tc_fence_after();
@@ -183,46 +189,47 @@ __global__ void __launch_bounds__(H_THREADS, 1) conv_tc_halo_kernel(const __grid
                     const int st = ac % C::A_STAGES;
                     const int ksteps = ch == chunks - 1 ? p.k_last : 4;
                     mbar_wait(&a_full[st], (ac / C::A_STAGES) & 1);
-                    const uint32_t a_lo0 = desc_lo(smem_u32(smem + st * C::A_STAGE_BYTES), 16);
-                    // taps in weight order t = r * k + s; the halo offset advances by one pixel per s and one halo row per r
-                    // (mirrored for the data gradient) -- no division or table lookup on the issue path
-                    const int step_s = p.flip ? -8 : 8, step_r = (p.flip ? -1 : 1) * (p.halo_c - p.ksize) * 8;
-                    uint32_t a_lo = a_lo0 + (p.flip ? (uint32_t)((p.ksize - 1) * p.halo_c + p.ksize - 1) * 8 : 0u);   // 8 x 16 B per pixel
+                    tc_fence_after();
+                    uint32_t a_lo = desc_lo(smem_u32(smem + st * C::A_STAGE_BYTES), 16) + a_first;
                     int tq = 0;
                     for (int tap = 0; tap < p.ntaps; ++tap, ++bc) {
                         const int sl = RES ? tap : bc % C::B_SLOTS;
-                        mbar_wait(&b_full[sl], RES ? ((reloads - 1) & 1) : ((bc / C::B_SLOTS) & 1));
-                        tc_fence_after();
-                        const uint32_t b_lo = desc_lo(smem_u32(smem + C::B_OFFSET + sl * C::B_BYTES), 16);
+                        if (fresh_b) {
+                            mbar_wait(&b_full[sl], RES ? ((reloads - 1) & 1) : ((bc / C::B_SLOTS) & 1));
+                            tc_fence_after();
+                        }
+                        const uint32_t b_lo = b_lo_base + (uint32_t)(sl * (C::B_BYTES / 16));
                         const uint32_t keep = (uint32_t)(ch | tap);                                         // 0: first k-block of the item
-                        if (leader) {
-                            // k outer, M-tile inner: consecutive MMAs accumulate into DIFFERENT TMEM accumulators
+                        // k outer, M-tile inner: consecutive MMAs accumulate into DIFFERENT TMEM accumulators
+                        if (ksteps == 4) {
 #pragma unroll
                             for (int k = 0; k < 4; ++k) {
-                                if (k < ksteps) {
 #pragma unroll
-                                    for (int mt = 0; mt < MT; ++mt)
-                                        umma_bf16_lohi(d_base + (uint32_t)(mt * BN), a_lo + (uint32_t)(mt * (H_A_TILE_STRIDE / 16) + 2 * k), a_hi,
-                                                       b_lo + (uint32_t)(2 * k), b_hi, idesc, k == 0 ? keep : 1u);
-                                }
+                                for (int mt = 0; mt < MT; ++mt)
+                                    umma_bf16_lohi_pred(d_base + (uint32_t)(mt * BN), a_lo + (uint32_t)(mt * (H_A_TILE_STRIDE / 16) + 2 * k), a_hi,
+                                                        b_lo + (uint32_t)(2 * k), b_hi, idesc, k == 0 ? keep : 1u, leader);
                             }
-                            if (!RES) umma_commit(&b_empty[sl]);
+                        } else {
+                            for (int k = 0; k < ksteps; ++k) {
+#pragma unroll
+                                for (int mt = 0; mt < MT; ++mt)
+                                    umma_bf16_lohi_pred(d_base + (uint32_t)(mt * BN), a_lo + (uint32_t)(mt * (H_A_TILE_STRIDE / 16) + 2 * k), a_hi,
+                                                        b_lo + (uint32_t)(2 * k), b_hi, idesc, k == 0 ? keep : 1u, leader);
+                            }
                         }
-                        __syncwarp();
+                        if (!RES) umma_commit_pred(&b_empty[sl], leader);
                         a_lo += (uint32_t)step_s;
                         if (++tq == p.ksize) { tq = 0; a_lo += (uint32_t)step_r; }
                     }
-                    if (leader) umma_commit(&a_empty[st]);
-                    __syncwarp();
+                    umma_commit_pred(&a_empty[st], leader);
                 }
-                if (leader) umma_commit(&acc_full[acc]);
+                umma_commit_pred(&acc_full[acc], leader);
                 if (RES) {
                     // last item on these weights?  then tell the producer when its MMAs are done
                     const int nxt = item + (int)gridDim.x;
                     const bool last_use = nxt >= p.total_items || (p.n_major ? nxt / p.supers : nxt % p.n_tiles) * BN != cur_n0;
-                    if (last_use && leader) umma_commit(b_free);
+                    if (last_use) umma_commit_pred(b_free, leader);
                 }
-                __syncwarp();
             }
         }
     } else if (warp >= 4) {
@@ -520,42 +527,38 @@ __global__ void __launch_bounds__(H_THREADS, 1) conv_tc_halo_wgrad_kernel(const 
     } else if (warp == 2) {
         // whole warp walks the loop (uniform datapath); lane 0 issues the MMAs and commits
         constexpr uint32_t idesc = make_idesc_bf16(128, 64, 1, 1);     // both operands MN-major
-        const bool leader = elect_one();
+        const uint32_t leader = elect_one() ? 1u : 0u;
         const uint32_t x_hi = desc_hi(1280, 2), dy_hi = desc_hi(1024, 2);
+        const uint32_t x_lo_base = desc_lo(smem_u32(smem + HW_X_OFFSET), 0);
+        const uint32_t dy_lo_base = desc_lo(smem_u32(smem + HW_DY_OFFSET), 1024);
         for (int it = 0; it < n_iter; ++it) {
             const int xs = it % HW_XS, ds = it % HW_DS;
             mbar_wait(&x_full[xs], (it / HW_XS) & 1);
             mbar_wait(&dy_full[ds], (it / HW_DS) & 1);
             tc_fence_after();
-            const uint32_t x_addr = smem_u32(smem + HW_X_OFFSET + xs * H_A_TILE_STRIDE);
-            const uint32_t dy_lo = desc_lo(smem_u32(smem + HW_DY_OFFSET + ds * HW_DY_BYTES), 1024);
+            const uint32_t xk = x_lo_base + (uint32_t)(xs * (H_A_TILE_STRIDE / 16));
+            const uint32_t dk = dy_lo_base + (uint32_t)(ds * (HW_DY_BYTES / 16));
             const uint32_t keep = (uint32_t)it;
-            if (leader) {
-                // k outer, tap pair inner: consecutive MMAs accumulate into different TMEM accumulators.
-                // Pair g = taps 2g and 2g+1 (tap 8 is paired with a dummy second half whose rows are never stored).
-                uint32_t xk = desc_lo(x_addr, 0), dk = dy_lo;
-#pragma unroll 1
-                for (int k = 0; k < 8; ++k) {        // 16 pixels = two tile rows per MMA: x advances 2 halo rows, dy 2 box rows
-                    const uint32_t en = k == 0 ? keep : 1u;
+            // Straight-line issue of the tile's 40 MMAs (k outer, tap pair inner: consecutive MMAs accumulate into different
+            // TMEM accumulators); every descriptor is (slot base + compile-time constant), the leader flag predicates the
+            // instruction itself.  Pair g = taps 2g and 2g+1 (tap 8 is paired with a dummy second half whose rows are never
+            // stored).  16 pixels = two tile rows per MMA: x advances 2 halo rows (160 x 16 B), dy 2 box rows (128 x 16 B).
 #pragma unroll
-                    for (int g = 0; g < 5; ++g) {
-                        constexpr int dummy = 0;
-                        const int ta = 2 * g, tb = g < 4 ? 2 * g + 1 : 8;
-                        const int off_a = ((ta / 3) * 10 + ta % 3) * 128, off_b = ((tb / 3) * 10 + tb % 3) * 128;
-                        const uint32_t lbo = g < 4 ? (uint32_t)(off_b - off_a) : 128u;
-                        // start-address field += off_a / 16; LBO field (bits 16..29) = lbo / 16: both compile-time constants
-                        umma_bf16_lohi(tmem_base + (uint32_t)(g * 64), xk + (uint32_t)((off_a >> 4) | ((lbo >> 4) << 16)) + dummy, x_hi, dk, dy_hi,
-                                       idesc, en);
-                    }
-                    xk += 160; dk += 128;
+            for (int k = 0; k < 8; ++k) {
+#pragma unroll
+                for (int g = 0; g < 5; ++g) {
+                    const int ta = 2 * g, tb = g < 4 ? 2 * g + 1 : 8;
+                    const int off_a = ((ta / 3) * 10 + ta % 3) * 128, off_b = ((tb / 3) * 10 + tb % 3) * 128;
+                    const uint32_t lbo = g < 4 ? (uint32_t)(off_b - off_a) : 128u;
+                    // start-address field += off_a / 16; LBO field (bits 16..29) = lbo / 16: both compile-time constants
+                    umma_bf16_lohi_pred(tmem_base + (uint32_t)(g * 64), xk + (uint32_t)(k * 160 + ((off_a >> 4) | ((lbo >> 4) << 16))), x_hi,
+                                        dk + (uint32_t)(k * 128), dy_hi, idesc, k == 0 ? keep : 1u, leader);
                 }
-                umma_commit(&x_empty[xs]);
-                umma_commit(&dy_empty[ds]);
             }
-            __syncwarp();
+            umma_commit_pred(&x_empty[xs], leader);
+            umma_commit_pred(&dy_empty[ds], leader);
         }
-        if (leader) umma_commit(acc_full);
-        __syncwarp();
+        umma_commit_pred(acc_full, leader);
     } else if (warp >= 4) {
         const int q = warp & 3;
         const int row = q * 32 + lane;                  // accumulator row: tap half (row >> 6), ci (row & 63)

@@ -1,6 +1,7 @@
 // Max-pool 2x2 with a 2-bit argmax code (instead of ATen's int64 flat indices), max-unpool,
 // bilinear x2 (align_corners=True) and adaptive average pooling.  All HBM-bound, NHWC.
 #include "common.cuh"
+#include <stdlib.h>
 
 namespace ssg {
 
@@ -204,6 +205,148 @@ __global__ void __launch_bounds__(256) upsample2x_bwd_kernel(const T* __restrict
     }
 }
 
+// ---- structured x2 kernels ------------------------------------------------------------------------------------------
+// With align_corners=True and an exact x2 factor the stencil is regular: outputs 2b-1 and 2b read inputs {b-1, b}
+// (clamped), and input i is read by outputs 2i-1 .. 2i+2 only (upsample2x_structure_ok() verifies this on the host for
+// the given size by replaying src_index in fp32).  The forward therefore produces a 2 x 2 output block per thread from
+// four input vectors (4 loads / 4 stores instead of 16 loads / 4 stores), the adjoint gathers from a 4 x 4 block.
+// The arithmetic (products and their order) is the same as in the generic kernels above.
+__device__ __forceinline__ void pair_weights(int o, float scale, int in_size, int ra, int rb, float& wa, float& wb) {
+    int i0, i1; float l;
+    src_index(o, scale, in_size, i0, i1, l);
+    wa = (i0 == ra ? 1.f - l : 0.f) + (i1 == ra ? l : 0.f);
+    wb = rb != ra ? (i0 == rb ? 1.f - l : 0.f) + (i1 == rb ? l : 0.f) : 0.f;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) upsample2x_fwd_blk_kernel(const T* __restrict__ x, T* __restrict__ y, int n, int h, int w, int c) {
+    constexpr int V = Vec<T>::N;
+    const int oh = 2 * h, ow = 2 * w, vpr = c / V;
+    const float sy = oh > 1 ? (float)(h - 1) / (float)(oh - 1) : 0.f;
+    const float sx = ow > 1 ? (float)(w - 1) / (float)(ow - 1) : 0.f;
+    const int row_items = (w + 1) * vpr;
+    for (int row = blockIdx.y; row < n * (h + 1); row += gridDim.y) {
+        const int nn = row / (h + 1), bi = row - nn * (h + 1);
+        const int ra = bi > 0 ? bi - 1 : 0, rb = bi < h ? bi : h - 1;
+        const int oy0 = 2 * bi - 1, oy1 = 2 * bi;
+        float wy[2][2];
+        pair_weights(oy0 < 0 ? 0 : oy0, sy, h, ra, rb, wy[0][0], wy[0][1]);
+        pair_weights(oy1 > oh - 1 ? oh - 1 : oy1, sy, h, ra, rb, wy[1][0], wy[1][1]);
+        const T* pa = x + ((long long)nn * h + ra) * w * c;
+        const T* pb = x + ((long long)nn * h + rb) * w * c;
+        for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < row_items; i += gridDim.x * blockDim.x) {
+            const int bk = i / vpr, cv = i - bk * vpr;
+            const int ca = bk > 0 ? bk - 1 : 0, cb = bk < w ? bk : w - 1;
+            const int ox0 = 2 * bk - 1, ox1 = 2 * bk;
+            float wx[2][2];
+            pair_weights(ox0 < 0 ? 0 : ox0, sx, w, ca, cb, wx[0][0], wx[0][1]);
+            pair_weights(ox1 > ow - 1 ? ow - 1 : ox1, sx, w, ca, cb, wx[1][0], wx[1][1]);
+            Vec<T> vaa, vab, vba, vbb;
+            vaa.load(pa + (long long)ca * c + cv * V); vab.load(pa + (long long)cb * c + cv * V);
+            vba.load(pb + (long long)ca * c + cv * V); vbb.load(pb + (long long)cb * c + cv * V);
+            float faa[V], fab[V], fba[V], fbb[V];
+            vaa.get(faa); vab.get(fab); vba.get(fba); vbb.get(fbb);
+#pragma unroll
+            for (int jy = 0; jy < 2; ++jy) {
+                const int oy = jy ? oy1 : oy0;
+                if (oy < 0 || oy >= oh) continue;
+#pragma unroll
+                for (int jx = 0; jx < 2; ++jx) {
+                    const int ox = jx ? ox1 : ox0;
+                    if (ox < 0 || ox >= ow) continue;
+                    float o[V];
+#pragma unroll
+                    for (int k = 0; k < V; ++k)
+                        o[k] = wy[jy][0] * (wx[jx][0] * faa[k] + wx[jx][1] * fab[k]) + wy[jy][1] * (wx[jx][0] * fba[k] + wx[jx][1] * fbb[k]);
+                    Vec<T> vo; vo.set(o);
+                    vo.store(y + (((long long)nn * oh + oy) * ow + ox) * c + cv * V);
+                }
+            }
+        }
+    }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) upsample2x_bwd_blk_kernel(const T* __restrict__ dy, T* __restrict__ dx, int n, int h, int w, int c) {
+    constexpr int V = Vec<T>::N;
+    const int oh = 2 * h, ow = 2 * w, vpr = c / V;
+    const float sy = oh > 1 ? (float)(h - 1) / (float)(oh - 1) : 0.f;
+    const float sx = ow > 1 ? (float)(w - 1) / (float)(ow - 1) : 0.f;
+    const int row_vecs = w * vpr;
+    for (int row = blockIdx.y; row < n * h; row += gridDim.y) {
+        const int nn = row / h, iy = row - nn * h;
+        float wy[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int o = 2 * iy - 1 + j;
+            float wa = 0.f, wb;
+            if (o >= 0 && o < oh) pair_weights(o, sy, h, iy, iy, wa, wb);
+            wy[j] = wa;
+        }
+        const T* b = dy + (long long)nn * oh * ow * c;
+        T* xo = dx + (long long)row * w * c;
+        for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < row_vecs; i += gridDim.x * blockDim.x) {
+            const int ix = i / vpr, cv = i - ix * vpr;
+            float wx[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int o = 2 * ix - 1 + j;
+                float wa = 0.f, wb;
+                if (o >= 0 && o < ow) pair_weights(o, sx, w, ix, ix, wa, wb);
+                wx[j] = wa;
+            }
+            float acc[V];
+#pragma unroll
+            for (int k = 0; k < V; ++k) acc[k] = 0.f;
+#pragma unroll
+            for (int jy = 0; jy < 4; ++jy) {
+                if (wy[jy] == 0.f) continue;                       // also skips rows outside the image
+                const T* rp = b + (long long)(2 * iy - 1 + jy) * ow * c + cv * V;
+                Vec<T> v[4];
+#pragma unroll
+                for (int jx = 0; jx < 4; ++jx)
+                    if (wx[jx] != 0.f) v[jx].load(rp + (long long)(2 * ix - 1 + jx) * c);
+#pragma unroll
+                for (int jx = 0; jx < 4; ++jx) {
+                    if (wx[jx] == 0.f) continue;
+                    float f[V]; v[jx].get(f);
+                    const float wgt = wy[jy] * wx[jx];
+#pragma unroll
+                    for (int k = 0; k < V; ++k) acc[k] = fmaf(wgt, f[k], acc[k]);
+                }
+            }
+            Vec<T> vo; vo.set(acc); vo.store(xo + (long long)i * V);
+        }
+    }
+}
+
+// host check of the stencil structure the *_blk kernels rely on (same fp32 arithmetic as src_index); cached per size
+static bool upsample2x_structure_ok(int in_size) {
+    static const bool generic_only = getenv("SSG_UPSAMPLE_GENERIC") != nullptr;      // debugging aid
+    if (generic_only) return false;
+    static int cache_size[16];
+    static int cache_ok[16];
+    static int cache_n = 0;
+    for (int i = 0; i < cache_n; ++i)
+        if (cache_size[i] == in_size) return cache_ok[i] != 0;
+    const int out = 2 * in_size;
+    const float scale = out > 1 ? (float)(in_size - 1) / (float)(out - 1) : 0.f;
+    bool ok = true;
+    for (int o = 0; o < out && ok; ++o) {
+        const float sf = scale * (float)o;
+        int i0 = (int)sf;
+        if (i0 > in_size - 1) i0 = in_size - 1;
+        const int i1 = i0 + (i0 < in_size - 1 ? 1 : 0);
+        const float l = sf - (float)i0;
+        const int b = (o + 1) / 2;
+        const int ra = b > 0 ? b - 1 : 0, rb = b < in_size ? b : in_size - 1;
+        if (i0 != ra && i0 != rb) ok = false;
+        if (i1 != ra && i1 != rb && l != 0.f) ok = false;          // a neighbour outside the pair may only carry weight 0
+    }
+    if (cache_n < 16) { cache_size[cache_n] = in_size; cache_ok[cache_n] = ok ? 1 : 0; ++cache_n; }
+    return ok;
+}
+
 // ---- adaptive average pool to (oh, ow), flattened channel-major like NCHW .view(batch, -1) -----------
 // ATen window: [floor(o*in/out), ceil((o+1)*in/out))
 template <typename T>
@@ -305,10 +448,32 @@ int ssg_gather2x2(const void* src, const uint8_t* code, void* dst, int dtype, in
 }
 int ssg_upsample2x_fwd(const void* x, void* y, int dtype, int n, int h, int w, int c, ssg_stream_t s) {
     SSG_CHECK_ARG(n > 0 && h > 0 && w > 0 && c > 0, "upsample2x: bad shape");
+    if (c % 8 == 0 && upsample2x_structure_ok(h) && upsample2x_structure_ok(w)) {
+        SSG_DISPATCH_DTYPE(dtype, {
+            if (c % Vec<T>::N == 0) {
+                const long long per_row = (long long)(w + 1) * (c / Vec<T>::N);
+                dim3 g((unsigned)((per_row + 255) / 256 > 64 ? 64 : (per_row + 255) / 256), (unsigned)(n * (h + 1) > 65535 ? 65535 : n * (h + 1)));
+                upsample2x_fwd_blk_kernel<T><<<g, 256, 0, (cudaStream_t)s>>>((const T*)x, (T*)y, n, h, w, c);
+                SSG_CHECK_LAUNCH();
+                return SSG_OK;
+            }
+        });
+    }
     SSG_ROW_LAUNCH(upsample2x_fwd_kernel, 2 * w, n * 2 * h, (const T*)x, (T*)y, n, h, w, c);
 }
 int ssg_upsample2x_bwd(const void* dy, void* dx, int dtype, int n, int h, int w, int c, ssg_stream_t s) {
     SSG_CHECK_ARG(n > 0 && h > 0 && w > 0 && c > 0, "upsample2x: bad shape");
+    if (c % 8 == 0 && upsample2x_structure_ok(h) && upsample2x_structure_ok(w)) {
+        SSG_DISPATCH_DTYPE(dtype, {
+            if (c % Vec<T>::N == 0) {
+                const long long per_row = (long long)w * (c / Vec<T>::N);
+                dim3 g((unsigned)((per_row + 255) / 256 > 64 ? 64 : (per_row + 255) / 256), (unsigned)(n * h > 65535 ? 65535 : n * h));
+                upsample2x_bwd_blk_kernel<T><<<g, 256, 0, (cudaStream_t)s>>>((const T*)dy, (T*)dx, n, h, w, c);
+                SSG_CHECK_LAUNCH();
+                return SSG_OK;
+            }
+        });
+    }
     SSG_ROW_LAUNCH(upsample2x_bwd_kernel, w, n * h, (const T*)dy, (T*)dx, n, h, w, c);
 }
 int ssg_adaptive_avgpool_flat_fwd(const void* x, void* y, int dtype, int n, int h, int w, int c, int oh, int ow, ssg_stream_t s) {

@@ -94,7 +94,8 @@ class GraphedGanStep:
     Static device buffers hold the inputs; `__call__(input, target)` copies the new batch into them (device or pinned-host
     sources) and replays.  The optimisers must be `optim.FusedClampAdam` (flat gradient arenas, device-resident step
     count); BatchNorm running statistics, Adam moments, parameters and the NCCL all-reduces (SyncBN statistics, gradient
-    arenas) are all updated by the replayed kernels exactly as in the eager step.  Returns the same OrderedDict of 0-dim
+    arenas) are all updated by the replayed kernels exactly as in the eager step.  Construction leaves parameters, buffers
+    and optimiser state exactly as it found them (the warm-up iterations are rolled back).  Returns the same OrderedDict of 0-dim
     tensors as `gan_train_step` (static outputs: read them before the next call); IoU/Dice are not part of the graph
     (they need a host round trip) -- compute them from `out["logits"]` when wanted."""
 
@@ -110,6 +111,16 @@ class GraphedGanStep:
         self.t[:, 0].fill_(1.0)
         optimizer_g.make_capturable()
         optimizer_d.make_capturable()
+        # Building the graph must not train the model: the warm-up iterations below run real optimiser steps on the static
+        # (zero) batch, so every piece of state they touch is snapshotted here and restored IN PLACE after the capture
+        # (same storage, so the captured kernels keep pointing at it).
+        snap = []
+        for opt in (optimizer_g, optimizer_d):
+            snap += [(t, t.clone()) for t in (opt.flat_p, opt.flat_m, opt.flat_v, opt._step_dev)]
+        for mod in (generator, discriminator):
+            snap += [(b, b.clone()) for b in mod.buffers()]
+            snap += [(q.data, q.data.clone()) for q in mod.parameters() if not q.requires_grad]
+        steps0 = (optimizer_g._step, optimizer_d._step)
         # warm up on a side stream (allocator, lazy kernel attributes, NCCL communicators), then capture
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
@@ -124,6 +135,12 @@ class GraphedGanStep:
         with torch.cuda.graph(self.graph):
             self.out = gan_train_step(self.g, self.d, self.og, self.od, self.x, self.t, **self.kw)
         self.launches_per_step = _lib.launch_count - l0
+        with torch.no_grad():
+            for live, saved in snap:
+                live.copy_(saved)
+        optimizer_g._step, optimizer_d._step = steps0
+        optimizer_g.flat_g.zero_()
+        optimizer_d.flat_g.zero_()
         ops.bump_weight_epoch()
 
     def load(self, input, target, non_blocking=True):

@@ -269,20 +269,19 @@ def test_graphed_step_matches_eager():
     o1 = (optim.FusedClampAdam(g1.parameters(), lr=2e-5), optim.FusedClampAdam(d1.parameters(), lr=2e-5))
     o2 = (optim.FusedClampAdam(g2.parameters(), lr=2e-5), optim.FusedClampAdam(d2.parameters(), lr=2e-5))
     graphed = train_step.GraphedGanStep(g2, d2, o2[0], o2[1], (2, 3, 64, 64), warmup=2)
-    # the graphed copy ran warm-up + capture iterations on its static (zero) inputs: replay the same history eagerly
-    x0 = torch.zeros(2, 3, 64, 64, device="cuda")
-    t0 = torch.zeros(2, 3, 64, 64, device="cuda"); t0[:, 0] = 1.0
-    for _ in range(2):
-        train_step.gan_train_step(g1, d1, o1[0], o1[1], x0, t0, with_metrics=False)
-    # (capture itself does not execute kernels)
+    # construction rolls its warm-up iterations back: parameters, BN buffers and Adam state are untouched
+    for a, b in zip(g1.state_dict().values(), g2.state_dict().values()):
+        assert torch.equal(a, b)
+    assert float(o2[0].flat_m.abs().max()) == 0.0 and float(o2[1]._step_dev) == 0.0
     for it in range(3):
         x, t = O.synthetic_batch(2, 3, 64, 64, seed=77 + it)
         r1 = train_step.gan_train_step(g1, d1, o1[0], o1[1], x.cuda(), t.cuda(), with_metrics=False)
         r2 = graphed(x.cuda(), t.cuda())
         for k in ("loss", "content", "adv_g", "adv_d"):
             a, b = float(r1[k]), float(r2[k])
-            # later iterations: the two copies have taken sign-like Adam steps on differently-rounded gradients
-            assert abs(a - b) < (1e-2 if it == 0 else 6e-2) * abs(a) + 1e-4, (it, k, a, b)
+            # iteration 0 starts from identical state (only the fp32 atomics order of wgrad differs); afterwards the two
+            # copies have taken sign-like Adam steps (|m / sqrt(v)| ~ 1 in the first steps) on differently-rounded gradients
+            assert abs(a - b) < (2e-3 if it == 0 else 6e-2) * abs(a) + 1e-4, (it, k, a, b)
     p1 = torch.cat([p.detach().reshape(-1) for p in g1.parameters()])
     p2 = torch.cat([p.detach().reshape(-1) for p in g2.parameters()])
     assert float((p1 - p2).abs().max()) <= 5 * 2e-5 * 2 + 1e-7       # a handful of sign-like Adam steps of lr each
