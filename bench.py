@@ -325,8 +325,7 @@ def main():
     e2e = imgs * scale / (ms_e2e / 1e3)
 
     if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
+        _finish(world)
         return
 
     peaks = {}
@@ -367,8 +366,18 @@ def main():
         line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
                                 "sample": "one full G+D step, batch %d x 3 x %d x %d fp32 (%.1f s), pixel-scaled to 512^2" % (b, s, s, t[0])}
     print(json.dumps(line), flush=True)
+    _finish(world)
+
+
+def _finish(world):
+    """Leave without tearing NCCL down: destroying a communicator whose collectives live in a still-referenced CUDA graph
+    can block forever (observed: the N = 2 run printed its line and then hung in destroy_process_group)."""
+    import torch
+    torch.cuda.synchronize()
+    sys.stdout.flush()
+    sys.stderr.flush()
     if world > 1:
-        dist.destroy_process_group()
+        os._exit(0)
 
 
 if __name__ == "__main__":
