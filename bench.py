@@ -281,21 +281,30 @@ def main():
     # timed alone on the compute stream (CUDA events, 50 back-to-back reduces after 10 warm-ups), smallest and largest layer
     stat_reduce_us = None
     if world > 1:
-        stat_reduce_us = {}
-        for c in (64, 768):
-            buf = torch.zeros(2 * c, dtype=torch.float64, device="cuda")
+        from ssunet_gan_b200 import ops as _ops
+        peer = _ops.PeerStatReducer.for_group(dist.group.WORLD)
+        stat_reduce_us = {"path_used_by_the_step": "nvlink peer-memory kernel (csrc/p2p.cu)" if peer is not None else "nccl all-reduce"}
+
+        def _time_reduce(fn, buf):
             for _ in range(10):
-                dist.all_reduce(buf)
+                fn(buf)
             barrier()
             a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             a0.record()
             for _ in range(50):
-                dist.all_reduce(buf)
+                fn(buf)
             a1.record()
             torch.cuda.synchronize()
             tt = torch.tensor([a0.elapsed_time(a1) / 50 * 1e3], device="cuda")
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-            stat_reduce_us["C=%d (%d B)" % (c, 16 * c)] = round(float(tt), 2)
+            return round(float(tt), 2)
+
+        for c in (64, 768):
+            buf = torch.zeros(2 * c, dtype=torch.float64, device="cuda")
+            key = "C=%d (%d B)" % (c, 16 * c)
+            stat_reduce_us[key] = {"nccl": _time_reduce(lambda b: dist.all_reduce(b), buf)}
+            if peer is not None:
+                stat_reduce_us[key]["peer_memory_kernel"] = _time_reduce(peer.all_reduce, buf)
 
     # BASELINE configs[4] (extra key, not the headline): inference-only segmentation, eval-mode BN, logits -> IoU / Dice
     # through metrics.py's kernels (host round trip for the two scalars included), batch 64 x 3 x size^2 resident in HBM

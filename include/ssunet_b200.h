@@ -269,6 +269,18 @@ int ssg_pad2d(const void* x, void* y, int dtype, int n, int h, int w, int c, int
 int ssg_resize_bilinear_fwd(const void* x, void* y, int dtype, int n, int h, int w, int c, int oh, int ow, ssg_stream_t s);
 int ssg_resize_bilinear_bwd(const void* dy, float* dx32, int dtype, int n, int h, int w, int c, int oh, int ow, ssg_stream_t s);
 
+/* ---- SyncBN statistics exchange over NVLink peer memory (batchnorm.py:95-112, comm.py:74-136) ---------------------- */
+/* Size in bytes of the symmetric receive buffer every rank must allocate (zero-filled before first use) and map into all
+ * ranks' address spaces: data [2][world][slot_len] fp64 + flags [2][world] uint32. */
+long long ssg_p2p_buffer_bytes(int world, int slot_len);
+/* In-place sum of `data` (n <= slot_len fp64 values: [sum x | sum x^2] or [sum dy | sum dy*xhat]) over all ranks.
+ * peer_bufs_dev: DEVICE array of `world` pointers, entry p = rank p's receive buffer as mapped in THIS process;
+ * epoch_dev: device uint32 call counter owned by this rank (starts at 0, advanced by the kernel).  One single-CTA launch:
+ * remote stores + release/acquire flags, reduction in rank order (bit-identical on all ranks).  Every rank must issue
+ * the same sequence of calls. */
+int ssg_p2p_allreduce_f64(double* data, int n, void* const* peer_bufs_dev, int rank, int world, int slot_len, unsigned* epoch_dev,
+                          ssg_stream_t s);
+
 #ifdef __cplusplus
 }
 #endif

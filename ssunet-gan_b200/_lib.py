@@ -74,13 +74,16 @@ def lib():
         L.ssg_pairwise_leaves_host.restype = ctypes.c_longlong
         L.ssg_pairwise_combine_host.argtypes = [ctypes.c_void_p, ctypes.c_longlong]
         L.ssg_pairwise_combine_host.restype = ctypes.c_float
+        L.ssg_p2p_buffer_bytes.argtypes = [ctypes.c_int, ctypes.c_int]
+        L.ssg_p2p_buffer_bytes.restype = ctypes.c_longlong
         _lib = L
     return _lib
 
 
 def exported_symbols():
     """Every symbol include/ssunet_b200.h declares (used by the CPU-side ABI test)."""
-    return sorted(list(_SIGS) + ["ssg_version", "ssg_last_error", "ssg_pairwise_leaves_host", "ssg_pairwise_combine_host"])
+    return sorted(list(_SIGS) + ["ssg_version", "ssg_last_error", "ssg_pairwise_leaves_host", "ssg_pairwise_combine_host",
+                                  "ssg_p2p_buffer_bytes"])
 
 
 def _ptr(t):

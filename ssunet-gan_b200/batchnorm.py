@@ -37,6 +37,11 @@ class _SynchronizedBatchNorm(_BatchNorm):
             self._slave_pipe = ctx.sync_master.register_slave(copy_id)
 
     def _set_process_group(self, group, world):
+        # None means "the default group" to torch.distributed, but `ops.batch_norm(group=None)` means "single device":
+        # resolve it here so a default-constructed DataParallelWithCallback really synchronises the statistics
+        if group is None and world > 1:
+            import torch.distributed as dist
+            group = dist.group.WORLD
         self._group, self._world = group, world
 
     def _data_parallel_master(self, intermediates):
