@@ -61,22 +61,47 @@ __global__ void __launch_bounds__(256) spade_bwd_kernel(const T* __restrict__ dy
     }
 }
 
+// 16-byte vector body + scalar tail (all buffers come from the torch allocator: 16-byte aligned bases)
 template <typename T>
-__global__ void act_fwd_kernel(const T* __restrict__ x, T* __restrict__ y, long long n, int act, float slope) {
-    const long long stride = (long long)gridDim.x * blockDim.x;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+__global__ void __launch_bounds__(256) act_fwd_kernel(const T* __restrict__ x, T* __restrict__ y, long long n, int act, float slope, int vec_ok) {
+    constexpr int V = Vec<T>::N;
+    const long long nv = vec_ok ? n / V : 0, stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nv; i += stride) {
+        Vec<T> v; v.load(x + i * V);
+        float f[V]; v.get(f);
+#pragma unroll
+        for (int k = 0; k < V; ++k) f[k] = apply_act(f[k], act, slope);
+        v.set(f); v.store(y + i * V);
+    }
+    for (long long i = nv * V + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
         y[i] = from_f<T>(apply_act(to_f(x[i]), act, slope));
 }
 template <typename T>
-__global__ void act_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ y, T* __restrict__ dx, long long n, int act, float slope) {
-    const long long stride = (long long)gridDim.x * blockDim.x;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+__global__ void __launch_bounds__(256) act_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ y, T* __restrict__ dx, long long n, int act, float slope, int vec_ok) {
+    constexpr int V = Vec<T>::N;
+    const long long nv = vec_ok ? n / V : 0, stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nv; i += stride) {
+        Vec<T> vd, vy; vd.load(dy + i * V); vy.load(y + i * V);
+        float fd[V], fy[V]; vd.get(fd); vy.get(fy);
+#pragma unroll
+        for (int k = 0; k < V; ++k) fd[k] *= act_grad_from_out(fy[k], act, slope);
+        vd.set(fd); vd.store(dx + i * V);
+    }
+    for (long long i = nv * V + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
         dx[i] = from_f<T>(to_f(dy[i]) * act_grad_from_out(to_f(y[i]), act, slope));
 }
 template <typename T>
-__global__ void add_kernel(const T* __restrict__ a, const T* __restrict__ b, T* __restrict__ o, long long n) {
-    const long long stride = (long long)gridDim.x * blockDim.x;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+__global__ void __launch_bounds__(256) add_kernel(const T* __restrict__ a, const T* __restrict__ b, T* __restrict__ o, long long n, int vec_ok) {
+    constexpr int V = Vec<T>::N;
+    const long long nv = vec_ok ? n / V : 0, stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nv; i += stride) {
+        Vec<T> va, vb; va.load(a + i * V); vb.load(b + i * V);
+        float fa[V], fb[V]; va.get(fa); vb.get(fb);
+#pragma unroll
+        for (int k = 0; k < V; ++k) fa[k] += fb[k];
+        va.set(fa); va.store(o + i * V);
+    }
+    for (long long i = nv * V + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
         o[i] = from_f<T>(to_f(a[i]) + to_f(b[i]));
 }
 __global__ void nan_scrub_fwd_kernel(const float* __restrict__ x, float* __restrict__ y, long long n) {
@@ -98,23 +123,42 @@ __global__ void clamp_kernel(float* __restrict__ g, long long n, float clip) {
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
         g[i] = fminf(fmaxf(g[i], -clip), clip);   // NaN propagates like torch.clamp
 }
+// one Adam element: g <- clamp(g * gscale); m, v, p updated exactly in torch.optim.Adam's operation order
+__device__ __forceinline__ void adam_elem(float& pi, float& gi, float& mi, float& vi, float b1, float b2, float eps, float bc2_sqrt,
+                                          float step, float clip, float gscale) {
+    gi *= gscale;
+    if (clip > 0.f) gi = fminf(fmaxf(gi, -clip), clip);
+    mi = b1 * mi + (1.f - b1) * gi;
+    vi = b2 * vi + (1.f - b2) * gi * gi;
+    const float denom = sqrtf(vi) / bc2_sqrt + eps;
+    pi = pi - step * (mi / denom);
+}
+// float4 body (the four arenas are torch allocations: 16-byte aligned) + scalar tail
+__device__ __forceinline__ void adam_span(float* __restrict__ p, float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
+                                          long long n, long long stride, float b1, float b2, float eps, float bc2_sqrt, float step,
+                                          float clip, float gscale) {
+    const bool vec = ((((uintptr_t)p | (uintptr_t)g | (uintptr_t)m | (uintptr_t)v) & 15) == 0);
+    const long long nv = vec ? n / 4 : 0;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nv; i += stride) {
+        float4 p4 = reinterpret_cast<float4*>(p)[i], g4 = reinterpret_cast<float4*>(g)[i];
+        float4 m4 = reinterpret_cast<float4*>(m)[i], v4 = reinterpret_cast<float4*>(v)[i];
+        adam_elem(p4.x, g4.x, m4.x, v4.x, b1, b2, eps, bc2_sqrt, step, clip, gscale);
+        adam_elem(p4.y, g4.y, m4.y, v4.y, b1, b2, eps, bc2_sqrt, step, clip, gscale);
+        adam_elem(p4.z, g4.z, m4.z, v4.z, b1, b2, eps, bc2_sqrt, step, clip, gscale);
+        adam_elem(p4.w, g4.w, m4.w, v4.w, b1, b2, eps, bc2_sqrt, step, clip, gscale);
+        reinterpret_cast<float4*>(p)[i] = p4; reinterpret_cast<float4*>(g)[i] = g4;
+        reinterpret_cast<float4*>(m)[i] = m4; reinterpret_cast<float4*>(v)[i] = v4;
+    }
+    for (long long i = nv * 4 + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+        adam_elem(p[i], g[i], m[i], v[i], b1, b2, eps, bc2_sqrt, step, clip, gscale);
+}
 // torch.optim.Adam (no amsgrad, no weight decay) after clip_gradient's element clamp.
 __global__ void __launch_bounds__(256) clamp_adam_kernel(float* __restrict__ p, float* __restrict__ g, float* __restrict__ m,
                                                           float* __restrict__ v, long long n, float lr, float b1, float b2,
                                                           float eps, float bc1, float bc2_sqrt, float clip, float gscale) {
     const long long stride = (long long)gridDim.x * blockDim.x;
     const float step = lr / bc1;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
-        float gi = g[i] * gscale;
-        if (clip > 0.f) gi = fminf(fmaxf(gi, -clip), clip);
-        g[i] = gi;
-        const float mi = b1 * m[i] + (1.f - b1) * gi;
-        const float vi = b2 * v[i] + (1.f - b2) * gi * gi;
-        m[i] = mi;
-        v[i] = vi;
-        const float denom = sqrtf(vi) / bc2_sqrt + eps;
-        p[i] = p[i] - step * (mi / denom);
-    }
+    adam_span(p, g, m, v, n, stride, b1, b2, eps, bc2_sqrt, step, clip, gscale);
 }
 // Graph-capturable variant: the step count lives on the device (a captured launch cannot carry per-step host scalars).
 __global__ void step_inc_kernel(float* step) { step[0] += 1.f; }
@@ -125,22 +169,16 @@ __global__ void __launch_bounds__(256) clamp_adam_dev_kernel(float* __restrict__
     const float t = step_dev[0];
     const float bc1 = 1.f - powf(b1, t), bc2_sqrt = sqrtf(1.f - powf(b2, t));
     const float step = lr / bc1;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
-        float gi = g[i] * gscale;
-        if (clip > 0.f) gi = fminf(fmaxf(gi, -clip), clip);
-        g[i] = gi;
-        const float mi = b1 * m[i] + (1.f - b1) * gi;
-        const float vi = b2 * v[i] + (1.f - b2) * gi * gi;
-        m[i] = mi;
-        v[i] = vi;
-        const float denom = sqrtf(vi) / bc2_sqrt + eps;
-        p[i] = p[i] - step * (mi / denom);
-    }
+    adam_span(p, g, m, v, n, stride, b1, b2, eps, bc2_sqrt, step, clip, gscale);
 }
 __global__ void scale_by_dev_kernel(const float* __restrict__ w, const float* __restrict__ sc, float* __restrict__ o, long long n) {
     const float s = sc[0];
     const long long stride = (long long)gridDim.x * blockDim.x;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) o[i] = w[i] * s;
+}
+
+static inline int aligned16(const void* a, const void* b = nullptr, const void* c = nullptr) {
+    return (((uintptr_t)a | (uintptr_t)b | (uintptr_t)c) & 15) == 0 ? 1 : 0;
 }
 
 }  // namespace ssg
@@ -168,19 +206,19 @@ int ssg_spade_modulate_bwd(const void* dy, const void* x, const void* gb, void* 
 }
 int ssg_act_fwd(const void* x, void* y, int dtype, long long n, int act, float slope, ssg_stream_t s) {
     if (n <= 0) return SSG_OK;
-    SSG_DISPATCH_DTYPE(dtype, act_fwd_kernel<T><<<grid_for(n, 1024), 256, 0, (cudaStream_t)s>>>((const T*)x, (T*)y, n, act, slope));
+    SSG_DISPATCH_DTYPE(dtype, act_fwd_kernel<T><<<grid_for(n, 2048), 256, 0, (cudaStream_t)s>>>((const T*)x, (T*)y, n, act, slope, aligned16(x, y)));
     SSG_CHECK_LAUNCH();
     return SSG_OK;
 }
 int ssg_act_bwd(const void* dy, const void* y, void* dx, int dtype, long long n, int act, float slope, ssg_stream_t s) {
     if (n <= 0) return SSG_OK;
-    SSG_DISPATCH_DTYPE(dtype, act_bwd_kernel<T><<<grid_for(n, 1024), 256, 0, (cudaStream_t)s>>>((const T*)dy, (const T*)y, (T*)dx, n, act, slope));
+    SSG_DISPATCH_DTYPE(dtype, act_bwd_kernel<T><<<grid_for(n, 2048), 256, 0, (cudaStream_t)s>>>((const T*)dy, (const T*)y, (T*)dx, n, act, slope, aligned16(dy, y, dx)));
     SSG_CHECK_LAUNCH();
     return SSG_OK;
 }
 int ssg_add(const void* a, const void* b, void* out, int dtype, long long n, ssg_stream_t s) {
     if (n <= 0) return SSG_OK;
-    SSG_DISPATCH_DTYPE(dtype, add_kernel<T><<<grid_for(n, 1024), 256, 0, (cudaStream_t)s>>>((const T*)a, (const T*)b, (T*)out, n));
+    SSG_DISPATCH_DTYPE(dtype, add_kernel<T><<<grid_for(n, 2048), 256, 0, (cudaStream_t)s>>>((const T*)a, (const T*)b, (T*)out, n, aligned16(a, b, out)));
     SSG_CHECK_LAUNCH();
     return SSG_OK;
 }
@@ -215,7 +253,7 @@ int ssg_clamp_adam_dev(float* p, float* g, float* m, float* v, long long n, floa
     if (n <= 0) return SSG_OK;
     SSG_CHECK_ARG(step_dev != nullptr, "clamp_adam_dev: step counter missing");
     step_inc_kernel<<<1, 1, 0, (cudaStream_t)s>>>(step_dev);
-    clamp_adam_dev_kernel<<<grid_for(n, 1024), 256, 0, (cudaStream_t)s>>>(p, g, m, v, n, lr, beta1, beta2, eps, step_dev, clip, grad_scale);
+    clamp_adam_dev_kernel<<<grid_for(n, 2048), 256, 0, (cudaStream_t)s>>>(p, g, m, v, n, lr, beta1, beta2, eps, step_dev, clip, grad_scale);
     SSG_CHECK_LAUNCH();
     return SSG_OK;
 }

@@ -10,7 +10,7 @@ constexpr int MCH = 8;
 // vectors (float4 weights, 4 x bf16 / float4 activations), MROWS batch rows at a time, so every weight element is read
 // once per MROWS rows and feeds MROWS FMAs; block-level tree reduction at the end.  (The first version gave each warp one
 // feature and issued one 2-byte activation load per FMA: 0.58 ms for fc1 at batch 16; the weight read alone is 12 us.)
-constexpr int LIN_JB = 4, LIN_MROWS = 16, LIN_THREADS = 256;
+constexpr int LIN_JB = 2, LIN_MROWS = 16, LIN_THREADS = 256;
 
 __device__ __forceinline__ void load4f(const float* p, float* f) {
     const float4 v = *reinterpret_cast<const float4*>(p);
@@ -89,11 +89,75 @@ __global__ void __launch_bounds__(LIN_THREADS) linear_fwd_kernel(const T* __rest
     }
 }
 
-// thread per input feature kk; j range split over blockIdx.y, combined with fp32 atomics into dx32
+// dx32[i][kk] += sum_j dy[i][j] * w[j][kk]: a thread owns 4 consecutive input features (one float4 of every weight row it
+// visits) and all MCH16 batch rows, so the weight matrix is streamed ONCE for up to 16 rows with 16-byte loads; the j range
+// is split over blockIdx.y and combined with fp32 atomics into dx32 (pre-zeroed).  dy is staged in shared memory.
+constexpr int MCH16 = 16, DG_JT = 64;
+
 template <typename T>
 __global__ void __launch_bounds__(256) linear_dgrad_kernel(const T* __restrict__ dy, const float* __restrict__ w,
                                                             float* __restrict__ dx32, int m, int k, int nout, int j_per_block,
                                                             const float* __restrict__ inv_scale) {
+    __shared__ float sdy[MCH16][DG_JT];
+    const int kk = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    const int j0 = blockIdx.y * j_per_block;
+    const int j1 = min(nout, j0 + j_per_block);
+    const float sc = inv_scale ? inv_scale[0] : 1.f;
+    const bool live = kk < k;            // k % 4 == 0 is checked by the launcher
+    for (int m0 = 0; m0 < m; m0 += MCH16) {
+        float acc[MCH16][4];
+#pragma unroll
+        for (int i = 0; i < MCH16; ++i) acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = 0.f;
+        for (int jt = j0; jt < j1; jt += DG_JT) {
+            __syncthreads();
+            for (int e = threadIdx.x; e < MCH16 * DG_JT; e += blockDim.x) {
+                const int i = e / DG_JT, j = jt + e % DG_JT;
+                sdy[i][e % DG_JT] = (m0 + i < m && j < j1) ? to_f(dy[(long long)(m0 + i) * nout + j]) : 0.f;
+            }
+            __syncthreads();
+            if (live) {
+                const int jn = min(DG_JT, j1 - jt);
+                int jj = 0;
+                for (; jj + 1 < jn; jj += 2) {
+                    const float4 w0 = *reinterpret_cast<const float4*>(w + (long long)(jt + jj) * k + kk);
+                    const float4 w1 = *reinterpret_cast<const float4*>(w + (long long)(jt + jj + 1) * k + kk);
+#pragma unroll
+                    for (int i = 0; i < MCH16; ++i) {
+                        const float d0 = sdy[i][jj], d1 = sdy[i][jj + 1];
+                        acc[i][0] = fmaf(w0.x, d0, fmaf(w1.x, d1, acc[i][0]));
+                        acc[i][1] = fmaf(w0.y, d0, fmaf(w1.y, d1, acc[i][1]));
+                        acc[i][2] = fmaf(w0.z, d0, fmaf(w1.z, d1, acc[i][2]));
+                        acc[i][3] = fmaf(w0.w, d0, fmaf(w1.w, d1, acc[i][3]));
+                    }
+                }
+                for (; jj < jn; ++jj) {
+                    const float4 w0 = *reinterpret_cast<const float4*>(w + (long long)(jt + jj) * k + kk);
+#pragma unroll
+                    for (int i = 0; i < MCH16; ++i) {
+                        const float d0 = sdy[i][jj];
+                        acc[i][0] = fmaf(w0.x, d0, acc[i][0]); acc[i][1] = fmaf(w0.y, d0, acc[i][1]);
+                        acc[i][2] = fmaf(w0.z, d0, acc[i][2]); acc[i][3] = fmaf(w0.w, d0, acc[i][3]);
+                    }
+                }
+            }
+        }
+        if (live) {
+#pragma unroll
+            for (int i = 0; i < MCH16; ++i)
+                if (m0 + i < m) {
+                    float* dst = dx32 + (long long)(m0 + i) * k + kk;
+                    atomicAdd(dst, acc[i][0] * sc); atomicAdd(dst + 1, acc[i][1] * sc);
+                    atomicAdd(dst + 2, acc[i][2] * sc); atomicAdd(dst + 3, acc[i][3] * sc);
+                }
+        }
+    }
+}
+
+// scalar fallback (k % 4 != 0): thread per input feature
+template <typename T>
+__global__ void __launch_bounds__(256) linear_dgrad_scalar_kernel(const T* __restrict__ dy, const float* __restrict__ w,
+                                                                   float* __restrict__ dx32, int m, int k, int nout, int j_per_block,
+                                                                   const float* __restrict__ inv_scale) {
     const int kk = blockIdx.x * blockDim.x + threadIdx.x;
     const int j0 = blockIdx.y * j_per_block;
     const int j1 = min(nout, j0 + j_per_block);
@@ -115,20 +179,47 @@ __global__ void __launch_bounds__(256) linear_dgrad_kernel(const T* __restrict__
     }
 }
 
+// dw[j][kk] = sum_i dy[i][j] * x[i][kk]: a thread owns 4 consecutive kk and WG_J output features, so every activation
+// element it loads feeds WG_J weight rows (the first version re-read x once per output feature).
+constexpr int WG_J = 8;
+
 template <typename T>
 __global__ void __launch_bounds__(256) linear_wgrad_kernel(const T* __restrict__ x, const T* __restrict__ dy, float* __restrict__ dw,
                                                             float* __restrict__ dbias, int m, int k, int nout) {
-    const int kk = blockIdx.x * blockDim.x + threadIdx.x;
-    const int j = blockIdx.y;
-    if (kk >= k) return;
-    float acc = 0.f, accb = 0.f;
-    for (int i = 0; i < m; ++i) {
-        const float d = to_f(dy[(long long)i * nout + j]);
-        acc = fmaf(d, to_f(x[(long long)i * k + kk]), acc);
-        accb += d;
+    const int kk = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    const int j0 = blockIdx.y * WG_J;
+    float acc[WG_J][4], accb[WG_J];
+#pragma unroll
+    for (int j = 0; j < WG_J; ++j) { acc[j][0] = acc[j][1] = acc[j][2] = acc[j][3] = 0.f; accb[j] = 0.f; }
+    if (kk < k) {
+        for (int i = 0; i < m; ++i) {
+            float xv[4];
+            if (kk + 3 < k) load4f(x + (long long)i * k + kk, xv);
+            else {
+#pragma unroll
+                for (int e = 0; e < 4; ++e) xv[e] = kk + e < k ? to_f(x[(long long)i * k + kk + e]) : 0.f;
+            }
+#pragma unroll
+            for (int j = 0; j < WG_J; ++j) {
+                const float d = j0 + j < nout ? to_f(dy[(long long)i * nout + j0 + j]) : 0.f;
+                acc[j][0] = fmaf(d, xv[0], acc[j][0]); acc[j][1] = fmaf(d, xv[1], acc[j][1]);
+                acc[j][2] = fmaf(d, xv[2], acc[j][2]); acc[j][3] = fmaf(d, xv[3], acc[j][3]);
+                accb[j] += d;
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < WG_J; ++j) {
+            if (j0 + j >= nout) break;
+            float* dst = dw + (long long)(j0 + j) * k + kk;
+            if (kk + 3 < k && (((long long)(j0 + j) * k + kk) & 3) == 0) *reinterpret_cast<float4*>(dst) = make_float4(acc[j][0], acc[j][1], acc[j][2], acc[j][3]);
+            else {
+#pragma unroll
+                for (int e = 0; e < 4; ++e)
+                    if (kk + e < k) dst[e] = acc[j][e];
+            }
+            if (dbias && kk == 0) dbias[j0 + j] = accb[j];
+        }
     }
-    dw[(long long)j * k + kk] = acc;
-    if (dbias && kk == 0) dbias[j] = accb;
 }
 
 }  // namespace ssg
@@ -149,20 +240,25 @@ int ssg_linear_dgrad(const void* dy, const float* w, float* dx, int dtype, int m
                      ssg_stream_t s) {
     SSG_CHECK_ARG(m > 0 && k > 0 && nout > 0, "linear_dgrad: bad shape");
     SSG_CHECK_CUDA(cudaMemsetAsync(dx, 0, sizeof(float) * (size_t)m * k, (cudaStream_t)s));
-    int kb = (k + 255) / 256;
-    int splits = (2 * sm_count_cached() + kb - 1) / kb;
+    const bool vec = k % 4 == 0;
+    int kb = vec ? (k / 4 + 255) / 256 : (k + 255) / 256;
+    int splits = (4 * sm_count_cached() + kb - 1) / kb;
     if (splits > nout) splits = nout;
     if (splits < 1) splits = 1;
     int jpb = (nout + splits - 1) / splits;
     dim3 grid((unsigned)kb, (unsigned)((nout + jpb - 1) / jpb));
-    SSG_DISPATCH_DTYPE(dtype, linear_dgrad_kernel<T><<<grid, 256, 0, (cudaStream_t)s>>>((const T*)dy, w, (float*)dx, m, k, nout, jpb, inv_scale_dev));
+    if (vec) {
+        SSG_DISPATCH_DTYPE(dtype, linear_dgrad_kernel<T><<<grid, 256, 0, (cudaStream_t)s>>>((const T*)dy, w, (float*)dx, m, k, nout, jpb, inv_scale_dev));
+    } else {
+        SSG_DISPATCH_DTYPE(dtype, linear_dgrad_scalar_kernel<T><<<grid, 256, 0, (cudaStream_t)s>>>((const T*)dy, w, (float*)dx, m, k, nout, jpb, inv_scale_dev));
+    }
     SSG_CHECK_LAUNCH();
     return SSG_OK;
 }
 
 int ssg_linear_wgrad(const void* x, const void* dy, float* dw, float* dbias, int dtype, int m, int k, int nout, ssg_stream_t s) {
-    SSG_CHECK_ARG(m > 0 && k > 0 && nout > 0 && nout <= 65535, "linear_wgrad: bad shape");
-    dim3 grid((unsigned)((k + 255) / 256), (unsigned)nout);
+    SSG_CHECK_ARG(m > 0 && k > 0 && nout > 0 && nout <= 65535 * WG_J, "linear_wgrad: bad shape");
+    dim3 grid((unsigned)(((k + 3) / 4 + 255) / 256), (unsigned)((nout + WG_J - 1) / WG_J));
     SSG_DISPATCH_DTYPE(dtype, linear_wgrad_kernel<T><<<grid, 256, 0, (cudaStream_t)s>>>((const T*)x, (const T*)dy, dw, dbias, m, k, nout));
     SSG_CHECK_LAUNCH();
     return SSG_OK;
