@@ -41,7 +41,7 @@ __global__ void __launch_bounds__(BN_THREADS) channel_reduce_vec_kernel(
             }
             // U rows per trip with all loads issued before the first use: U independent 16-byte requests per operand
             // in flight per thread (a single dependent load per trip left this kernel latency-bound at < 20 % of HBM)
-            constexpr int U = 4;
+            constexpr int U = 4;                        // (8 rows in flight measured slower for the single-operand mode)
             long long r = r_begin + rsub;
             for (; r + (long long)(U - 1) * rpb < r_end; r += (long long)U * rpb) {
                 Vec<T> va[U], vx[U], vy[U];

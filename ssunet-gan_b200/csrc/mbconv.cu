@@ -75,6 +75,110 @@ __global__ void __launch_bounds__(DW_THREADS) dwconv_fwd_kernel(const T* __restr
     }
 }
 
+// Sliding-window forward for the kernel sizes / strides the encoder uses: a thread produces DW_OW consecutive output
+// pixels of one row for its 16-byte channel vector, so each input vector it loads feeds up to K / S outputs
+// (3x3 s1: 4.5 loads per output instead of 9; 5x5 s1: 10 instead of 25).  FLIP stages the weights mirrored, which turns
+// the same kernel into the stride-1 data gradient (dx = dy (*) flipped w with pad' = K - 1 - pad).
+constexpr int DW_OW = 4;
+
+template <typename T, int K, int S, bool FLIP>
+__global__ void __launch_bounds__(DW_THREADS) dwconv_slide_kernel(const T* __restrict__ x, const float* __restrict__ w,
+                                                                  const float* __restrict__ bias, T* __restrict__ y, int N, int H,
+                                                                  int W, int C, int pad_t, int pad_l, int OH, int OW) {
+    constexpr int V = Vec<T>::N;
+    constexpr int CHUNK = DW_LANES * V;
+    constexpr int COLS = (DW_OW - 1) * S + K;           // input columns one thread touches per row
+    extern __shared__ float sw[];
+    const int c_base = blockIdx.y * CHUNK;
+    for (int i = threadIdx.x; i < K * K * CHUNK; i += blockDim.x) {
+        const int cl = i / (K * K), tap = i - cl * (K * K);
+        const int c = c_base + cl;
+        sw[(FLIP ? K * K - 1 - tap : tap) * CHUNK + cl] = c < C ? w[(long long)c * K * K + tap] : 0.f;
+    }
+    __syncthreads();
+    const int lane = threadIdx.x % DW_LANES, prow = threadIdx.x / DW_LANES;
+    const int c0 = c_base + lane * V;
+    if (c0 >= C) return;
+    const int groups_x = (OW + DW_OW - 1) / DW_OW;
+    const long long groups = (long long)N * OH * groups_x;
+    float fb[V];
+#pragma unroll
+    for (int j = 0; j < V; ++j) fb[j] = bias ? bias[c0 + j] : 0.f;
+    for (long long gidx = (long long)blockIdx.x * DW_PIX + prow; gidx < groups; gidx += (long long)gridDim.x * DW_PIX) {
+        const int gx = (int)(gidx % groups_x);
+        const int oy = (int)((gidx / groups_x) % OH);
+        const int n = (int)(gidx / ((long long)groups_x * OH));
+        const int ox0 = gx * DW_OW;
+        float acc[DW_OW][V];
+#pragma unroll
+        for (int o = 0; o < DW_OW; ++o)
+#pragma unroll
+            for (int j = 0; j < V; ++j) acc[o][j] = fb[j];
+        const int iy0 = oy * S - pad_t, ix0 = ox0 * S - pad_l;
+#pragma unroll(K <= 3 ? K : 1)
+        for (int ky = 0; ky < K; ++ky) {            // wide filters: one row of loads in flight at a time (register budget)
+            const int iy = iy0 + ky;
+            const bool row_ok = iy >= 0 && iy < H;
+            const T* xrow = x + ((long long)(n * H + (row_ok ? iy : 0)) * W) * C + c0;
+            // branch-free row: every load goes to a clamped (always valid) address and is zeroed by a select when the tap
+            // falls outside the image, so the COLS loads of the row are independent and can all be in flight
+            Vec<T> vx[COLS];
+#pragma unroll
+            for (int jx = 0; jx < COLS; ++jx) {
+                const int ix = ix0 + jx;
+                vx[jx].load(xrow + (long long)(ix < 0 ? 0 : (ix >= W ? W - 1 : ix)) * C);
+            }
+#pragma unroll
+            for (int jx = 0; jx < COLS; ++jx) {
+                const int ix = ix0 + jx;
+                const bool keep = row_ok && ix >= 0 && ix < W;
+                float fx[V]; vx[jx].get(fx);
+#pragma unroll
+                for (int j = 0; j < V; ++j) fx[j] = keep ? fx[j] : 0.f;
+#pragma unroll
+                for (int o = 0; o < DW_OW; ++o) {
+                    const int kx = jx - o * S;              // compile-time after unrolling
+                    if (kx < 0 || kx >= K) continue;
+                    const float* wt = sw + (ky * K + kx) * CHUNK + lane * V;
+#pragma unroll
+                    for (int j = 0; j < V; ++j) acc[o][j] = fmaf(fx[j], wt[j], acc[o][j]);
+                }
+            }
+        }
+#pragma unroll
+        for (int o = 0; o < DW_OW; ++o) {
+            if (ox0 + o >= OW) break;
+            Vec<T> vo; vo.set(acc[o]);
+            vo.store(y + (((long long)n * OH + oy) * OW + ox0 + o) * C + c0);
+        }
+    }
+}
+
+template <typename T, int K, int S, bool FLIP>
+static int launch_dw_slide(const T* x, const float* w, const float* bias, T* y, int n, int h, int w_, int c, int pad_t, int pad_l, int oh,
+                           int ow, cudaStream_t st) {
+    constexpr int CHUNK = DW_LANES * Vec<T>::N;
+    const long long groups = (long long)n * oh * ((ow + DW_OW - 1) / DW_OW);
+    // few fat blocks: every block first stages its weight slice, so it must amortise that over many pixel groups
+    const int chunks = (c + CHUNK - 1) / CHUNK;
+    dim3 grid(grid_for(groups, DW_PIX * 2, chunks >= 4 ? 1 : (chunks >= 2 ? 2 : 4)), chunks);
+    dwconv_slide_kernel<T, K, S, FLIP><<<grid, DW_THREADS, sizeof(float) * K * K * CHUNK, st>>>(x, w, bias, y, n, h, w_, c, pad_t, pad_l, oh, ow);
+    SSG_CHECK_LAUNCH();
+    return SSG_OK;
+}
+
+// returns SSG_ERR_UNSUPPORTED when no sliding-window instance covers (k, stride): the caller falls back to the generic kernel
+template <typename T, bool FLIP>
+static int dispatch_dw_slide(const T* x, const float* w, const float* bias, T* y, int n, int h, int w_, int c, int k, int stride, int pad_t,
+                             int pad_l, int oh, int ow, cudaStream_t st) {
+    if (k == 3 && stride == 1) return launch_dw_slide<T, 3, 1, FLIP>(x, w, bias, y, n, h, w_, c, pad_t, pad_l, oh, ow, st);
+    if (k == 5 && stride == 1) return launch_dw_slide<T, 5, 1, FLIP>(x, w, bias, y, n, h, w_, c, pad_t, pad_l, oh, ow, st);
+    if (k == 9 && stride == 1) return launch_dw_slide<T, 9, 1, FLIP>(x, w, bias, y, n, h, w_, c, pad_t, pad_l, oh, ow, st);
+    if (!FLIP && k == 3 && stride == 2) return launch_dw_slide<T, 3, 2, false>(x, w, bias, y, n, h, w_, c, pad_t, pad_l, oh, ow, st);
+    if (!FLIP && k == 5 && stride == 2) return launch_dw_slide<T, 5, 2, false>(x, w, bias, y, n, h, w_, c, pad_t, pad_l, oh, ow, st);
+    return SSG_ERR_UNSUPPORTED;
+}
+
 // dx[n,iy,ix,c] = sum_taps dy[n,(iy+pad_t-ky)/s,(ix+pad_l-kx)/s,c] * w[c,ky,kx]   (only where the division is exact)
 template <typename T>
 __global__ void __launch_bounds__(DW_THREADS) dwconv_dgrad_kernel(const T* __restrict__ dy, const float* __restrict__ w,
@@ -452,8 +556,10 @@ int ssg_dwconv2d_fwd(const void* x, const float* w, const float* bias, void* y, 
     SSG_DISPATCH_DTYPE(dtype, {
         int rc = dw_geometry_ok<T>(n, h, w_, c, k, stride, pad_t, pad_l, oh, ow);
         if (rc) return rc;
+        rc = dispatch_dw_slide<T, false>((const T*)x, w, bias, (T*)y, n, h, w_, c, k, stride, pad_t, pad_l, oh, ow, (cudaStream_t)s);
+        if (rc != SSG_ERR_UNSUPPORTED) return rc;
         constexpr int CHUNK = DW_LANES * Vec<T>::N;
-        dim3 grid(grid_for((long long)n * oh * ow, DW_PIX * 4, 16), (c + CHUNK - 1) / CHUNK);
+        dim3 grid(grid_for((long long)n * oh * ow, DW_PIX * 4, 4), (c + CHUNK - 1) / CHUNK);
         dwconv_fwd_kernel<T><<<grid, DW_THREADS, sizeof(float) * k * k * CHUNK, (cudaStream_t)s>>>(
             (const T*)x, w, bias, (T*)y, n, h, w_, c, k, stride, pad_t, pad_l, oh, ow);
     });
@@ -466,8 +572,12 @@ int ssg_dwconv2d_dgrad(const void* dy, const float* w, void* dx, int dtype, int 
     SSG_DISPATCH_DTYPE(dtype, {
         int rc = dw_geometry_ok<T>(n, h, w_, c, k, stride, pad_t, pad_l, oh, ow);
         if (rc) return rc;
+        if (stride == 1) {      // dx = dy (*) mirrored weights, leading pad k - 1 - pad: the forward kernel with FLIP
+            rc = dispatch_dw_slide<T, true>((const T*)dy, w, nullptr, (T*)dx, n, oh, ow, c, k, 1, k - 1 - pad_t, k - 1 - pad_l, h, w_, (cudaStream_t)s);
+            if (rc != SSG_ERR_UNSUPPORTED) return rc;
+        }
         constexpr int CHUNK = DW_LANES * Vec<T>::N;
-        dim3 grid(grid_for((long long)n * h * w_, DW_PIX * 4, 16), (c + CHUNK - 1) / CHUNK);
+        dim3 grid(grid_for((long long)n * h * w_, DW_PIX * 4, 4), (c + CHUNK - 1) / CHUNK);
         dwconv_dgrad_kernel<T><<<grid, DW_THREADS, sizeof(float) * k * k * CHUNK, (cudaStream_t)s>>>(
             (const T*)dy, w, (T*)dx, n, h, w_, c, k, stride, pad_t, pad_l, oh, ow);
     });

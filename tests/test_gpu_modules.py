@@ -286,3 +286,48 @@ def test_graphed_step_matches_eager():
     p2 = torch.cat([p.detach().reshape(-1) for p in g2.parameters()])
     assert float((p1 - p2).abs().max()) <= 5 * 2e-5 * 2 + 1e-7       # a handful of sign-like Adam steps of lr each
     assert int(d2.state_dict()["conv_blocks.1.conv_block.1.num_batches_tracked"]) == int(d1.state_dict()["conv_blocks.1.conv_block.1.num_batches_tracked"])
+
+
+@pytest.mark.parametrize("dtype,impl,tol", [(torch.float32, "simt", 1e-4), (torch.bfloat16, "auto", 3e-2)])
+def test_generator_4band_input_vs_oracle(dtype, impl, tol):
+    """BASELINE configs[3] shape family (SpaceNet7-style 4-band tiles, preprocess_SN7 layout): `input_channels=4`,
+    eval-mode forward against the CPU oracle on a 1 x 4 x 96 x 96 tile (the 4-channel stem is stored channel-padded to 8
+    in tensor-core mode)."""
+    import ssunet_oracle as O
+    import ssunet_gan_b200 as ssg
+    from ssunet_gan_b200 import models_seg_gan
+    ssg.set_compute_dtype(dtype)
+    ssg.set_conv_impl(impl)
+    spec = O.unet_r_ss_v2_spec(3, 4, prefix="net.")
+    g = models_seg_gan.Generator({"arch": "UNet_R_SS_v2", "num_classes": 3, "input_channels": 4, "deep_supervision": False})
+    assert [(k, tuple(v.shape)) for k, v in g.state_dict().items()] == [(k, tuple(s)) for k, s in spec]
+    sd = O.portable_state_dict(spec)
+    g.load_state_dict(sd)
+    g.cuda().eval()
+    x, _ = O.synthetic_batch(1, 4, 96, 96, seed=4321)
+    with torch.no_grad():
+        y = g(x.cuda())
+        ref = O.unet_r_ss_v2(sd, x, False, prefix="net.")
+    assert tuple(y.shape) == (1, 3, 96, 96) and y.dtype == torch.float32
+    assert rel(y, ref) < tol
+
+
+def test_inference_batch_metrics_bit_exact_vs_numpy():
+    """BASELINE configs[4]: inference-only segmentation -- eval forward on a batch, then IoU (bit-identical) and Dice
+    against the reference's numpy arithmetic (metrics.py:6-35) applied to THIS forward's logits."""
+    import numpy as np
+    import ssunet_oracle as O
+    import ssunet_gan_b200 as ssg
+    from ssunet_gan_b200 import metrics
+    g = _make_g(O, torch.bfloat16, "auto").eval()
+    x, t = O.synthetic_batch(4, 3, 128, 128, seed=99, blobby=True)
+    with torch.no_grad():
+        logits = g(x.cuda())
+    out, tar = logits[:, 1:].contiguous(), t[:, 1:].contiguous().cuda()
+    iou, dice = metrics.iou_score(out, tar), metrics.dice_coef(out, tar)
+    o = torch.sigmoid(out).cpu().numpy()          # metrics.py:10-13, 28-31
+    tt = tar.cpu().numpy()
+    inter, union = ((o > 0.5) & (tt > 0.5)).sum(), ((o > 0.5) | (tt > 0.5)).sum()
+    assert iou == (inter + 1e-5) / (union + 1e-5)                                  # bit-identical
+    ref_dice = (2. * (o.reshape(-1) * tt.reshape(-1)).sum() + 1e-5) / (o.sum() + tt.sum() + 1e-5)
+    assert abs(float(dice) - float(ref_dice)) < 2e-6 * abs(float(ref_dice))         # device expf vs torch.sigmoid: last-ulp probabilities
