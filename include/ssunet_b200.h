@@ -110,6 +110,11 @@ int ssg_conv2d_dgrad_tc(const void* dy, const void* w_packed, void* dx, int n, i
 int ssg_conv2d_wgrad_tc(const void* x0, int c0, const void* x1, int c1, const void* dy, int cout, float* dw_oihw, int cout_real,
                         int cin_real, int n, int h, int w, int ksize, int stride, int pad, ssg_stream_t s);
 
+/* Same, but dw_oihw is ACCUMULATED into (dw += ...) instead of overwritten: the caller passes the parameter's slot of the
+ * flat gradient arena (zeroed by zero_grad), which removes the per-layer memset, temporary and gradient-accumulation add. */
+int ssg_conv2d_wgrad_tc_acc(const void* x0, int c0, const void* x1, int c1, const void* dy, int cout, float* dw_oihw, int cout_real,
+                            int cin_real, int n, int h, int w, int ksize, int stride, int pad, ssg_stream_t s);
+
 /* ---- per-channel statistics / batch norm -------------------------------------------------- */
 /* batchnorm.py:59-64 (_sum_ft of x and x**2): sums[0:C] = sum x, sums[C:2C] = sum x^2 (fp64,
  * overwritten).  With with_sq == 0 only sums[0:C] is produced (bias gradients). */
@@ -159,6 +164,11 @@ int ssg_spade_modulate_fwd(const void* x, const void* gb, void* y, int dtype, lo
 /* dx_part = dy*(1+gamma); dgb = [dy*x, dy] */
 int ssg_spade_modulate_bwd(const void* dy, const void* x, const void* gb, void* dx, void* dgb, int dtype, long long rows,
                            int c, ssg_stream_t s);
+
+/* Same, and colsum[0:2C] (fp64, overwritten) = per-channel sums of the stored dgb = the bias gradients of the gamma | beta
+ * convolutions (normalization.py:97-98): saves the separate reduction pass over dgb.  C % 8 == 0 (bf16) / C % 4 == 0 (fp32). */
+int ssg_spade_modulate_bwd_sums(const void* dy, const void* x, const void* gb, void* dx, void* dgb, int dtype, long long rows,
+                                int c, double* colsum, ssg_stream_t s);
 
 /* ---- elementwise ---------------------------------------------------------------------------- */
 int ssg_act_fwd(const void* x, void* y, int dtype, long long n, int act, float slope, ssg_stream_t s);

@@ -49,11 +49,12 @@ def dgrad(dy, weight, dx, stride, pad):
          flops=_flops(n, dy.shape[2], dy.shape[3], cin, cout, k))
 
 
-def wgrad(x, dy, dw, stride, pad, x1=None):
-    """dW (OIHW fp32, real channel extents) on tensor cores from (possibly channel-padded) x and dy."""
+def wgrad(x, dy, dw, stride, pad, x1=None, accumulate=False):
+    """dW (OIHW fp32, real channel extents) on tensor cores from (possibly channel-padded) x and dy.
+    accumulate: dw += ... (dw is the parameter's slot of the flat gradient arena) instead of dw = ..."""
     n, c0, h, w = x.shape
     c1 = x1.shape[1] if x1 is not None else 0
     cout, cin, k, _ = dw.shape
-    call("ssg_conv2d_wgrad_tc", x, c0, x1, c1, dy, dy.shape[1], dw, cout, cin, n, h, w, k, stride, pad,
+    call("ssg_conv2d_wgrad_tc_acc" if accumulate else "ssg_conv2d_wgrad_tc", x, c0, x1, c1, dy, dy.shape[1], dw, cout, cin, n, h, w, k, stride, pad,
          flops=_flops(n, dy.shape[2], dy.shape[3], cin, cout, k))
     return True

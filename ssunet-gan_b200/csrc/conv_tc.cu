@@ -566,8 +566,21 @@ static int launch_wgrad(const CUtensorMap& x0, const CUtensorMap& x1, const CUte
 }  // namespace tc
 }  // namespace ssg
 
+static int wgrad_tc_impl(const void* x0, int c0, const void* x1, int c1, const void* dy, int cout, float* dw_oihw, int cout_real,
+                         int cin_real, int n, int h, int w, int ksize, int stride, int pad, bool accumulate, ssg_stream_t s);
+
 extern "C" int ssg_conv2d_wgrad_tc(const void* x0, int c0, const void* x1, int c1, const void* dy, int cout, float* dw_oihw,
                                    int cout_real, int cin_real, int n, int h, int w, int ksize, int stride, int pad, ssg_stream_t s) {
+    return wgrad_tc_impl(x0, c0, x1, c1, dy, cout, dw_oihw, cout_real, cin_real, n, h, w, ksize, stride, pad, false, s);
+}
+
+extern "C" int ssg_conv2d_wgrad_tc_acc(const void* x0, int c0, const void* x1, int c1, const void* dy, int cout, float* dw_oihw,
+                                       int cout_real, int cin_real, int n, int h, int w, int ksize, int stride, int pad, ssg_stream_t s) {
+    return wgrad_tc_impl(x0, c0, x1, c1, dy, cout, dw_oihw, cout_real, cin_real, n, h, w, ksize, stride, pad, true, s);
+}
+
+static int wgrad_tc_impl(const void* x0, int c0, const void* x1, int c1, const void* dy, int cout, float* dw_oihw, int cout_real,
+                         int cin_real, int n, int h, int w, int ksize, int stride, int pad, bool accumulate, ssg_stream_t s) {
     using namespace ssg;
     using namespace ssg::tc;
     SSG_CHECK_ARG(n > 0 && h > 0 && w > 0 && cout > 0 && cout % 8 == 0 && c0 > 0 && c0 % 8 == 0 && c1 >= 0 && c1 % 8 == 0 &&
@@ -579,7 +592,7 @@ extern "C" int ssg_conv2d_wgrad_tc(const void* x0, int c0, const void* x1, int c
     SSG_CHECK_ARG(oh > 0 && ow > 0, "conv2d_wgrad_tc: empty dy");
     const int taps = ksize * ksize;
     cudaStream_t st = (cudaStream_t)s;
-    SSG_CHECK_CUDA(cudaMemsetAsync(dw_oihw, 0, sizeof(float) * (size_t)cout_real * cin_real * taps, st));
+    if (!accumulate) SSG_CHECK_CUDA(cudaMemsetAsync(dw_oihw, 0, sizeof(float) * (size_t)cout_real * cin_real * taps, st));
     if (ksize == 3 && stride == 1 && pad == 1 && use_halo_kernel())
         return run_wgrad_halo(x0, c0, x1, c1, dy, cout, dw_oihw, cout_real, cin_real, n, h, w, st);
     int twl, thl;

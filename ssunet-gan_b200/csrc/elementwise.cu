@@ -62,6 +62,48 @@ __global__ void __launch_bounds__(256) spade_bwd_kernel(const T* __restrict__ dy
 }
 
 // 16-byte vector body + scalar tail (all buffers come from the torch allocator: 16-byte aligned bases)
+// Row-strided SPADE backward that also reduces the bias gradients of the gamma|beta convolution: a thread keeps ONE channel
+// vector for its whole life (like bn_*_rows), accumulates sum(dy*x) and sum(dy) of the bf16-ROUNDED values it stores, and the
+// block folds them through shared memory into fp64 colsum[2C] (pre-zeroed) -- the separate per-channel reduction pass over
+// dgb (2C channels, the largest tensor of the block) disappears.
+template <typename T>
+__global__ void __launch_bounds__(256) spade_bwd_rows_kernel(const T* __restrict__ dy, const T* __restrict__ x, const T* __restrict__ gb,
+                                                              T* __restrict__ dx, T* __restrict__ dgb, long long rows, int C,
+                                                              double* __restrict__ colsum) {
+    constexpr int V = Vec<T>::N;
+    extern __shared__ float sred[];            // [2C]
+    for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) sred[i] = 0.f;
+    __syncthreads();
+    const int lanes = C / V, rpb = 256 / lanes;
+    const int lane = threadIdx.x % lanes, rsub = threadIdx.x / lanes;
+    if (rsub < rpb) {
+        const long long rstride = (long long)gridDim.x * rpb;
+        const int c0 = lane * V;
+        float s_g[V], s_b[V];
+#pragma unroll
+        for (int k = 0; k < V; ++k) s_g[k] = s_b[k] = 0.f;
+        for (long long r = (long long)blockIdx.x * rpb + rsub; r < rows; r += rstride) {
+            Vec<T> vd, vx, vg;
+            vd.load(dy + r * C + c0); vx.load(x + r * C + c0); vg.load(gb + r * 2 * C + c0);
+            float fd[V], fx[V], fg[V], o1[V], o2[V];
+            vd.get(fd); vx.get(fx); vg.get(fg);
+#pragma unroll
+            for (int k = 0; k < V; ++k) { o1[k] = fd[k] * (1.f + fg[k]); o2[k] = fd[k] * fx[k]; }
+            Vec<T> v;
+            v.set(o1); v.store(dx + r * C + c0);
+            v.set(o2); v.store(dgb + r * 2 * C + c0);
+            v.get(o2);                                  // the rounded values, as the reduction pass would have read them
+            vd.store(dgb + r * 2 * C + C + c0);
+#pragma unroll
+            for (int k = 0; k < V; ++k) { s_g[k] += o2[k]; s_b[k] += fd[k]; }
+        }
+#pragma unroll
+        for (int k = 0; k < V; ++k) { atomicAdd(&sred[c0 + k], s_g[k]); atomicAdd(&sred[C + c0 + k], s_b[k]); }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) atomicAdd(&colsum[i], (double)sred[i]);
+}
+
 template <typename T>
 __global__ void __launch_bounds__(256) act_fwd_kernel(const T* __restrict__ x, T* __restrict__ y, long long n, int act, float slope, int vec_ok) {
     constexpr int V = Vec<T>::N;
@@ -200,6 +242,22 @@ int ssg_spade_modulate_bwd(const void* dy, const void* x, const void* gb, void* 
     SSG_DISPATCH_DTYPE(dtype, {
         if (c % Vec<T>::N == 0) spade_bwd_kernel<T, true><<<grid_for(rows * c / Vec<T>::N, 256), 256, 0, (cudaStream_t)s>>>((const T*)dy, (const T*)x, (const T*)gb, (T*)dx, (T*)dgb, rows, c);
         else spade_bwd_kernel<T, false><<<grid_for(rows * c, 256), 256, 0, (cudaStream_t)s>>>((const T*)dy, (const T*)x, (const T*)gb, (T*)dx, (T*)dgb, rows, c);
+    });
+    SSG_CHECK_LAUNCH();
+    return SSG_OK;
+}
+int ssg_spade_modulate_bwd_sums(const void* dy, const void* x, const void* gb, void* dx, void* dgb, int dtype, long long rows, int c,
+                                double* colsum, ssg_stream_t s) {
+    SSG_CHECK_ARG(rows > 0 && c > 0 && colsum, "spade_modulate_bwd_sums: bad arguments");
+    SSG_CHECK_CUDA(cudaMemsetAsync(colsum, 0, sizeof(double) * 2 * (size_t)c, (cudaStream_t)s));
+    SSG_DISPATCH_DTYPE(dtype, {
+        constexpr int V = Vec<T>::N;
+        SSG_CHECK_ARG(c % V == 0 && c / V <= 256, "spade_modulate_bwd_sums: C=%d unsupported", c);
+        const int rpb = 256 / (c / V);
+        long long b = (rows + rpb - 1) / rpb, cap = (long long)sm_count_cached() * 8;
+        if (b > cap) b = cap;
+        spade_bwd_rows_kernel<T><<<(unsigned)b, 256, sizeof(float) * 2 * c, (cudaStream_t)s>>>((const T*)dy, (const T*)x, (const T*)gb, (T*)dx,
+                                                                                               (T*)dgb, rows, c, colsum);
     });
     SSG_CHECK_LAUNCH();
     return SSG_OK;

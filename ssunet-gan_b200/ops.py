@@ -227,11 +227,13 @@ class _Conv2d(torch.autograd.Function):
         cout, cin, kh, kw = weight.shape
         cout_s = dy.shape[1]
         dt = x.dtype
+        colsum = getattr(dy, "_ssg_colsum", None)      # per-channel sums of dy already reduced by its producer (SPADE backward)
         dy = _as_storage(dy, dt)
         if act != ACT_NONE:
             dz = torch.empty_like(dy)
             call("ssg_act_bwd", dy, y, dz, dtype_code(dt), dy.numel(), act, slope)
             dy = dz
+            colsum = None
         dx = dw = db = None
         if use_tc:
             from . import conv_tc
@@ -243,15 +245,27 @@ class _Conv2d(torch.autograd.Function):
                 wp = packed_weight(weight, W_RSKC, dt)
                 call("ssg_conv2d_dgrad_simt", dy, wp, dx, dtype_code(dt), n, h, w, cin, cout, kh, kw, stride, pad)
         if ctx.needs_input_grad[1]:
-            dw = torch.empty_like(weight, dtype=torch.float32)
-            if use_tc:
+            slot = weight.grad if weight.is_leaf else None
+            if (use_tc and slot is not None and getattr(slot, "_ssg_arena", None) is not None and slot.dtype == torch.float32
+                    and slot.is_contiguous() and not torch.is_grad_enabled()):
+                # the parameter's gradient lives in the optimiser's flat arena (optim.FusedClampAdam, zeroed by zero_grad):
+                # the tensor-core kernel adds straight into it -- no memset, no temporary, no accumulation kernel.  Autograd
+                # gets None for this input (its AccumulateGrad node has nothing left to do).
+                conv_tc.wgrad(x, dy, slot, stride, pad, accumulate=True)
+                dw = None
+            elif use_tc:
+                dw = torch.empty_like(weight, dtype=torch.float32)
                 conv_tc.wgrad(x, dy, dw, stride, pad)
             else:
+                dw = torch.empty_like(weight, dtype=torch.float32)
                 call("ssg_conv2d_wgrad_simt", x, dy, dw, dtype_code(dt), n, h, w, cin, cout, kh, kw, stride, pad)
         if has_bias and ctx.needs_input_grad[2]:
-            sums = torch.empty(2 * cout_s, dtype=torch.float64, device=x.device)
-            call("ssg_channel_stats", dy, dtype_code(dt), _rows(dy), cout_s, sums, 0)
-            db = sums[:cout].float()
+            if colsum is not None and colsum.numel() == cout_s:
+                db = colsum[:cout].float()
+            else:
+                sums = torch.empty(2 * cout_s, dtype=torch.float64, device=x.device)
+                call("ssg_channel_stats", dy, dtype_code(dt), _rows(dy), cout_s, sums, 0)
+                db = sums[:cout].float()
         return dx, dw, db, None, None, None, None, None, None
 
 
@@ -550,7 +564,14 @@ class _SpadeModulate(torch.autograd.Function):
         dy = _as_storage(dy, x.dtype)
         dx = empty_nhwc(n, c, h, w, x.dtype, x.device)
         dgb = empty_nhwc(n, 2 * c, h, w, x.dtype, x.device)
-        call("ssg_spade_modulate_bwd", dy, x, gb, dx, dgb, dtype_code(x.dtype), _rows(x), c)
+        vec = 8 if x.dtype == torch.bfloat16 else 4
+        if c % vec == 0 and c // vec <= 256:
+            # the bias gradients of the gamma | beta convolution ride along: `_Conv2d.backward` finds them on the tensor
+            colsum = torch.empty(4 * c, dtype=torch.float64, device=x.device)[:2 * c]
+            call("ssg_spade_modulate_bwd_sums", dy, x, gb, dx, dgb, dtype_code(x.dtype), _rows(x), c, colsum)
+            dgb._ssg_colsum = colsum
+        else:
+            call("ssg_spade_modulate_bwd", dy, x, gb, dx, dgb, dtype_code(x.dtype), _rows(x), c)
         return dx, dgb
 
 
