@@ -291,6 +291,16 @@ long long ssg_p2p_buffer_bytes(int world, int slot_len);
 int ssg_p2p_allreduce_f64(double* data, int n, void* const* peer_bufs_dev, int rank, int world, int slot_len, unsigned* epoch_dev,
                           ssg_stream_t s);
 
+/* ---- tiled inference merge (aerial_image_segmentation_api.py:129-217) ------------------------------ */
+/* values: fp32 [patches][classes][patch_size][patch_size] (NCHW logits with apply_sigmoid != 0, else probabilities in
+ * [0, 1]); windows: int32 [patches][2] = (top, left) of each patch in the h x w raster.  Adds, per class and pixel, one
+ * vote when (uint8)(p * 255) > 127 into pos_votes int32 [classes][h][w], and 1 into patch_count int32 [h][w] (both must be
+ * zeroed by the caller before the first batch; batches accumulate). */
+int ssg_mask_vote(const float* values, const int* windows, int patches, int classes, int patch_size, int h, int w, int apply_sigmoid,
+                  int* pos_votes, int* patch_count, ssg_stream_t s);
+/* masks uint8 [classes][h][w] = post_process((uint8)(votes / max(count, 1) * 255)) in {0, 255}, fp64 arithmetic as numpy */
+int ssg_mask_finalize(const int* pos_votes, const int* patch_count, int classes, int h, int w, unsigned char* masks, ssg_stream_t s);
+
 #ifdef __cplusplus
 }
 #endif

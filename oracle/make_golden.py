@@ -258,9 +258,41 @@ def efficientnet_golden():
     print("efficientnet.npz: %d bytes, %d arrays" % (os.path.getsize(os.path.join(OUT, "efficientnet.npz")), len(out)))
 
 
+def tiles_golden():
+    """patch_gen / patch_merge of the unmodified aerial_image_segmentation_api.py on a synthetic 150 x 200 raster."""
+    import types
+    for name in ("albumentations", "albumentations.augmentations", "albumentations.augmentations.transforms",
+                 "albumentations.core", "albumentations.core.composition", "tensorboardX", "torchsummary"):
+        sys.modules.setdefault(name, types.ModuleType(name))
+    sys.modules["albumentations.core.composition"].Compose = object
+    sys.modules["albumentations.core.composition"].OneOf = object
+    sys.modules["albumentations.augmentations"].transforms = sys.modules["albumentations.augmentations.transforms"]
+    sys.modules["tensorboardX"].SummaryWriter = object
+    sys.modules["torchsummary"].summary = lambda *a, **k: None
+    import aerial_image_segmentation_api as api
+    rng = np.random.RandomState(7)
+    H, W, P, C, OV = 150, 200, 64, 3, 0.5
+    img = rng.randint(0, 255, size=(H, W, 3)).astype("uint8")
+    patches, _ = api.patch_gen(img, img, P, OV)
+    # window order: recover (h1, w1) of every patch from a coordinate image
+    coord = np.stack(list(np.meshgrid(np.arange(H), np.arange(W), indexing="ij")) + [np.zeros((H, W), dtype=int)], -1)
+    cp, _ = api.patch_gen(coord, coord, P, OV)
+    wins = np.array([[p[0, 0, 0], p[0, 0, 1]] for p in cp], dtype=np.int32)
+    # smooth probability maps (values near the 127 threshold included)
+    base = rng.rand(len(patches), C, P // 8, P // 8).astype("float32")
+    probs = O.tile_test_probs(base)
+    merged = api.patch_merge(img, [p for p in probs], P, {"num_classes": C}, OV)
+    np.savez_compressed(os.path.join(OUT, "tiles_merge_150x200.npz"), windows=wins, base=base, merged=np.stack(merged),
+                        n_patches=np.int64(len(patches)), probs_csum=np.float64(probs.astype(np.float64).sum()))
+    print("tiles_merge_150x200.npz: %d patches, %d bytes" % (len(patches), os.path.getsize(os.path.join(OUT, "tiles_merge_150x200.npz"))))
+
+
 if __name__ == "__main__":
-    if len(sys.argv) > 1 and sys.argv[1] == "efficientnet":
+    if len(sys.argv) > 1 and sys.argv[1] == "tiles":
+        tiles_golden()
+    elif len(sys.argv) > 1 and sys.argv[1] == "efficientnet":
         efficientnet_golden()
     else:
         main()
         efficientnet_golden()
+        tiles_golden()

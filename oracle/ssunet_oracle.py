@@ -601,6 +601,60 @@ def attentive_cnn(sd, images, model_name="efficientnet-b2", training=True):
 
 
 # --------------------------------------------------------------------------------------
+# Tiled inference merge (aerial_image_segmentation_api.py:30-217), numpy like the reference
+# --------------------------------------------------------------------------------------
+def tile_windows(img_h, img_w, p_size, overlap):
+    """(h1, w1) per patch in the order patch_gen / patch_merge visit them (:45-126, :141-205)."""
+    step = int(math.ceil((1 - overlap) * p_size))
+    i_w = int(math.floor((img_w - p_size) / step)) + 1
+    i_h = int(math.floor((img_h - p_size) / step)) + 1
+    grid = [(i, j) for i in range(i_w) for j in range(i_h)]
+    wins = [(j * step, i * step) for i, j in grid]
+    wins += [(img_h - j * step - p_size, img_w - i * step - p_size) for i, j in grid]
+    wins += [(img_h - j * step - p_size, i * step) for i, j in grid]
+    wins += [(j * step, img_w - i * step - p_size) for i, j in grid]
+    return wins
+
+
+def tile_test_probs(base):
+    """Deterministic probability maps for the merge fixtures from a coarse [P, C, s, s] float32 seed: x8 block upsampling
+    plus an integer ripple (exact float32 arithmetic only, so generator and tests rebuild identical bits)."""
+    base = np.asarray(base, dtype=np.float32)
+    P, C, s, _ = base.shape
+    up = np.repeat(np.repeat(base, 8, axis=2), 8, axis=3)
+    p = np.arange(P, dtype=np.int64).reshape(P, 1, 1, 1)
+    c = np.arange(C, dtype=np.int64).reshape(1, C, 1, 1)
+    y = np.arange(8 * s, dtype=np.int64).reshape(1, 1, -1, 1)
+    x = np.arange(8 * s, dtype=np.int64).reshape(1, 1, 1, -1)
+    ripple = ((y * 7 + x * 13 + p * 3 + c * 5) % 32).astype(np.float32) / np.float32(128)
+    return np.clip(up * np.float32(0.75) + ripple, np.float32(0), np.float32(1)).astype(np.float32)
+
+
+def _threshold127(m):
+    """post_process_resized_mask (:30-42)."""
+    m = m.copy()
+    m[(m > 127) & (m < 255)] = 255
+    m[(m > 0) & (m <= 127)] = 0
+    return m
+
+
+def tile_merge(img_h, img_w, masks, p_size, num_classes, overlap):
+    """patch_merge (:129-217) for maps whose size equals the patch size (cv2.resize is then the identity)."""
+    wins = tile_windows(img_h, img_w, p_size, overlap)
+    out = []
+    for c in range(num_classes):
+        merged = np.zeros((img_h, img_w))
+        div = np.zeros((img_h, img_w))
+        for (h1, w1), m in zip(wins, masks):
+            u8 = (np.asarray(m[c]) * 255).astype("uint8")
+            merged[h1:h1 + p_size, w1:w1 + p_size] += _threshold127(u8) / 255.0
+            div[h1:h1 + p_size, w1:w1 + p_size] += 1.0
+        div[div == 0] = 1.0
+        out.append(_threshold127((np.divide(merged, div) * 255).astype("uint8")))
+    return out
+
+
+# --------------------------------------------------------------------------------------
 # bf16-storage emulation of the generator forward (what an ideal bf16 implementation computes)
 # --------------------------------------------------------------------------------------
 def _q(t):

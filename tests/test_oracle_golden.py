@@ -238,3 +238,17 @@ def test_attentive_cnn_b2_matches_reference(golden_dir):
     y = O.attentive_cnn(sd, img, "efficientnet-b2", False)
     assert tuple(y.shape) == (1, 1024, 8, 8)          # 260 -> 130 -> 65 -> 32 -> 16 -> 8 (static pads from the nominal size)
     _close(y.numpy(), z["att_b2:y_eval"], rtol=1e-3, atol=1e-5)
+
+
+def test_tile_windows_and_merge_match_reference(golden_dir):
+    """patch_gen's window order and patch_merge's uint8 masks (aerial_image_segmentation_api.py:45-217)."""
+    z = np.load(os.path.join(golden_dir, "tiles_merge_150x200.npz"))
+    H, W, P, C, OV = 150, 200, 64, 3, 0.5
+    wins = O.tile_windows(H, W, P, OV)
+    assert len(wins) == int(z["n_patches"]) == 60
+    assert np.array_equal(np.array(wins, dtype=np.int32), z["windows"])
+    probs = O.tile_test_probs(z["base"])
+    assert float(probs.astype(np.float64).sum()) == float(z["probs_csum"])
+    merged = O.tile_merge(H, W, list(probs), P, C, OV)
+    assert np.array_equal(np.stack(merged), z["merged"])                 # bit-identical uint8 masks
+    assert set(np.unique(z["merged"])) <= {0, 255} and 0.2 < (z["merged"] == 255).mean() < 0.8
