@@ -264,7 +264,7 @@ def main():
     # roofline leg: the dominant kernels (tcgen05 convolutions) timed one by one with CUDA events on the launching stream,
     # live, over eager steps of the same workload (a captured graph cannot carry per-kernel events)
     prof_steps = 2
-    PROF = ["ssg_conv2d_fwd_tc", "ssg_conv2d_dgrad_tc", "ssg_conv2d_wgrad_tc"]
+    PROF = ["ssg_conv2d_fwd_tc", "ssg_conv2d_dgrad_tc", "ssg_conv2d_wgrad_tc", "ssg_conv2d_wgrad_tc_acc"]
     train_step.gan_train_step(g, d, og, od, dev[0][0], dev[0][1], with_metrics=False)
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -351,7 +351,14 @@ def main():
         roof.update({"achieved": ach, "frac": ach / peak_tf, "launches": prof["n"], "kernel_ms_per_step": prof["ms"] / prof_steps,
                      "share_of_step": prof["ms"] / ms_prof,
                      "how": "CUDA events around every tcgen05 conv launch over %d eager steps; achieved = algorithmic conv FLOPs (2*MACs, "
-                            "unpadded channels) / summed launch time" % prof_steps})
+                            "unpadded channels) / summed launch time" % prof_steps,
+                     "by_entry_point": {k: {"tflops": round(v["flops"] / (v["ms"] / 1e3) / 1e12, 1) if v["ms"] > 0 else None,
+                                            "ms_per_step": round(v["ms"] / prof_steps, 3), "launches_per_step": v["n"] // prof_steps}
+                                        for k, v in sorted(prof.get("by_name", {}).items())},
+                     # one `ncu --set full` capture of the most frequent instance (profiles/r01_ncu_halo_conv_l0_fwd.txt):
+                     # conv0_0.conv2 forward, 16 x 512^2 x 64 -> 64: DRAM bytes vs the algorithmic read-x-once + write-y-once
+                     "traffic_example": {"kernel": "conv_tc_halo_kernel<2,64,2,RES> (conv0_0.conv2 fwd)", "dram_bytes": 1.0277e9,
+                                         "algorithmic_bytes": 1.0737e9}})
     step_tf = STEP_GFLOP_512 * 1e9 * scale * world * batch * args.steps / (ms / 1e3) / 1e12
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",

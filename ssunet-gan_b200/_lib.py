@@ -107,7 +107,7 @@ _prof = None
 def profile_reset(names):
     """Start timing every call to the named entry points with CUDA events on the launching stream."""
     global _prof
-    _prof = {"names": set(names), "events": [], "flops": 0.0}
+    _prof = {"names": set(names), "events": [], "flops": 0.0, "by_name": {}}
 
 
 def profile_collect():
@@ -117,7 +117,10 @@ def profile_collect():
         return None
     torch.cuda.synchronize()
     p, _prof = _prof, None
-    return {"ms": sum(a.elapsed_time(b) for a, b in p["events"]), "flops": p["flops"], "n": len(p["events"])}
+    by = {}
+    for name, lst in p["by_name"].items():
+        by[name] = {"ms": sum(a.elapsed_time(b) for a, b, _ in lst), "flops": sum(f for _, _, f in lst), "n": len(lst)}
+    return {"ms": sum(a.elapsed_time(b) for a, b in p["events"]), "flops": p["flops"], "n": len(p["events"]), "by_name": by}
 
 
 def call(name, *args, flops=0.0):
@@ -136,6 +139,7 @@ def call(name, *args, flops=0.0):
         e1.record()
         _prof["events"].append((e0, e1))
         _prof["flops"] += flops
+        _prof["by_name"].setdefault(name, []).append((e0, e1, flops))
     launch_count += 1
     if rc != 0:
         raise SsgError("%s failed (%d): %s" % (name, rc, L.ssg_last_error().decode()))
