@@ -207,6 +207,8 @@ int run_conv_halo(const void* x0, int c0, const void* x1, int c1, const void* w_
                   void* y, int n, int h, int w, int gemm_n, int ksize, int flip, int act, float slope, double* stats, cudaStream_t st);
 int run_wgrad_halo(const void* x0, int c0, const void* x1, int c1, const void* dy, int cout_s, float* dw, int cout_real, int cin_real,
                    int n, int h, int w, cudaStream_t st);
+int run_wgrad_thin(const void* x, const void* dy, int cout_s, float* dw, int cout_real, int cin_real, int n, int h, int w,
+                   cudaStream_t st);
 int encode_bf16_map(CUtensorMap* map, const void* ptr, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
                     const uint32_t* box, CUtensorMapSwizzle swizzle, const uint32_t* elem_strides);
 
@@ -593,6 +595,9 @@ static int wgrad_tc_impl(const void* x0, int c0, const void* x1, int c1, const v
     const int taps = ksize * ksize;
     cudaStream_t st = (cudaStream_t)s;
     if (!accumulate) SSG_CHECK_CUDA(cudaMemsetAsync(dw_oihw, 0, sizeof(float) * (size_t)cout_real * cin_real * taps, st));
+    static const bool no_thin = getenv("SSG_NO_THIN_WGRAD") != nullptr;
+    if (ksize == 3 && stride == 1 && pad == 1 && c0 == 8 && c1 == 0 && !no_thin)      // image stems, SPADE's 8-channel maps
+        return run_wgrad_thin(x0, dy, cout, dw_oihw, cout_real, cin_real, n, h, w, st);
     if (ksize == 3 && stride == 1 && pad == 1 && use_halo_kernel())
         return run_wgrad_halo(x0, c0, x1, c1, dy, cout, dw_oihw, cout_real, cin_real, n, h, w, st);
     int twl, thl;

@@ -628,5 +628,168 @@ int run_wgrad_halo(const void* x0, int c0, const void* x1, int c1, const void* d
     return SSG_OK;
 }
 
+// =====================================================================================================
+// Thin-input weight gradient (3x3, stride 1, same size, x stored with 8 channels: image stems, SPADE's label / hidden
+// maps).  The halo kernel above spends an M = 128 accumulator on two taps x 64 input channels, 56 of which are zero
+// fill here -- five MMAs per 16 pixels for 8 live channels.  This kernel puts ALL nine taps into one accumulator:
+//   D[m = tap * 8 + ci][n = co] += A^T B,   K = pixels,
+// with the A operand assembled as an im2col image in shared memory by nine small TMA boxes {8 ch, 8 w, 16 h} (one per
+// tap, shifted by the tap offset, zero-filled outside the image): 128 pixels x 16 B = 2048 B per tap.  Eight consecutive
+// pixels x 16 B are exactly one no-swizzle MN-major core matrix (8 K-rows of 8 contiguous M elements), so the UMMA
+// descriptor is: no swizzle, LBO (K direction) = 128 B, SBO (M direction) = 2048 B (semantics verified on B200 by
+// scratch/nosw_test.cu).  Groups 9..15 of M read whatever follows in shared memory; their accumulator rows are never
+// stored.  B = dy box(es) {64 ch, 8, 16} SWIZZLE_128B MN-major as in the halo kernel (two boxes for a 128-wide co tile,
+// reached through the LBO).  One MMA per 16 pixels instead of five; x traffic 18 KB instead of a 23 KB zero-filled halo.
+// =====================================================================================================
+constexpr int TW_STAGES = 4;
+constexpr int TW_A_BYTES = 9 * 2048;
+constexpr int TW_A_REGION = ((TW_STAGES * TW_A_BYTES + 7 * 2048 + 1023) / 1024) * 1024;   // + readable tail for M groups 9..15
+
+struct ThinWgradParams {
+    float* dw;                   // OIHW fp32 [cout][cin][3][3], accumulated into
+    int N, H, W;
+    int cout, cin;               // real channel extents of dw
+    int tiles_x, tiles_y, m_tiles;
+};
+
+template <int BN>
+__global__ void __launch_bounds__(H_THREADS, 1) conv_tc_thin_wgrad_kernel(const __grid_constant__ CUtensorMap tmX,
+                                                                           const __grid_constant__ CUtensorMap tmDY,
+                                                                           const ThinWgradParams p) {
+    constexpr int DY_BYTES = BN * 256;                 // 128 pixels x BN channels x 2 B
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* s_a = smem;
+    uint8_t* s_dy = smem + TW_A_REGION;
+    uint64_t* full = reinterpret_cast<uint64_t*>(s_dy + TW_STAGES * DY_BYTES);
+    uint64_t* empty = full + TW_STAGES;
+    uint64_t* acc_full = empty + TW_STAGES;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_full + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int co0 = blockIdx.x * BN;
+    const int tiles_per_img = p.tiles_x * p.tiles_y;
+    const int n_iter = (p.m_tiles - (int)blockIdx.y + (int)gridDim.y - 1) / (int)gridDim.y;
+
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < TW_STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+        mbar_init(acc_full, 1);
+        fence_barrier_init();
+    }
+    if (warp == 2) tmem_alloc(tmem_slot, BN < 32 ? 32 : BN);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
+
+    if (warp == 0) {
+        if (lane == 0) {
+            tma_prefetch_desc(&tmX);
+            tma_prefetch_desc(&tmDY);
+            for (int it = 0; it < n_iter; ++it) {
+                const int t = blockIdx.y + it * gridDim.y;
+                const int img = t / tiles_per_img, rem = t - img * tiles_per_img;
+                const int ty = rem / p.tiles_x, tx = rem - ty * p.tiles_x;
+                const int sl = it % TW_STAGES;
+                mbar_wait(&empty[sl], ((it / TW_STAGES) & 1) ^ 1);
+                mbar_expect_tx(&full[sl], TW_A_BYTES + DY_BYTES);
+                uint8_t* a_dst = s_a + sl * TW_A_BYTES;
+#pragma unroll
+                for (int tap = 0; tap < 9; ++tap)
+                    tma_load_4d(a_dst + tap * 2048, &tmX, 0, tx * H_TW + tap % 3 - 1, ty * H_TH + tap / 3 - 1, img, &full[sl]);
+#pragma unroll
+                for (int hb = 0; hb < BN / 64; ++hb)
+                    tma_load_4d(s_dy + sl * DY_BYTES + hb * 16384, &tmDY, co0 + hb * 64, tx * H_TW, ty * H_TH, img, &full[sl]);
+            }
+        }
+    } else if (warp == 2) {
+        constexpr uint32_t idesc = make_idesc_bf16(128, BN, 1, 1);     // both operands MN-major
+        const uint32_t leader = elect_one() ? 1u : 0u;
+        const uint32_t a_hi = desc_hi(2048, 0), dy_hi = desc_hi(1024, 2);
+        const uint32_t a_lo_base = desc_lo(smem_u32(s_a), 128);
+        const uint32_t dy_lo_base = desc_lo(smem_u32(s_dy), 16384);    // LBO: second 64-channel box of a 128-wide co tile
+        for (int it = 0; it < n_iter; ++it) {
+            const int sl = it % TW_STAGES;
+            mbar_wait(&full[sl], (it / TW_STAGES) & 1);
+            tc_fence_after();
+            const uint32_t ak = a_lo_base + (uint32_t)(sl * (TW_A_BYTES / 16));
+            const uint32_t dk = dy_lo_base + (uint32_t)(sl * (DY_BYTES / 16));
+            const uint32_t keep = (uint32_t)it;
+#pragma unroll
+            for (int k = 0; k < 8; ++k)            // 16 pixels per MMA: A advances 2 core matrices (256 B), dy 16 rows (2048 B)
+                umma_bf16_lohi_pred(tmem_base, ak + (uint32_t)(k * 16), a_hi, dk + (uint32_t)(k * 128), dy_hi, idesc, k == 0 ? keep : 1u, leader);
+            umma_commit_pred(&empty[sl], leader);
+        }
+        umma_commit_pred(acc_full, leader);
+    } else if (warp >= 4) {
+        const int q = warp & 3;
+        const int row = q * 32 + lane;                  // accumulator row = tap * 8 + ci
+        const int tap = row >> 3, ci = row & 7;
+        mbar_wait(acc_full, 0);
+        tc_fence_after();
+        if (n_iter > 0 && q < 3) {                      // rows 96..127 hold nothing
+            const bool row_ok = tap < 9 && ci < p.cin;
+#pragma unroll 1
+            for (int c0 = 0; c0 < BN; c0 += 32) {
+                uint32_t v[32];
+                tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
+                tmem_ld_wait();
+                if (!row_ok) continue;
+                float* dst = p.dw + ((long long)(co0 + c0) * p.cin + ci) * 9 + tap;
+#pragma unroll
+                for (int j = 0; j < 32; ++j)
+                    if (co0 + c0 + j < p.cout) atomicAdd(dst + (long long)j * p.cin * 9, __uint_as_float(v[j]));
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) tmem_dealloc(tmem_base, BN < 32 ? 32 : BN);
+}
+
+template <int BN>
+static int launch_thin_wgrad(const CUtensorMap& mx, const CUtensorMap& mdy, const ThinWgradParams& p, int co_tiles, cudaStream_t st) {
+    constexpr int TOTAL = TW_A_REGION + TW_STAGES * BN * 256 + 256 + 1024;
+    static_assert(TOTAL <= 227 * 1024, "shared memory budget");
+    static bool attr_set = false;
+    if (!attr_set) {
+        SSG_CHECK_CUDA(cudaFuncSetAttribute(conv_tc_thin_wgrad_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, TOTAL));
+        attr_set = true;
+    }
+    int splits = (2 * sm_count_cached() + co_tiles - 1) / co_tiles;      // ~two waves of CTAs
+    if (splits > p.m_tiles) splits = p.m_tiles;
+    if (splits < 1) splits = 1;
+    dim3 grid((unsigned)co_tiles, (unsigned)splits);
+    conv_tc_thin_wgrad_kernel<BN><<<grid, H_THREADS, TOTAL, st>>>(mx, mdy, p);
+    SSG_CHECK_LAUNCH();
+    return SSG_OK;
+}
+
+// x: stored with exactly 8 channels; dy: stored channels cout_s.  dw is accumulated into (zeroed by the caller when needed).
+int run_wgrad_thin(const void* x, const void* dy, int cout_s, float* dw, int cout_real, int cin_real, int n, int h, int w,
+                   cudaStream_t st) {
+    ThinWgradParams p;
+    memset(&p, 0, sizeof(p));
+    p.dw = dw; p.N = n; p.H = h; p.W = w; p.cout = cout_real; p.cin = cin_real;
+    p.tiles_x = (w + H_TW - 1) / H_TW; p.tiles_y = (h + H_TH - 1) / H_TH; p.m_tiles = n * p.tiles_x * p.tiles_y;
+    CUtensorMap mx, mdy;
+    {
+        uint64_t dims[4] = {8, (uint64_t)w, (uint64_t)h, (uint64_t)n};
+        uint64_t str[3] = {16, (uint64_t)w * 16, (uint64_t)h * w * 16};
+        uint32_t box[4] = {8, H_TW, H_TH, 1};
+        int rc = encode_bf16_map(&mx, x, 4, dims, str, box, CU_TENSOR_MAP_SWIZZLE_NONE, nullptr);
+        if (rc) return rc;
+    }
+    {
+        uint64_t dims[4] = {(uint64_t)cout_s, (uint64_t)w, (uint64_t)h, (uint64_t)n};
+        uint64_t str[3] = {(uint64_t)cout_s * 2, (uint64_t)w * cout_s * 2, (uint64_t)h * w * cout_s * 2};
+        uint32_t box[4] = {64, H_TW, H_TH, 1};
+        int rc = encode_bf16_map(&mdy, dy, 4, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B, nullptr);
+        if (rc) return rc;
+    }
+    if (cout_real > 64) return launch_thin_wgrad<128>(mx, mdy, p, (cout_real + 127) / 128, st);
+    return launch_thin_wgrad<64>(mx, mdy, p, (cout_real + 63) / 64, st);
+}
+
 }  // namespace tc
 }  // namespace ssg
