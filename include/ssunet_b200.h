@@ -153,6 +153,15 @@ int ssg_gather2x2(const void* src, const uint8_t* code, void* dst, int dtype, in
 /* nn.Upsample(scale_factor=2, bilinear, align_corners=True) (archs.py:573,664,667) and adjoint */
 int ssg_upsample2x_fwd(const void* x, void* y, int dtype, int n, int h, int w, int c, ssg_stream_t s);
 int ssg_upsample2x_bwd(const void* dy, void* dx, int dtype, int n, int h, int w, int c, ssg_stream_t s);
+/* nn.Upsample(scale_factor=2) (default mode 'nearest'; up_conv, archs.py:848-861) and adjoint (sum of the 2x2 block);
+ * x / dx [n,h,w,c], y / dy [n,2h,2w,c] */
+int ssg_upsample_nearest2x_fwd(const void* x, void* y, int dtype, int n, int h, int w, int c, ssg_stream_t s);
+int ssg_upsample_nearest2x_bwd(const void* dy, void* dx, int dtype, int n, int h, int w, int c, ssg_stream_t s);
+/* Attention gate (Attention_block.forward, archs.py:136-142): y[r,:] = x[r,:] * sigmoid(z[r]); z is the [rows] output of
+ * psi's BatchNorm2d(1).  Backward: dx = dy * s, dz[r] = s (1 - s) * sum_c dy[r,c] x[r,c]. */
+int ssg_pixel_gate_fwd(const void* x, const void* z, void* y, int dtype, long long rows, int c, ssg_stream_t s);
+int ssg_pixel_gate_bwd(const void* dy, const void* x, const void* z, void* dx, void* dz, int dtype, long long rows, int c,
+                       ssg_stream_t s);
 /* nn.AdaptiveAvgPool2d((oh,ow)) + view(batch,-1) (models_seg_gan.py:277,295-296): y is [n, c*oh*ow] in the
  * reference's NCHW flatten order (channel-major). */
 int ssg_adaptive_avgpool_flat_fwd(const void* x, void* y, int dtype, int n, int h, int w, int c, int oh, int ow, ssg_stream_t s);
@@ -225,6 +234,12 @@ int ssg_clamp_adam(float* p, float* g, float* m, float* v, long long n, float lr
  * captured in a CUDA graph and replayed. */
 int ssg_clamp_adam_dev(float* p, float* g, float* m, float* v, long long n, float lr, float beta1, float beta2, float eps,
                        float* step_dev, float clip, float grad_scale, ssg_stream_t s);
+/* Both with torch.optim.Adam's L2 `weight_decay` (train.py:290, config "weight_decay"): the moments see g + wd * p, the stored
+ * gradient stays the clamped one. */
+int ssg_clamp_adam_wd(float* p, float* g, float* m, float* v, long long n, float lr, float beta1, float beta2, float eps,
+                      float bias_corr1, float bias_corr2, float clip, float grad_scale, float weight_decay, ssg_stream_t s);
+int ssg_clamp_adam_wd_dev(float* p, float* g, float* m, float* v, long long n, float lr, float beta1, float beta2, float eps,
+                          float* step_dev, float clip, float grad_scale, float weight_decay, ssg_stream_t s);
 
 /* ---- spectral norm (spectral_norm.py:38-88) ---------------------------------------------------- */
 /* One power iteration on W [rows, cols] fp32: v = normalize(W^T u); u = normalize(W v); sigma = u.(W v).

@@ -1,0 +1,200 @@
+"""CPU oracle for the rest of the reference's model zoo (TEST INFRASTRUCTURE ONLY).
+
+Functional restatement, in plain CPU PyTorch fp32 on flat ``state_dict`` mappings, of the seven
+`archs.__all__` networks other than UNet_R_SS_v2 (which lives in ssunet_oracle.py) plus ProgUNet.
+Only tests/ may import this file.  Pinned against the unmodified reference by
+oracle/make_golden_archs.py -> tests/golden/archs_*.npz / archs_layout.json, checked by
+tests/test_oracle_golden.py::test_arch_zoo_oracle_matches_reference.
+
+All file:line citations are relative to /root/reference/scripts/.
+"""
+from __future__ import annotations
+
+import json
+import os
+
+import torch
+import torch.nn.functional as F
+
+import ssunet_oracle as O
+
+ARCHS = ("UNet", "NestedUNet", "SSUNet", "UNet_ori", "UNet_B_SS", "AttUNet", "UNet_R_SS")   # archs.py:8 minus UNet_R_SS_v2
+GOLDEN = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden")
+
+
+def arch_spec(name, deep_supervision=False):
+    """[(key, shape)] of `archs.<name>(3, 3, deep_supervision).state_dict()` in registration order, as recorded from the
+    reference by make_golden_archs.py."""
+    lay = json.load(open(os.path.join(GOLDEN, "archs_layout.json")))
+    return [(k, tuple(s)) for k, s in lay[name + ("_ds" if deep_supervision else "")]]
+
+
+def _conv_bn(sd, pc, pb, x, training, stride=1, pad=0):
+    y = F.conv2d(x, sd[pc + ".weight"], sd.get(pc + ".bias"), stride, pad)
+    return O.batch_norm(sd, pb, y, training)
+
+
+def vgg_block(sd, p, x, training=True):
+    """archs.py:103-112."""
+    out = F.relu(_conv_bn(sd, p + ".conv1", p + ".bn1", x, training, pad=1))
+    return F.relu(_conv_bn(sd, p + ".conv2", p + ".bn2", out, training, pad=1))
+
+
+def bottleneck(sd, p, x, training=True):
+    """archs.py:263-269."""
+    out = F.relu(_conv_bn(sd, p + ".conv1", p + ".bn1", x, training))
+    out = F.relu(_conv_bn(sd, p + ".conv2", p + ".bn2", out, training, pad=1))
+    out = _conv_bn(sd, p + ".conv3", p + ".bn3", out, training)
+    if p + ".shortcut.0.weight" in sd:
+        sc = _conv_bn(sd, p + ".shortcut.0", p + ".shortcut.1", x, training)
+    else:
+        sc = x
+    return F.relu(out + sc)
+
+
+def conv_block(sd, p, x, training=True):
+    """archs.py:831-846."""
+    out = F.relu(_conv_bn(sd, p + ".conv.0", p + ".conv.1", x, training, pad=1))
+    return F.relu(_conv_bn(sd, p + ".conv.3", p + ".conv.4", out, training, pad=1))
+
+
+def up_conv(sd, p, x, training=True):
+    """archs.py:848-861: nn.Upsample(scale_factor=2) is nearest-neighbour."""
+    x = F.interpolate(x, scale_factor=2, mode="nearest")
+    return F.relu(_conv_bn(sd, p + ".up.1", p + ".up.2", x, training, pad=1))
+
+
+def attention_block(sd, p, g, x, training=True):
+    """archs.py:136-142."""
+    g1 = _conv_bn(sd, p + ".W_g.0", p + ".W_g.1", g, training)
+    x1 = _conv_bn(sd, p + ".W_x.0", p + ".W_x.1", x, training)
+    psi = F.relu(g1 + x1)
+    psi = torch.sigmoid(_conv_bn(sd, p + ".psi.0", p + ".psi.1", psi, training))
+    return x * psi
+
+
+_BLOCK = {"UNet": vgg_block, "ProgUNet": vgg_block, "SSUNet": vgg_block, "NestedUNet": vgg_block, "UNet_B_SS": bottleneck,
+          "UNet_R_SS": lambda sd, p, x, training=True: O.basic_block(sd, p, x, training)}
+
+
+def _plain(sd, name, x, training):
+    """UNet / SSUNet / UNet_B_SS / UNet_R_SS forward wiring (archs.py:375-403,532-555,720-742,815-829)."""
+    blk = _BLOCK[name]
+
+    def stage(tag, t):
+        t = blk(sd, "conv" + tag, t, training)
+        if "SPADE%s.x2map.weight" % tag in sd:
+            t = O.spade(sd, "SPADE" + tag, t)
+        return t
+
+    pool = lambda t: F.max_pool2d(t, 2, 2)
+    x0_0 = stage("0_0", x)
+    x1_0 = stage("1_0", pool(x0_0))
+    x2_0 = stage("2_0", pool(x1_0))
+    x3_0 = stage("3_0", pool(x2_0))
+    x4_0 = stage("4_0", pool(x3_0))
+    if "conv5_0.conv1.weight" in sd:
+        x5_0 = stage("5_0", pool(x4_0))
+        x4_1 = stage("4_1", torch.cat([x4_0, O._up(x5_0)], 1))
+        x3_1 = stage("3_1", torch.cat([x3_0, O._up(x4_1)], 1))
+    else:
+        x3_1 = stage("3_1", torch.cat([x3_0, O._up(x4_0)], 1))
+    x2_2 = stage("2_2", torch.cat([x2_0, O._up(x3_1)], 1))
+    x1_3 = stage("1_3", torch.cat([x1_0, O._up(x2_2)], 1))
+    x0_4 = stage("0_4", torch.cat([x0_0, O._up(x1_3)], 1))
+    return x0_4, x1_3, x2_2, x3_1
+
+
+def _head(sd, p, x):
+    return F.conv2d(x, sd[p + ".weight"], sd[p + ".bias"])
+
+
+def nested_unet(sd, x, training=True):
+    """archs.py:904-933."""
+    b = lambda tag, t: vgg_block(sd, "conv" + tag, t, training)
+    pool = lambda t: F.max_pool2d(t, 2, 2)
+    up = O._up
+    x0_0 = b("0_0", x)
+    x1_0 = b("1_0", pool(x0_0))
+    x0_1 = b("0_1", torch.cat([x0_0, up(x1_0)], 1))
+    x2_0 = b("2_0", pool(x1_0))
+    x1_1 = b("1_1", torch.cat([x1_0, up(x2_0)], 1))
+    x0_2 = b("0_2", torch.cat([x0_0, x0_1, up(x1_1)], 1))
+    x3_0 = b("3_0", pool(x2_0))
+    x2_1 = b("2_1", torch.cat([x2_0, up(x3_0)], 1))
+    x1_2 = b("1_2", torch.cat([x1_0, x1_1, up(x2_1)], 1))
+    x0_3 = b("0_3", torch.cat([x0_0, x0_1, x0_2, up(x1_2)], 1))
+    x4_0 = b("4_0", pool(x3_0))
+    x3_1 = b("3_1", torch.cat([x3_0, up(x4_0)], 1))
+    x2_2 = b("2_2", torch.cat([x2_0, x2_1, up(x3_1)], 1))
+    x1_3 = b("1_3", torch.cat([x1_0, x1_1, x1_2, up(x2_2)], 1))
+    x0_4 = b("0_4", torch.cat([x0_0, x0_1, x0_2, x0_3, up(x1_3)], 1))
+    if "final1.weight" in sd:
+        return [_head(sd, "final1", x0_1), _head(sd, "final2", x0_2), _head(sd, "final3", x0_3), _head(sd, "final4", x0_4)]
+    return _head(sd, "final", x0_4)
+
+
+def att_unet(sd, x, training=True):
+    """UNet_ori (archs.py:961-996) and AttUNet (archs.py:303-342): the gates exist iff the state_dict has `Att*` keys."""
+    pool = lambda t: F.max_pool2d(t, 2, 2)
+    x1 = conv_block(sd, "Conv1", x, training)
+    x2 = conv_block(sd, "Conv2", pool(x1), training)
+    x3 = conv_block(sd, "Conv3", pool(x2), training)
+    x4 = conv_block(sd, "Conv4", pool(x3), training)
+    d = conv_block(sd, "Conv5", pool(x4), training)
+    for lvl, skip in ((5, x4), (4, x3), (3, x2), (2, x1)):
+        d = up_conv(sd, "Up%d" % lvl, d, training)
+        if "Att%d.psi.0.weight" % lvl in sd:
+            skip = attention_block(sd, "Att%d" % lvl, d, skip, training)
+        d = conv_block(sd, "Up_conv%d" % lvl, torch.cat((skip, d), 1), training)
+    return _head(sd, "Conv_1x1", d)
+
+
+def arch_forward(name, sd, x, training=True):
+    """Logits (or the list of logits under deep supervision / ProgUNet) of `archs.<name>` on NCHW fp32 `x`."""
+    if name == "NestedUNet":
+        return nested_unet(sd, x, training)
+    if name in ("UNet_ori", "AttUNet"):
+        return att_unet(sd, x, training)
+    outs = _plain(sd, name, x, training)
+    if name == "ProgUNet":
+        return [_head(sd, "final%d" % i, o) for i, o in enumerate(outs)]
+    return _head(sd, "final", outs[0])
+
+
+def supervised_loss(outputs, target):
+    """train.py:85-108: BCEDiceLoss, averaged over the outputs under deep supervision."""
+    if isinstance(outputs, (list, tuple)):
+        loss = 0
+        for o in outputs:
+            loss = loss + O.bce_dice_loss(o, target)
+        return loss / len(outputs)
+    return O.bce_dice_loss(outputs, target)
+
+
+def supervised_train_step(name, sd, opt, x, target, clip, num_classes=3):
+    """One iteration of train.py:85-116 on the flat state_dict: forward, loss, metrics, the in-place WEIGHT clamp
+    (:111-112, after the forward and before the backward: autograd's saved parameters alias the clamped storage, so the
+    backward pass reads clamped weights), backward, Adam.  ``opt`` is an ssunet_oracle.AdamState."""
+    O._leafify(sd)
+    if name == "UNet_R_SS_v2":
+        out = O.unet_r_ss_v2(sd, x, True)
+    else:
+        out = arch_forward(name, sd, x, True)
+    if isinstance(out, list):
+        loss = supervised_loss(out, target)
+        last = out[-1]
+        iou, dice = O.iou_score(last, target), O.dice_coef(last, target)
+    else:
+        out = torch.where(torch.isnan(out), torch.zeros_like(out), out)       # :101
+        loss = O.bce_dice_loss(out, target)
+        iou = O.iou_score(out[:, 1:num_classes].detach().clone(), target[:, 1:num_classes].clone())
+        dice = O.dice_coef(out[:, 1:num_classes].detach().clone(), target[:, 1:num_classes].clone())
+        last = out
+    keys = O.trainable_keys(sd)
+    with torch.no_grad():
+        for k in keys:
+            sd[k].data.clamp_(-clip, clip)
+    grads = torch.autograd.grad(loss, [sd[k] for k in keys], allow_unused=True)
+    opt.step(sd, dict(zip(keys, grads)))
+    return {"loss": float(loss), "iou": iou, "dice": dice, "logits": last.detach()}

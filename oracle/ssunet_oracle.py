@@ -376,12 +376,13 @@ def numpy_pairwise_sum_f32(a: np.ndarray) -> np.float32:
 
 
 class AdamState:
-    """torch.optim.Adam(lr, betas=(0.9, 0.999), eps=1e-8, weight_decay=0) restated
-    (train_seg_gan.py:452,468) preceded by clip_gradient's element clamp (srgan_utils.py:186-195)."""
+    """torch.optim.Adam(lr, betas=(0.9, 0.999), eps=1e-8, weight_decay) restated
+    (train_seg_gan.py:452,468; train.py:290 passes config['weight_decay']) preceded by clip_gradient's element clamp
+    (srgan_utils.py:186-195).  A parameter whose gradient is None is skipped entirely, as torch does."""
 
-    def __init__(self, names, lr, betas=(0.9, 0.999), eps=1e-8):
+    def __init__(self, names, lr, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0):
         self.names = list(names)
-        self.lr, self.betas, self.eps = lr, betas, eps
+        self.lr, self.betas, self.eps, self.weight_decay = lr, betas, eps, weight_decay
         self.t = 0
         self.m = {}
         self.v = {}
@@ -398,6 +399,8 @@ class AdamState:
                     continue
                 if grad_clip is not None:
                     g = g.clamp(-grad_clip, grad_clip)
+                if self.weight_decay:
+                    g = g.add(sd[k], alpha=self.weight_decay)
                 if k not in self.m:
                     self.m[k] = torch.zeros_like(g)
                     self.v[k] = torch.zeros_like(g)

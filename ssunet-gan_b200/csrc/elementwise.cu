@@ -165,53 +165,57 @@ __global__ void clamp_kernel(float* __restrict__ g, long long n, float clip) {
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
         g[i] = fminf(fmaxf(g[i], -clip), clip);   // NaN propagates like torch.clamp
 }
-// one Adam element: g <- clamp(g * gscale); m, v, p updated exactly in torch.optim.Adam's operation order
+// one Adam element: g <- clamp(g * gscale) [+ wd * p: torch.optim.Adam's L2 weight decay, train.py:290]; m, v, p updated exactly
+// in torch.optim.Adam's operation order
 __device__ __forceinline__ void adam_elem(float& pi, float& gi, float& mi, float& vi, float b1, float b2, float eps, float bc2_sqrt,
-                                          float step, float clip, float gscale) {
+                                          float step, float clip, float gscale, float wd = 0.f) {
     gi *= gscale;
     if (clip > 0.f) gi = fminf(fmaxf(gi, -clip), clip);
-    mi = b1 * mi + (1.f - b1) * gi;
-    vi = b2 * vi + (1.f - b2) * gi * gi;
+    float ge = gi;                           // .grad keeps the clamped gradient; the decayed one is a temporary in torch too
+    if (wd != 0.f) ge = gi + wd * pi;
+    mi = b1 * mi + (1.f - b1) * ge;
+    vi = b2 * vi + (1.f - b2) * ge * ge;
     const float denom = sqrtf(vi) / bc2_sqrt + eps;
     pi = pi - step * (mi / denom);
 }
 // float4 body (the four arenas are torch allocations: 16-byte aligned) + scalar tail
 __device__ __forceinline__ void adam_span(float* __restrict__ p, float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
                                           long long n, long long stride, float b1, float b2, float eps, float bc2_sqrt, float step,
-                                          float clip, float gscale) {
+                                          float clip, float gscale, float wd = 0.f) {
     const bool vec = ((((uintptr_t)p | (uintptr_t)g | (uintptr_t)m | (uintptr_t)v) & 15) == 0);
     const long long nv = vec ? n / 4 : 0;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nv; i += stride) {
         float4 p4 = reinterpret_cast<float4*>(p)[i], g4 = reinterpret_cast<float4*>(g)[i];
         float4 m4 = reinterpret_cast<float4*>(m)[i], v4 = reinterpret_cast<float4*>(v)[i];
-        adam_elem(p4.x, g4.x, m4.x, v4.x, b1, b2, eps, bc2_sqrt, step, clip, gscale);
-        adam_elem(p4.y, g4.y, m4.y, v4.y, b1, b2, eps, bc2_sqrt, step, clip, gscale);
-        adam_elem(p4.z, g4.z, m4.z, v4.z, b1, b2, eps, bc2_sqrt, step, clip, gscale);
-        adam_elem(p4.w, g4.w, m4.w, v4.w, b1, b2, eps, bc2_sqrt, step, clip, gscale);
+        adam_elem(p4.x, g4.x, m4.x, v4.x, b1, b2, eps, bc2_sqrt, step, clip, gscale, wd);
+        adam_elem(p4.y, g4.y, m4.y, v4.y, b1, b2, eps, bc2_sqrt, step, clip, gscale, wd);
+        adam_elem(p4.z, g4.z, m4.z, v4.z, b1, b2, eps, bc2_sqrt, step, clip, gscale, wd);
+        adam_elem(p4.w, g4.w, m4.w, v4.w, b1, b2, eps, bc2_sqrt, step, clip, gscale, wd);
         reinterpret_cast<float4*>(p)[i] = p4; reinterpret_cast<float4*>(g)[i] = g4;
         reinterpret_cast<float4*>(m)[i] = m4; reinterpret_cast<float4*>(v)[i] = v4;
     }
     for (long long i = nv * 4 + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
-        adam_elem(p[i], g[i], m[i], v[i], b1, b2, eps, bc2_sqrt, step, clip, gscale);
+        adam_elem(p[i], g[i], m[i], v[i], b1, b2, eps, bc2_sqrt, step, clip, gscale, wd);
 }
 // torch.optim.Adam (no amsgrad, no weight decay) after clip_gradient's element clamp.
 __global__ void __launch_bounds__(256) clamp_adam_kernel(float* __restrict__ p, float* __restrict__ g, float* __restrict__ m,
                                                           float* __restrict__ v, long long n, float lr, float b1, float b2,
-                                                          float eps, float bc1, float bc2_sqrt, float clip, float gscale) {
+                                                          float eps, float bc1, float bc2_sqrt, float clip, float gscale, float wd) {
     const long long stride = (long long)gridDim.x * blockDim.x;
     const float step = lr / bc1;
-    adam_span(p, g, m, v, n, stride, b1, b2, eps, bc2_sqrt, step, clip, gscale);
+    adam_span(p, g, m, v, n, stride, b1, b2, eps, bc2_sqrt, step, clip, gscale, wd);
 }
 // Graph-capturable variant: the step count lives on the device (a captured launch cannot carry per-step host scalars).
 __global__ void step_inc_kernel(float* step) { step[0] += 1.f; }
 __global__ void __launch_bounds__(256) clamp_adam_dev_kernel(float* __restrict__ p, float* __restrict__ g, float* __restrict__ m,
                                                               float* __restrict__ v, long long n, float lr, float b1, float b2,
-                                                              float eps, const float* __restrict__ step_dev, float clip, float gscale) {
+                                                              float eps, const float* __restrict__ step_dev, float clip, float gscale,
+                                                              float wd) {
     const long long stride = (long long)gridDim.x * blockDim.x;
     const float t = step_dev[0];
     const float bc1 = 1.f - powf(b1, t), bc2_sqrt = sqrtf(1.f - powf(b2, t));
     const float step = lr / bc1;
-    adam_span(p, g, m, v, n, stride, b1, b2, eps, bc2_sqrt, step, clip, gscale);
+    adam_span(p, g, m, v, n, stride, b1, b2, eps, bc2_sqrt, step, clip, gscale, wd);
 }
 __global__ void scale_by_dev_kernel(const float* __restrict__ w, const float* __restrict__ sc, float* __restrict__ o, long long n) {
     const float s = sc[0];
@@ -298,22 +302,31 @@ int ssg_clamp_(float* g, long long n, float clip, ssg_stream_t s) {
     SSG_CHECK_LAUNCH();
     return SSG_OK;
 }
-int ssg_clamp_adam(float* p, float* g, float* m, float* v, long long n, float lr, float beta1, float beta2, float eps,
-                   float bias_corr1, float bias_corr2, float clip, float grad_scale, ssg_stream_t s) {
+int ssg_clamp_adam_wd(float* p, float* g, float* m, float* v, long long n, float lr, float beta1, float beta2, float eps,
+                      float bias_corr1, float bias_corr2, float clip, float grad_scale, float weight_decay, ssg_stream_t s) {
     if (n <= 0) return SSG_OK;
     clamp_adam_kernel<<<grid_for(n, 1024), 256, 0, (cudaStream_t)s>>>(p, g, m, v, n, lr, beta1, beta2, eps, bias_corr1,
-                                                                      sqrtf(bias_corr2), clip, grad_scale);
+                                                                      sqrtf(bias_corr2), clip, grad_scale, weight_decay);
+    SSG_CHECK_LAUNCH();
+    return SSG_OK;
+}
+int ssg_clamp_adam(float* p, float* g, float* m, float* v, long long n, float lr, float beta1, float beta2, float eps,
+                   float bias_corr1, float bias_corr2, float clip, float grad_scale, ssg_stream_t s) {
+    return ssg_clamp_adam_wd(p, g, m, v, n, lr, beta1, beta2, eps, bias_corr1, bias_corr2, clip, grad_scale, 0.f, s);
+}
+int ssg_clamp_adam_wd_dev(float* p, float* g, float* m, float* v, long long n, float lr, float beta1, float beta2, float eps,
+                          float* step_dev, float clip, float grad_scale, float weight_decay, ssg_stream_t s) {
+    if (n <= 0) return SSG_OK;
+    SSG_CHECK_ARG(step_dev != nullptr, "clamp_adam_dev: step counter missing");
+    step_inc_kernel<<<1, 1, 0, (cudaStream_t)s>>>(step_dev);
+    clamp_adam_dev_kernel<<<grid_for(n, 2048), 256, 0, (cudaStream_t)s>>>(p, g, m, v, n, lr, beta1, beta2, eps, step_dev, clip, grad_scale,
+                                                                          weight_decay);
     SSG_CHECK_LAUNCH();
     return SSG_OK;
 }
 int ssg_clamp_adam_dev(float* p, float* g, float* m, float* v, long long n, float lr, float beta1, float beta2, float eps,
                        float* step_dev, float clip, float grad_scale, ssg_stream_t s) {
-    if (n <= 0) return SSG_OK;
-    SSG_CHECK_ARG(step_dev != nullptr, "clamp_adam_dev: step counter missing");
-    step_inc_kernel<<<1, 1, 0, (cudaStream_t)s>>>(step_dev);
-    clamp_adam_dev_kernel<<<grid_for(n, 2048), 256, 0, (cudaStream_t)s>>>(p, g, m, v, n, lr, beta1, beta2, eps, step_dev, clip, grad_scale);
-    SSG_CHECK_LAUNCH();
-    return SSG_OK;
+    return ssg_clamp_adam_wd_dev(p, g, m, v, n, lr, beta1, beta2, eps, step_dev, clip, grad_scale, 0.f, s);
 }
 int ssg_scale_by_dev(const float* w, const float* inv_sigma, float* out, long long n, ssg_stream_t s) {
     if (n <= 0) return SSG_OK;

@@ -528,6 +528,58 @@ class _Concat2(torch.autograd.Function):
         return da, db
 
 
+class _UpsampleNearest2x(torch.autograd.Function):
+    """nn.Upsample(scale_factor=2) in its default 'nearest' mode (up_conv, archs.py:848-861)."""
+
+    @staticmethod
+    def forward(ctx, x):
+        n, c, h, w = x.shape
+        y = empty_nhwc(n, c, 2 * h, 2 * w, x.dtype, x.device)
+        call("ssg_upsample_nearest2x_fwd", x, y, dtype_code(x.dtype), n, h, w, c)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        n, c, h2, w2 = dy.shape
+        dy = _as_storage(dy)
+        dx = empty_nhwc(n, c, h2 // 2, w2 // 2, dy.dtype, dy.device)
+        call("ssg_upsample_nearest2x_bwd", dy, dx, dtype_code(dy.dtype), n, h2 // 2, w2 // 2, c)
+        return dx
+
+
+class _PixelGate(torch.autograd.Function):
+    """x * sigmoid(z) with one gate value per pixel (Attention_block, archs.py:136-142): z is N x 1 x H x W."""
+
+    @staticmethod
+    def forward(ctx, x, z):
+        n, c, h, w = x.shape
+        assert tuple(z.shape) == (n, 1, h, w) and z.dtype == x.dtype
+        z = z.contiguous()
+        y = empty_nhwc(n, c, h, w, x.dtype, x.device)
+        call("ssg_pixel_gate_fwd", x, z, y, dtype_code(x.dtype), _rows(x), c)
+        ctx.save_for_backward(x, z)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, z = ctx.saved_tensors
+        n, c, h, w = x.shape
+        dy = _as_storage(dy, x.dtype)
+        dx = empty_nhwc(n, c, h, w, x.dtype, x.device)
+        dz = torch.empty_like(z)
+        call("ssg_pixel_gate_bwd", dy, x, z, dx, dz, dtype_code(x.dtype), _rows(x), c)
+        return dx, dz
+
+
+def upsample_nearest2x(x):
+    return _UpsampleNearest2x.apply(to_nhwc(x))
+
+
+def pixel_gate(x, z):
+    x = to_nhwc(x)
+    return _PixelGate.apply(x, to_nhwc(z, x.dtype))
+
+
 def max_pool2x2(x):
     return _MaxPool.apply(to_nhwc(x))
 

@@ -23,11 +23,12 @@ def flat_arena_of(grads):
 
 
 class FusedClampAdam(torch.optim.Optimizer):
-    """torch.optim.Adam(params, lr, betas=(0.9, 0.999), eps=1e-8) semantics (no weight decay, no amsgrad)."""
+    """torch.optim.Adam(params, lr, betas=(0.9, 0.999), eps=1e-8, weight_decay=0) semantics (L2 weight decay as in
+    train.py:290; no amsgrad)."""
 
-    def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, grad_clip=None):
+    def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, grad_clip=None, weight_decay=0.0):
         params = [p for p in params if p.requires_grad]
-        super().__init__(params, dict(lr=lr, betas=betas, eps=eps))
+        super().__init__(params, dict(lr=lr, betas=betas, eps=eps, weight_decay=weight_decay))
         self._clip = grad_clip
         self._pending_clip = None
         self._step = 0
@@ -61,6 +62,14 @@ class FusedClampAdam(torch.optim.Optimizer):
     def defer_clip(self, grad_clip):
         self._pending_clip = grad_clip
 
+    @torch.no_grad()
+    def clamp_weights(self, clip):
+        """`for p in model.parameters(): p.data.clamp_(-clip, clip)` (train.py:111-112) as ONE launch on the parameter arena.
+        Like the reference's in-place clamp it lands between forward and backward, so the backward pass that follows reads
+        the clamped values (packed-weight caches are invalidated)."""
+        call("ssg_clamp_", self.flat_p, self.flat_p.numel(), float(clip))
+        ops.bump_weight_epoch()
+
     def zero_grad(self, set_to_none=False):
         self.flat_g.zero_()
         for p in self._params:   # re-attach views if autograd replaced them
@@ -90,11 +99,13 @@ class FusedClampAdam(torch.optim.Optimizer):
         self._step += 1
         clip = self._pending_clip if self._pending_clip is not None else self._clip
         self._pending_clip = None
+        wd = float(group.get("weight_decay", 0.0) or 0.0)
         if self._step_dev is not None:
-            call("ssg_clamp_adam_dev", self.flat_p, self.flat_g, self.flat_m, self.flat_v, self.flat_p.numel(), float(group["lr"]),
-                 float(b1), float(b2), float(group["eps"]), self._step_dev, float(clip) if clip is not None else 0.0, float(grad_scale))
+            call("ssg_clamp_adam_wd_dev", self.flat_p, self.flat_g, self.flat_m, self.flat_v, self.flat_p.numel(), float(group["lr"]),
+                 float(b1), float(b2), float(group["eps"]), self._step_dev, float(clip) if clip is not None else 0.0, float(grad_scale),
+                 wd)
         else:
-            call("ssg_clamp_adam", self.flat_p, self.flat_g, self.flat_m, self.flat_v, self.flat_p.numel(), float(group["lr"]),
+            call("ssg_clamp_adam_wd", self.flat_p, self.flat_g, self.flat_m, self.flat_v, self.flat_p.numel(), float(group["lr"]),
                  float(b1), float(b2), float(group["eps"]), 1.0 - b1 ** self._step, 1.0 - b2 ** self._step,
-                 float(clip) if clip is not None else 0.0, float(grad_scale))
+                 float(clip) if clip is not None else 0.0, float(grad_scale), wd)
         ops.bump_weight_epoch()

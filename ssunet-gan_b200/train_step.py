@@ -155,3 +155,101 @@ class GraphedGanStep:
     def __call__(self, input, target):
         self.load(input, target)
         return self.replay()
+
+
+# ----------------------------------------------------------------------------------------------
+# the supervised trainer's loop body and the validation loop body
+# ----------------------------------------------------------------------------------------------
+def make_supervised_optimizer(model, config):
+    """train.py:285-290 for `optimizer == 'Adam'`: Adam(lr, weight_decay) over every trainable parameter, as ONE
+    flat-arena optimiser.  Parameters of modules that are constructed but never called (UNet_R_SS.sp_up1_3,
+    archs.py:513) get no gradient in the reference, so torch's Adam skips them; they stay outside the arena."""
+    from .archs import SubPixelConvolutionalBlock
+    from .optim import FusedClampAdam
+    if config.get("optimizer", "Adam") != "Adam":
+        raise ops._lib.SsgError("make_supervised_optimizer: only config['optimizer'] == 'Adam' (config_v1.json) is built")
+    idle = set()
+    for m in model.modules():
+        if isinstance(m, SubPixelConvolutionalBlock):
+            idle.update(id(p) for p in m.parameters())
+    params = [p for p in model.parameters() if p.requires_grad and id(p) not in idle]
+    opt = FusedClampAdam(params, lr=float(config["lr"]), weight_decay=float(config.get("weight_decay", 0.0)))
+    opt._idle_params = [p for p in model.parameters() if id(p) in idle]
+    return opt
+
+
+def _clamp_weights(model, optimizer, clip):
+    """`for p in model.parameters(): p.data.clamp_(-clip, clip)` (train.py:111-112)."""
+    if hasattr(optimizer, "clamp_weights"):
+        optimizer.clamp_weights(clip)
+        rest = getattr(optimizer, "_idle_params", [])
+    else:
+        rest = list(model.parameters())
+    for p in rest:
+        ops._lib.call("ssg_clamp_", p.data, p.numel(), float(clip))
+    if rest:
+        ops.bump_weight_epoch()
+
+
+def _outputs_loss_metrics(config, model, criterion, input, target, with_metrics):
+    """train.py:85-108 == train.py:155-175 == train_seg_gan.py:266-276: forward, loss, IoU / Dice."""
+    num_class = int(config["num_classes"])
+    iou = dice = None
+    if config.get("deep_supervision"):
+        outputs = model(input)
+        loss = 0
+        for output in outputs:
+            loss = loss + criterion(output, target)
+        loss = loss / len(outputs)
+        if with_metrics:
+            iou = iou_score(outputs[-1], target)
+            dice = dice_coef(outputs[-1], target)
+        return outputs[-1], loss, iou, dice
+    output = ops.nan_to_zero(model(input))                                     # train.py:101
+    if with_metrics:
+        out_m = output[:, 1:num_class].detach().contiguous()                   # :102
+        tar_m = target[:, 1:num_class].contiguous()                            # :103
+        iou = iou_score(out_m, tar_m)                                          # :107
+        dice = dice_coef(out_m, tar_m)                                         # :108
+    loss = criterion(output, target)                                           # :105
+    return output, loss, iou, dice
+
+
+def supervised_train_step(config, model, criterion, optimizer, input, target, cnn_optimizer=None, epoch=0, with_metrics=True):
+    """One iteration of the supervised trainer (train.py:81-120): forward, BCEDice (averaged over the outputs under deep
+    supervision), metrics, the WEIGHT clamp to +-config['clip'] (placed, as in the reference, after the forward and before
+    the backward), zero_grad / backward / step.  `model.train()` is the caller's job (train.py:73).
+    Returns OrderedDict(loss, iou, dice, logits)."""
+    output, loss, iou, dice = _outputs_loss_metrics(config, model, criterion, input, target, with_metrics)
+    _clamp_weights(model, optimizer, float(config["clip"]))                    # :111-112
+    optimizer.zero_grad()                                                      # :114
+    loss.backward()                                                            # :115
+    optimizer.step()                                                           # :116
+    if cnn_optimizer is not None and epoch > 1:                                # :118-120
+        cnn_optimizer.step()
+    return OrderedDict([("loss", loss.detach()), ("iou", iou), ("dice", dice), ("logits", output.detach())])
+
+
+def validate_step(config, model, criterion, input, target, with_metrics=True):
+    """One iteration of `validate` (train.py:152-176, train_seg_gan.py:262-276) under no_grad; `model.eval()` is the
+    caller's job (:146 / :259).  Returns OrderedDict(loss, iou, dice, logits)."""
+    with torch.no_grad():
+        output, loss, iou, dice = _outputs_loss_metrics(config, model, criterion, input, target, with_metrics)
+    return OrderedDict([("loss", loss), ("iou", iou), ("dice", dice), ("logits", output)])
+
+
+def validate(config, val_loader, model, criterion):
+    """train.py:140-196 / train_seg_gan.py:253-294 without the progress bar: running averages weighted by batch size.
+    `val_loader` yields the reference dataset's 5-tuples `(ori_img, input, target, targets, meta)` (dataset.py:144) or
+    `(input, target)` pairs."""
+    from .srgan_utils import AverageMeter
+    avg = {"loss": AverageMeter(), "iou": AverageMeter(), "dice": AverageMeter()}
+    model.eval()
+    for batch in val_loader:
+        input, target = (batch[1], batch[2]) if len(batch) >= 5 else (batch[0], batch[1])
+        out = validate_step(config, model, criterion, input.cuda(), target.cuda())
+        n = input.size(0)
+        avg["loss"].update(out["loss"].item(), n)
+        avg["iou"].update(out["iou"], n)
+        avg["dice"].update(out["dice"], n)
+    return OrderedDict([("loss", avg["loss"].avg), ("iou", avg["iou"].avg), ("dice", avg["dice"].avg)])

@@ -252,3 +252,91 @@ def test_tile_windows_and_merge_match_reference(golden_dir):
     merged = O.tile_merge(H, W, list(probs), P, C, OV)
     assert np.array_equal(np.stack(merged), z["merged"])                 # bit-identical uint8 masks
     assert set(np.unique(z["merged"])) <= {0, 255} and 0.2 < (z["merged"] == 255).mean() < 0.8
+
+
+# ---------------------------------------------------------------------------------------------
+# the rest of the model zoo, the supervised step, the validation step
+# ---------------------------------------------------------------------------------------------
+import pytest  # noqa: E402
+
+ARCH_CASES = [("UNet", False, 32), ("NestedUNet", False, 32), ("NestedUNet", True, 32), ("SSUNet", False, 32), ("UNet_ori", False, 32),
+              ("UNet_B_SS", False, 32), ("AttUNet", False, 32), ("UNet_R_SS", False, 64), ("ProgUNet", False, 32)]
+
+
+def _bias_before_bn(key):
+    """Conv biases that feed a BatchNorm directly (VGGBlock, conv_block, up_conv, Attention_block): zero gradient."""
+    import re
+    return bool(re.search(r"(^conv\d_\d\.conv[12]\.bias$)|(\.conv\.[03]\.bias$)|(\.up\.1\.bias$)|(\.(W_g|W_x|psi)\.0\.bias$)", key))
+
+
+@pytest.mark.parametrize("idx", range(len(ARCH_CASES)), ids=[n + ("_ds" if d else "") for n, d, _ in ARCH_CASES])
+def test_arch_zoo_oracle_matches_reference(golden_dir, idx):
+    import archs_oracle as A
+    name, ds, hw = ARCH_CASES[idx]
+    tag = name + ("_ds" if ds else "")
+    z = np.load(os.path.join(golden_dir, "archs_%s.npz" % tag))
+    spec = A.arch_spec(name, ds)
+    sd = O.portable_state_dict(spec, salt=idx + 1)
+    O._leafify(sd)
+    x, t = O.synthetic_batch(2, 3, hw, hw, seed=1234)
+    out = A.arch_forward(name, sd, x, True)
+    outs = out if isinstance(out, list) else [out]
+    if name == "ProgUNet":
+        loss = O.bce_dice_loss(outs[0], t) + sum(o.square().mean() for o in outs[1:])
+    else:
+        loss = A.supervised_loss(out, t)
+    for i, o in enumerate(outs):
+        _close(o.detach().numpy(), z["logits%d" % i], rtol=1e-4, atol=2e-5)
+    _close(float(loss.detach()), float(z["loss"]), rtol=1e-5)
+    keys = O.trainable_keys(sd)
+    grads = dict(zip(keys, torch.autograd.grad(loss, [sd[k] for k in keys], allow_unused=True)))
+    assert sorted(k for k in keys if grads[k] is None) == sorted(str(k) for k in z["nograd_keys"])
+    for k, c in zip(z["grad_keys"], z["grad_csum"]):
+        if _bias_before_bn(str(k)):       # analytically zero (BN removes the mean): both sides hold rounding noise only
+            assert c[1] < 1e-4 and _csum(grads[str(k)])[1] < 1e-4
+            continue
+        _close(_csum(grads[str(k)])[1:], c[1:], rtol=3e-3, atol=1e-7)
+    for k, c in zip(z["bn_keys"], z["bn_running_var_csum"]):
+        _close(_csum(sd[str(k)]), c, rtol=1e-4, atol=1e-7)
+    # eval mode + the validation loop body
+    sd = O.portable_state_dict(spec, salt=idx + 1)
+    xe, te = O.synthetic_batch(1, 3, hw, hw, seed=77, blobby=True)
+    with torch.no_grad():
+        oe = A.arch_forward(name, sd, xe, False)
+    oes = oe if isinstance(oe, list) else [oe]
+    for i, o in enumerate(oes):
+        _close(o.numpy(), z["eval_logits%d" % i], rtol=1e-4, atol=2e-5)
+    if name == "ProgUNet":
+        v = (O.bce_dice_loss(oes[0], te), O.iou_score(oes[0], te), O.dice_coef(oes[0], te))
+    elif isinstance(oe, list):
+        v = (A.supervised_loss(oe, te), O.iou_score(oes[-1], te), O.dice_coef(oes[-1], te))
+    else:
+        v = (O.bce_dice_loss(oe, te), O.iou_score(oe[:, 1:3], te[:, 1:3]), O.dice_coef(oe[:, 1:3].clone(), te[:, 1:3].clone()))
+    _close(float(v[0]), z["val_scalars"][0], rtol=1e-5)
+    _close(float(v[1]), z["val_scalars"][1], rtol=1e-3)      # a logit within fp32 noise of 0 may flip one pixel
+    _close(float(v[2]), z["val_scalars"][2], rtol=1e-5)
+
+
+@pytest.mark.parametrize("name,ds,hw", [("UNet_R_SS_v2", False, 64), ("NestedUNet", True, 32)])
+def test_supervised_step_oracle_matches_reference(golden_dir, name, ds, hw):
+    """train.py:85-116 for two iterations: Adam(lr 1e-4, weight_decay 1e-7), weight clamp 0.7 between forward and backward."""
+    import archs_oracle as A
+    tag = name + ("_ds" if ds else "")
+    z = np.load(os.path.join(golden_dir, "supervised_step_%s.npz" % tag))
+    spec = O.unet_r_ss_v2_spec(3, 3) if name == "UNet_R_SS_v2" else A.arch_spec(name, ds)
+    sd = O.portable_state_dict(spec, salt=31)
+    opt = O.AdamState(O.trainable_keys(sd), lr=1e-4, weight_decay=1e-7)
+    for it in range(2):
+        x, t = O.synthetic_batch(2, 3, hw, hw, seed=4321 + it, blobby=(it == 1))
+        r = A.supervised_train_step(name, sd, opt, x, t, clip=0.7)
+        _close([r["loss"], r["dice"]], z["it%d_scalars" % it][[0, 2]], rtol=2e-5)
+        _close(r["iou"], z["it%d_scalars" % it][1], rtol=1e-3)
+        _close(r["logits"].numpy(), z["it%d_logits" % it], rtol=2e-4, atol=5e-5)
+    for k, c in zip(z["keys"], z["csum"]):
+        k = str(k)
+        if sd[k].is_floating_point():
+            # a conv bias in front of a BatchNorm has an analytically zero gradient; Adam turns its rounding noise into
+            # +-lr steps, so its signed sum is not reproducible (and it cannot influence any output): magnitudes only
+            lo = 1 if _bias_before_bn(k) else 0
+            _close(_csum(sd[k])[lo:], c[lo:], rtol=2e-4, atol=1e-5)
+    _close(sd[str(z["probe_key"])].detach().numpy(), z["probe"], rtol=1e-4, atol=1e-6)
