@@ -223,6 +223,17 @@ int ssg_dice_leaf_sums(const float* logits, const float* target, const long long
 /* combines leaf sums (host memory) up the same tree; returns the float32 total */
 float ssg_pairwise_combine_host(const float* leaf_sums_host, long long n);
 
+/* ---- data feed (dataset.py:95-144; Normalize / Flip of the pipelines at train_seg_gan.py:366-382) -------------------- */
+/* img: uint8 [n,h,w,c] (cv2.imread layout, c <= 8).  out = (float(img) - sub[c]) * mul[c] with sub = mean * max_pixel_value and
+ * mul = 1 / (std * max_pixel_value) precomputed in float32 (albumentations' Normalize).  nchw != 0: out is the reference's
+ * NCHW tensor [n,c,h,w] in `dtype`; nchw == 0: out is NHWC [n,h,w,c_store] with zero padding channels (the layout the first
+ * convolution reads).  flip_codes (optional, int per sample): bit 0 reverses x, bit 1 reverses y (albumentations Flip). */
+int ssg_feed_image_u8(const unsigned char* img, void* out, int dtype, int nchw, int n, int h, int w, int c, int c_store, const float* sub,
+                      const float* mul, const int* flip_codes, ssg_stream_t s);
+/* mask: uint8 [n,h,w,classes] (the per-class PNGs of dataset.py:126-131 stacked): out fp32 [n,classes,h,w] =
+ * (uint8)(float32(mask) / 255.0), i.e. 1.0 only where the PNG holds 255; same flip codes. */
+int ssg_feed_mask_u8(const unsigned char* mask, float* out_nchw, int n, int h, int w, int classes, const int* flip_codes, ssg_stream_t s);
+
 /* ---- optimiser (srgan_utils.py:186-195 + torch.optim.Adam, train_seg_gan.py:452,468) ---------- */
 int ssg_clamp_(float* g, long long n, float clip, ssg_stream_t s);
 /* g <- clamp(g*grad_scale, +-clip) (clip <= 0: no clamp); Adam update of p, m, v in place */

@@ -198,3 +198,48 @@ def supervised_train_step(name, sd, opt, x, target, clip, num_classes=3):
     grads = torch.autograd.grad(loss, [sd[k] for k in keys], allow_unused=True)
     opt.step(sd, dict(zip(keys, grads)))
     return {"loss": float(loss), "iou": iou, "dice": dice, "logits": last.detach()}
+
+
+# --------------------------------------------------------------------------------------
+# data feed -- numpy restatement
+# --------------------------------------------------------------------------------------
+def feed_normalize(img_u8, mean, std, max_pixel_value=255.0):
+    """albumentations.augmentations.functional.normalize as published (albumentations is NOT installed here, so this
+    restatement is unpinned; the reference calls it through transforms.Normalize, train_seg_gan.py:376,381):
+    mean *= max_pixel; std *= max_pixel; denominator = reciprocal(std); img = (float32(img) - mean) * denominator."""
+    import numpy as np
+    mean = np.array(mean, dtype=np.float32) * np.float32(max_pixel_value)
+    std = np.array(std, dtype=np.float32) * np.float32(max_pixel_value)
+    den = np.reciprocal(std, dtype=np.float32)
+    img = img_u8.astype(np.float32)
+    img -= mean
+    img *= den
+    return img
+
+
+def feed_image(img_u8_nhwc, mean, std, flip_cv2_codes=None):
+    """Normalize -> Flip (cv2.flip semantics, as albumentations' Flip applies them) -> `img.astype('float32')`,
+    `transpose(2, 0, 1)` (dataset.py:137-138).  Normalising before or after the flip gives identical values."""
+    import numpy as np
+    out = []
+    for i, im in enumerate(img_u8_nhwc):
+        f = feed_normalize(im, mean, std)
+        if flip_cv2_codes is not None and flip_cv2_codes[i] is not None:
+            d = flip_cv2_codes[i]
+            f = f[::-1] if d == 0 else (f[:, ::-1] if d == 1 else f[::-1, ::-1])
+        out.append(np.ascontiguousarray(f.transpose(2, 0, 1)))
+    return np.stack(out)
+
+
+def feed_mask(mask_u8_nhwc, flip_cv2_codes=None):
+    """dataset.py:126-140 for the multi-class layout: `(png.astype('float32') / 255.0).astype('uint8')`, stacked, flipped
+    with the image, `1.0 * mask.astype('float32')`, CHW."""
+    import numpy as np
+    out = []
+    for i, m in enumerate(mask_u8_nhwc):
+        b = (m.astype("float32") / 255.0).astype("uint8")
+        if flip_cv2_codes is not None and flip_cv2_codes[i] is not None:
+            d = flip_cv2_codes[i]
+            b = b[::-1] if d == 0 else (b[:, ::-1] if d == 1 else b[::-1, ::-1])
+        out.append(np.ascontiguousarray((1.0 * b.astype("float32")).transpose(2, 0, 1)))
+    return np.stack(out)
