@@ -103,6 +103,13 @@ int ssg_conv2d_fwd_tc_has_stats(int ksize, int stride, int pad);
  * small stride-1 convolution over dy with 1, 2, 2 and 4 taps) written interleaved into dx. */
 int ssg_conv2d_dgrad_tc(const void* dy, const void* w_packed, void* dx, int n, int h, int w, int cin, int cout, int ksize,
                         int stride, int pad, ssg_stream_t s);
+/* Same, but dx += gradient (TMA reduce-add in the epilogue, bf16 addition at the L2): the second consumer of an activation adds
+ * its contribution into the buffer the first one wrote -- replaces autograd's separate addition pass for BasicBlock's
+ * conv1 + shortcut (archs.py:229-234) and SPADE's x2map + modulation (normalization.py:112-120).  Only for the geometries
+ * ssg_conv2d_dgrad_tc_can_acc() accepts (same-size stride-1 1x1 / 3x3); otherwise SSG_ERR_UNSUPPORTED. */
+int ssg_conv2d_dgrad_tc_acc(const void* dy, const void* w_packed, void* dx, int n, int h, int w, int cin, int cout, int ksize,
+                            int stride, int pad, ssg_stream_t s);
+int ssg_conv2d_dgrad_tc_can_acc(int ksize, int stride, int pad);
 
 /* Weight gradient of the same convolution on tensor cores (both operands MN-major straight from the NHWC
  * tensors, split-K over pixel tiles, fp32 atomics into dw): dw_oihw fp32 [cout_real][cin_real][k][k] is

@@ -42,10 +42,12 @@ class BasicBlock(nn.Module):
 
     def forward(self, x):
         x = ops.to_nhwc(x)
-        y1, s1 = self.conv1(x, want_stats=self.training)  # BN statistics are reduced in the conv epilogue when possible
+        # x feeds conv1 and the 1x1 shortcut: one gradient buffer for both (the second data-gradient kernel adds in its epilogue)
+        sink = ops.grad_sink_for(x) if len(self.shortcut) else None
+        y1, s1 = self.conv1(x, want_stats=self.training, dx_sink=sink)  # BN statistics are reduced in the conv epilogue when possible
         out = self.bn1(y1, act=ACT_RELU, sums=s1)
         y2, s2 = self.conv2(out, want_stats=self.training)
-        sc = self.shortcut[0](x) if len(self.shortcut) else x
+        sc = self.shortcut[0](x, dx_sink=sink) if len(self.shortcut) else x
         return self.bn2(y2, residual=sc, act=ACT_RELU, sums=s2)
 
 

@@ -38,14 +38,20 @@ def forward(x, weight, bias, y, stride, pad, act, slope, x1=None, stats=None):
          slope, stats, flops=_flops(n, oh, ow, cin, cout, k))
 
 
-def dgrad(dy, weight, dx, stride, pad):
-    """dx (n, cin_s, h, w) from dy (n, cout_s, oh, ow); weights packed [tap][cin_s][cout_s] (K-major in cout)."""
+def can_accumulate(k, stride, pad):
+    """True when the data-gradient kernel can add into an existing dx (TMA reduce-add epilogue)."""
+    return bool(_lib.lib().ssg_conv2d_dgrad_tc_can_acc(int(k), int(stride), int(pad)))
+
+
+def dgrad(dy, weight, dx, stride, pad, accumulate=False):
+    """dx (n, cin_s, h, w) from dy (n, cout_s, oh, ow); weights packed [tap][cin_s][cout_s] (K-major in cout).
+    accumulate: dx += ... (only for the geometries `can_accumulate` accepts)."""
     from .ops import packed_weight
     n, cin_s, h, w = dx.shape
     cout, cin, k, _ = weight.shape
     cout_s = dy.shape[1]
     wp = packed_weight(weight, W_RSCK, torch.bfloat16, cout_p=cout_s, cin_p=cin_s)
-    call("ssg_conv2d_dgrad_tc", dy, wp, dx, n, h, w, cin_s, cout_s, k, stride, pad,
+    call("ssg_conv2d_dgrad_tc_acc" if accumulate else "ssg_conv2d_dgrad_tc", dy, wp, dx, n, h, w, cin_s, cout_s, k, stride, pad,
          flops=_flops(n, dy.shape[2], dy.shape[3], cin, cout, k))
 
 

@@ -204,7 +204,8 @@ static PFN_cuTensorMapEncodeTiled_v12000 get_encode() {
 
 // bf16 tensor map; dims/box innermost first; strides in BYTES for dims 1..rank-1
 int run_conv_halo(const void* x0, int c0, const void* x1, int c1, const void* w_packed, int w_taps, const float* bias, int bias_n,
-                  void* y, int n, int h, int w, int gemm_n, int ksize, int flip, int act, float slope, double* stats, cudaStream_t st);
+                  void* y, int n, int h, int w, int gemm_n, int ksize, int flip, int act, float slope, double* stats, cudaStream_t st,
+                  int accumulate = 0);
 int run_wgrad_halo(const void* x0, int c0, const void* x1, int c1, const void* dy, int cout_s, float* dw, int cout_real, int cin_real,
                    int n, int h, int w, cudaStream_t st);
 int run_wgrad_thin(const void* x, const void* dy, int cout_s, float* dw, int cout_real, int cin_real, int n, int h, int w,
@@ -344,6 +345,25 @@ int ssg_conv2d_fwd_tc(const void* x0, int c0, const void* x1, int c1, const void
 
 int ssg_conv2d_fwd_tc_has_stats(int ksize, int stride, int pad) {
     return (stride == 1 && 2 * pad == ksize - 1 && (ksize == 1 || ksize == 3) && use_halo_kernel()) ? 1 : 0;
+}
+
+int ssg_conv2d_dgrad_tc_can_acc(int ksize, int stride, int pad) {
+    return (stride == 1 && 2 * pad == ksize - 1 && (ksize == 1 || ksize == 3) && use_halo_kernel()) ? 1 : 0;
+}
+
+// dx += data gradient (same-size stride-1 convolutions only): the epilogue's TMA store becomes a TMA reduce-add, so the
+// gradient contributions of two consumers of one activation (BasicBlock's conv1 + shortcut, archs.py:229-234; SPADE's
+// x2map + modulation, normalization.py:112-120) meet in one buffer without a separate addition pass.
+int ssg_conv2d_dgrad_tc_acc(const void* dy, const void* w_packed, void* dx, int n, int h, int w, int cin, int cout, int ksize, int stride,
+                            int pad, ssg_stream_t s) {
+    SSG_CHECK_ARG(n > 0 && h > 0 && w > 0 && cin > 0 && cout > 0 && cout % 8 == 0 && cin % 8 == 0,
+                  "conv2d_dgrad_tc_acc: stored channel counts must be multiples of 8 (cin=%d cout=%d)", cin, cout);
+    if (!ssg_conv2d_dgrad_tc_can_acc(ksize, stride, pad)) {
+        set_error("conv2d_dgrad_tc_acc: only same-size stride-1 1x1 / 3x3 convolutions accumulate (k=%d stride=%d pad=%d)", ksize, stride, pad);
+        return SSG_ERR_UNSUPPORTED;
+    }
+    return run_conv_halo(dy, cout, nullptr, 0, w_packed, ksize * ksize, nullptr, 0, dx, n, h, w, cin, ksize, 1, 0, 0.f, nullptr,
+                         (cudaStream_t)s, 1);
 }
 
 int ssg_conv2d_dgrad_tc(const void* dy, const void* w_packed, void* dx, int n, int h, int w, int cin, int cout, int ksize, int stride,

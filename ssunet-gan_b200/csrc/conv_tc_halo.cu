@@ -52,6 +52,7 @@ struct HaloParams {
     int act;
     float slope;
     double* stats;               // optional [2][cout] fp64 (pre-zeroed): per-channel sum / sum of squares of the stored y
+    int accumulate;              // 1: y += result (TMA reduce-add) instead of y = result
 };
 
 // ACCS accumulator sets (2: epilogue overlaps the next item's MMAs).  RES: single-chunk (Cin <= 64) convolutions keep
@@ -322,7 +323,8 @@ __global__ void __launch_bounds__(H_THREADS, 1) conv_tc_halo_kernel(const __grid
                     fence_proxy_async();
                     __syncwarp();
                     if (lane == 0) {
-                        tma_store_4d(&tmY, stage, n0 + h0, tx * H_TW, ty * H_TH + 4 * q, img);
+                        if (p.accumulate) tma_reduce_add_4d(&tmY, stage, n0 + h0, tx * H_TW, ty * H_TH + 4 * q, img);
+                        else tma_store_4d(&tmY, stage, n0 + h0, tx * H_TW, ty * H_TH + 4 * q, img);
                         tma_store_commit();
                     }
                     if (want_stats) {
@@ -375,10 +377,12 @@ static int launch_halo(const CUtensorMap& a0, const CUtensorMap& a1, const CUten
 
 // Same-size stride-1 convolution (flip = 0) / data gradient (flip = 1: tap t reads the mirrored halo offset).
 int run_conv_halo(const void* x0, int c0, const void* x1, int c1, const void* w_packed, int w_taps, const float* bias, int bias_n,
-                  void* y, int n, int h, int w, int gemm_n, int ksize, int flip, int act, float slope, double* stats, cudaStream_t st) {
+                  void* y, int n, int h, int w, int gemm_n, int ksize, int flip, int act, float slope, double* stats, cudaStream_t st,
+                  int accumulate) {
     HaloParams p;
     memset(&p, 0, sizeof(p));
     p.stats = stats;
+    p.accumulate = accumulate;
     if (stats) SSG_CHECK_CUDA(cudaMemsetAsync(stats, 0, sizeof(double) * 2 * (size_t)gemm_n, st));
     p.y = (bf16*)y; p.bias = bias; p.bias_n = bias_n; p.N = n; p.H = h; p.W = w; p.cout = gemm_n;
     p.tiles_x = (w + H_TW - 1) / H_TW; p.tiles_y = (h + H_TH - 1) / H_TH; p.m_tiles = n * p.tiles_x * p.tiles_y;

@@ -43,9 +43,12 @@ class SPADE(nn.Module):
     def forward(self, x, segmap):
         x = ops.to_nhwc(x)
         # the 3- and h-channel maps are stored channel-padded (ops.thin_pad) so they can feed the TMA/tcgen05 kernels
-        seg = self.x2map(segmap, cout_store=ops.thin_pad(self.x2map.out_channels))
+        # self-conditioned use (segmap is x): x feeds x2map AND the modulation; their two gradient contributions meet in one
+        # buffer (ops.GradSink: the x2map data-gradient kernel adds into what the modulation's backward wrote)
+        sink = ops.grad_sink_for(x) if segmap is x else None
+        seg = self.x2map(segmap, cout_store=ops.thin_pad(self.x2map.out_channels), dx_sink=sink)
         actv = self.mlp_shared[0](seg, act=ACT_RELU, cout_store=ops.thin_pad(self.mlp_shared[0].out_channels))
         w_gb = torch.cat([self.mlp_gamma.weight, self.mlp_beta.weight], 0)
         b_gb = torch.cat([self.mlp_gamma.bias, self.mlp_beta.bias], 0)
         gb = ops.conv2d(actv, w_gb, b_gb, 1, self._pw)
-        return ops.spade_modulate(x, gb)
+        return ops.spade_modulate(x, gb, dx_sink=sink)

@@ -186,13 +186,53 @@ def _tc_eligible(cin_s, cout_s, k, stride, dtype):
     return conv_tc.eligible(cin_s, cout_s, k, stride)
 
 
+class GradSink:
+    """One gradient buffer shared by the backward passes of the `expected` consumers of ONE activation inside a module
+    (BasicBlock: conv1 + shortcut; SPADE: x2map + modulation).  The first consumer to run its backward writes its
+    contribution into a fresh buffer and reports no gradient to autograd; the last one ADDS its contribution in place (for
+    a convolution: inside the data-gradient kernel's epilogue, TMA reduce-add) and hands the finished buffer to autograd.
+    Autograd therefore sees exactly one contribution from the group and never runs its own addition pass for it; any
+    other consumer of the same activation is accumulated by autograd as usual.  Created per forward call by the module;
+    every member's output must reach the loss (true for the two modules above)."""
+
+    __slots__ = ("expected", "arrived", "buf")
+
+    def __init__(self, expected=2):
+        self.expected, self.arrived, self.buf = expected, 0, None
+
+    def contribute(self, write, accumulate):
+        """write() -> new tensor holding this contribution; accumulate(buf) adds it into buf.  Returns the gradient to
+        report to autograd: None until the last member has contributed."""
+        self.arrived += 1
+        if self.buf is None:
+            self.buf = write()
+        else:
+            accumulate(self.buf)
+        if self.arrived < self.expected:
+            return None
+        out, self.buf, self.arrived = self.buf, None, 0
+        return out
+
+
+def grad_sink_for(x, expected=2):
+    """A GradSink when gradients for `x` will be needed and the tensor-core path (whose epilogue can accumulate) is on."""
+    if tc_mode() and torch.is_grad_enabled() and torch.is_tensor(x) and x.requires_grad:
+        return GradSink(expected)
+    return None
+
+
+def _add_into(buf, t):
+    call("ssg_add", buf, t, buf, dtype_code(buf.dtype), buf.numel())
+
+
 class _Conv2d(torch.autograd.Function):
     """nn.Conv2d (square kernel, symmetric padding, groups=1) with optional fused bias + activation.
     x may be stored with more channels than the weight has inputs, and the output may be stored with `cout_store`
     >= Cout channels (thin_pad): the extra channels are zeros."""
 
     @staticmethod
-    def forward(ctx, x, weight, bias, stride, pad, act, slope, cout_store, want_stats):
+    def forward(ctx, x, weight, bias, stride, pad, act, slope, cout_store, want_stats, dx_sink=None):
+        ctx.dx_sink = dx_sink
         n, cin_s, h, w = x.shape
         cout, cin, kh, kw = weight.shape
         cout_s = cout_store or cout
@@ -238,12 +278,22 @@ class _Conv2d(torch.autograd.Function):
         if use_tc:
             from . import conv_tc
         if ctx.needs_input_grad[0]:
-            dx = empty_nhwc(n, cin_s, h, w, dt, x.device)
-            if use_tc:
-                conv_tc.dgrad(dy, weight, dx, stride, pad)
-            else:
-                wp = packed_weight(weight, W_RSKC, dt)
-                call("ssg_conv2d_dgrad_simt", dy, wp, dx, dtype_code(dt), n, h, w, cin, cout, kh, kw, stride, pad)
+            def write():
+                t = empty_nhwc(n, cin_s, h, w, dt, x.device)
+                if use_tc:
+                    conv_tc.dgrad(dy, weight, t, stride, pad)
+                else:
+                    wp = packed_weight(weight, W_RSKC, dt)
+                    call("ssg_conv2d_dgrad_simt", dy, wp, t, dtype_code(dt), n, h, w, cin, cout, kh, kw, stride, pad)
+                return t
+
+            def accumulate(buf):
+                if use_tc and buf.dtype == dt and tuple(buf.shape) == (n, cin_s, h, w) and conv_tc.can_accumulate(kh, stride, pad):
+                    conv_tc.dgrad(dy, weight, buf, stride, pad, accumulate=True)      # dx += ... inside the kernel's epilogue
+                else:
+                    _add_into(buf, write())
+
+            dx = write() if ctx.dx_sink is None else ctx.dx_sink.contribute(write, accumulate)
         if ctx.needs_input_grad[1]:
             slot = weight.grad if weight.is_leaf else None
             if (use_tc and slot is not None and getattr(slot, "_ssg_arena", None) is not None and slot.dtype == torch.float32
@@ -266,14 +316,14 @@ class _Conv2d(torch.autograd.Function):
                 sums = torch.empty(2 * cout_s, dtype=torch.float64, device=x.device)
                 call("ssg_channel_stats", dy, dtype_code(dt), _rows(dy), cout_s, sums, 0)
                 db = sums[:cout].float()
-        return dx, dw, db, None, None, None, None, None, None
+        return dx, dw, db, None, None, None, None, None, None, None
 
 
-def conv2d(x, weight, bias=None, stride=1, pad=0, act=ACT_NONE, slope=0.0, cout_store=None, want_stats=None):
+def conv2d(x, weight, bias=None, stride=1, pad=0, act=ACT_NONE, slope=0.0, cout_store=None, want_stats=None, dx_sink=None):
     """want_stats (True / False; None = plain call returning y): return `(y, sums)` where sums is the fp64
     [sum y | sum y^2] per-channel statistics of the output when requested and the kernel can produce them in its epilogue
     (else None)."""
-    y, sums = _Conv2d.apply(to_nhwc(x), weight, bias, stride, pad, act, slope, cout_store, bool(want_stats))
+    y, sums = _Conv2d.apply(to_nhwc(x), weight, bias, stride, pad, act, slope, cout_store, bool(want_stats), dx_sink)
     return (y, sums) if want_stats is not None else y
 
 
@@ -602,11 +652,12 @@ def concat_channels(a, b):
 # ----------------------------------------------------------------------------------------------
 class _SpadeModulate(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x, gb):
+    def forward(ctx, x, gb, dx_sink=None):
         n, c, h, w = x.shape
         y = empty_nhwc(n, c, h, w, x.dtype, x.device)
         call("ssg_spade_modulate_fwd", x, gb, y, dtype_code(x.dtype), _rows(x), c)
         ctx.save_for_backward(x, gb)
+        ctx.dx_sink = dx_sink
         return y
 
     @staticmethod
@@ -624,11 +675,13 @@ class _SpadeModulate(torch.autograd.Function):
             dgb._ssg_colsum = colsum
         else:
             call("ssg_spade_modulate_bwd", dy, x, gb, dx, dgb, dtype_code(x.dtype), _rows(x), c)
-        return dx, dgb
+        if ctx.dx_sink is not None:      # x also feeds SPADE's x2map convolution: its data gradient is added into this buffer
+            dx = ctx.dx_sink.contribute(lambda: dx, lambda buf: _add_into(buf, dx))
+        return dx, dgb, None
 
 
-def spade_modulate(x, gb):
-    return _SpadeModulate.apply(to_nhwc(x), gb)
+def spade_modulate(x, gb, dx_sink=None):
+    return _SpadeModulate.apply(to_nhwc(x), gb, dx_sink)
 
 
 class _Act(torch.autograd.Function):

@@ -151,3 +151,74 @@ def test_conv_epilogue_bn_statistics(cfg):
     assert rel(ref, want) < 1e-5
     assert rel(sums, want) < 1e-5
     assert float((sums[cout:] - want[cout:]).abs().max() / want[cout:].abs().max()) < 1e-4
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# data gradient accumulated into an existing buffer (TMA reduce-add epilogue) and the module-level GradSink
+# ------------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("cfg", [(2, 64, 64, 16, 16, 3), (1, 192, 64, 40, 24, 1), (1, 128, 256, 19, 13, 3), (2, 64, 8, 33, 20, 3),
+                                 (1, 8, 128, 24, 24, 3), (1, 64, 192, 200, 168, 3)])
+def test_conv_tc_dgrad_accumulate(cfg):
+    """dx += dgrad(dy) inside the kernel == bf16(dx + bf16(dgrad(dy))): the second consumer's contribution lands in the
+    buffer the first one wrote (cin / cout here are the STORED channel counts, thin ones included)."""
+    from ssunet_gan_b200 import conv_tc, ops
+    n, cin, cout, h, w, k = cfg
+    pad = k // 2
+    assert conv_tc.can_accumulate(k, 1, pad) and not conv_tc.can_accumulate(3, 2, 1)
+    g = torch.Generator().manual_seed(sum(cfg))
+    wgt = (torch.randn(cout, cin, k, k, generator=g) / math.sqrt(cin * k * k)).cuda()
+    dy = ops.to_nhwc(torch.randn(n, cout, h, w, generator=g).cuda(), torch.bfloat16)
+    base = ops.to_nhwc(torch.randn(n, cin, h, w, generator=g).cuda(), torch.bfloat16)
+    plain = ops.empty_nhwc(n, cin, h, w, torch.bfloat16)
+    conv_tc.dgrad(dy, wgt, plain, 1, pad)
+    acc = base.clone(memory_format=torch.preserve_format)
+    assert ops.is_nhwc(acc)
+    conv_tc.dgrad(dy, wgt, acc, 1, pad, accumulate=True)
+    want = (base.float() + plain.float()).to(torch.bfloat16)
+    torch.cuda.synchronize()
+    diff = (acc.float() - want.float()).abs()
+    # identical up to the rounding mode of the L2's bf16 adder: at most one bf16 ulp of the result
+    assert bool((diff <= want.float().abs() * 2.0 ** -7 + 1e-30).all()), float(diff.max())
+    assert rel(acc.float(), want.float()) < 2e-3
+
+
+@pytest.mark.parametrize("which", ["basic_block", "spade"])
+def test_grad_sink_equals_autograd_accumulation(which, monkeypatch):
+    """BasicBlock (conv1 + shortcut) and SPADE (x2map + modulation) with the shared gradient buffer against the same module
+    with the sink switched off (autograd adds the two contributions): same input gradient, same parameter gradients."""
+    import ssunet_gan_b200 as ssg
+    from ssunet_gan_b200 import archs, normalization, ops
+    ssg.set_compute_dtype(torch.bfloat16)
+    ssg.set_conv_impl("auto")
+    torch.manual_seed(7)
+    if which == "basic_block":
+        mod = archs.BasicBlock(192, 64).cuda().train()
+        x0 = torch.randn(2, 192, 40, 24)
+        run = lambda t: mod(t)
+    else:
+        mod = normalization.SPADE("spadebatch3x3", 128, 3, 128 / 16).cuda().train()
+        x0 = torch.randn(2, 128, 40, 24)
+        run = lambda t: mod(t, t)
+    gy = torch.randn(2, 64 if which == "basic_block" else 128, 40, 24)
+
+    def once():
+        x = ops.to_nhwc(x0.cuda()).detach().requires_grad_(True)
+        xin = ops.relu(x)                        # a non-leaf producer, so the module's input gradient flows through autograd
+        for p in mod.parameters():
+            p.grad = None
+        y = run(xin)
+        y.backward(ops.to_nhwc(gy.cuda()))
+        return y.detach().float(), x.grad.detach().float().clone(), {k: p.grad.clone() for k, p in mod.named_parameters() if p.grad is not None}
+
+    made = []
+    orig = ops.grad_sink_for
+    monkeypatch.setattr(ops, "grad_sink_for", lambda t, expected=2: made.append(orig(t, expected)) or made[-1])
+    y1, dx1, g1 = once()
+    assert len(made) == 1 and made[0] is not None and made[0].buf is None and made[0].arrived == 0     # used and reset
+    monkeypatch.setattr(ops, "grad_sink_for", lambda t, expected=2: None)
+    y2, dx2, g2 = once()
+    assert torch.equal(y1, y2)
+    assert rel(dx1, dx2) < 2e-3, rel(dx1, dx2)
+    assert g1.keys() == g2.keys()
+    for k in g1:
+        assert rel(g1[k], g2[k]) < 1e-5, (k, rel(g1[k], g2[k]))
