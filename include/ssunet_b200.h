@@ -110,6 +110,11 @@ int ssg_conv2d_dgrad_tc(const void* dy, const void* w_packed, void* dx, int n, i
 int ssg_conv2d_dgrad_tc_acc(const void* dy, const void* w_packed, void* dx, int n, int h, int w, int cin, int cout, int ksize,
                             int stride, int pad, ssg_stream_t s);
 int ssg_conv2d_dgrad_tc_can_acc(int ksize, int stride, int pad);
+/* Data gradient of a convolution over the virtual concatenation [x0 | x1] (ssg_conv2d_fwd_tc with x1 != NULL): gradient channels
+ * [0, c0) go to dx0 [n,h,w,c0], channels [c0, c0+c1) to dx1 [n,h,w,c1] (c0 % 64 == 0, c1 % 8 == 0), written or -- accumulate != 0 --
+ * added.  Replaces torch.cat's backward (archs.py:651-667).  Same geometries as ssg_conv2d_dgrad_tc_acc. */
+int ssg_conv2d_dgrad_tc_split(const void* dy, const void* w_packed, void* dx0, int c0, void* dx1, int c1, int n, int h, int w, int cout,
+                              int ksize, int stride, int pad, int accumulate, ssg_stream_t s);
 
 /* Weight gradient of the same convolution on tensor cores (both operands MN-major straight from the NHWC
  * tensors, split-K over pixel tiles, fp32 atomics into dw): dw_oihw fp32 [cout_real][cin_real][k][k] is

@@ -173,6 +173,35 @@ def main():
     rec("swish fwd", "utils.py:36-41", xi.numel() * 4, lambda: call("ssg_swish_fwd", xi, yo, DT, xi.numel()))
     rec("swish bwd", "utils.py:43-48", xi.numel() * 6, lambda: call("ssg_swish_bwd", yo, xi, yo, DT, xi.numel()))
 
+    del xi, yo
+    # ---- arch-zoo kernels: AttUNet / UNet_ori at 16 x 512^2, level-0 decoder tensors ----
+    n, h, w, c = 16, 256, 256, 64
+    xs = torch.randn(n * h * w, c, device=dev).to(BF)
+    yb = torch.empty(n * 4 * h * w, c, dtype=BF, device=dev)
+    rec("upsample nearest x2 fwd", "archs.py:852 (up_conv)", xs.numel() * 2 * 5, lambda: call("ssg_upsample_nearest2x_fwd", xs, yb, DT, n, h, w, c))
+    rec("upsample nearest x2 bwd", "autograd of archs.py:852", xs.numel() * 2 * 5, lambda: call("ssg_upsample_nearest2x_bwd", yb, xs, DT, n, h, w, c))
+    R2 = n * 512 * 512
+    xg = yb                                         # 16 x 512 x 512 x 64
+    zg = torch.randn(R2, device=dev).to(BF)
+    yg = torch.empty_like(xg)
+    dzg = torch.empty_like(zg)
+    rec("attention gate fwd (x * sigmoid z)", "archs.py:142", xg.numel() * 4 + R2 * 2, lambda: call("ssg_pixel_gate_fwd", xg, zg, yg, DT, R2, c))
+    rec("attention gate bwd", "autograd of archs.py:142", xg.numel() * 6 + R2 * 4,
+        lambda: call("ssg_pixel_gate_bwd", yg, xg, zg, yg, dzg, DT, R2, c), "dx aliases dy (in place) for the measurement")
+    del xs, yb, yg, zg, dzg
+    # ---- data feed: 16 x 512 x 512 x 3 uint8 rasters + 3 mask planes ----
+    img = torch.randint(0, 256, (16, 512, 512, 3), dtype=torch.uint8, device=dev)
+    sub = torch.tensor([123.675, 116.28, 103.53], device=dev)
+    mul = 1.0 / torch.tensor([58.395, 57.12, 57.375], device=dev)
+    o8 = torch.empty(16 * 512 * 512, 8, dtype=BF, device=dev)
+    o3 = torch.empty(16, 3, 512, 512, device=dev)
+    rec("feed image u8 -> NHWC bf16 x8", "dataset.py:137-138 + Normalize", img.numel() + o8.numel() * 2,
+        lambda: call("ssg_feed_image_u8", img, o8, DT, 0, 16, 512, 512, 3, 8, sub, mul, None), "80 MB: fits L2, flushed")
+    rec("feed image u8 -> NCHW fp32", "dataset.py:137-138 + Normalize", img.numel() + o3.numel() * 4,
+        lambda: call("ssg_feed_image_u8", img, o3, 0, 1, 16, 512, 512, 3, 3, sub, mul, None), "63 MB: fits L2, flushed")
+    rec("feed mask u8 -> NCHW fp32", "dataset.py:128-140", img.numel() + o3.numel() * 4,
+        lambda: call("ssg_feed_mask_u8", img, o3, 16, 512, 512, 3, None), "63 MB: fits L2, flushed")
+
     res = {"device": torch.cuda.get_device_name(0), "peak_GBps": peak, "peak_source": peak_src,
            "method": "CUDA events per launch, 20 timed launches after 5 warm-ups, 256 MB L2 flush between launches", "kernels": rows}
     with open(args.out, "w") as f:

@@ -41,7 +41,11 @@ class BasicBlock(nn.Module):
         init.xavier_normal_(self.shortcut[0].weight)
 
     def forward(self, x):
-        x = ops.to_nhwc(x)
+        if isinstance(x, ops.CatPair):           # virtual concat [skip | upsampled]: both convolutions must be able to read it
+            if not (len(self.shortcut) and ops._cat_conv_ok(x, self.conv1.weight, 1, 1) and self.conv1.stride == (1, 1)):
+                x = x.materialise()
+        else:
+            x = ops.to_nhwc(x)
         # x feeds conv1 and the 1x1 shortcut: one gradient buffer for both (the second data-gradient kernel adds in its epilogue)
         sink = ops.grad_sink_for(x) if len(self.shortcut) else None
         y1, s1 = self.conv1(x, want_stats=self.training, dx_sink=sink)  # BN statistics are reduced in the conv epilogue when possible
@@ -166,17 +170,17 @@ class UNet_R_SS_v2(nn.Module):
         enc_5 = self.conv5_0(p4)
         enc_5 = self.SPADE5_0(enc_5, enc_5)
         enc_5 = self.conv_head5_0(enc_5)
-        dec_4 = self.conv4_1(ops.concat_channels(enc_4, self.unpool(enc_5, i4)))
+        dec_4 = self.conv4_1(ops.concat_channels(enc_4, self.unpool(enc_5, i4), virtual=True))
         dec_4 = self.SPADE4_1(dec_4, dec_4)
         dec_4 = self.conv_head4_1(dec_4)
-        dec_3 = self.conv3_1(ops.concat_channels(enc_3, self.unpool(dec_4, i3)))
+        dec_3 = self.conv3_1(ops.concat_channels(enc_3, self.unpool(dec_4, i3), virtual=True))
         dec_3 = self.SPADE3_1(dec_3, dec_3)
         dec_3 = self.conv_head3_1(dec_3)
-        dec_2 = self.conv2_1(ops.concat_channels(enc_2, self.unpool(dec_3, i2)))
+        dec_2 = self.conv2_1(ops.concat_channels(enc_2, self.unpool(dec_3, i2), virtual=True))
         dec_2 = self.SPADE2_1(dec_2, dec_2)
-        dec_1 = self.conv1_1(ops.concat_channels(enc_1, self.up(dec_2)))
+        dec_1 = self.conv1_1(ops.concat_channels(enc_1, self.up(dec_2), virtual=True))
         dec_1 = self.SPADE1_1(dec_1, dec_1)
-        dec_0 = self.conv0_1(ops.concat_channels(enc_0, self.up(dec_1)))
+        dec_0 = self.conv0_1(ops.concat_channels(enc_0, self.up(dec_1), virtual=True))
         dec_0 = self.SPADE0_1(dec_0, dec_0)
         nc = self.final.out_channels
         return ops.to_nchw_f32(self.final(dec_0, cout_store=ops.thin_pad(nc)), channels=nc)

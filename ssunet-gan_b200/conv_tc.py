@@ -55,6 +55,20 @@ def dgrad(dy, weight, dx, stride, pad, accumulate=False):
          flops=_flops(n, dy.shape[2], dy.shape[3], cin, cout, k))
 
 
+def dgrad_split(dy, weight, dx0, dx1, stride, pad, accumulate=False):
+    """Data gradient of a convolution over the virtual concatenation [x0 | x1]: gradient channels [0, c0) -> dx0, the rest -> dx1
+    (written, or added when `accumulate`).  c0 % 64 == 0; only the geometries `can_accumulate` accepts."""
+    from .ops import packed_weight
+    n, c0, h, w = dx0.shape
+    c1 = dx1.shape[1]
+    cout, cin, k, _ = weight.shape
+    assert cin == c0 + c1 and c0 % 64 == 0 and c1 % 8 == 0
+    cout_s = dy.shape[1]
+    wp = packed_weight(weight, W_RSCK, torch.bfloat16, cout_p=cout_s, cin_p=cin)
+    call("ssg_conv2d_dgrad_tc_split", dy, wp, dx0, c0, dx1, c1, n, h, w, cout_s, k, stride, pad, int(bool(accumulate)),
+         flops=_flops(n, dy.shape[2], dy.shape[3], cin, cout, k))
+
+
 def wgrad(x, dy, dw, stride, pad, x1=None, accumulate=False):
     """dW (OIHW fp32, real channel extents) on tensor cores from (possibly channel-padded) x and dy.
     accumulate: dw += ... (dw is the parameter's slot of the flat gradient arena) instead of dw = ..."""

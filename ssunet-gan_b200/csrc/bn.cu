@@ -18,10 +18,14 @@ __global__ void __launch_bounds__(BN_THREADS) channel_reduce_vec_kernel(
     long long rows, int C, long long rows_per_block, const float* __restrict__ mean, const float* __restrict__ inv_std,
     int act, float slope, int with_sq, double* __restrict__ sums) {
     constexpr int V = Vec<T>::N;
-    extern __shared__ float sm[];  // [2][C]
-    float* s0 = sm;
-    float* s1 = sm + C;
-    for (int i = threadIdx.x; i < 2 * C; i += BN_THREADS) sm[i] = 0.f;
+    // Block-level accumulators are fp64: the order in which the threads' partial sums meet (shared-memory atomics) then
+    // cannot change the result beyond 1e-16, so the statistics are reproducible run to run.  With fp32 accumulators the
+    // mean / inv_std of a few channels moved by one fp32 ulp between identical launches, which the 8-sample BatchNorm at a
+    // U-Net bottleneck occasionally amplified to 1e-3 on the logits.
+    extern __shared__ double smd[];  // [2][C]
+    double* s0 = smd;
+    double* s1 = smd + C;
+    for (int i = threadIdx.x; i < 2 * C; i += BN_THREADS) smd[i] = 0.0;
     __syncthreads();
     const int vpr = C / V;
     const int lanes = vpr < BN_THREADS ? vpr : BN_THREADS;   // threads cooperating on one row
@@ -101,15 +105,15 @@ __global__ void __launch_bounds__(BN_THREADS) channel_reduce_vec_kernel(
             }
 #pragma unroll
             for (int i = 0; i < V; ++i) {
-                atomicAdd(&s0[v * V + i], acc0[i]);
-                if (with_sq) atomicAdd(&s1[v * V + i], acc1[i]);
+                atomicAdd(&s0[v * V + i], (double)acc0[i]);
+                if (with_sq) atomicAdd(&s1[v * V + i], (double)acc1[i]);
             }
         }
     }
     __syncthreads();
     for (int c = threadIdx.x; c < C; c += BN_THREADS) {
-        atomicAdd(&sums[c], (double)s0[c]);
-        if (with_sq) atomicAdd(&sums[C + c], (double)s1[c]);
+        atomicAdd(&sums[c], s0[c]);
+        if (with_sq) atomicAdd(&sums[C + c], s1[c]);
     }
 }
 
@@ -119,10 +123,10 @@ __global__ void __launch_bounds__(BN_THREADS) channel_reduce_scalar_kernel(
     const T* __restrict__ a, const T* __restrict__ yout, const T* __restrict__ xin, long long rows, int C,
     long long rows_per_block, const float* __restrict__ mean, const float* __restrict__ inv_std, int act, float slope,
     int with_sq, double* __restrict__ sums) {
-    extern __shared__ float sm[];
-    float* s0 = sm;
-    float* s1 = sm + C;
-    for (int i = threadIdx.x; i < 2 * C; i += BN_THREADS) sm[i] = 0.f;
+    extern __shared__ double smd[];      // fp64 block accumulators: see channel_reduce_vec_kernel
+    double* s0 = smd;
+    double* s1 = smd + C;
+    for (int i = threadIdx.x; i < 2 * C; i += BN_THREADS) smd[i] = 0.0;
     __syncthreads();
     const long long e_begin = (long long)blockIdx.x * rows_per_block * C;
     long long e_end = e_begin + rows_per_block * C;
@@ -131,18 +135,18 @@ __global__ void __launch_bounds__(BN_THREADS) channel_reduce_scalar_kernel(
         const int c = (int)(e % C);
         float v = to_f(a[e]);
         if (MODE == 0) {
-            atomicAdd(&s0[c], v);
-            if (with_sq) atomicAdd(&s1[c], v * v);
+            atomicAdd(&s0[c], (double)v);
+            if (with_sq) atomicAdd(&s1[c], (double)(v * v));
         } else {
             if (act != SSG_ACT_NONE) v *= act_grad_from_out(to_f(yout[e]), act, slope);
-            atomicAdd(&s0[c], v);
-            atomicAdd(&s1[c], v * (to_f(xin[e]) - mean[c]) * inv_std[c]);
+            atomicAdd(&s0[c], (double)v);
+            atomicAdd(&s1[c], (double)(v * (to_f(xin[e]) - mean[c]) * inv_std[c]));
         }
     }
     __syncthreads();
     for (int c = threadIdx.x; c < C; c += BN_THREADS) {
-        atomicAdd(&sums[c], (double)s0[c]);
-        if (with_sq) atomicAdd(&sums[C + c], (double)s1[c]);
+        atomicAdd(&sums[c], s0[c]);
+        if (with_sq) atomicAdd(&sums[C + c], s1[c]);
     }
 }
 
@@ -157,7 +161,17 @@ static int launch_channel_reduce(const T* a, const T* y, const T* x, long long r
     long long rpb = (rows + blocks - 1) / blocks;
     if (rpb < 64) rpb = 64;
     blocks = (rows + rpb - 1) / rpb;
-    size_t smem = sizeof(float) * 2 * C;
+    size_t smem = sizeof(double) * 2 * C;
+    if (smem > 48 * 1024) {     // C > 3072: opt in to the large dynamic shared-memory window once per instantiation
+        static bool big_v = false, big_s = false;
+        if (C % V == 0 && !big_v) {
+            SSG_CHECK_CUDA(cudaFuncSetAttribute(channel_reduce_vec_kernel<T, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024));
+            big_v = true;
+        } else if (C % V != 0 && !big_s) {
+            SSG_CHECK_CUDA(cudaFuncSetAttribute(channel_reduce_scalar_kernel<T, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024));
+            big_s = true;
+        }
+    }
     if (C % V == 0)
         channel_reduce_vec_kernel<T, MODE><<<(unsigned)blocks, BN_THREADS, smem, st>>>(a, y, x, rows, C, rpb, mean, inv_std, act, slope, with_sq, sums);
     else

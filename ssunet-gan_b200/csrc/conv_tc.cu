@@ -205,7 +205,7 @@ static PFN_cuTensorMapEncodeTiled_v12000 get_encode() {
 // bf16 tensor map; dims/box innermost first; strides in BYTES for dims 1..rank-1
 int run_conv_halo(const void* x0, int c0, const void* x1, int c1, const void* w_packed, int w_taps, const float* bias, int bias_n,
                   void* y, int n, int h, int w, int gemm_n, int ksize, int flip, int act, float slope, double* stats, cudaStream_t st,
-                  int accumulate = 0);
+                  int accumulate = 0, void* y1 = nullptr, int split_c = 0);
 int run_wgrad_halo(const void* x0, int c0, const void* x1, int c1, const void* dy, int cout_s, float* dw, int cout_real, int cin_real,
                    int n, int h, int w, cudaStream_t st);
 int run_wgrad_thin(const void* x, const void* dy, int cout_s, float* dw, int cout_real, int cin_real, int n, int h, int w,
@@ -364,6 +364,20 @@ int ssg_conv2d_dgrad_tc_acc(const void* dy, const void* w_packed, void* dx, int 
     }
     return run_conv_halo(dy, cout, nullptr, 0, w_packed, ksize * ksize, nullptr, 0, dx, n, h, w, cin, ksize, 1, 0, 0.f, nullptr,
                          (cudaStream_t)s, 1);
+}
+
+// Data gradient of a convolution whose input was the VIRTUAL concatenation [x0 | x1] (archs.py:651-667): channels [0, c0) of the
+// gradient are written (or added) to dx0, the rest to dx1 -- torch.cat's backward (the split copy) disappears.
+int ssg_conv2d_dgrad_tc_split(const void* dy, const void* w_packed, void* dx0, int c0, void* dx1, int c1, int n, int h, int w, int cout,
+                              int ksize, int stride, int pad, int accumulate, ssg_stream_t s) {
+    SSG_CHECK_ARG(n > 0 && h > 0 && w > 0 && c0 > 0 && c1 > 0 && cout > 0 && cout % 8 == 0 && c0 % 64 == 0 && c1 % 8 == 0 && dx0 && dx1,
+                  "conv2d_dgrad_tc_split: c0 %% 64 == 0, c1 %% 8 == 0, cout %% 8 == 0 required (c0=%d c1=%d cout=%d)", c0, c1, cout);
+    if (!ssg_conv2d_dgrad_tc_can_acc(ksize, stride, pad)) {
+        set_error("conv2d_dgrad_tc_split: only same-size stride-1 1x1 / 3x3 convolutions (k=%d stride=%d pad=%d)", ksize, stride, pad);
+        return SSG_ERR_UNSUPPORTED;
+    }
+    return run_conv_halo(dy, cout, nullptr, 0, w_packed, ksize * ksize, nullptr, 0, dx0, n, h, w, c0 + c1, ksize, 1, 0, 0.f, nullptr,
+                         (cudaStream_t)s, accumulate ? 1 : 0, dx1, c0);
 }
 
 int ssg_conv2d_dgrad_tc(const void* dy, const void* w_packed, void* dx, int n, int h, int w, int cin, int cout, int ksize, int stride,

@@ -53,6 +53,8 @@ struct HaloParams {
     float slope;
     double* stats;               // optional [2][cout] fp64 (pre-zeroed): per-channel sum / sum of squares of the stored y
     int accumulate;              // 1: y += result (TMA reduce-add) instead of y = result
+    int split_c;                 // > 0 (multiple of 64): output channels [0, split_c) go to tmY, [split_c, cout) to tmY1 -- the
+                                 // data gradient of a virtually concatenated input lands in its two source tensors
 };
 
 // ACCS accumulator sets (2: epilogue overlaps the next item's MMAs).  RES: single-chunk (Cin <= 64) convolutions keep
@@ -83,7 +85,8 @@ template <int MT, int BN, int ACCS, bool RES>
 __global__ void __launch_bounds__(H_THREADS, 1) conv_tc_halo_kernel(const __grid_constant__ CUtensorMap tmA0,
                                                                      const __grid_constant__ CUtensorMap tmA1,
                                                                      const __grid_constant__ CUtensorMap tmB,
-                                                                     const __grid_constant__ CUtensorMap tmY, const HaloParams p) {
+                                                                     const __grid_constant__ CUtensorMap tmY,
+                                                                     const __grid_constant__ CUtensorMap tmY1, const HaloParams p) {
     using C = HaloCfg<MT, BN, ACCS, RES>;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -323,8 +326,12 @@ __global__ void __launch_bounds__(H_THREADS, 1) conv_tc_halo_kernel(const __grid
                     fence_proxy_async();
                     __syncwarp();
                     if (lane == 0) {
-                        if (p.accumulate) tma_reduce_add_4d(&tmY, stage, n0 + h0, tx * H_TW, ty * H_TH + 4 * q, img);
-                        else tma_store_4d(&tmY, stage, n0 + h0, tx * H_TW, ty * H_TH + 4 * q, img);
+                        const int cg = n0 + h0;
+                        const bool second = p.split_c > 0 && cg >= p.split_c;
+                        const CUtensorMap* ymap = second ? &tmY1 : &tmY;
+                        const int cy = second ? cg - p.split_c : cg;
+                        if (p.accumulate) tma_reduce_add_4d(ymap, stage, cy, tx * H_TW, ty * H_TH + 4 * q, img);
+                        else tma_store_4d(ymap, stage, cy, tx * H_TW, ty * H_TH + 4 * q, img);
                         tma_store_commit();
                     }
                     if (want_stats) {
@@ -356,8 +363,8 @@ __global__ void __launch_bounds__(H_THREADS, 1) conv_tc_halo_kernel(const __grid
 }
 
 template <int MT, int BN, int ACCS, bool RES>
-static int launch_halo(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b, const CUtensorMap& ym, HaloParams& p,
-                       cudaStream_t st) {
+static int launch_halo(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b, const CUtensorMap& ym, const CUtensorMap& ym1,
+                       HaloParams& p, cudaStream_t st) {
     using C = HaloCfg<MT, BN, ACCS, RES>;
     static bool attr_set = false;
     if (!attr_set) {
@@ -370,7 +377,7 @@ static int launch_halo(const CUtensorMap& a0, const CUtensorMap& a1, const CUten
     p.n_major = RES ? 1 : 0;
     int grid = sm_count_cached();
     if (grid > p.total_items) grid = p.total_items;
-    conv_tc_halo_kernel<MT, BN, ACCS, RES><<<grid, H_THREADS, C::TOTAL, st>>>(a0, a1, b, ym, p);
+    conv_tc_halo_kernel<MT, BN, ACCS, RES><<<grid, H_THREADS, C::TOTAL, st>>>(a0, a1, b, ym, ym1, p);
     SSG_CHECK_LAUNCH();
     return SSG_OK;
 }
@@ -378,11 +385,14 @@ static int launch_halo(const CUtensorMap& a0, const CUtensorMap& a1, const CUten
 // Same-size stride-1 convolution (flip = 0) / data gradient (flip = 1: tap t reads the mirrored halo offset).
 int run_conv_halo(const void* x0, int c0, const void* x1, int c1, const void* w_packed, int w_taps, const float* bias, int bias_n,
                   void* y, int n, int h, int w, int gemm_n, int ksize, int flip, int act, float slope, double* stats, cudaStream_t st,
-                  int accumulate) {
+                  int accumulate, void* y1, int split_c) {
     HaloParams p;
     memset(&p, 0, sizeof(p));
     p.stats = stats;
     p.accumulate = accumulate;
+    p.split_c = y1 ? split_c : 0;
+    SSG_CHECK_ARG(!y1 || (split_c > 0 && split_c % 64 == 0 && split_c < gemm_n && (gemm_n - split_c) % 8 == 0 && !stats),
+                  "conv halo: split output needs split_c %% 64 == 0 and 0 < split_c < cout (split_c=%d cout=%d)", split_c, gemm_n);
     if (stats) SSG_CHECK_CUDA(cudaMemsetAsync(stats, 0, sizeof(double) * 2 * (size_t)gemm_n, st));
     p.y = (bf16*)y; p.bias = bias; p.bias_n = bias_n; p.N = n; p.H = h; p.W = w; p.cout = gemm_n;
     p.tiles_x = (w + H_TW - 1) / H_TW; p.tiles_y = (h + H_TH - 1) / H_TH; p.m_tiles = n * p.tiles_x * p.tiles_y;
@@ -425,20 +435,26 @@ int run_conv_halo(const void* x0, int c0, const void* x1, int c1, const void* w_
         rc = encode_bf16_map(&mb, w_packed, 3, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B, nullptr);
         if (rc) return rc;
     }
-    CUtensorMap my;
-    {
-        uint64_t dims[4] = {(uint64_t)gemm_n, (uint64_t)w, (uint64_t)h, (uint64_t)n};
-        uint64_t str[3] = {(uint64_t)gemm_n * 2, (uint64_t)w * gemm_n * 2, (uint64_t)h * w * gemm_n * 2};
+    CUtensorMap my, my1;
+    auto enc_out = [&](CUtensorMap* m, void* ptr, int c) {
+        uint64_t dims[4] = {(uint64_t)c, (uint64_t)w, (uint64_t)h, (uint64_t)n};
+        uint64_t str[3] = {(uint64_t)c * 2, (uint64_t)w * c * 2, (uint64_t)h * w * c * 2};
         uint32_t box[4] = {64, H_TW, 4, 1};
-        rc = encode_bf16_map(&my, y, 4, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B, nullptr);
+        return encode_bf16_map(m, ptr, 4, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B, nullptr);
+    };
+    rc = enc_out(&my, y, p.split_c ? p.split_c : gemm_n);
+    if (rc) return rc;
+    my1 = my;
+    if (p.split_c) {
+        rc = enc_out(&my1, y1, gemm_n - p.split_c);
         if (rc) return rc;
     }
     static const char* res_env = getenv("SSG_HALO_RES");          // "264" (default) or "164"
-    if (shape == 264 && res_env && atoi(res_env) == 164) return launch_halo<1, 64, 4, true>(ma0, ma1, mb, my, p, st);
-    if (shape == 264) return launch_halo<2, 64, 2, true>(ma0, ma1, mb, my, p, st);
-    if (shape == 2128) return launch_halo<2, 128, 2, false>(ma0, ma1, mb, my, p, st);
-    if (shape == 416) return launch_halo<4, 16, 2, false>(ma0, ma1, mb, my, p, st);
-    return launch_halo<4, 64, 2, false>(ma0, ma1, mb, my, p, st);
+    if (shape == 264 && res_env && atoi(res_env) == 164) return launch_halo<1, 64, 4, true>(ma0, ma1, mb, my, my1, p, st);
+    if (shape == 264) return launch_halo<2, 64, 2, true>(ma0, ma1, mb, my, my1, p, st);
+    if (shape == 2128) return launch_halo<2, 128, 2, false>(ma0, ma1, mb, my, my1, p, st);
+    if (shape == 416) return launch_halo<4, 16, 2, false>(ma0, ma1, mb, my, my1, p, st);
+    return launch_halo<4, 64, 2, false>(ma0, ma1, mb, my, my1, p, st);
 }
 
 }  // namespace tc

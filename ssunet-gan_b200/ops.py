@@ -215,8 +215,9 @@ class GradSink:
 
 
 def grad_sink_for(x, expected=2):
-    """A GradSink when gradients for `x` will be needed and the tensor-core path (whose epilogue can accumulate) is on."""
-    if tc_mode() and torch.is_grad_enabled() and torch.is_tensor(x) and x.requires_grad:
+    """A GradSink when gradients for `x` (a tensor or a CatPair) will be needed and the tensor-core path (whose epilogue can
+    accumulate) is on."""
+    if tc_mode() and torch.is_grad_enabled() and (torch.is_tensor(x) or isinstance(x, CatPair)) and x.requires_grad:
         return GradSink(expected)
     return None
 
@@ -319,10 +320,105 @@ class _Conv2d(torch.autograd.Function):
         return dx, dw, db, None, None, None, None, None, None, None
 
 
+class CatPair(tuple):
+    """(a, b) standing for torch.cat([a, b], 1) WITHOUT materialising it (archs.py:651-667): the tensor-core convolutions
+    read the two tensors through two tensor maps (forward, weight gradient) and write the data gradient straight back into
+    two tensors, so neither torch.cat nor its backward copy exists.  Produced by `concat_channels(a, b, virtual=True)`,
+    consumed by `conv2d` / `BasicBlock`."""
+
+    @property
+    def requires_grad(self):
+        return self[0].requires_grad or self[1].requires_grad
+
+    def materialise(self):
+        return _Concat2.apply(self[0], self[1])
+
+
+def _cat_conv_ok(pair, weight, stride, pad):
+    from . import conv_tc
+    k = weight.shape[-1]
+    return (tc_mode() and pair[0].dtype == torch.bfloat16 and weight.shape[1] == pair[0].shape[1] + pair[1].shape[1]
+            and conv_tc.can_accumulate(k, stride, pad))
+
+
+class _Conv2dCat(torch.autograd.Function):
+    """`_Conv2d` over the virtual concatenation [x0 | x1] (same-size stride-1 1x1 / 3x3 on the tensor-core kernels only)."""
+
+    @staticmethod
+    def forward(ctx, x0, x1, weight, bias, stride, pad, act, slope, cout_store, want_stats, dx_sink):
+        from . import conv_tc
+        n, c0, h, w = x0.shape
+        cout = weight.shape[0]
+        cout_s = cout_store or cout
+        y = empty_nhwc(n, cout_s, h, w, x0.dtype, x0.device)
+        sums = None
+        if want_stats and conv_tc.has_stats(weight.shape[-1], stride, pad):
+            sums = torch.empty(2 * cout_s, dtype=torch.float64, device=x0.device)
+        conv_tc.forward(x0, weight, bias, y, stride, pad, act, slope, x1=x1, stats=sums)
+        ctx.save_for_backward(x0, x1, weight, y if act != ACT_NONE else None)
+        ctx.cfg = (stride, pad, act, slope, bias is not None)
+        ctx.dx_sink = dx_sink
+        if sums is not None:
+            ctx.mark_non_differentiable(sums)
+        return y, sums
+
+    @staticmethod
+    def backward(ctx, dy, _dsums=None):
+        from . import conv_tc
+        x0, x1, weight, y = ctx.saved_tensors
+        stride, pad, act, slope, has_bias = ctx.cfg
+        n, c0, h, w = x0.shape
+        c1 = x1.shape[1]
+        cout = weight.shape[0]
+        cout_s = dy.shape[1]
+        dt = x0.dtype
+        colsum = getattr(dy, "_ssg_colsum", None)
+        dy = _as_storage(dy, dt)
+        if act != ACT_NONE:
+            dz = torch.empty_like(dy)
+            call("ssg_act_bwd", dy, y, dz, dtype_code(dt), dy.numel(), act, slope)
+            dy = dz
+            colsum = None
+        dx0 = dx1 = dw = db = None
+        if ctx.needs_input_grad[0] or ctx.needs_input_grad[1]:
+            def write():
+                t0, t1 = empty_nhwc(n, c0, h, w, dt, x0.device), empty_nhwc(n, c1, h, w, dt, x0.device)
+                conv_tc.dgrad_split(dy, weight, t0, t1, stride, pad)
+                return (t0, t1)
+
+            def accumulate(buf):
+                conv_tc.dgrad_split(dy, weight, buf[0], buf[1], stride, pad, accumulate=True)
+
+            res = write() if ctx.dx_sink is None else ctx.dx_sink.contribute(write, accumulate)
+            if res is not None:
+                dx0, dx1 = res
+        if ctx.needs_input_grad[2]:
+            slot = weight.grad if weight.is_leaf else None
+            if (slot is not None and getattr(slot, "_ssg_arena", None) is not None and slot.dtype == torch.float32
+                    and slot.is_contiguous() and not torch.is_grad_enabled()):
+                conv_tc.wgrad(x0, dy, slot, stride, pad, x1=x1, accumulate=True)      # straight into the optimiser's gradient arena
+            else:
+                dw = torch.empty_like(weight, dtype=torch.float32)
+                conv_tc.wgrad(x0, dy, dw, stride, pad, x1=x1)
+        if has_bias and ctx.needs_input_grad[3]:
+            if colsum is not None and colsum.numel() == cout_s:
+                db = colsum[:cout].float()
+            else:
+                sums = torch.empty(2 * cout_s, dtype=torch.float64, device=x0.device)
+                call("ssg_channel_stats", dy, dtype_code(dt), _rows(dy), cout_s, sums, 0)
+                db = sums[:cout].float()
+        return dx0, dx1, dw, db, None, None, None, None, None, None, None
+
+
 def conv2d(x, weight, bias=None, stride=1, pad=0, act=ACT_NONE, slope=0.0, cout_store=None, want_stats=None, dx_sink=None):
     """want_stats (True / False; None = plain call returning y): return `(y, sums)` where sums is the fp64
     [sum y | sum y^2] per-channel statistics of the output when requested and the kernel can produce them in its epilogue
     (else None)."""
+    if isinstance(x, CatPair):
+        if _cat_conv_ok(x, weight, stride, pad):
+            y, sums = _Conv2dCat.apply(x[0], x[1], weight, bias, stride, pad, act, slope, cout_store, bool(want_stats), dx_sink)
+            return (y, sums) if want_stats is not None else y
+        x = x.materialise()
     y, sums = _Conv2d.apply(to_nhwc(x), weight, bias, stride, pad, act, slope, cout_store, bool(want_stats), dx_sink)
     return (y, sums) if want_stats is not None else y
 
@@ -642,9 +738,14 @@ def upsample_bilinear2x(x):
     return _Upsample2x.apply(to_nhwc(x))
 
 
-def concat_channels(a, b):
+def concat_channels(a, b, virtual=False):
+    """torch.cat([a, b], 1).  virtual: return a `CatPair` (no copy) when the tensor-core convolutions can consume it
+    (bf16, a's channel count a multiple of 64, b's a multiple of 8); the consumer materialises it if it cannot."""
     a = to_nhwc(a)
-    return _Concat2.apply(a, to_nhwc(b, a.dtype))
+    b = to_nhwc(b, a.dtype)
+    if virtual and tc_mode() and a.dtype == torch.bfloat16 and a.shape[1] % 64 == 0 and b.shape[1] % 8 == 0:
+        return CatPair((a, b))
+    return _Concat2.apply(a, b)
 
 
 # ----------------------------------------------------------------------------------------------

@@ -222,3 +222,61 @@ def test_grad_sink_equals_autograd_accumulation(which, monkeypatch):
     assert g1.keys() == g2.keys()
     for k in g1:
         assert rel(g1[k], g2[k]) < 1e-5, (k, rel(g1[k], g2[k]))
+
+
+@pytest.mark.parametrize("cfg", [(2, 64, 128, 64, 16, 16, 3), (1, 128, 256, 128, 40, 24, 1), (1, 384, 384, 384, 19, 13, 3), (1, 64, 8, 64, 33, 20, 3)])
+def test_conv_tc_dgrad_split_outputs(cfg):
+    """Data gradient written straight into the two sources of a virtual concatenation == slices of the plain data gradient."""
+    from ssunet_gan_b200 import conv_tc, ops
+    n, c0, c1, cout, h, w, k = cfg
+    pad = k // 2
+    g = torch.Generator().manual_seed(sum(cfg))
+    wgt = (torch.randn(cout, c0 + c1, k, k, generator=g) / math.sqrt((c0 + c1) * k * k)).cuda()
+    dy = ops.to_nhwc(torch.randn(n, cout, h, w, generator=g).cuda(), torch.bfloat16)
+    full = ops.empty_nhwc(n, c0 + c1, h, w, torch.bfloat16)
+    conv_tc.dgrad(dy, wgt, full, 1, pad)
+    d0, d1 = ops.empty_nhwc(n, c0, h, w, torch.bfloat16), ops.empty_nhwc(n, c1, h, w, torch.bfloat16)
+    conv_tc.dgrad_split(dy, wgt, d0, d1, 1, pad)
+    torch.cuda.synchronize()
+    assert torch.equal(d0, full[:, :c0]) and torch.equal(d1, full[:, c0:])
+    conv_tc.dgrad_split(dy, wgt, d0, d1, 1, pad, accumulate=True)           # d += d: exactly 2 x in bf16
+    torch.cuda.synchronize()
+    assert torch.equal(d0.float(), 2 * full[:, :c0].float()) and torch.equal(d1.float(), 2 * full[:, c0:].float())
+
+
+def test_basic_block_virtual_concat_equals_materialised():
+    """Decoder BasicBlock on CatPair(skip, up) (no torch.cat, no split in the backward) against the same block on the
+    materialised concatenation: outputs, both input gradients and every parameter gradient."""
+    import ssunet_gan_b200 as ssg
+    from ssunet_gan_b200 import archs, ops
+    ssg.set_compute_dtype(torch.bfloat16)
+    ssg.set_conv_impl("auto")
+    torch.manual_seed(11)
+    mod = archs.BasicBlock(64 + 128, 64).cuda().train()
+    a0, b0 = torch.randn(2, 64, 40, 24), torch.randn(2, 128, 40, 24)
+    gy = torch.randn(2, 64, 40, 24)
+
+    def once(virtual):
+        a = ops.to_nhwc(a0.cuda()).detach().requires_grad_(True)
+        b = ops.to_nhwc(b0.cuda()).detach().requires_grad_(True)
+        for p in mod.parameters():
+            p.grad = None
+        x = ops.concat_channels(ops.relu(a), ops.relu(b), virtual=virtual)
+        assert isinstance(x, ops.CatPair) == virtual
+        l0 = ops._lib.launch_count
+        y = mod(x)
+        y.backward(ops.to_nhwc(gy.cuda()))
+        return (y.detach().float(), a.grad.float().clone(), b.grad.float().clone(),
+                {k: p.grad.clone() for k, p in mod.named_parameters()}, ops._lib.launch_count - l0)
+
+    y1, da1, db1, g1, n1 = once(True)
+    y2, da2, db2, g2, n2 = once(False)
+    assert rel(y1, y2) < 1e-3
+    assert rel(da1, da2) < 3e-3 and rel(db1, db2) < 3e-3, (rel(da1, da2), rel(db1, db2))
+    for k in g1:
+        assert rel(g1[k], g2[k]) < 2e-3, (k, rel(g1[k], g2[k]))
+    with torch.no_grad():      # inference path
+        mod.eval()
+        ye = mod(ops.concat_channels(ops.to_nhwc(a0.cuda()), ops.to_nhwc(b0.cuda()), virtual=True))
+        yr = mod(ops.concat_channels(ops.to_nhwc(a0.cuda()), ops.to_nhwc(b0.cuda())))
+        assert rel(ye.float(), yr.float()) < 1e-3
