@@ -264,7 +264,7 @@ def main():
     # roofline leg: the dominant kernels (tcgen05 convolutions) timed one by one with CUDA events on the launching stream,
     # live, over eager steps of the same workload (a captured graph cannot carry per-kernel events)
     prof_steps = 2
-    PROF = ["ssg_conv2d_fwd_tc", "ssg_conv2d_dgrad_tc", "ssg_conv2d_dgrad_tc_acc", "ssg_conv2d_wgrad_tc", "ssg_conv2d_wgrad_tc_acc"]
+    PROF = ["ssg_conv2d_fwd_tc", "ssg_conv2d_dgrad_tc", "ssg_conv2d_dgrad_tc_acc", "ssg_conv2d_dgrad_tc_split", "ssg_conv2d_wgrad_tc", "ssg_conv2d_wgrad_tc_acc"]
     train_step.gan_train_step(g, d, og, od, dev[0][0], dev[0][1], with_metrics=False)
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -328,6 +328,22 @@ def main():
                  "what": "Generator.eval() forward + iou_score, batch %d x 3 x %d x %d bf16" % (ib, size, size)}
         g.train()
 
+    # Weak-scaling anchor (extra key, not the headline): BASELINE configs[1] runs batch 16 on one GPU but configs[2] runs batch 8 PER
+    # GPU on 2/4/8 GPUs, so value(N) / (N * value(1)) compares different per-GPU work.  The same step at batch 8 on this one GPU is
+    # the per-GPU work of the N > 1 runs: value(N) / (N * anchor) is the scaling efficiency at equal work per GPU.
+    anchor = None
+    if world == 1 and not args.batch and graphed is not None and batch > 8:
+        b8 = 8
+        xs = [(x[:b8].contiguous(), t[:b8].contiguous()) for x, t in dev]
+        g8 = train_step.GraphedGanStep(g, d, og, od, (b8, 3, size, size))
+        for i in range(2):
+            g8(*xs[i % n_sets])
+        ms8 = timed(lambda i: g8(*xs[i % n_sets]), args.steps)
+        anchor = {"value": b8 * args.steps * (size * size) / (512.0 * 512.0) / (ms8 / 1e3), "unit": UNIT, "batch_per_gpu": b8,
+                  "ms_per_step": ms8 / args.steps,
+                  "what": "the same captured G+D step at batch 8 on one GPU = the per-GPU work of BASELINE configs[2] (N = 2/4/8)"}
+        del g8
+
     imgs = world * batch * args.steps
     scale = (size * size) / (512.0 * 512.0)
     value = imgs * scale / (ms / 1e3)
@@ -375,6 +391,8 @@ def main():
         line["syncbn_stat_reduce_us"] = stat_reduce_us
     if infer is not None:
         line["inference"] = infer
+    if anchor is not None:
+        line["weak_scaling_anchor"] = anchor
     if not args.no_cpu_baseline and world == 1:
         b, s = [int(v) for v in args.cpu_sample.split("x")]
         t = cpu_reference_step(b, s, steps=1, warmup=0)

@@ -20,7 +20,7 @@ sys.path.insert(0, ROOT)
 import ssunet_gan_b200 as ssg  # noqa: E402
 from ssunet_gan_b200 import _lib, archs, losses, train_step  # noqa: E402
 
-CONV = ("ssg_conv2d_fwd_tc", "ssg_conv2d_dgrad_tc", "ssg_conv2d_dgrad_tc_acc", "ssg_conv2d_wgrad_tc", "ssg_conv2d_wgrad_tc_acc")
+CONV = ("ssg_conv2d_fwd_tc", "ssg_conv2d_dgrad_tc", "ssg_conv2d_dgrad_tc_acc", "ssg_conv2d_dgrad_tc_split", "ssg_conv2d_wgrad_tc", "ssg_conv2d_wgrad_tc_acc")
 
 
 def main():

@@ -18,19 +18,19 @@ __global__ void __launch_bounds__(BN_THREADS) channel_reduce_vec_kernel(
     long long rows, int C, long long rows_per_block, const float* __restrict__ mean, const float* __restrict__ inv_std,
     int act, float slope, int with_sq, double* __restrict__ sums) {
     constexpr int V = Vec<T>::N;
-    // Block-level accumulators are fp64: the order in which the threads' partial sums meet (shared-memory atomics) then
-    // cannot change the result beyond 1e-16, so the statistics are reproducible run to run.  With fp32 accumulators the
-    // mean / inv_std of a few channels moved by one fp32 ulp between identical launches, which the 8-sample BatchNorm at a
-    // U-Net bottleneck occasionally amplified to 1e-3 on the logits.
-    extern __shared__ double smd[];  // [2][C]
-    double* s0 = smd;
-    double* s1 = smd + C;
-    for (int i = threadIdx.x; i < 2 * C; i += BN_THREADS) smd[i] = 0.0;
-    __syncthreads();
+    // Block-level combination without atomics: every thread parks its fp32 partial sums in shared memory ([row group][C]), then
+    // thread c adds the row groups of channel c in a fixed order in fp64 and issues ONE fp64 atomic into the result.  The
+    // statistics are therefore reproducible run to run (only the cross-block fp64 atomics are unordered: 1e-16).  The first
+    // version used fp32 shared-memory atomics: the order in which warps hit them moved mean / inv_std of a few channels by one
+    // fp32 ulp between identical launches, which the 8-sample BatchNorm at a U-Net bottleneck occasionally amplified to 1e-3
+    // on the logits; it also serialised badly for thin tensors (C = 8: 256 threads on 16 addresses).
+    extern __shared__ float part[];  // [2][rpb][C]
     const int vpr = C / V;
     const int lanes = vpr < BN_THREADS ? vpr : BN_THREADS;   // threads cooperating on one row
     const int rpb = BN_THREADS / lanes;                       // rows processed per iteration
     const int lane = threadIdx.x % lanes, rsub = threadIdx.x / lanes;
+    float* p0 = part;
+    float* p1 = part + (size_t)rpb * C;
     const long long r_begin = (long long)blockIdx.x * rows_per_block;
     long long r_end = r_begin + rows_per_block;
     if (r_end > rows) r_end = rows;
@@ -104,16 +104,18 @@ __global__ void __launch_bounds__(BN_THREADS) channel_reduce_vec_kernel(
                 }
             }
 #pragma unroll
-            for (int i = 0; i < V; ++i) {
-                atomicAdd(&s0[v * V + i], (double)acc0[i]);
-                if (with_sq) atomicAdd(&s1[v * V + i], (double)acc1[i]);
+            for (int i = 0; i < V; ++i) {            // slot (rsub, channel) has exactly one owner in the block
+                p0[(size_t)rsub * C + v * V + i] = acc0[i];
+                p1[(size_t)rsub * C + v * V + i] = acc1[i];
             }
         }
     }
     __syncthreads();
     for (int c = threadIdx.x; c < C; c += BN_THREADS) {
-        atomicAdd(&sums[c], s0[c]);
-        if (with_sq) atomicAdd(&sums[C + c], s1[c]);
+        double a0 = 0.0, a1 = 0.0;
+        for (int r = 0; r < rpb; ++r) { a0 += (double)p0[(size_t)r * C + c]; a1 += (double)p1[(size_t)r * C + c]; }
+        atomicAdd(&sums[c], a0);
+        if (with_sq) atomicAdd(&sums[C + c], a1);
     }
 }
 
@@ -161,7 +163,9 @@ static int launch_channel_reduce(const T* a, const T* y, const T* x, long long r
     long long rpb = (rows + blocks - 1) / blocks;
     if (rpb < 64) rpb = 64;
     blocks = (rows + rpb - 1) / rpb;
-    size_t smem = sizeof(double) * 2 * C;
+    const int vpr_h = C / V, lanes_h = vpr_h < BN_THREADS ? vpr_h : BN_THREADS;
+    // vec kernel: fp32 partials [2][row groups][C]; scalar kernel (C not a multiple of the vector width): fp64 [2][C]
+    size_t smem = (C % V == 0) ? sizeof(float) * 2 * (size_t)(BN_THREADS / (lanes_h > 0 ? lanes_h : 1)) * C : sizeof(double) * 2 * C;
     if (smem > 48 * 1024) {     // C > 3072: opt in to the large dynamic shared-memory window once per instantiation
         static bool big_v = false, big_s = false;
         if (C % V == 0 && !big_v) {
