@@ -10,4 +10,5 @@ from . import ops  # noqa: F401
 from .ops import set_compute_dtype, compute_dtype, set_conv_impl  # noqa: F401
 
 __all__ = ["ops", "archs", "models_seg_gan", "normalization", "batchnorm", "comm", "replicate", "spectral_norm",
-           "losses", "metrics", "srgan_utils", "optim", "train_step", "set_compute_dtype", "compute_dtype", "set_conv_impl"]
+           "losses", "metrics", "srgan_utils", "optim", "train_step", "dataset", "aerial_image_segmentation_api", "xresidualblock",
+           "efficientnet_pytorch", "set_compute_dtype", "compute_dtype", "set_conv_impl"]

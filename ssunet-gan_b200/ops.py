@@ -214,10 +214,20 @@ class GradSink:
         return out
 
 
+_GRAD_SINK = True
+
+
+def set_grad_sink(enabled):
+    """Debugging switch: False makes every module fall back to autograd's own accumulation of its consumers' gradients."""
+    global _GRAD_SINK
+    _GRAD_SINK = bool(enabled)
+
+
 def grad_sink_for(x, expected=2):
     """A GradSink when gradients for `x` (a tensor or a CatPair) will be needed and the tensor-core path (whose epilogue can
     accumulate) is on."""
-    if tc_mode() and torch.is_grad_enabled() and (torch.is_tensor(x) or isinstance(x, CatPair)) and x.requires_grad:
+    if (_GRAD_SINK and tc_mode() and torch.is_grad_enabled() and (torch.is_tensor(x) or isinstance(x, CatPair))
+            and x.requires_grad):
         return GradSink(expected)
     return None
 

@@ -159,3 +159,50 @@ def test_data_parallel_host_logic_gloo_world2():
         assert par == (True, rank, world)
         assert grad_ok, "gradient averaging does not reproduce the global-batch gradient"
         assert bn_ok, "SyncBN statistics exchange does not reproduce full-batch BN"
+
+
+def test_dataset_decodes_reference_layout(tmp_path):
+    """dataset.Dataset keeps the reference's file layout and decode order (dataset.py:95-144): images/<id><ext> via cv2.imread
+    (BGR uint8 HWC), masks/<class>/<id><ext> stacked along the last axis; conversion to float / CHW is the device feed's job."""
+    cv2 = pytest.importorskip("cv2")
+    import numpy as np
+    from ssunet_gan_b200 import dataset
+    rng = np.random.RandomState(0)
+    img_dir, mask_dir = tmp_path / "images", tmp_path / "masks"
+    img_dir.mkdir()
+    ids = ["a01", "b02"]
+    imgs, masks = {}, {}
+    for i in ids:
+        imgs[i] = rng.randint(0, 256, size=(12, 10, 3)).astype(np.uint8)
+        cv2.imwrite(str(img_dir / (i + ".png")), imgs[i])
+        masks[i] = []
+        for c in range(3):
+            (mask_dir / str(c)).mkdir(parents=True, exist_ok=True)
+            m = rng.choice(np.array([0, 255], dtype=np.uint8), size=(12, 10))
+            cv2.imwrite(str(mask_dir / str(c) / (i + ".png")), m)
+            masks[i].append(m)
+    ds = dataset.Dataset(ids, str(img_dir), str(mask_dir), ".png", ".png", num_classes=3)
+    assert len(ds) == 2
+    ori, img, mask, extra, meta = ds[1]
+    assert meta == {"img_id": "b02"} and extra == []
+    assert img.dtype == np.uint8 and np.array_equal(img, imgs["b02"]) and np.array_equal(ori, imgs["b02"])
+    assert mask.shape == (12, 10, 3) and all(np.array_equal(mask[..., c], masks["b02"][c]) for c in range(3))
+    # a host transform (albumentations-style callable) is still honoured before the feed
+    ds2 = dataset.Dataset(ids, str(img_dir), str(mask_dir), ".png", ".png", 3, transform=lambda image, mask: {"image": image[::-1], "mask": mask[::-1]})
+    _, img2, mask2, _, _ = ds2[0]
+    assert np.array_equal(img2, imgs["a01"][::-1]) and np.array_equal(mask2[..., 2], masks["a01"][2][::-1])
+    # single-class / single-band layout (dataset.py:103-113)
+    cv2.imwrite(str(mask_dir / "a01.png"), masks["a01"][0])
+    ds1 = dataset.Dataset(["a01"], str(img_dir), str(mask_dir), ".png", ".png", num_classes=1, input_channels=1)
+    _, g1, m1, _, _ = ds1[0]
+    assert g1.shape == (12, 10, 1) and m1.shape == (12, 10, 1) and np.array_equal(m1[..., 0], masks["a01"][0])
+
+
+def test_device_feed_refuses_cpu():
+    import torch
+    from ssunet_gan_b200 import dataset
+    from ssunet_gan_b200._lib import SsgError
+    if torch.cuda.is_available():
+        pytest.skip("CUDA present")
+    with pytest.raises(SsgError):
+        dataset.DeviceFeed()
