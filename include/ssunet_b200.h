@@ -239,9 +239,11 @@ float ssg_pairwise_combine_host(const float* leaf_sums_host, long long n);
 /* img: uint8 [n,h,w,c] (cv2.imread layout, c <= 8).  out = (float(img) - sub[c]) * mul[c] with sub = mean * max_pixel_value and
  * mul = 1 / (std * max_pixel_value) precomputed in float32 (albumentations' Normalize).  nchw != 0: out is the reference's
  * NCHW tensor [n,c,h,w] in `dtype`; nchw == 0: out is NHWC [n,h,w,c_store] with zero padding channels (the layout the first
- * convolution reads).  flip_codes (optional, int per sample): bit 0 reverses x, bit 1 reverses y (albumentations Flip). */
+ * convolution reads).  post_div != 0: the result is then divided by post_div in float32 (`get_patched_input` divides the
+ * normalised patch by 255 once more, aerial_image_segmentation_api.py:367).  flip_codes (optional, int per sample): bit 0
+ * reverses x, bit 1 reverses y (albumentations Flip). */
 int ssg_feed_image_u8(const unsigned char* img, void* out, int dtype, int nchw, int n, int h, int w, int c, int c_store, const float* sub,
-                      const float* mul, const int* flip_codes, ssg_stream_t s);
+                      const float* mul, float post_div, const int* flip_codes, ssg_stream_t s);
 /* mask: uint8 [n,h,w,classes] (the per-class PNGs of dataset.py:126-131 stacked): out fp32 [n,classes,h,w] =
  * (uint8)(float32(mask) / 255.0), i.e. 1.0 only where the PNG holds 255; same flip codes. */
 int ssg_feed_mask_u8(const unsigned char* mask, float* out_nchw, int n, int h, int w, int classes, const int* flip_codes, ssg_stream_t s);
@@ -338,6 +340,17 @@ int ssg_mask_vote(const float* values, const int* windows, int patches, int clas
                   int* pos_votes, int* patch_count, ssg_stream_t s);
 /* masks uint8 [classes][h][w] = post_process((uint8)(votes / max(count, 1) * 255)) in {0, 255}, fp64 arithmetic as numpy */
 int ssg_mask_finalize(const int* pos_votes, const int* patch_count, int classes, int h, int w, unsigned char* masks, ssg_stream_t s);
+/* The reference's resize bridge (patch_size != network size, e.g. config_v1.json: 1024 vs 512).
+ * ssg_resize_u8_linear: cv2.resize(uint8 NHWC [n,h,w,c] -> [n,oh,ow,c]) with the default INTER_LINEAR, bit-exact (OpenCV's 11-bit
+ * fixed-point arithmetic; exact 2x shrinking takes cv::resize's INTER_AREA fast path) -- `get_patched_input`'s shrink of every
+ * image patch (:361).  xtab / ytab: [ow] / [oh] entries of 4 int32 {tap index 0, tap index 1, coef 0, coef 1} built by the host
+ * (may be NULL for the exact 2x shrink).
+ * ssg_mask_vote_resized: ssg_mask_vote for map_size x map_size maps that `patch_merge` first quantises to uint8 and upsamples to
+ * patch_size with cv2.resize (:150-152); the upsampled map is never materialised (tables over the patch_size outputs). */
+int ssg_resize_u8_linear(const unsigned char* src, unsigned char* dst, int n, int h, int w, int c, int oh, int ow, const int* xtab,
+                         const int* ytab, ssg_stream_t s);
+int ssg_mask_vote_resized(const float* values, const int* windows, int patches, int classes, int map_size, int patch_size, int h, int w,
+                          int apply_sigmoid, const int* xtab, const int* ytab, int* pos_votes, int* patch_count, ssg_stream_t s);
 
 #ifdef __cplusplus
 }

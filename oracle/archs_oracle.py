@@ -243,3 +243,88 @@ def feed_mask(mask_u8_nhwc, flip_cv2_codes=None):
             b = b[::-1] if d == 0 else (b[:, ::-1] if d == 1 else b[::-1, ::-1])
         out.append(np.ascontiguousarray((1.0 * b.astype("float32")).transpose(2, 0, 1)))
     return np.stack(out)
+
+
+# --------------------------------------------------------------------------------------
+# cv2.resize(uint8, INTER_LINEAR) restated (the resize bridge of tiled inference:
+# aerial_image_segmentation_api.py:151-152 upsamples every uint8 mask patch to patch_size, :361 shrinks every image
+# patch to the network's input size).  Pinned against cv2 itself by tests/test_oracle_golden.py.
+# Algorithm = OpenCV's resizeGeneric_ for 8U: 11-bit fixed-point coefficients, horizontal pass in int32, vertical pass
+# ((b0 * (r0 >> 4)) >> 16) + ((b1 * (r1 >> 4)) >> 16) + 2) >> 2; exact 2x shrinking is rerouted by cv::resize to the
+# INTER_AREA fast path (a + b + c + d + 2) >> 2.
+# --------------------------------------------------------------------------------------
+def cv2_linear_tables(src, dst):
+    """(ofs[dst], coef[dst, 2]) of OpenCV's linear resize along one axis of length `src` -> `dst`: source index of the
+    left tap and the two 11-bit coefficients (x-axis convention: taps clamped by zeroing the fraction at the borders)."""
+    import numpy as np
+    scale = 1.0 / (float(dst) / float(src))                    # double, as cv::resize computes it
+    d = np.arange(dst, dtype=np.float64)
+    f = ((d + 0.5) * scale - 0.5).astype(np.float32)
+    s = np.floor(f).astype(np.int64)
+    f = (f - s.astype(np.float32)).astype(np.float32)
+    lo = s < 0
+    f[lo], s[lo] = 0.0, 0
+    hi = s >= src - 1
+    f[hi], s[hi] = 0.0, src - 1
+    coef = np.stack([np.float32(1.0) - f, f], 1) * np.float32(2048.0)
+    return s.astype(np.int32), np.clip(np.rint(coef), -32768, 32767).astype(np.int32)
+
+
+def cv2_resize_linear_u8(img, dsize):
+    """cv2.resize(img, dsize) for uint8 `img` [H, W] or [H, W, C] with the default INTER_LINEAR; dsize = (width, height)."""
+    import numpy as np
+    ow, oh = dsize
+    a = img if img.ndim == 3 else img[..., None]
+    h, w, _ = a.shape
+    if w == 2 * ow and h == 2 * oh:                            # cv::resize: INTER_LINEAR at exactly 1/2 -> INTER_AREA fast path
+        s = a.astype(np.int32)
+        out = (s[0::2, 0::2] + s[0::2, 1::2] + s[1::2, 0::2] + s[1::2, 1::2] + 2) >> 2
+    else:
+        xo, xa = cv2_linear_tables(w, ow)
+        # the y axis keeps its fraction at the borders and clamps the two ROW indices instead (resizeGeneric_Invoker)
+        scale = 1.0 / (float(oh) / float(h))
+        fy = ((np.arange(oh, dtype=np.float64) + 0.5) * scale - 0.5).astype(np.float32)
+        sy = np.floor(fy).astype(np.int64)
+        fy = (fy - sy.astype(np.float32)).astype(np.float32)
+        yb = np.clip(np.rint(np.stack([np.float32(1.0) - fy, fy], 1) * np.float32(2048.0)), -32768, 32767).astype(np.int64)
+        y0, y1 = np.clip(sy, 0, h - 1), np.clip(sy + 1, 0, h - 1)
+        s = a.astype(np.int64)
+        x1 = np.minimum(xo + 1, w - 1)
+        rows = s[:, xo] * xa[:, 0][None, :, None] + s[:, x1] * xa[:, 1][None, :, None]          # [H, ow, C] int
+        r0, r1 = rows[y0], rows[y1]
+        out = (((yb[:, 0][:, None, None] * (r0 >> 4)) >> 16) + ((yb[:, 1][:, None, None] * (r1 >> 4)) >> 16) + 2) >> 2
+    out = np.clip(out, 0, 255).astype(np.uint8)
+    return out if img.ndim == 3 else out[..., 0]
+
+
+def tile_merge_resized(img_h, img_w, masks, p_size, num_classes, overlap):
+    """patch_merge (aerial_image_segmentation_api.py:129-217) for maps of ANY size: each (mask * 255).astype('uint8') is
+    resized to (p_size, p_size) with cv2.resize's arithmetic (:150-152) before the 127 threshold."""
+    import numpy as np
+    wins = O.tile_windows(img_h, img_w, p_size, overlap)
+    out = []
+    for c in range(num_classes):
+        merged = np.zeros((img_h, img_w))
+        div = np.zeros((img_h, img_w))
+        for (h1, w1), m in zip(wins, masks):
+            u8 = (np.asarray(m[c]) * 255).astype("uint8")
+            u8 = cv2_resize_linear_u8(u8, (p_size, p_size))
+            merged[h1:h1 + p_size, w1:w1 + p_size] += O._threshold127(u8) / 255.0
+            div[h1:h1 + p_size, w1:w1 + p_size] += 1.0
+        div[div == 0] = 1.0
+        out.append(O._threshold127((np.divide(merged, div) * 255).astype("uint8")))
+    return out
+
+
+def patched_input(img_u8, p_size, size, overlap, mean=(0.485, 0.456, 0.406), std=(0.229, 0.224, 0.225)):
+    """get_patched_input (:336-373) without file I/O: patch_gen windows, cv2.resize of each patch to (size, size),
+    albumentations' default Normalize() (restated, unpinned: see feed_normalize), `/ 255` again (:367), CHW."""
+    import numpy as np
+    wins = O.tile_windows(img_u8.shape[0], img_u8.shape[1], p_size, overlap)
+    out = []
+    for h1, w1 in wins:
+        patch = cv2_resize_linear_u8(np.ascontiguousarray(img_u8[h1:h1 + p_size, w1:w1 + p_size]), (size, size))
+        f = feed_normalize(patch, mean, std)
+        f = f.astype("float32") / 255
+        out.append(np.ascontiguousarray(f.transpose(2, 0, 1)))
+    return np.array(out)

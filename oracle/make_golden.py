@@ -285,6 +285,24 @@ def tiles_golden():
     np.savez_compressed(os.path.join(OUT, "tiles_merge_150x200.npz"), windows=wins, base=base, merged=np.stack(merged),
                         n_patches=np.int64(len(patches)), probs_csum=np.float64(probs.astype(np.float64).sum()))
     print("tiles_merge_150x200.npz: %d patches, %d bytes" % (len(patches), os.path.getsize(os.path.join(OUT, "tiles_merge_150x200.npz"))))
+    # ---- the resize bridge (patch_size != map size): the reference's own patch_merge + cv2.resize on S x S maps ----
+    rec = {}
+    for tag, (S, P2) in {"up2": (32, 64), "up_ragged": (40, 64), "down": (96, 64), "down2": (128, 64)}.items():
+        pw, _ = api.patch_gen(img, img, P2, OV)
+        b = rng.rand(len(pw), C, S // 8, S // 8).astype("float32")
+        pr = O.tile_test_probs(b)                                  # [P, C, S, S]
+        mg = api.patch_merge(img, [p for p in pr], P2, {"num_classes": C}, OV)
+        rec[tag + "_base"] = b
+        rec[tag + "_merged"] = np.stack(mg)
+        rec[tag + "_cfg"] = np.array([S, P2], dtype=np.int64)
+    # cv2.resize itself on random uint8 rasters (the image-side shrink of get_patched_input, :361)
+    import cv2
+    for tag, (h, w, oh, ow) in {"r_half": (64, 64, 32, 32), "r_up": (37, 41, 50, 64), "r_down": (100, 90, 33, 47), "r_quarter": (64, 64, 16, 16)}.items():
+        im = rng.randint(0, 256, size=(h, w, 3)).astype("uint8")
+        rec[tag + "_src"] = im
+        rec[tag + "_dst"] = cv2.resize(im, (ow, oh))
+    np.savez_compressed(os.path.join(OUT, "tiles_resize_bridge.npz"), **rec)
+    print("tiles_resize_bridge.npz: %d bytes" % os.path.getsize(os.path.join(OUT, "tiles_resize_bridge.npz")))
 
 
 if __name__ == "__main__":

@@ -196,9 +196,9 @@ def main():
     o8 = torch.empty(16 * 512 * 512, 8, dtype=BF, device=dev)
     o3 = torch.empty(16, 3, 512, 512, device=dev)
     rec("feed image u8 -> NHWC bf16 x8", "dataset.py:137-138 + Normalize", img.numel() + o8.numel() * 2,
-        lambda: call("ssg_feed_image_u8", img, o8, DT, 0, 16, 512, 512, 3, 8, sub, mul, None), "80 MB: fits L2, flushed")
+        lambda: call("ssg_feed_image_u8", img, o8, DT, 0, 16, 512, 512, 3, 8, sub, mul, 0.0, None), "80 MB: fits L2, flushed")
     rec("feed image u8 -> NCHW fp32", "dataset.py:137-138 + Normalize", img.numel() + o3.numel() * 4,
-        lambda: call("ssg_feed_image_u8", img, o3, 0, 1, 16, 512, 512, 3, 3, sub, mul, None), "63 MB: fits L2, flushed")
+        lambda: call("ssg_feed_image_u8", img, o3, 0, 1, 16, 512, 512, 3, 3, sub, mul, 0.0, None), "63 MB: fits L2, flushed")
     rec("feed mask u8 -> NCHW fp32", "dataset.py:128-140", img.numel() + o3.numel() * 4,
         lambda: call("ssg_feed_mask_u8", img, o3, 16, 512, 512, 3, None), "63 MB: fits L2, flushed")
 

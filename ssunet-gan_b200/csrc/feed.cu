@@ -17,13 +17,18 @@ __device__ __forceinline__ long long src_pixel(long long img, int y, int x, int 
     return (img * h + y) * (long long)w + x;
 }
 
+__device__ __forceinline__ float feed_value(unsigned char s, float sub, float mul, float post_div) {
+    const float v = ((float)s - sub) * mul;
+    return post_div != 0.f ? v / post_div : v;          // IEEE float32 division, as numpy's `img.astype('float32') / 255`
+}
+
 // albumentations.augmentations.functional.normalize: mean *= max_pixel; std *= max_pixel; denom = 1 / std (float32);
 // img = (float32(img) - mean) * denom.   sub[c] = mean[c] * max_pixel, mul[c] = 1 / (std[c] * max_pixel) arrive precomputed
 // in float32 by the host, so the kernel performs the same two float32 operations per element.
 template <typename T, bool NCHW>
 __global__ void __launch_bounds__(256) feed_image_kernel(const unsigned char* __restrict__ img, T* __restrict__ out, int n, int h, int w,
                                                           int c, int c_store, const float* __restrict__ sub, const float* __restrict__ mul,
-                                                          const int* __restrict__ flip) {
+                                                          float post_div, const int* __restrict__ flip) {
     const long long hw = (long long)h * w, total = (long long)n * hw, stride = (long long)gridDim.x * blockDim.x;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
         const int x = (int)(i % w), y = (int)((i / w) % h);
@@ -31,17 +36,17 @@ __global__ void __launch_bounds__(256) feed_image_kernel(const unsigned char* __
         const unsigned char* s = img + src_pixel(im, y, x, h, w, flip) * c;
         if (NCHW) {
             for (int k = 0; k < c; ++k)
-                out[(im * c + k) * hw + (long long)y * w + x] = from_f<T>(((float)s[k] - sub[k]) * mul[k]);
+                out[(im * c + k) * hw + (long long)y * w + x] = from_f<T>(feed_value(s[k], sub[k], mul[k], post_div));
         } else {
             T* d = out + i * c_store;
-            for (int k = 0; k < c_store; ++k) d[k] = from_f<T>(k < c ? ((float)s[k] - sub[k]) * mul[k] : 0.f);
+            for (int k = 0; k < c_store; ++k) d[k] = from_f<T>(k < c ? feed_value(s[k], sub[k], mul[k], post_div) : 0.f);
         }
     }
 }
 // the common case of the tensor-core path: 3 (or 4) bands stored as 8 bf16 channels -> one 16-byte store per pixel
 __global__ void __launch_bounds__(256) feed_image_nhwc8_kernel(const unsigned char* __restrict__ img, bf16* __restrict__ out, int n, int h,
                                                                 int w, int c, const float* __restrict__ sub, const float* __restrict__ mul,
-                                                                const int* __restrict__ flip) {
+                                                                float post_div, const int* __restrict__ flip) {
     const long long hw = (long long)h * w, total = (long long)n * hw, stride = (long long)gridDim.x * blockDim.x;
     float sb[8], ml[8];
 #pragma unroll
@@ -51,7 +56,7 @@ __global__ void __launch_bounds__(256) feed_image_nhwc8_kernel(const unsigned ch
         const unsigned char* s = img + src_pixel(i / hw, y, x, h, w, flip) * c;
         float f[8];
 #pragma unroll
-        for (int k = 0; k < 8; ++k) f[k] = k < c ? ((float)s[k] - sb[k]) * ml[k] : 0.f;
+        for (int k = 0; k < 8; ++k) f[k] = k < c ? feed_value(s[k], sb[k], ml[k], post_div) : 0.f;
         Vec<bf16> v; v.set(f); v.store(out + i * 8);
     }
 }
@@ -74,16 +79,16 @@ using namespace ssg;
 extern "C" {
 
 int ssg_feed_image_u8(const unsigned char* img, void* out, int dtype, int nchw, int n, int h, int w, int c, int c_store, const float* sub,
-                      const float* mul, const int* flip_codes, ssg_stream_t s) {
+                      const float* mul, float post_div, const int* flip_codes, ssg_stream_t s) {
     SSG_CHECK_ARG(img && out && sub && mul && n > 0 && h > 0 && w > 0 && c > 0 && c <= 8 && c_store >= c, "feed_image_u8: bad arguments");
     SSG_CHECK_ARG(!nchw || c_store == c, "feed_image_u8: NCHW output is never channel-padded");
     const unsigned g = grid_for((long long)n * h * w, 256 * 2);
     if (!nchw && dtype == SSG_BF16 && c_store == 8) {
-        feed_image_nhwc8_kernel<<<g, 256, 0, (cudaStream_t)s>>>(img, (bf16*)out, n, h, w, c, sub, mul, flip_codes);
+        feed_image_nhwc8_kernel<<<g, 256, 0, (cudaStream_t)s>>>(img, (bf16*)out, n, h, w, c, sub, mul, post_div, flip_codes);
     } else {
         SSG_DISPATCH_DTYPE(dtype, {
-            if (nchw) feed_image_kernel<T, true><<<g, 256, 0, (cudaStream_t)s>>>(img, (T*)out, n, h, w, c, c_store, sub, mul, flip_codes);
-            else feed_image_kernel<T, false><<<g, 256, 0, (cudaStream_t)s>>>(img, (T*)out, n, h, w, c, c_store, sub, mul, flip_codes);
+            if (nchw) feed_image_kernel<T, true><<<g, 256, 0, (cudaStream_t)s>>>(img, (T*)out, n, h, w, c, c_store, sub, mul, post_div, flip_codes);
+            else feed_image_kernel<T, false><<<g, 256, 0, (cudaStream_t)s>>>(img, (T*)out, n, h, w, c, c_store, sub, mul, post_div, flip_codes);
         });
     }
     SSG_CHECK_LAUNCH();

@@ -104,7 +104,9 @@ class DeviceFeed:
             raise SsgError("DeviceFeed: one flip code per sample expected")
         return c.to(self.device, non_blocking=True)
 
-    def images(self, img_u8, flip_codes=None, nchw=False):
+    def images(self, img_u8, flip_codes=None, nchw=False, post_div=0.0):
+        """post_div: divide the normalised values by this (float32) -- `get_patched_input` divides by 255 once more
+        (aerial_image_segmentation_api.py:367)."""
         t = self._u8(img_u8)
         n, h, w, c = t.shape
         if c > self.sub.numel():
@@ -112,12 +114,12 @@ class DeviceFeed:
         fc = self._flip(flip_codes, n)
         if nchw:
             out = torch.empty((n, c, h, w), dtype=torch.float32, device=self.device)
-            call("ssg_feed_image_u8", t, out, dtype_code(torch.float32), 1, n, h, w, c, c, self.sub, self.mul, fc)
+            call("ssg_feed_image_u8", t, out, dtype_code(torch.float32), 1, n, h, w, c, c, self.sub, self.mul, float(post_div), fc)
             return out
         dt = ops.compute_dtype()
         cs = ops.thin_pad(c)
         out = ops.empty_nhwc(n, cs, h, w, dt, self.device)
-        call("ssg_feed_image_u8", t, out, dtype_code(dt), 0, n, h, w, c, cs, self.sub, self.mul, fc)
+        call("ssg_feed_image_u8", t, out, dtype_code(dt), 0, n, h, w, c, cs, self.sub, self.mul, float(post_div), fc)
         return out
 
     def masks(self, mask_u8, flip_codes=None, binarise=True):
@@ -129,7 +131,7 @@ class DeviceFeed:
             call("ssg_feed_mask_u8", t, out, n, h, w, k, fc)
         else:       # mask.astype('float32') / 1.0 (dataset.py:112,123): the identity normalisation
             one = torch.ones(k, dtype=torch.float32, device=self.device)
-            call("ssg_feed_image_u8", t, out, dtype_code(torch.float32), 1, n, h, w, k, k, torch.zeros_like(one), one, fc)
+            call("ssg_feed_image_u8", t, out, dtype_code(torch.float32), 1, n, h, w, k, k, torch.zeros_like(one), one, 0.0, fc)
         return out
 
     def __call__(self, img_u8, mask_u8, flip_codes=None, nchw=False):

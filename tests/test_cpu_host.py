@@ -206,3 +206,27 @@ def test_device_feed_refuses_cpu():
         pytest.skip("CUDA present")
     with pytest.raises(SsgError):
         dataset.DeviceFeed()
+
+
+def test_cvresize_header_and_product_tables_match_cv2(tmp_path, golden_dir):
+    """The per-pixel fixed-point function the CUDA resize / vote kernels call (csrc/cvresize.h), compiled for the host and fed
+    with the PRODUCT's coefficient tables, reproduces cv2.resize on the fixtures written by cv2 itself."""
+    import subprocess
+    import numpy as np
+    from ssunet_gan_b200 import aerial_image_segmentation_api as api
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    so = str(tmp_path / "cvresize_host.so")
+    subprocess.run(["g++", "-O2", "-shared", "-fPIC", "-o", so, os.path.join(root, "tests", "cvresize_host.cpp")], check=True)
+    L = ctypes.CDLL(so)
+    L.host_resize_u8.argtypes = [ctypes.c_void_p] * 2 + [ctypes.c_int] * 6 + [ctypes.c_void_p] * 2
+    z = np.load(os.path.join(golden_dir, "tiles_resize_bridge.npz"))
+    for tag in ("r_half", "r_up", "r_down", "r_quarter"):
+        src, want = np.ascontiguousarray(z[tag + "_src"]), z[tag + "_dst"]
+        h, w, c = src.shape
+        oh, ow = want.shape[:2]
+        xt = api._linear_table(w, ow, "x", "cpu").numpy()
+        yt = api._linear_table(h, oh, "y", "cpu").numpy()
+        assert xt.dtype == np.int32 and xt.shape == (ow, 4) and bool((xt[:, 2] + xt[:, 3] == 2048).all())
+        dst = np.empty((oh, ow, c), dtype=np.uint8)
+        L.host_resize_u8(src.ctypes.data, dst.ctypes.data, 1, h, w, c, oh, ow, xt.ctypes.data, yt.ctypes.data)
+        assert np.array_equal(dst, want), tag

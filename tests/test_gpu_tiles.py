@@ -79,3 +79,79 @@ def test_segmentation_inference_batched_matches_per_patch_oracle_merge():
     # 128 / 255 could flip a vote
     assert diff <= 2, diff
     assert got_gt is got or all(np.array_equal(a, b) for a, b in zip(got, got_gt))
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# the cv2.resize bridge (patch size != network size, e.g. config_v1.json: 1024 vs 512)
+# ------------------------------------------------------------------------------------------------------------------
+def test_resize_u8_bit_exact_vs_cv2_fixtures(golden_dir):
+    from ssunet_gan_b200 import aerial_image_segmentation_api as api
+    z = np.load(os.path.join(golden_dir, "tiles_resize_bridge.npz"))
+    for tag in ("r_half", "r_up", "r_down", "r_quarter"):
+        src, want = z[tag + "_src"], z[tag + "_dst"]
+        batch = torch.from_numpy(np.stack([src, src[::-1].copy()])).cuda()
+        got = api.resize_u8(batch, want.shape[0], want.shape[1]).cpu().numpy()
+        assert got.dtype == np.uint8 and np.array_equal(got[0], want), tag
+    import archs_oracle as A            # a larger raster against the numpy restatement (itself pinned to cv2)
+    rng = np.random.RandomState(8)
+    big = rng.randint(0, 256, size=(3, 256, 256, 3)).astype(np.uint8)
+    for (oh, ow) in ((128, 128), (512, 512), (200, 300)):
+        got = api.resize_u8(torch.from_numpy(big).cuda(), oh, ow).cpu().numpy()
+        for i in range(3):
+            assert np.array_equal(got[i], A.cv2_resize_linear_u8(big[i], (ow, oh))), (oh, ow, i)
+
+
+def test_patch_merge_with_resize_bridge_bit_exact_vs_reference(golden_dir):
+    """Maps smaller / larger than the patch: the device merge == the unmodified reference's patch_merge (cv2.resize inside)."""
+    import ssunet_oracle as O
+    from ssunet_gan_b200 import aerial_image_segmentation_api as api
+    z = np.load(os.path.join(golden_dir, "tiles_resize_bridge.npz"))
+    H, W, C, OV = 150, 200, 3, 0.5
+    img = np.zeros((H, W, 3), dtype=np.uint8)
+    for tag in ("up2", "up_ragged", "down", "down2"):
+        S, P2 = (int(v) for v in z[tag + "_cfg"])
+        probs = O.tile_test_probs(z[tag + "_base"])
+        merged = api.patch_merge(img, torch.from_numpy(probs).cuda(), P2, {"num_classes": C}, OV)
+        assert np.array_equal(np.stack(merged), z[tag + "_merged"]), tag
+
+
+def test_get_patched_input_device_vs_oracle():
+    """Image side of the bridge: windows, cv2.resize shrink, Normalize(), / 255, CHW -- bit-exact against the numpy restatement."""
+    import archs_oracle as A
+    from ssunet_gan_b200 import aerial_image_segmentation_api as api
+    rng = np.random.RandomState(4)
+    raster = rng.randint(0, 256, size=(150, 200, 3)).astype(np.uint8)
+    for (P, S) in ((64, 32), (64, 48), (64, 64)):
+        cfg = {"patch_size": P, "input_w": S, "input_h": S, "patch_overlap": 0.5, "num_classes": 3}
+        img, patches, raw = api.get_patched_input(raster, cfg, False, chunk=7)
+        want = A.patched_input(raster, P, S, 0.5)
+        assert img is raster and patches.dtype == torch.float32 and tuple(patches.shape) == want.shape
+        assert np.array_equal(patches.cpu().numpy(), want), (P, S)
+        assert raw.shape == (want.shape[0], P, P, 3)
+
+
+def test_segmentation_inference_with_resize_bridge():
+    """End to end at patch 128 / network 64: device shrink + batched forward + resizing vote == the reference flow (cv2-style
+    resize of the uint8 sigmoid maps, host merge) applied to the SAME logits."""
+    import archs_oracle as A
+    import ssunet_oracle as O
+    import ssunet_gan_b200 as ssg
+    from ssunet_gan_b200 import aerial_image_segmentation_api as api, models_seg_gan
+    ssg.set_compute_dtype(torch.bfloat16)
+    g = models_seg_gan.Generator({"arch": "UNet_R_SS_v2", "num_classes": 3, "input_channels": 3, "deep_supervision": False})
+    g.load_state_dict(O.portable_state_dict(O.unet_r_ss_v2_spec(3, 3, prefix="net.")))
+    g.cuda().eval()
+    H, W, P, S, OV = 300, 420, 128, 64, 0.5
+    raster = np.random.RandomState(12).randint(0, 256, size=(H, W, 3)).astype(np.uint8)
+    cfg = {"patch_size": P, "input_w": S, "input_h": S, "patch_overlap": OV, "num_classes": 3}
+    img, patch_set, raw = api.get_patched_input(raster, cfg, False)
+    got, _ = api.segmentation_inference(g, img, patch_set, raw, cfg, False, batch_size=16)
+    with torch.no_grad():
+        logits = torch.cat([g(patch_set[i:i + 16]) for i in range(0, len(patch_set), 16)])
+        probs = torch.sigmoid(logits).cpu().numpy()
+    want = A.tile_merge_resized(H, W, list(probs), P, 3, OV)
+    assert got[0].shape == (H, W) and got[0].dtype == np.uint8
+    diff = sum(int((a != b).sum()) for a, b in zip(got, want))
+    # sigmoid in the kernel vs torch.sigmoid may differ in the last ulp: a probability within one ulp of a uint8 step can move
+    # one quantised sample by 1, which only matters where the interpolated value sits exactly at the 127 threshold
+    assert diff <= 8, diff

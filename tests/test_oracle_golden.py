@@ -340,3 +340,35 @@ def test_supervised_step_oracle_matches_reference(golden_dir, name, ds, hw):
             lo = 1 if _bias_before_bn(k) else 0
             _close(_csum(sd[k])[lo:], c[lo:], rtol=2e-4, atol=1e-5)
     _close(sd[str(z["probe_key"])].detach().numpy(), z["probe"], rtol=1e-4, atol=1e-6)
+
+
+# ---------------------------------------------------------------------------------------------
+# tiled inference: the cv2.resize bridge (patch size != network size)
+# ---------------------------------------------------------------------------------------------
+def test_cv2_resize_restatement_matches_cv2(golden_dir):
+    import archs_oracle as A
+    z = np.load(os.path.join(golden_dir, "tiles_resize_bridge.npz"))
+    for tag in ("r_half", "r_up", "r_down", "r_quarter"):
+        src, dst = z[tag + "_src"], z[tag + "_dst"]
+        assert np.array_equal(A.cv2_resize_linear_u8(src, (dst.shape[1], dst.shape[0])), dst), tag
+    try:
+        import cv2
+    except ImportError:
+        return
+    rng = np.random.RandomState(5)
+    for (h, w, oh, ow) in ((512, 512, 1024, 1024), (33, 33, 100, 100), (16, 16, 17, 15), (5, 7, 64, 64), (128, 128, 127, 129), (64, 48, 32, 24)):
+        im = rng.randint(0, 256, size=(h, w)).astype(np.uint8)
+        assert np.array_equal(A.cv2_resize_linear_u8(im, (ow, oh)), cv2.resize(im, (ow, oh))), (h, w, oh, ow)
+
+
+def test_tile_merge_resized_matches_reference(golden_dir):
+    """oracle patch_merge with the resize bridge == the unmodified reference's patch_merge (which calls cv2.resize)."""
+    import archs_oracle as A
+    z = np.load(os.path.join(golden_dir, "tiles_resize_bridge.npz"))
+    H, W, C, OV = 150, 200, 3, 0.5
+    for tag in ("up2", "up_ragged", "down", "down2"):
+        S, P2 = (int(v) for v in z[tag + "_cfg"])
+        probs = O.tile_test_probs(z[tag + "_base"])
+        assert probs.shape[-1] == S
+        got = A.tile_merge_resized(H, W, list(probs), P2, C, OV)
+        assert np.array_equal(np.stack(got), z[tag + "_merged"]), tag
