@@ -230,3 +230,41 @@ def test_cvresize_header_and_product_tables_match_cv2(tmp_path, golden_dir):
         dst = np.empty((oh, ow, c), dtype=np.uint8)
         L.host_resize_u8(src.ctypes.data, dst.ctypes.data, 1, h, w, c, oh, ow, xt.ctypes.data, yt.ctypes.data)
         assert np.array_equal(dst, want), tag
+
+
+def test_grad_sink_protocol():
+    """ops.GradSink: the first member writes, later members accumulate, only the LAST one reports a gradient; the sink resets
+    itself afterwards (a second backward through the same graph starts clean)."""
+    from ssunet_gan_b200 import ops
+    log = []
+    sink = ops.GradSink(expected=3)
+
+    def member(tag, val):
+        return sink.contribute(lambda: log.append(("write", tag)) or [val], lambda buf: (log.append(("acc", tag)), buf.__setitem__(0, buf[0] + val)))
+
+    for rnd in range(2):
+        assert member("a", 1) is None
+        assert member("b", 10) is None
+        out = member("c", 100)
+        assert out == [111] and sink.buf is None and sink.arrived == 0
+    assert log == [("write", "a"), ("acc", "b"), ("acc", "c")] * 2
+    # no sink without the tensor-core path / without gradients
+    import torch
+    assert ops.grad_sink_for(torch.zeros(2, requires_grad=False)) is None
+    ops.set_grad_sink(False)
+    try:
+        assert ops.grad_sink_for(torch.zeros(2, requires_grad=True)) is None
+    finally:
+        ops.set_grad_sink(True)
+
+
+def test_cat_pair_is_a_tuple_of_two_sources():
+    import torch
+    from ssunet_gan_b200 import ops
+    a, b = torch.zeros(1, 64, 2, 2, requires_grad=True), torch.zeros(1, 8, 2, 2)
+    pair = ops.CatPair((a, b))
+    assert pair[0] is a and pair[1] is b and len(pair) == 2 and pair.requires_grad
+    assert not ops.CatPair((b, b)).requires_grad
+    # on the CPU (no tensor-core path) concat_channels refuses rather than silently materialising with torch
+    with pytest.raises(ops._lib.SsgError):
+        ops.concat_channels(a, b, virtual=True)
