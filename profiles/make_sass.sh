@@ -9,7 +9,7 @@ for f in conv_tc_halo conv_tc; do
     /Function : /{ if (name != "") printf("%-110s UTCHMMA %4d  LDTM %3d  UTMALDG %3d  UTMASTG %3d  UTMAREDG %3d  SYNCS %4d\n", name, m, l, t, s, r, y);
                    name = $3; m = l = t = s = y = r = 0 }
     /UTCHMMA/{m++} /LDTM/{l++} /UTMALDG/{t++} /UTMASTG/{s++} /UTMAREDG/{r++} /SYNCS/{y++}
-    END{ printf("%-110s UTCHMMA %4d  LDTM %3d  UTMALDG %3d  UTMASTG %3d  SYNCS %4d\n", name, m, l, t, s, y) }' | cu++filt | cut -c1-240
+    END{ printf("%-110s UTCHMMA %4d  LDTM %3d  UTMALDG %3d  UTMASTG %3d  SYNCS %4d\n", name, m, l, t, s, y) }' | cu++filt | cut -c1-320
 done
 echo
 echo "ptxas resource usage of the same kernels:"
