@@ -191,6 +191,16 @@ int ssg_spade_modulate_bwd(const void* dy, const void* x, const void* gb, void* 
 int ssg_spade_modulate_bwd_sums(const void* dy, const void* x, const void* gb, void* dx, void* dgb, int dtype, long long rows,
                                 int c, double* colsum, ssg_stream_t s);
 
+/* Whole self-conditioned SPADE forward in one kernel (normalization.py:106-122 with segmap = x): x is staged once per 16 x 16
+ * tile with a 3-pixel halo, the three thin convolutions run as warp-level mma.sync out of shared memory and the modulation is
+ * applied to the accumulators (csrc/spade_fused.cu).  OPT-IN (not the default path yet).  x [n,h,w,c] bf16 with c in {64, 128};
+ * w1 bf16 [9][8][c] (x2map, tap-major, rows >= label_nc zero); w2 bf16 [8][80] (mlp_shared, k = tap * 8 + ci, zero padded);
+ * w3 bf16 [2c][80] (gamma rows then beta rows); b1 / b2 fp32 [8], b3 fp32 [2c]; outputs seg / actv bf16 [n,h,w,8],
+ * gb bf16 [n,h,w,2c] (may be NULL: inference) and y bf16 [n,h,w,c]. */
+int ssg_spade_fused_supported(int c, int label_nc, int hidden);
+int ssg_spade_fused_fwd(const void* x, const void* w1, const float* b1, const void* w2, const float* b2, const void* w3, const float* b3,
+                        void* seg, void* actv, void* gb, void* y, int n, int h, int w, int c, ssg_stream_t s);
+
 /* ---- elementwise ---------------------------------------------------------------------------- */
 int ssg_act_fwd(const void* x, void* y, int dtype, long long n, int act, float slope, ssg_stream_t s);
 int ssg_act_bwd(const void* dy, const void* y, void* dx, int dtype, long long n, int act, float slope, ssg_stream_t s);

@@ -42,6 +42,9 @@ class SPADE(nn.Module):
 
     def forward(self, x, segmap):
         x = ops.to_nhwc(x)
+        if (segmap is x and self._pw == 1 and x.dtype == torch.bfloat16
+                and ops.spade_fused_enabled(x.shape[1], self.x2map.out_channels, self.mlp_shared[0].out_channels)):
+            return ops.spade_fused(x, self.x2map, self.mlp_shared[0], self.mlp_gamma, self.mlp_beta)      # opt-in, DESIGN.md §7.1
         # the 3- and h-channel maps are stored channel-padded (ops.thin_pad) so they can feed the TMA/tcgen05 kernels
         # self-conditioned use (segmap is x): x feeds x2map AND the modulation; their two gradient contributions meet in one
         # buffer (ops.GradSink: the x2map data-gradient kernel adds into what the modulation's backward wrote)

@@ -795,6 +795,112 @@ def spade_modulate(x, gb, dx_sink=None):
     return _SpadeModulate.apply(to_nhwc(x), gb, dx_sink)
 
 
+# ----------------------------------------------------------------------------------------------
+# fused self-conditioned SPADE (csrc/spade_fused.cu) -- OPT-IN until it has been validated on the GPU
+# ----------------------------------------------------------------------------------------------
+import os as _os
+
+_SPADE_FUSED = _os.environ.get("SSG_SPADE_FUSED") == "1"
+
+
+def set_spade_fused(enabled):
+    """Route self-conditioned SPADE blocks with 64 / 128 channels through the one-kernel forward."""
+    global _SPADE_FUSED
+    _SPADE_FUSED = bool(enabled)
+
+
+def spade_fused_enabled(c, label_nc, hidden):
+    return (_SPADE_FUSED and tc_mode() and bool(_lib.lib().ssg_spade_fused_supported(int(c), int(label_nc), int(hidden))))
+
+
+def _pad_to(t, dim, size):
+    if t.shape[dim] == size:
+        return t
+    shape = list(t.shape)
+    shape[dim] = size - t.shape[dim]
+    return torch.cat([t, t.new_zeros(shape)], dim)
+
+
+def _spade_fused_operands(w1, b1, w2, b2, wg, bg, wb, bb):
+    """Operand layouts of ssg_spade_fused_fwd from the four convolutions' OIHW parameters (parameter plumbing: tiny tensors)."""
+    label, c = w1.shape[0], w1.shape[1]
+    h = w2.shape[0]
+    p1 = _pad_to(w1.detach().permute(2, 3, 0, 1).reshape(9, label, c), 1, 8).to(torch.bfloat16).contiguous()
+    p2 = _pad_to(_pad_to(w2.detach().permute(0, 2, 3, 1), 3, 8).reshape(h, 72), 1, 80)
+    p2 = _pad_to(p2, 0, 8).to(torch.bfloat16).contiguous()
+    w3 = torch.cat([wg.detach(), wb.detach()], 0)
+    p3 = _pad_to(_pad_to(w3.permute(0, 2, 3, 1), 3, 8).reshape(2 * c, 72), 1, 80).to(torch.bfloat16).contiguous()
+    q1 = _pad_to(b1.detach().float(), 0, 8).contiguous()
+    q2 = _pad_to(b2.detach().float(), 0, 8).contiguous()
+    q3 = torch.cat([bg.detach(), bb.detach()], 0).float().contiguous()
+    return p1, q1, p2, q2, p3, q3
+
+
+class _SpadeFused(torch.autograd.Function):
+    """y = x * (1 + gamma(actv)) + beta(actv), actv = relu(mlp_shared(x2map(x))): forward = ONE kernel; backward = the unfused
+    chain's kernels driven by hand on the saved thin intermediates (seg, actv) and gamma|beta."""
+
+    @staticmethod
+    def forward(ctx, x, w1, b1, w2, b2, wg, bg, wb, bb):
+        n, c, h, w = x.shape
+        dev = x.device
+        need_grad = any(ctx.needs_input_grad)      # (grad mode is always off inside Function.forward)
+        seg = empty_nhwc(n, 8, h, w, torch.bfloat16, dev)
+        actv = empty_nhwc(n, 8, h, w, torch.bfloat16, dev)
+        gb = empty_nhwc(n, 2 * c, h, w, torch.bfloat16, dev) if need_grad else None
+        y = empty_nhwc(n, c, h, w, torch.bfloat16, dev)
+        p1, q1, p2, q2, p3, q3 = _spade_fused_operands(w1, b1, w2, b2, wg, bg, wb, bb)
+        call("ssg_spade_fused_fwd", x, p1, q1, p2, q2, p3, q3, seg, actv, gb, y, n, h, w, c)
+        if need_grad:
+            ctx.save_for_backward(x, seg, actv, gb, w1, w2, wg, wb)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        from . import conv_tc
+        x, seg, actv, gb, w1, w2, wg, wb = ctx.saved_tensors
+        n, c, h, w = x.shape
+        dt, dev = x.dtype, x.device
+        rows = _rows(x)
+        dy = _as_storage(dy, dt)
+        # modulation: dx_part = dy (1 + gamma), dgb = [dy x | dy], bias gradients of gamma | beta ride along
+        dx = empty_nhwc(n, c, h, w, dt, dev)
+        dgb = empty_nhwc(n, 2 * c, h, w, dt, dev)
+        colsum = torch.empty(4 * c, dtype=torch.float64, device=dev)[:2 * c]
+        call("ssg_spade_modulate_bwd_sums", dy, x, gb, dx, dgb, dtype_code(dt), rows, c, colsum)
+        # gamma | beta convolution (h -> 2C)
+        w3 = torch.cat([wg, wb], 0)
+        d_actv = empty_nhwc(n, 8, h, w, dt, dev)
+        conv_tc.dgrad(dgb, w3, d_actv, 1, 1)
+        dw3 = torch.empty_like(w3, dtype=torch.float32)
+        conv_tc.wgrad(actv, dgb, dw3, 1, 1)
+        db3 = colsum.float()
+        # ReLU, mlp_shared (label_nc -> h)
+        dz = torch.empty_like(d_actv)
+        call("ssg_act_bwd", d_actv, actv, dz, dtype_code(dt), dz.numel(), ACT_RELU, 0.0)
+        d_seg = empty_nhwc(n, 8, h, w, dt, dev)
+        conv_tc.dgrad(dz, w2, d_seg, 1, 1)
+        dw2 = torch.empty_like(w2, dtype=torch.float32)
+        conv_tc.wgrad(seg, dz, dw2, 1, 1)
+        s2 = torch.empty(16, dtype=torch.float64, device=dev)
+        call("ssg_channel_stats", dz, dtype_code(dt), rows, 8, s2, 0)
+        db2 = s2[:w2.shape[0]].float()
+        # x2map (C -> label_nc): its data gradient is ADDED into dx by the kernel's epilogue
+        conv_tc.dgrad(d_seg, w1, dx, 1, 1, accumulate=True)
+        dw1 = torch.empty_like(w1, dtype=torch.float32)
+        conv_tc.wgrad(x, d_seg, dw1, 1, 1)
+        s1 = torch.empty(16, dtype=torch.float64, device=dev)
+        call("ssg_channel_stats", d_seg, dtype_code(dt), rows, 8, s1, 0)
+        db1 = s1[:w1.shape[0]].float()
+        return dx, dw1, db1, dw2, db2, dw3[:c], db3[:c], dw3[c:], db3[c:]
+
+
+def spade_fused(x, x2map, mlp_shared, mlp_gamma, mlp_beta):
+    """The four convolution modules of a SPADE block (3x3, padding 1, with bias) applied to x as its own segmentation map."""
+    return _SpadeFused.apply(to_nhwc(x), x2map.weight, x2map.bias, mlp_shared.weight, mlp_shared.bias,
+                             mlp_gamma.weight, mlp_gamma.bias, mlp_beta.weight, mlp_beta.bias)
+
+
 class _Act(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, act, slope):

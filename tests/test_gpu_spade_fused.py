@@ -1,0 +1,61 @@
+"""Opt-in one-kernel SPADE forward (csrc/spade_fused.cu) against the unfused chain of the same module: forward
+and every gradient.  The kernel is not the default path yet, so this file only runs when SSG_SPADE_FUSED_TEST=1."""
+import os
+
+import pytest
+import torch
+
+pytestmark = [pytest.mark.gpu, pytest.mark.skipif(os.environ.get("SSG_SPADE_FUSED_TEST") != "1", reason="opt-in kernel: set SSG_SPADE_FUSED_TEST=1")]
+
+
+def rel(a, b):
+    a, b = a.detach().double().cpu(), b.detach().double().cpu()
+    return float((a - b).norm() / (b.norm() + 1e-30))
+
+
+@pytest.mark.parametrize("c,hw", [(64, (40, 24)), (128, (33, 50)), (64, (16, 16)), (128, (7, 5))])
+def test_spade_fused_matches_unfused_chain(c, hw):
+    import ssunet_gan_b200 as ssg
+    from ssunet_gan_b200 import normalization, ops
+    ssg.set_compute_dtype(torch.bfloat16)
+    ssg.set_conv_impl("auto")
+    torch.manual_seed(c + hw[0])
+    mod = normalization.SPADE("spadebatch3x3", c, 3, c / 16).cuda().train()
+    with torch.no_grad():          # biases away from zero, weights large enough that gamma / beta matter
+        for p in mod.parameters():
+            if p.dim() == 1:
+                p.uniform_(-0.5, 0.5)
+    x0 = torch.randn(2, c, *hw)
+    gy = torch.randn(2, c, *hw)
+
+    def once(fused):
+        ops.set_spade_fused(fused)
+        try:
+            x = ops.to_nhwc(x0.cuda()).detach().requires_grad_(True)
+            xin = ops.relu(x)
+            for p in mod.parameters():
+                p.grad = None
+            y = mod(xin, xin)
+            y.backward(ops.to_nhwc(gy.cuda()))
+            return y.detach().float(), x.grad.float().clone(), {k: p.grad.clone() for k, p in mod.named_parameters() if p.grad is not None}
+        finally:
+            ops.set_spade_fused(False)
+
+    assert ops.spade_fused_enabled(c, 3, int(max(c / 16, 4))) is False
+    y1, dx1, g1 = once(True)
+    y2, dx2, g2 = once(False)
+    # same bf16 rounding points; only the fp32 accumulation order of the three contractions differs
+    assert rel(y1, y2) < 5e-3, rel(y1, y2)
+    assert rel(dx1, dx2) < 1e-2, rel(dx1, dx2)
+    assert g1.keys() == g2.keys()
+    for k in g1:
+        assert rel(g1[k], g2[k]) < 2e-2, (k, rel(g1[k], g2[k]))
+    with torch.no_grad():          # inference: no gamma|beta tensor is written
+        ops.set_spade_fused(True)
+        try:
+            xe = ops.to_nhwc(x0.cuda())
+            ye = mod(xe, xe)
+        finally:
+            ops.set_spade_fused(False)
+        xr = ops.to_nhwc(x0.cuda())
+        assert rel(ye.float(), mod(xr, xr).float()) < 5e-3
