@@ -30,6 +30,16 @@ D_FWD_GFLOP_512 = 49.4
 STEP_GFLOP_512 = 3 * G_FWD_GFLOP_512 + 8 * D_FWD_GFLOP_512     # 1646.9 required per image per step
 
 
+def synthetic_batch(batch, cin, h, w, num_classes=3, seed=1234):
+    """SURVEY.md §8(d) synthetic inputs for the GPU arm: input = randn, target = (rand > 0.5), drawn in that order from one
+    seeded CPU generator (the oracle's generator draws the same stream; the product arm does not import the oracle)."""
+    import torch
+    g = torch.Generator().manual_seed(seed)
+    x = torch.randn(batch, cin, h, w, generator=g)
+    t = (torch.rand(batch, num_classes, h, w, generator=g) > 0.5).float()
+    return x, t
+
+
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -163,7 +173,6 @@ def main():
 
     import ssunet_gan_b200 as ssg
     from ssunet_gan_b200 import _lib, batchnorm, models_seg_gan, optim, replicate, train_step
-    import ssunet_oracle as O      # synthetic data + portable weights only (not on the timed path)
 
     ssg.set_compute_dtype(torch.bfloat16)
     ssg.set_conv_impl(args.conv)
@@ -182,7 +191,7 @@ def main():
     n_sets = 2
     host = []
     for i in range(n_sets):
-        x, t = O.synthetic_batch(batch, 3, size, size, seed=1234 + rank + 97 * i)
+        x, t = synthetic_batch(batch, 3, size, size, seed=1234 + rank + 97 * i)
         host.append((x.pin_memory(), t.pin_memory()))
     dev = [(x.cuda(), t.cuda()) for x, t in host]
 
