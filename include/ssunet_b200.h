@@ -200,6 +200,10 @@ int ssg_spade_modulate_bwd_sums(const void* dy, const void* x, const void* gb, v
 int ssg_spade_fused_supported(int c, int label_nc, int hidden);
 int ssg_spade_fused_fwd(const void* x, const void* w1, const float* b1, const void* w2, const float* b2, const void* w3, const float* b3,
                         void* seg, void* actv, void* gb, void* y, int n, int h, int w, int c, ssg_stream_t s);
+/* Second version (persistent CTAs, weights-stationary x2map, register-blocked gamma|beta stage; c == 64, label_nc <= 3): w1m is
+ * bf16 [32][c] with row tap * label_nc + class (zero rows beyond 9 * label_nc).  Written after v1's measurement, not yet run. */
+int ssg_spade_fused_fwd_v2(const void* x, const void* w1m, const float* b1, const void* w2, const float* b2, const void* w3, const float* b3,
+                           void* seg, void* actv, void* gb, void* y, int n, int h, int w, int c, int label_nc, ssg_stream_t s);
 
 /* ---- elementwise ---------------------------------------------------------------------------- */
 int ssg_act_fwd(const void* x, void* y, int dtype, long long n, int act, float slope, ssg_stream_t s);

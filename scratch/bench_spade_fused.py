@@ -9,7 +9,7 @@ ssg.set_compute_dtype(torch.bfloat16)
 for c, hw in ((64, 512), (128, 256)):
     mod = normalization.SPADE("spadebatch3x3", c, 3, c / 16).cuda().train()
     x = ops.to_nhwc(torch.randn(16, c, hw, hw, device="cuda"))
-    for fused in (False, True):
+    for fused in (0, 1, 2):
         ops.set_spade_fused(fused)
         for grad in (False, True):
             with torch.set_grad_enabled(grad):

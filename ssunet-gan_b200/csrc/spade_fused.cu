@@ -241,6 +241,252 @@ static int launch(const Params& p, cudaStream_t st) {
     return SSG_OK;
 }
 
+
+// =====================================================================================================================
+// Version 2 (C = 64, label_nc <= 3; opt-in with SSG_SPADE_FUSED=2, NOT yet run on a GPU when this was written).
+// v1 measured 1.40 ms against 1.245 ms for the unfused chain at level 0; static analysis (profiles/r01_spade_fused_v1.txt)
+// blames the shared-memory port: every one of v1's 2 285 MMAs per tile fetches both operands from shared memory, stage A
+// alone re-reads each x element nine times (once per tap).  v2 changes three things:
+//   1. persistent CTAs (grid = SM count): the mlp_shared / gamma|beta operands are loaded into shared memory ONCE per CTA
+//      and the x2map operand lives in registers for the whole kernel;
+//   2. stage A is turned around ("weights stationary"): P[tap * L + c][pixel] = sum_k W1[tap, c, k] x[pixel, k] is computed
+//      once per x pixel with the WEIGHTS as the 16-row A operand (32 rows = 9 taps x L <= 3 classes, zero padded) and 8
+//      pixels as the N dimension -- each x element is read from shared memory once -- and seg[pixel][c] is then the sum
+//      of nine shifted P values (fp32, through a 62 KB shared buffer);
+//   3. stage C keeps the activation fragments of BOTH of a warp's M-tiles in registers and applies every weight fragment it
+//      fetches to the two of them.
+// Estimated shared-memory traffic per tile: ~1.1 MB -> ~0.48 MB.
+// =====================================================================================================================
+constexpr int PSP = 488;                                                   // pixel pitch (floats) of the P buffer: 61 n-tiles x 8
+
+struct Smem2 {
+    static constexpr int C = 64;
+    static constexpr int XS = 0;                                       // [XR*XR][C] bf16, swizzled as in v1
+    static constexpr int PS = XS + XR * XR * C * 2;                    // [32][PSP] fp32
+    static constexpr int SEG = PS + 32 * PSP * 4;
+    static constexpr int ACT = SEG + (SR * SR + 1) * 16;
+    static constexpr int W2 = ACT + (AR * AR + 1) * 16;
+    static constexpr int W3 = W2 + 8 * K3P * 2;
+    static constexpr int TOTAL = W3 + 2 * C * K3P * 2;                 // 160 KB: one CTA per SM
+};
+
+struct Params2 {
+    Params b;             // b.w1 here is the [32][C] "weights stationary" layout: row tap * label_nc + c, rows >= 9 * label_nc zero
+    int label_nc;
+    int tiles_x, tiles_y, ntiles;
+};
+
+__global__ void __launch_bounds__(256, 1) spade_fused_fwd_v2_kernel(const Params2 pp) {
+    using S = Smem2;
+    constexpr int C = 64, CH = C / 8;
+    const Params& p = pp.b;
+    extern __shared__ __align__(128) uint8_t smem[];
+    float* ps = reinterpret_cast<float*>(smem + S::PS);
+    bf16* segs = reinterpret_cast<bf16*>(smem + S::SEG);
+    bf16* acts = reinterpret_cast<bf16*>(smem + S::ACT);
+    bf16* w2s = reinterpret_cast<bf16*>(smem + S::W2);
+    bf16* w3s = reinterpret_cast<bf16*>(smem + S::W3);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int g = lane >> 2, t4 = lane & 3;
+    const int L = pp.label_nc;
+
+    // ---- once per CTA: mlp_shared / gamma|beta operands -> shared memory; x2map operand -> registers (A fragments) ----
+    for (int i = tid; i < (8 + 2 * C) * 10; i += 256) {
+        const int row = i / 10, k = i - row * 10;
+        const bf16* src = row < 8 ? p.w2 + (size_t)row * 80 : p.w3 + (size_t)(row - 8) * 80;
+        bf16* dst = row < 8 ? w2s + (size_t)row * K3P : w3s + (size_t)(row - 8) * K3P;
+        *reinterpret_cast<uint4*>(dst + k * 8) = __ldg(reinterpret_cast<const uint4*>(src) + k);
+    }
+    if (tid < 2) *reinterpret_cast<uint4*>(tid == 0 ? segs + SR * SR * 8 : acts + AR * AR * 8) = make_uint4(0u, 0u, 0u, 0u);
+    // A fragment of mma.m16n8k16 (row-major 16 x 16): a0 = (row g, k 2t..2t+1), a1 = (row g + 8, same k), a2 = (row g, k + 8), a3 = (row g + 8, k + 8)
+    uint32_t wa[2][C / 16][4];
+#pragma unroll
+    for (int m = 0; m < 2; ++m)
+#pragma unroll
+        for (int kc = 0; kc < C / 16; ++kc) {
+            const bf16* r0 = p.w1 + (size_t)(m * 16 + g) * C + kc * 16 + 2 * t4;
+            const bf16* r1 = r0 + 8 * C;
+            wa[m][kc][0] = __ldg(reinterpret_cast<const uint32_t*>(r0));
+            wa[m][kc][1] = __ldg(reinterpret_cast<const uint32_t*>(r1));
+            wa[m][kc][2] = __ldg(reinterpret_cast<const uint32_t*>(r0 + 8));
+            wa[m][kc][3] = __ldg(reinterpret_cast<const uint32_t*>(r1 + 8));
+        }
+    const uint32_t xs_a = smem_addr(smem + S::XS), seg_a = smem_addr(segs), act_a = smem_addr(acts);
+    const uint32_t w2_a = smem_addr(w2s), w3_a = smem_addr(w3s);
+    const int arow = lane & 15, ahalf = lane >> 4;
+    const int bn = lane & 7, bhalf = (lane >> 3) & 1;
+    const int per_img = pp.tiles_x * pp.tiles_y;
+
+    for (int tile = blockIdx.x; tile < pp.ntiles; tile += gridDim.x) {
+        const int img = tile / per_img, trem = tile - img * per_img;
+        const int ty0 = (trem / pp.tiles_x) * TILE, tx0 = (trem % pp.tiles_x) * TILE;
+        const bf16* ximg = p.x + (long long)img * p.H * p.W * C;
+        __syncthreads();                                                 // the previous tile is done with xs / segs / acts
+        for (int i = tid; i < XR * XR * CH; i += 256) {
+            const int q = i / CH, k = i - q * CH;
+            const int iy = ty0 - 3 + q / XR, ix = tx0 - 3 + q % XR;
+            uint4 v = make_uint4(0u, 0u, 0u, 0u);
+            if (iy >= 0 && iy < p.H && ix >= 0 && ix < p.W) v = __ldg(reinterpret_cast<const uint4*>(ximg + ((long long)iy * p.W + ix) * C) + k);
+            *reinterpret_cast<uint4*>(smem + S::XS + (size_t)q * C * 2 + ((k ^ (q & 7)) << 4)) = v;
+        }
+        __syncthreads();
+
+        // ---- stage A1: P[32][484 pixels] = W1 (registers) x pixels: 61 n-tiles of 8 pixels, B = x rows straight from the tile ----
+        for (int nt = warp; nt < (XR * XR + 7) / 8; nt += 8) {
+            int q = nt * 8 + bn;                                         // the x pixel whose row address this lane supplies
+            if (q >= XR * XR) q = XR * XR - 1;                           // ragged last tile: any valid row, results unused
+            float acc[2][4];
+#pragma unroll
+            for (int m = 0; m < 2; ++m)
+#pragma unroll
+                for (int e = 0; e < 4; ++e) acc[m][e] = 0.f;
+#pragma unroll
+            for (int kc = 0; kc < C / 16; ++kc) {
+                uint32_t b[2];
+                ldsm_x2(b, xs_a + (uint32_t)q * (C * 2) + ((uint32_t)((2 * kc + bhalf) ^ (q & 7)) << 4));
+                mma_bf16(acc[0], wa[0][kc], b);
+                mma_bf16(acc[1], wa[1][kc], b);
+            }
+            // D: rows (tap * L + c) g and g + 8 of each 16-row half, columns = pixels nt * 8 + 2 t4, + 1
+            const int px = nt * 8 + 2 * t4;
+            if (px < PSP) {
+#pragma unroll
+                for (int m = 0; m < 2; ++m) {
+                    *reinterpret_cast<float2*>(ps + (size_t)(m * 16 + g) * PSP + px) = make_float2(acc[m][0], acc[m][1]);
+                    *reinterpret_cast<float2*>(ps + (size_t)(m * 16 + g + 8) * PSP + px) = make_float2(acc[m][2], acc[m][3]);
+                }
+            }
+        }
+        __syncthreads();
+        // ---- stage A2: seg[pixel][c] = b1[c] + sum over the nine taps of the shifted P values (fixed order, fp32) ----
+        for (int pq = tid; pq < SR * SR; pq += 256) {
+            const int sy = pq / SR, sx = pq - sy * SR;
+            const int iy = ty0 - 2 + sy, ix = tx0 - 2 + sx;
+            const bool inside = iy >= 0 && iy < p.H && ix >= 0 && ix < p.W;
+            float v[4] = {0.f, 0.f, 0.f, 0.f};
+            if (inside) {
+                for (int c = 0; c < L; ++c) {
+                    float a = 0.f;
+#pragma unroll
+                    for (int tap = 0; tap < 9; ++tap) a += ps[(size_t)(tap * L + c) * PSP + (sy + tap / 3) * XR + sx + tap % 3];
+                    v[c] = a + __ldg(p.b1 + c);
+                }
+            }
+            const uint4 o = make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), 0u, 0u);
+            *reinterpret_cast<uint4*>(segs + pq * 8) = o;
+            if (inside && sy >= 2 && sy < 2 + TILE && sx >= 2 && sx < 2 + TILE)
+                *reinterpret_cast<uint4*>(p.seg + (((long long)img * p.H + iy) * p.W + ix) * 8) = o;
+        }
+        __syncthreads();
+
+        // ---- stage B: identical to v1 ----
+        for (int mt = warp; mt < (AR * AR + 15) / 16; mt += 8) {
+            const int pa = mt * 16 + arow;
+            const int aay = pa / AR, aax = pa - aay * AR;
+            float acc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+            for (int j = 0; j < 5; ++j) {
+                const int tap = 2 * j + ahalf;
+                const int q = (pa < AR * AR && tap < 9) ? (aay + tap / 3) * SR + aax + tap % 3 : SR * SR;
+                uint32_t a[4], b[2];
+                ldsm_x4(a, seg_a + (uint32_t)q * 16);
+                ldsm_x2(b, w2_a + (uint32_t)(bn * K3P + j * 16 + bhalf * 8) * 2);
+                mma_bf16(acc, a, b);
+            }
+            const float bia0 = __ldg(p.b2 + 2 * t4), bia1 = __ldg(p.b2 + 2 * t4 + 1);
+#pragma unroll
+            for (int hrow = 0; hrow < 2; ++hrow) {
+                const int pq = mt * 16 + g + 8 * hrow;
+                if (pq >= AR * AR) continue;
+                const int ay = pq / AR, ax = pq - ay * AR;
+                const int iy = ty0 - 1 + ay, ix = tx0 - 1 + ax;
+                const bool inside = iy >= 0 && iy < p.H && ix >= 0 && ix < p.W;
+                const uint32_t v = inside ? pack_bf16(fmaxf(acc[2 * hrow] + bia0, 0.f), fmaxf(acc[2 * hrow + 1] + bia1, 0.f)) : 0u;
+                *reinterpret_cast<uint32_t*>(acts + pq * 8 + 2 * t4) = v;
+                if (inside && ay >= 1 && ay < 1 + TILE && ax >= 1 && ax < 1 + TILE)
+                    *reinterpret_cast<uint32_t*>(p.actv + (((long long)img * p.H + iy) * p.W + ix) * 8 + 2 * t4) = v;
+            }
+        }
+        __syncthreads();
+
+        // ---- stage C: the warp's two M-tiles (warp, warp + 8) share every weight fragment ----
+        uint32_t a2[2][5][4];
+        int oy[2][2], ox[2][2];
+        bool ok[2][2];
+        long long gpix[2][2];
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            const int mt = warp + 8 * u;
+            const int pa = mt * 16 + arow;
+            const int oay = pa / TILE, oax = pa - oay * TILE;
+#pragma unroll
+            for (int j = 0; j < 5; ++j) {
+                const int tap = 2 * j + ahalf;
+                const int q = tap < 9 ? (oay + tap / 3) * AR + oax + tap % 3 : AR * AR;
+                ldsm_x4(a2[u][j], act_a + (uint32_t)q * 16);
+            }
+#pragma unroll
+            for (int hrow = 0; hrow < 2; ++hrow) {
+                const int pq = mt * 16 + g + 8 * hrow;
+                oy[u][hrow] = pq / TILE; ox[u][hrow] = pq - oy[u][hrow] * TILE;
+                const int iy = ty0 + oy[u][hrow], ix = tx0 + ox[u][hrow];
+                ok[u][hrow] = iy < p.H && ix < p.W;
+                gpix[u][hrow] = ((long long)img * p.H + iy) * p.W + ix;
+            }
+        }
+#pragma unroll 1
+        for (int cj = 0; cj < C / 8; ++cj) {
+            float ag[2][4], ab[2][4];
+#pragma unroll
+            for (int u = 0; u < 2; ++u)
+#pragma unroll
+                for (int e = 0; e < 4; ++e) { ag[u][e] = 0.f; ab[u][e] = 0.f; }
+#pragma unroll
+            for (int j = 0; j < 5; ++j) {
+                uint32_t bgm[2], bbt[2];
+                ldsm_x2(bgm, w3_a + (uint32_t)((cj * 8 + bn) * K3P + j * 16 + bhalf * 8) * 2);
+                ldsm_x2(bbt, w3_a + (uint32_t)((C + cj * 8 + bn) * K3P + j * 16 + bhalf * 8) * 2);
+#pragma unroll
+                for (int u = 0; u < 2; ++u) {
+                    mma_bf16(ag[u], a2[u][j], bgm);
+                    mma_bf16(ab[u], a2[u][j], bbt);
+                }
+            }
+            const int ch = cj * 8 + 2 * t4;
+            const float g0 = __ldg(p.b3 + ch), g1 = __ldg(p.b3 + ch + 1), e0 = __ldg(p.b3 + C + ch), e1 = __ldg(p.b3 + C + ch + 1);
+#pragma unroll
+            for (int u = 0; u < 2; ++u)
+#pragma unroll
+                for (int hrow = 0; hrow < 2; ++hrow) {
+                    if (!ok[u][hrow]) continue;
+                    const float gm0 = bf16_round(ag[u][2 * hrow] + g0), gm1 = bf16_round(ag[u][2 * hrow + 1] + g1);
+                    const float bt0 = bf16_round(ab[u][2 * hrow] + e0), bt1 = bf16_round(ab[u][2 * hrow + 1] + e1);
+                    const int q = (oy[u][hrow] + 3) * XR + ox[u][hrow] + 3;
+                    const uint32_t xv = *reinterpret_cast<const uint32_t*>(smem + S::XS + (size_t)q * C * 2 + ((cj ^ (q & 7)) << 4) + t4 * 4);
+                    const float x0 = __uint_as_float(xv << 16), x1 = __uint_as_float(xv & 0xffff0000u);
+                    *reinterpret_cast<uint32_t*>(p.y + gpix[u][hrow] * C + ch) = pack_bf16(fmaf(x0, 1.f + gm0, bt0), fmaf(x1, 1.f + gm1, bt1));
+                    if (p.gb) {
+                        *reinterpret_cast<uint32_t*>(p.gb + gpix[u][hrow] * (2 * C) + ch) = pack_bf16(gm0, gm1);
+                        *reinterpret_cast<uint32_t*>(p.gb + gpix[u][hrow] * (2 * C) + C + ch) = pack_bf16(bt0, bt1);
+                    }
+                }
+        }
+    }
+}
+
+static int launch_v2(const Params2& pp, cudaStream_t st) {
+    static bool attr = false;
+    if (!attr) {
+        SSG_CHECK_CUDA(cudaFuncSetAttribute(spade_fused_fwd_v2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem2::TOTAL));
+        attr = true;
+    }
+    int grid = sm_count_cached();
+    if (grid > pp.ntiles) grid = pp.ntiles;
+    spade_fused_fwd_v2_kernel<<<grid, 256, Smem2::TOTAL, st>>>(pp);
+    SSG_CHECK_LAUNCH();
+    return SSG_OK;
+}
+
 }  // namespace spf
 }  // namespace ssg
 using namespace ssg;
@@ -262,6 +508,25 @@ int ssg_spade_fused_fwd(const void* x, const void* w1, const float* b1, const vo
     if (c == 128) return spf::launch<128>(p, (cudaStream_t)s);
     set_error("spade_fused_fwd: C = %d is not built (64 or 128)", c);
     return SSG_ERR_UNSUPPORTED;
+}
+
+/* v2 (see the block comment above the kernel): c == 64, label_nc <= 3; w1 is the [32][c] weights-stationary layout. */
+int ssg_spade_fused_fwd_v2(const void* x, const void* w1m, const float* b1, const void* w2, const float* b2, const void* w3, const float* b3,
+                           void* seg, void* actv, void* gb, void* y, int n, int h, int w, int c, int label_nc, ssg_stream_t s) {
+    SSG_CHECK_ARG(x && w1m && b1 && w2 && b2 && w3 && b3 && seg && actv && y && n > 0 && h > 0 && w > 0, "spade_fused_fwd_v2: bad arguments");
+    if (c != 64 || label_nc < 1 || label_nc > 3) {
+        set_error("spade_fused_fwd_v2: built for C = 64, label_nc <= 3 (got %d, %d)", c, label_nc);
+        return SSG_ERR_UNSUPPORTED;
+    }
+    spf::Params2 pp;
+    pp.b.x = (const bf16*)x; pp.b.w1 = (const bf16*)w1m; pp.b.w2 = (const bf16*)w2; pp.b.w3 = (const bf16*)w3;
+    pp.b.b1 = b1; pp.b.b2 = b2; pp.b.b3 = b3; pp.b.seg = (bf16*)seg; pp.b.actv = (bf16*)actv; pp.b.gb = (bf16*)gb; pp.b.y = (bf16*)y;
+    pp.b.N = n; pp.b.H = h; pp.b.W = w; pp.label_nc = label_nc;
+    pp.tiles_x = (w + spf::TILE - 1) / spf::TILE; pp.tiles_y = (h + spf::TILE - 1) / spf::TILE;
+    const long long nt = (long long)n * pp.tiles_x * pp.tiles_y;
+    SSG_CHECK_ARG(nt < (1LL << 31), "spade_fused_fwd_v2: too many tiles");
+    pp.ntiles = (int)nt;
+    return spf::launch_v2(pp, (cudaStream_t)s);
 }
 
 }  // extern "C"

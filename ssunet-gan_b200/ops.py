@@ -800,17 +800,19 @@ def spade_modulate(x, gb, dx_sink=None):
 # ----------------------------------------------------------------------------------------------
 import os as _os
 
-_SPADE_FUSED = _os.environ.get("SSG_SPADE_FUSED") == "1"
+_SPADE_FUSED = {"1": 1, "2": 2}.get(_os.environ.get("SSG_SPADE_FUSED", ""), 0)
 
 
 def set_spade_fused(enabled):
-    """Route self-conditioned SPADE blocks with 64 / 128 channels through the one-kernel forward."""
+    """Route self-conditioned SPADE blocks with 64 / 128 channels through the one-kernel forward.
+    True / 1: version 1 (verified on B200, slower than the chain); 2: version 2 where it applies (C = 64, label_nc <= 3;
+    persistent CTAs, weights-stationary x2map -- written after v1's measurement, still to be run), version 1 elsewhere."""
     global _SPADE_FUSED
-    _SPADE_FUSED = bool(enabled)
+    _SPADE_FUSED = int(enabled)
 
 
 def spade_fused_enabled(c, label_nc, hidden):
-    return (_SPADE_FUSED and tc_mode() and bool(_lib.lib().ssg_spade_fused_supported(int(c), int(label_nc), int(hidden))))
+    return bool(_SPADE_FUSED and tc_mode() and _lib.lib().ssg_spade_fused_supported(int(c), int(label_nc), int(hidden)))
 
 
 def _pad_to(t, dim, size):
@@ -850,7 +852,13 @@ class _SpadeFused(torch.autograd.Function):
         gb = empty_nhwc(n, 2 * c, h, w, torch.bfloat16, dev) if need_grad else None
         y = empty_nhwc(n, c, h, w, torch.bfloat16, dev)
         p1, q1, p2, q2, p3, q3 = _spade_fused_operands(w1, b1, w2, b2, wg, bg, wb, bb)
-        call("ssg_spade_fused_fwd", x, p1, q1, p2, q2, p3, q3, seg, actv, gb, y, n, h, w, c)
+        label = w1.shape[0]
+        if _SPADE_FUSED == 2 and c == 64 and label <= 3:
+            # weights-stationary layout of the x2map operand: [32][C], row = tap * label_nc + class
+            p1m = _pad_to(w1.detach().permute(2, 3, 0, 1).reshape(9 * label, c), 0, 32).to(torch.bfloat16).contiguous()
+            call("ssg_spade_fused_fwd_v2", x, p1m, q1, p2, q2, p3, q3, seg, actv, gb, y, n, h, w, c, label)
+        else:
+            call("ssg_spade_fused_fwd", x, p1, q1, p2, q2, p3, q3, seg, actv, gb, y, n, h, w, c)
         if need_grad:
             ctx.save_for_backward(x, seg, actv, gb, w1, w2, wg, wb)
         return y

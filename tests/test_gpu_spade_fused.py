@@ -13,8 +13,9 @@ def rel(a, b):
     return float((a - b).norm() / (b.norm() + 1e-30))
 
 
-@pytest.mark.parametrize("c,hw", [(64, (40, 24)), (128, (33, 50)), (64, (16, 16)), (128, (7, 5))])
-def test_spade_fused_matches_unfused_chain(c, hw):
+@pytest.mark.parametrize("version", [1, 2])
+@pytest.mark.parametrize("c,hw", [(64, (40, 24)), (128, (33, 50)), (64, (16, 16)), (128, (7, 5)), (64, (100, 70))])
+def test_spade_fused_matches_unfused_chain(c, hw, version):
     import ssunet_gan_b200 as ssg
     from ssunet_gan_b200 import normalization, ops
     ssg.set_compute_dtype(torch.bfloat16)
@@ -29,7 +30,7 @@ def test_spade_fused_matches_unfused_chain(c, hw):
     gy = torch.randn(2, c, *hw)
 
     def once(fused):
-        ops.set_spade_fused(fused)
+        ops.set_spade_fused(version if fused else 0)
         try:
             x = ops.to_nhwc(x0.cuda()).detach().requires_grad_(True)
             xin = ops.relu(x)
@@ -51,7 +52,7 @@ def test_spade_fused_matches_unfused_chain(c, hw):
     for k in g1:
         assert rel(g1[k], g2[k]) < 2e-2, (k, rel(g1[k], g2[k]))
     with torch.no_grad():          # inference: no gamma|beta tensor is written
-        ops.set_spade_fused(True)
+        ops.set_spade_fused(version)
         try:
             xe = ops.to_nhwc(x0.cuda())
             ye = mod(xe, xe)
