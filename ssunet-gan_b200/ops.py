@@ -823,8 +823,26 @@ def _pad_to(t, dim, size):
     return torch.cat([t, t.new_zeros(shape)], dim)
 
 
+_SPADE_OPERANDS = {}
+
+
 def _spade_fused_operands(w1, b1, w2, b2, wg, bg, wb, bb):
-    """Operand layouts of ssg_spade_fused_fwd from the four convolutions' OIHW parameters (parameter plumbing: tiny tensors)."""
+    """Operand layouts of ssg_spade_fused_fwd from the four convolutions' OIHW parameters (parameter plumbing: tiny tensors),
+    cached until a parameter changes (same invalidation rule as `packed_weight`)."""
+    ps = (w1, b1, w2, b2, wg, bg, wb, bb)
+    key = w1.data_ptr()
+    token = (_WEIGHT_EPOCH,) + tuple((t.data_ptr(), t._version) for t in ps)
+    hit = _SPADE_OPERANDS.get(key)
+    if hit is not None and hit[0] == token:
+        return hit[1]
+    out = _spade_fused_operands_build(*ps)
+    if len(_SPADE_OPERANDS) > 256:
+        _SPADE_OPERANDS.clear()
+    _SPADE_OPERANDS[key] = (token, out)
+    return out
+
+
+def _spade_fused_operands_build(w1, b1, w2, b2, wg, bg, wb, bb):
     label, c = w1.shape[0], w1.shape[1]
     h = w2.shape[0]
     p1 = _pad_to(w1.detach().permute(2, 3, 0, 1).reshape(9, label, c), 1, 8).to(torch.bfloat16).contiguous()
