@@ -44,7 +44,8 @@ def timed(fn, flush, iters=20, warm=5):
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--out", default=os.path.join(ROOT, "profiles", "r01_hbm_kernels.json"))
+    ap.add_argument("--out", default=os.path.join(ROOT, "profiles", "r02_hbm_kernels.json"))
+    ap.add_argument("--only", default="", help="'bn': stop after the BatchNorm family (used by the ncu captures)")
     args = ap.parse_args()
     torch.cuda.set_device(0)
     ssg.set_compute_dtype(BF)
@@ -95,6 +96,8 @@ def main():
         lambda: call("ssg_bn_bwd_apply", dy, y, x, dx, None, DT, R, c, mean, istd, gam, sums, float(R), 1, 0.0, 1))
     rec("bn_bwd_apply + dres", "autograd of archs.py:233", 5 * E,
         lambda: call("ssg_bn_bwd_apply", dy, y, x, dx, dres, DT, R, c, mean, istd, gam, sums, float(R), 1, 0.0, 1))
+    if args.only == "bn":
+        return
     gb = torch.randn(R, 2 * c, device=dev).to(BF)
     dgb = torch.empty_like(gb)
     rec("spade_modulate fwd", "normalization.py:120", 4 * E, lambda: call("ssg_spade_modulate_fwd", x, gb, y, DT, R, c))

@@ -372,3 +372,75 @@ def test_tile_merge_resized_matches_reference(golden_dir):
         assert probs.shape[-1] == S
         got = A.tile_merge_resized(H, W, list(probs), P2, C, OV)
         assert np.array_equal(np.stack(got), z[tag + "_merged"]), tag
+
+
+# ----------------------------------------------------------------------------------------------
+# headline-shape fixtures (oracle/make_golden_headline.py): 2 x 3 x 512 x 512 GAN iteration, 4-band SN7-shaped step
+# ----------------------------------------------------------------------------------------------
+def _sample_idx(n, sample=2048):
+    step = max(1, n // sample)
+    return torch.arange(0, n, step)[:sample]
+
+
+def _check_grad_samples(gmap, keys, norms, samples, rtol):
+    worst = 0.0
+    for k, nrm, smp in zip(keys, norms, samples):
+        g = gmap[str(k)].detach().reshape(-1)
+        idx = _sample_idx(g.numel())
+        want = torch.from_numpy(smp[:idx.numel()]).double()
+        got = g[idx].double()
+        if nrm < 1e-6:          # exactly-cancelling gradients (conv biases in front of a BN): rounding noise on both sides
+            continue
+        scale = max(float(want.norm()), nrm * (idx.numel() / g.numel()) ** 0.5)
+        worst = max(worst, float((got - want).norm()) / scale)
+        assert abs(float(g.double().norm()) - nrm) <= rtol * nrm, (k, float(g.double().norm()), nrm)
+    assert worst < rtol, worst
+
+
+def test_headline_gan_step_oracle_matches_reference(golden_dir):
+    """One G+D iteration at the headline tile size (2 x 3 x 512 x 512): oracle vs the unmodified reference, logits, the six
+    scalars and a strided sample + norm of every parameter gradient of both networks."""
+    import functools
+    z = np.load(os.path.join(golden_dir, "headline_gan_step_2x512.npz"))
+    sd_g = O.portable_state_dict(O.unet_r_ss_v2_spec(3, 3, prefix="net."))
+    sd_d = O.portable_state_dict(O.discriminator_spec(3))
+    x, t = O.synthetic_batch(2, 3, 512, 512, seed=1234, blobby=True)
+    orig = O.unet_r_ss_v2
+    O.unet_r_ss_v2 = functools.partial(orig, prefix="net.")
+    try:
+        r = O.gan_train_step(sd_g, sd_d, O.AdamState(O.trainable_keys(sd_g), 2e-5), O.AdamState(O.trainable_keys(sd_d), 2e-5), x, t)
+    finally:
+        O.unet_r_ss_v2 = orig
+    ref = torch.from_numpy(z["logits"]).double()
+    err = float((r["logits"].double() - ref).norm() / ref.norm())
+    # same ATen kernels as the reference; another thread partition of the host moves the logits by `self_1thread` (2.2e-4)
+    assert err < 3 * float(z["self_1thread"]) + 1e-6, err
+    sc = z["scalars"]
+    for k, want in zip(("loss", "content", "adv_g", "adv_d"), sc[:4]):
+        _close(r[k], want, rtol=2e-4)
+    _close(r["iou"], sc[4], rtol=2e-4)
+    _close(r["dice"], sc[5], rtol=2e-4)
+    _check_grad_samples(r["g_grads"], z["g_grad_keys"], z["g_grad_norm"], z["g_grad_sample"], 2e-2)
+    _check_grad_samples(r["d_grads"], z["d_grad_keys"], z["d_grad_norm"], z["d_grad_sample"], 2e-2)
+    # the yardstick the bf16 tests use: the reference's own logits move by ~sqrt(eps) under an eps input perturbation
+    assert 2.5 < float(z["sens_eps_0.001"]) / float(z["sens_eps_0.0001"]) < 4.0
+    assert 2.5 < float(z["sens_eps_0.0001"]) / float(z["sens_eps_1e-05"]) < 4.0
+
+
+def test_sn7_four_band_step_oracle_matches_reference(golden_dir):
+    """Generator(input_channels=4) forward + BCEDice + backward + clip + Adam on 2 x 4 x 64 x 64 (BASELINE configs[3] layout)."""
+    z = np.load(os.path.join(golden_dir, "sn7_train_step_2x4x64.npz"))
+    sd = O.portable_state_dict(O.unet_r_ss_v2_spec(3, 4, prefix="net."))
+    x, t = O.synthetic_batch(2, 4, 64, 64, seed=4321, blobby=True)
+    O._leafify(sd)
+    out = O.unet_r_ss_v2(sd, x, True, prefix="net.")
+    loss = O.bce_dice_loss(out, t)
+    keys = O.trainable_keys(sd)
+    grads = dict(zip(keys, torch.autograd.grad(loss, [sd[k] for k in keys], allow_unused=True)))
+    _close(out.detach().numpy(), z["logits"], rtol=1e-4, atol=2e-5)
+    _close(float(loss.detach()), float(z["loss"]), rtol=1e-5)
+    _check_grad_samples(grads, z["grad_keys"], z["grad_norm"], z["grad_sample"], 5e-3)
+    opt = O.AdamState(keys, 2e-5)
+    opt.step(sd, grads, 0.8)
+    for i, k in enumerate(z["upd_keys"]):
+        _close(sd[str(k)].detach().numpy(), z["upd_%d" % i], rtol=1e-5, atol=1e-7)
