@@ -65,6 +65,14 @@ int ssg_pack_conv_weight(const float* w_oihw, void* dst, int dtype, int layout, 
 /* Same, zero-padded to [.. cout_p ..][.. cin_p ..] channel extents (operands of channel-padded activations). */
 int ssg_pack_conv_weight_pad(const float* w_oihw, void* dst, int dtype, int layout, int cout, int cin, int kh, int kw, int cout_p,
                              int cin_p, const float* inv_scale_dev, ssg_stream_t s);
+/* Every packed operand of a network refreshed by ONE launch (after the optimiser step: srgan_utils.py:192-195 + Adam changed all
+ * weights).  descs_dev: DEVICE array of n_descs records of SSG_PACK_DESC_BYTES bytes, little-endian, no padding:
+ *   u64 src (fp32 OIHW), u64 dst, i32 layout, i32 cout, i32 cin, i32 ksize, i32 cout_p, i32 cin_p, i64 first_block
+ * `first_block` is the running sum of ceil(cout_p*cin_p*ksize^2 / SSG_PACK_BLOCK_ELEMS) over the preceding records and
+ * total_blocks the sum over all of them. */
+#define SSG_PACK_DESC_BYTES 48
+#define SSG_PACK_BLOCK_ELEMS 2048
+int ssg_pack_conv_weights_multi(const void* descs_dev, int n_descs, long long total_blocks, int dtype, ssg_stream_t s);
 
 /* ---- convolution, CUDA-core implicit GEMM (any shape; the only path for tiny channel counts) */
 /* nn.Conv2d forward (archs.py:210,212,218; normalization.py:93-98; models_seg_gan.py:38-39).
@@ -153,6 +161,26 @@ int ssg_bn_bwd_apply(const void* dy, const void* y, const void* x, void* dx, voi
                      double count, int act, float slope, int training, ssg_stream_t s);
 /* dgamma = sums[C:2C], dbeta = sums[0:C] as fp32 */
 int ssg_bn_param_grads(const double* sums, int c, float* dgamma, float* dbeta, ssg_stream_t s);
+/* Same, ADDED into dgamma / dbeta: the caller passes the parameters' slots of the optimiser's flat gradient arena (zeroed by
+ * zero_grad; the discriminator runs two backward passes per step), replacing autograd's AccumulateGrad addition. */
+int ssg_bn_param_grads_acc(const double* sums, int c, float* dgamma, float* dbeta, ssg_stream_t s);
+/* dst[i] += (float)src[i]: a bias gradient (fp64 column sums of dy) added into its gradient-arena slot. */
+int ssg_accum_f64_f32(const double* src, float* dst, int n, ssg_stream_t s);
+/* ssg_bn_finalize that also advances nn.BatchNorm2d's `num_batches_tracked` (int64 device scalar, may be NULL): the
+ * F.batch_norm path of batchnorm.py:52-55 / torch's BatchNorm2d.forward increments it once per training forward. */
+int ssg_bn_finalize_count(const double* sums, double count, int c, float eps, float momentum, int sync_quirk, float* running_mean,
+                          float* running_var, float* mean, float* inv_std, long long* num_batches_tracked, const float* gamma,
+                          const float* beta, float* sc_out, float* sh_out, ssg_stream_t s);
+/* BN backward for layers WITHOUT a residual operand that does not re-read the forward output: the activation mask is
+ * recomputed from x with the forward's own expression act'(fma(x, sc, sh)), sc / sh as ssg_bn_finalize_count stored them at
+ * forward time (a weight clamp between forward and backward, train.py:111-112, must not move the mask) -- one full-size
+ * operand less per pass (archs.py:231, models_seg_gan.py:43-49).  bf16: C % 8 == 0 and C <= 2048; fp32: C % 4 == 0, C <= 1024.
+ * `gamma` is the LIVE parameter (dx = gamma * inv_std * (...), as torch's backward reads it). */
+int ssg_bn_bwd_reduce_rc(const void* dy, const void* x, int dtype, long long rows, int c, const float* mean, const float* inv_std,
+                         const float* fwd_sc, const float* fwd_sh, int act, float slope, double* sums, ssg_stream_t s);
+int ssg_bn_bwd_apply_rc(const void* dy, const void* x, void* dx, int dtype, long long rows, int c, const float* mean,
+                        const float* inv_std, const float* gamma, const float* fwd_sc, const float* fwd_sh, const double* sums,
+                        double count, int act, float slope, int training, ssg_stream_t s);
 
 /* ---- pooling / resampling ------------------------------------------------------------------ */
 /* nn.MaxPool2d(2,2,return_indices=True) (archs.py:571): y [n,h/2,w/2,c]; code in {0..3} = 2*dy+dx of the
@@ -279,6 +307,10 @@ int ssg_clamp_adam_wd(float* p, float* g, float* m, float* v, long long n, float
                       float bias_corr1, float bias_corr2, float clip, float grad_scale, float weight_decay, ssg_stream_t s);
 int ssg_clamp_adam_wd_dev(float* p, float* g, float* m, float* v, long long n, float lr, float beta1, float beta2, float eps,
                           float* step_dev, float clip, float grad_scale, float weight_decay, ssg_stream_t s);
+/* Same with the hyper-parameters on the device too: hp_dev = float[8] {lr, beta1, beta2, eps, clip (0 = none), grad_scale,
+ * weight_decay, unused}.  A launch captured in a CUDA graph then follows an LR scheduler or a changed clip: the host rewrites
+ * hp_dev between replays. */
+int ssg_clamp_adam_hp_dev(float* p, float* g, float* m, float* v, long long n, const float* hp_dev, float* step_dev, ssg_stream_t s);
 
 /* ---- spectral norm (spectral_norm.py:38-88) ---------------------------------------------------- */
 /* One power iteration on W [rows, cols] fp32: v = normalize(W^T u); u = normalize(W v); sigma = u.(W v).
@@ -344,6 +376,12 @@ long long ssg_p2p_buffer_bytes(int world, int slot_len);
  * the same sequence of calls. */
 int ssg_p2p_allreduce_f64(double* data, int n, void* const* peer_bufs_dev, int rank, int world, int slot_len, unsigned* epoch_dev,
                           ssg_stream_t s);
+/* Same with a wall-clock bound on the wait for the peers: after timeout_ns nanoseconds (%globaltimer) the kernel stops
+ * waiting, stores 1 + the index of the first missing source rank into *status_dev (device uint32, 0 = healthy) and returns;
+ * the context stays usable and the host reports the failure when it next looks at the flag.  timeout_ns <= 0 waits forever
+ * (what NCCL would do). */
+int ssg_p2p_allreduce_f64_to(double* data, int n, void* const* peer_bufs_dev, int rank, int world, int slot_len, unsigned* epoch_dev,
+                             long long timeout_ns, unsigned* status_dev, ssg_stream_t s);
 
 /* ---- tiled inference merge (aerial_image_segmentation_api.py:129-217) ------------------------------ */
 /* values: fp32 [patches][classes][patch_size][patch_size] (NCHW logits with apply_sigmoid != 0, else probabilities in

@@ -123,9 +123,58 @@ def headline():
     opt_d.step()
     scalars = np.array([loss.item(), content.item(), adv.item(), advd.item(), float(iou), float(dice)], dtype=np.float64)
     print("scalars", scalars, flush=True)
+    # ---- the reference's gradients against ITSELF: the same iteration with ATen's native convolution instead of oneDNN
+    # (another fp32 summation order).  Per parameter: rel-L2 of the strided sample -- what "equal up to fp32 rounding"
+    # means for each gradient of this discontinuous network; the GPU tests hold each parameter to a multiple of it.
+    g2 = models_seg_gan.Generator({"arch": "UNet_R_SS_v2", "num_classes": 3, "input_channels": 3, "deep_supervision": False})
+    d2 = models_seg_gan.Discriminator(3)
+    g2.load_state_dict(O.portable_state_dict(O.unet_r_ss_v2_spec(3, 3, prefix="net.")))
+    d2.load_state_dict(O.portable_state_dict(O.discriminator_spec(3)))
+    g2.train(); d2.train()
+    with torch.backends.mkldnn.flags(enabled=False):
+        go2 = g2(inp)
+        l2 = crit(go2, tar) + 1e-4 * con_c(go2, tar) + 1e-3 * adv_c(d2(go2), torch.ones(2, 1))
+        l2.backward()
+        gk2, gn2, gs2 = grad_record(g2.named_parameters())
+        for p_ in d2.parameters():
+            p_.grad = None
+        a2 = adv_c(d2(go2.detach()), torch.zeros(2, 1)) + adv_c(d2(tar), torch.ones(2, 1))
+        a2.backward()
+        dk2, dn2, ds2 = grad_record(d2.named_parameters())
+    assert list(gk2) == list(gk) and list(dk2) == list(dk)
+    # ---- and against itself when only its INPUT (and the masks' consumer: nothing else) is rounded to bf16: the gradient
+    # counterpart of `sens_input_bf16`, the yardstick for the bf16 tensor-core path's per-parameter gradients
+    g3 = models_seg_gan.Generator({"arch": "UNet_R_SS_v2", "num_classes": 3, "input_channels": 3, "deep_supervision": False})
+    d3 = models_seg_gan.Discriminator(3)
+    g3.load_state_dict(O.portable_state_dict(O.unet_r_ss_v2_spec(3, 3, prefix="net.")))
+    d3.load_state_dict(O.portable_state_dict(O.discriminator_spec(3)))
+    g3.train(); d3.train()
+    go3 = g3(inp.bfloat16().float())
+    l3 = crit(go3, tar) + 1e-4 * con_c(go3, tar) + 1e-3 * adv_c(d3(go3), torch.ones(2, 1))
+    l3.backward()
+    gk3, gn3, gs3 = grad_record(g3.named_parameters())
+    for p_ in d3.parameters():
+        p_.grad = None
+    a3 = adv_c(d3(go3.detach()), torch.zeros(2, 1)) + adv_c(d3(tar), torch.ones(2, 1))
+    a3.backward()
+    dk3, dn3, ds3 = grad_record(d3.named_parameters())
+
+    def selferr(a, b, norms):
+        out = []
+        for sa, sb, nrm in zip(a, b, norms):
+            den = max(float(np.linalg.norm(sa.astype(np.float64))), 1e-30)
+            out.append(float(np.linalg.norm(sa.astype(np.float64) - sb.astype(np.float64))) / den)
+        return np.array(out)
+    g_self, d_self = selferr(gs, gs2, gn), selferr(ds, ds2, dn)
+    g_b16, d_b16 = selferr(gs, gs3, gn), selferr(ds, ds3, dn)
+    print("gradient self-deviation (oneDNN vs native conv): G median %.3e max %.3e | D median %.3e max %.3e"
+          % (np.median(g_self), g_self.max(), np.median(d_self), d_self.max()), flush=True)
+    print("gradient deviation under a bf16-rounded input: G median %.3e max %.3e | D median %.3e max %.3e"
+          % (np.median(g_b16), g_b16.max(), np.median(d_b16), d_b16.max()), flush=True)
     np.savez_compressed(os.path.join(OUT, "headline_gan_step_2x512.npz"), logits=go.detach().numpy(), scalars=scalars,
                         sr_logit=sr.detach().numpy(), hr_logit=hr.detach().numpy(),
                         g_grad_keys=gk, g_grad_norm=gn, g_grad_sample=gs, d_grad_keys=dk, d_grad_norm=dn, d_grad_sample=ds,
+                        g_grad_selferr=g_self, d_grad_selferr=d_self, g_grad_sens_bf16in=g_b16, d_grad_sens_bf16in=d_b16,
                         **{k: np.float64(v) for k, v in sens.items()})
 
 

@@ -1,0 +1,68 @@
+"""DRAM traffic per launch of the captured kernels (one `ncu --set full` capture each, profiles/capture_r02.sh) next to their
+algorithmic bytes -> profiles/r02_traffic.json (bench.py's roofline.traffic reads the dominant kernel's row from it).
+
+    python profiles/traffic_from_ncu.py gpurun_out r02a
+"""
+import csv
+import json
+import os
+import subprocess
+import sys
+
+UNIT = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12, "ns": 1e-3, "us": 1.0, "ms": 1e3, "s": 1e6}
+E = 16 * 512 * 512 * 64 * 2          # one 16 x 512 x 512 x 64 bf16 activation
+# capture name -> (what it ran, algorithmic bytes = every live tensor read once + written once, algorithmic FLOPs)
+CASES = {
+    "halo_wgrad_l0": ("conv0_0.conv2 weight gradient, 16x512x512, 64->64, 3x3", 2 * E + 64 * 64 * 9 * 4, 2.0 * 16 * 512 * 512 * 64 * 64 * 9),
+    "halo_wgrad_l1c": ("conv1_1.conv1 weight gradient, 16x256x256, 384->128, 3x3", 16 * 256 * 256 * (384 + 128) * 2 + 384 * 128 * 9 * 4,
+                       2.0 * 16 * 256 * 256 * 384 * 128 * 9),
+    "thin_wgrad_gb": ("SPADE gamma|beta weight gradient, 16x512x512, 8->128, 3x3", 16 * 512 * 512 * (8 + 128) * 2 + 8 * 128 * 9 * 4,
+                      2.0 * 16 * 512 * 512 * 4 * 128 * 9),
+    "s2_dgrad_l0": ("D block1 data gradient, stride 2, 16x512x512 <- 16x256x256, 64<-64", E + E // 4, 2.0 * 16 * 256 * 256 * 64 * 64 * 9),
+    "s2_fwd_l0": ("D block1 forward, stride 2, 16x512x512 -> 16x256x256, 64->64", E + E // 4, 2.0 * 16 * 256 * 256 * 64 * 64 * 9),
+    "s2_wgrad_l0": ("D block1 weight gradient, stride 2", E + E // 4 + 64 * 64 * 9 * 4, 2.0 * 16 * 256 * 256 * 64 * 64 * 9),
+    "halo_fwd_l0": ("conv0_0.conv2 forward, 16x512x512, 64->64, 3x3", 2 * E, 2.0 * 16 * 512 * 512 * 64 * 64 * 9),
+    "halo_dgrad_l0": ("conv0_0.conv2 data gradient, 16x512x512, 64<-64, 3x3", 2 * E, 2.0 * 16 * 512 * 512 * 64 * 64 * 9),
+    "bn_bwd_apply": ("BN backward apply (dy, y, x -> dx), 16x512x512x64", 4 * E, 0.0),
+    "bn_bwd_reduce": ("BN backward reduce (dy, y, x -> sums), 16x512x512x64", 3 * E, 0.0),
+}
+
+
+def read(rep):
+    out = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(out.splitlines()))
+    h, u, r = rows[0], rows[1], rows[2]
+
+    def val(k):
+        i = h.index(k)
+        return float(r[i].replace(",", "")) * UNIT.get(u[i], 1.0)
+    return {"kernel": r[h.index("Kernel Name")][:80], "dram_read_bytes": val("dram__bytes_read.sum"),
+            "dram_write_bytes": val("dram__bytes_write.sum"), "duration_us": val("gpu__time_duration.sum"),
+            "tensor_pipe_active_pct": float(r[h.index("sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed")])}
+
+
+def main():
+    d, tag = sys.argv[1], sys.argv[2]
+    res = []
+    for name, (what, alg, flops) in CASES.items():
+        rep = os.path.join(d, "%s_%s.ncu-rep" % (tag, name))
+        if not os.path.exists(rep):
+            continue
+        m = read(rep)
+        m.update({"capture": "%s_%s" % (tag, name), "what": what, "algorithmic_bytes": alg,
+                  "dram_bytes": m["dram_read_bytes"] + m["dram_write_bytes"]})
+        m["traffic_over_algorithmic"] = round(m["dram_bytes"] / alg, 3)
+        if flops:
+            m["tflops_under_ncu"] = round(flops / (m["duration_us"] * 1e-6) / 1e12, 1)
+        else:
+            m["GBps_under_ncu"] = round(alg / (m["duration_us"] * 1e-6) / 1e9, 1)
+        res.append(m)
+        print("%-16s %-60s dram %.3f GB (x%.2f of algorithmic) %.1f us tensor %.1f%%" % (
+            name, what[:60], m["dram_bytes"] / 1e9, m["traffic_over_algorithmic"], m["duration_us"], m["tensor_pipe_active_pct"]))
+    with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "r02_traffic.json"), "w") as f:
+        json.dump({"how": "one `ncu --set full --clock-control none` capture per kernel (profiles/capture_r02.sh), dram__bytes_read.sum + "
+                          "dram__bytes_write.sum per launch; durations under ncu are cold-cache and serialised", "kernels": res}, f, indent=1)
+
+
+if __name__ == "__main__":
+    main()

@@ -59,11 +59,11 @@ class _SynchronizedBatchNorm(_BatchNorm):
         shape = input.shape
         x = self._to4d(input)
         parallel = self._is_parallel and self.training
-        if self.training and not parallel and self.num_batches_tracked is not None:
-            self.num_batches_tracked.add_(1)          # F.batch_norm path (batchnorm.py:52-55)
+        # F.batch_norm path (batchnorm.py:52-55) advances num_batches_tracked; the parallel path never does
+        nbt = self.num_batches_tracked if (self.training and not parallel and self.num_batches_tracked is not None) else None
         y = ops.batch_norm(x, self.weight, self.bias, self.running_mean, self.running_var, self.training,
                            self.momentum, self.eps, residual, act, slope,
-                           self._group if parallel else None, sync_quirk=parallel, sums=sums)
+                           self._group if parallel else None, sync_quirk=parallel, sums=sums, nbt=nbt)
         if y.shape != shape:
             y = ops.to_nchw_f32(y).reshape(shape)
         return y
@@ -96,8 +96,13 @@ class SynchronizedBatchNorm3d(_SynchronizedBatchNorm):
 def convert_model(module):
     """Replace every BatchNorm{1,2,3}d by its synchronised twin, sharing running stats and cloning the
     affine parameters (batchnorm.py:320-361).  A DataParallel wrapper becomes DataParallelWithCallback."""
-    if isinstance(module, (torch.nn.DataParallel, DataParallelWithCallback)):
-        return DataParallelWithCallback(convert_model(module.module))
+    if isinstance(module, DataParallelWithCallback):
+        # already this package's wrapper: convert the wrapped network and reuse the wrapper's configuration (a second wrapper
+        # around the first would register a second set of gradient hooks: two all-reduces per backward)
+        module._remove_hooks()
+        return DataParallelWithCallback(convert_model(module.module), device_ids=module.device_ids, process_group=module.process_group)
+    if isinstance(module, torch.nn.DataParallel):
+        return DataParallelWithCallback(convert_model(module.module), device_ids=module.device_ids)
     mod = module
     for src, dst in ((torch.nn.BatchNorm1d, SynchronizedBatchNorm1d), (torch.nn.BatchNorm2d, SynchronizedBatchNorm2d),
                      (torch.nn.BatchNorm3d, SynchronizedBatchNorm3d)):

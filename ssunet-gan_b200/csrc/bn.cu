@@ -8,6 +8,11 @@ namespace ssg {
 
 constexpr int BN_THREADS = 256;
 
+// The forward's per-channel affine y = fmaf(x, sc, sh): sc = inv_std * gamma, sh = beta - mean * sc.  ONE definition, explicit
+// rounding, because the backward re-derives the activation mask from x with it and must reproduce the forward bit for bit.
+__device__ __forceinline__ float bn_scale(float inv_std, float gamma) { return __fmul_rn(inv_std, gamma); }
+__device__ __forceinline__ float bn_shift(float beta, float mean, float sc) { return __fmaf_rn(-mean, sc, beta); }
+
 // Generic "reduce over rows, per channel" skeleton.  F(c, vals...) is applied by the callers.
 // REDUCE_MODE 0: stats (sum x, sum x^2); 1: BN backward (sum dz, sum dz*xhat)
 template <typename T, int MODE>
@@ -16,7 +21,11 @@ __global__ void __launch_bounds__(BN_THREADS) channel_reduce_vec_kernel(
     const T* __restrict__ yout,   // MODE1: post-activation output (may be null when act == none)
     const T* __restrict__ xin,    // MODE1: BN input x
     long long rows, int C, long long rows_per_block, const float* __restrict__ mean, const float* __restrict__ inv_std,
-    int act, float slope, int with_sq, double* __restrict__ sums) {
+    int act, float slope, int with_sq, double* __restrict__ sums,
+    const float* __restrict__ fsc = nullptr, const float* __restrict__ fsh = nullptr, int recompute = 0) {
+    // recompute (MODE 1, no residual): the activation mask is re-derived from x with the forward's own expression
+    // fmaf(x, sc, sh) (bn_apply_rows_kernel; sc / sh as bn_finalize_kernel stored them at forward time) instead of being read
+    // back from y -- one operand less to stream.
     constexpr int V = Vec<T>::N;
     // Block-level combination without atomics: every thread parks its fp32 partial sums in shared memory ([row group][C]), then
     // thread c adds the row groups of channel c in a fixed order in fp64 and issues ONE fp64 atomic into the result.  The
@@ -39,10 +48,18 @@ __global__ void __launch_bounds__(BN_THREADS) channel_reduce_vec_kernel(
             float acc0[V], acc1[V], mu[V], is[V];
 #pragma unroll
             for (int i = 0; i < V; ++i) { acc0[i] = 0.f; acc1[i] = 0.f; mu[i] = 0.f; is[i] = 1.f; }
+            float rsc[V], rsh[V];
+#pragma unroll
+            for (int i = 0; i < V; ++i) { rsc[i] = 0.f; rsh[i] = 0.f; }
             if (MODE == 1) {
 #pragma unroll
                 for (int i = 0; i < V; ++i) { mu[i] = mean[v * V + i]; is[i] = inv_std[v * V + i]; }
+                if (recompute) {
+#pragma unroll
+                    for (int i = 0; i < V; ++i) { rsc[i] = fsc[v * V + i]; rsh[i] = fsh[v * V + i]; }
+                }
             }
+            const bool read_y = (MODE == 1) && act != SSG_ACT_NONE && !recompute;
             // U rows per trip with all loads issued before the first use: U independent 16-byte requests per operand
             // in flight per thread (a single dependent load per trip left this kernel latency-bound at < 20 % of HBM)
             constexpr int U = 4;                        // (8 rows in flight measured slower for the single-operand mode)
@@ -54,7 +71,7 @@ __global__ void __launch_bounds__(BN_THREADS) channel_reduce_vec_kernel(
                 if (MODE == 1) {
 #pragma unroll
                     for (int u = 0; u < U; ++u) vx[u].load(xin + (r + (long long)u * rpb) * C + (long long)v * V);
-                    if (act != SSG_ACT_NONE) {
+                    if (read_y) {
 #pragma unroll
                         for (int u = 0; u < U; ++u) vy[u].load(yout + (r + (long long)u * rpb) * C + (long long)v * V);
                     }
@@ -67,10 +84,13 @@ __global__ void __launch_bounds__(BN_THREADS) channel_reduce_vec_kernel(
                         for (int i = 0; i < V; ++i) { acc0[i] += fa[i]; acc1[i] = fmaf(fa[i], fa[i], acc1[i]); }
                     } else {
                         float fx[V]; vx[u].get(fx);
-                        if (act != SSG_ACT_NONE) {
+                        if (read_y) {
                             float fy[V]; vy[u].get(fy);
 #pragma unroll
                             for (int i = 0; i < V; ++i) fa[i] *= act_grad_from_out(fy[i], act, slope);
+                        } else if (recompute) {
+#pragma unroll
+                            for (int i = 0; i < V; ++i) fa[i] *= act_grad_from_out(fmaf(fx[i], rsc[i], rsh[i]), act, slope);
                         }
 #pragma unroll
                         for (int i = 0; i < V; ++i) {
@@ -90,11 +110,14 @@ __global__ void __launch_bounds__(BN_THREADS) channel_reduce_vec_kernel(
                 } else {
                     Vec<T> vx; vx.load(xin + off);
                     float fx[V]; vx.get(fx);
-                    if (act != SSG_ACT_NONE) {
+                    if (read_y) {
                         Vec<T> vy; vy.load(yout + off);
                         float fy[V]; vy.get(fy);
 #pragma unroll
                         for (int i = 0; i < V; ++i) fa[i] *= act_grad_from_out(fy[i], act, slope);
+                    } else if (recompute) {
+#pragma unroll
+                        for (int i = 0; i < V; ++i) fa[i] *= act_grad_from_out(fmaf(fx[i], rsc[i], rsh[i]), act, slope);
                     }
 #pragma unroll
                     for (int i = 0; i < V; ++i) {
@@ -154,9 +177,11 @@ __global__ void __launch_bounds__(BN_THREADS) channel_reduce_scalar_kernel(
 
 template <typename T, int MODE>
 static int launch_channel_reduce(const T* a, const T* y, const T* x, long long rows, int C, const float* mean,
-                                 const float* inv_std, int act, float slope, int with_sq, double* sums, cudaStream_t st) {
+                                 const float* inv_std, int act, float slope, int with_sq, double* sums, cudaStream_t st,
+                                 const float* fsc = nullptr, const float* fsh = nullptr, int recompute = 0) {
     constexpr int V = Vec<T>::N;
     SSG_CHECK_ARG(rows > 0 && C > 0 && C <= 8192, "channel reduce: rows=%lld C=%d unsupported", rows, C);
+    SSG_CHECK_ARG(!recompute || C % V == 0, "channel reduce: mask recomputation needs C %% %d == 0", V);
     SSG_CHECK_CUDA(cudaMemsetAsync(sums, 0, sizeof(double) * 2 * C, st));
     // aim for ~8 waves of blocks, but keep >= 64 rows per block so the fp64 atomics stay negligible
     long long blocks = (long long)sm_count_cached() * 8;
@@ -177,7 +202,8 @@ static int launch_channel_reduce(const T* a, const T* y, const T* x, long long r
         }
     }
     if (C % V == 0)
-        channel_reduce_vec_kernel<T, MODE><<<(unsigned)blocks, BN_THREADS, smem, st>>>(a, y, x, rows, C, rpb, mean, inv_std, act, slope, with_sq, sums);
+        channel_reduce_vec_kernel<T, MODE><<<(unsigned)blocks, BN_THREADS, smem, st>>>(a, y, x, rows, C, rpb, mean, inv_std, act, slope, with_sq, sums,
+                                                                                       fsc, fsh, recompute);
     else
         channel_reduce_scalar_kernel<T, MODE><<<(unsigned)blocks, BN_THREADS, smem, st>>>(a, y, x, rows, C, rpb, mean, inv_std, act, slope, with_sq, sums);
     SSG_CHECK_LAUNCH();
@@ -185,8 +211,11 @@ static int launch_channel_reduce(const T* a, const T* y, const T* x, long long r
 }
 
 __global__ void bn_finalize_kernel(const double* __restrict__ sums, double count, int C, float eps, float momentum,
-                                   int sync_quirk, float* running_mean, float* running_var, float* mean, float* inv_std) {
+                                   int sync_quirk, float* running_mean, float* running_var, float* mean, float* inv_std,
+                                   long long* num_batches_tracked = nullptr, const float* gamma = nullptr,
+                                   const float* beta = nullptr, float* sc_out = nullptr, float* sh_out = nullptr) {
     int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c == 0 && num_batches_tracked) num_batches_tracked[0] += 1;      // nn.BatchNorm2d's counter (F.batch_norm path)
     if (c >= C) return;
     const double s = sums[c], ss = sums[C + c];
     const double mu = s / count;
@@ -204,6 +233,11 @@ __global__ void bn_finalize_kernel(const double* __restrict__ sums, double count
     if (running_mean) {
         running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * (float)mu;
         running_var[c] = (1.f - momentum) * running_var[c] + momentum * (float)unbias_var;
+    }
+    if (sc_out) {          // the forward's affine y = fma(x, sc, sh), kept for the backward's mask recomputation
+        const float sc = bn_scale(inv_std[c], gamma ? gamma[c] : 1.f);
+        sc_out[c] = sc;
+        sh_out[c] = bn_shift(beta ? beta[c] : 0.f, mean[c], sc);
     }
 }
 
@@ -224,9 +258,9 @@ __global__ void __launch_bounds__(256) bn_apply_kernel(const T* __restrict__ x, 
     float* sc = sm;
     float* sh = sm + C;
     for (int c = threadIdx.x; c < C; c += blockDim.x) {
-        float s = inv_std[c] * (gamma ? gamma[c] : 1.f);
+        float s = bn_scale(inv_std[c], gamma ? gamma[c] : 1.f);
         sc[c] = s;
-        sh[c] = (beta ? beta[c] : 0.f) - mean[c] * s;
+        sh[c] = bn_shift(beta ? beta[c] : 0.f, mean[c], s);
     }
     __syncthreads();
     const long long stride = (long long)gridDim.x * blockDim.x;
@@ -339,9 +373,9 @@ __global__ void __launch_bounds__(256) bn_apply_rows_kernel(const T* __restrict_
 #pragma unroll
     for (int k = 0; k < V; ++k) {
         const int c = lane * V + k;
-        const float s = inv_std[c] * (gamma ? gamma[c] : 1.f);
+        const float s = bn_scale(inv_std[c], gamma ? gamma[c] : 1.f);
         sc[k] = s;
-        sh[k] = (beta ? beta[c] : 0.f) - mean[c] * s;
+        sh[k] = bn_shift(beta ? beta[c] : 0.f, mean[c], s);
     }
     const long long rstride = (long long)gridDim.x * rpb;
     const long long col = (long long)lane * V;
@@ -389,24 +423,28 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_rows_kernel(const T* __restr
                                                                  long long rows, int C, const float* __restrict__ mean,
                                                                  const float* __restrict__ inv_std, const float* __restrict__ gamma,
                                                                  const double* __restrict__ sums, double count, int act, float slope,
-                                                                 int training) {
+                                                                 int training, const float* __restrict__ fsc = nullptr,
+                                                                 const float* __restrict__ fsh = nullptr, int recompute = 0) {
     constexpr int V = Vec<T>::N;
     constexpr int U = 4;
     const int lanes = C / V, rpb = 256 / lanes;
     const int lane = threadIdx.x % lanes, rsub = threadIdx.x / lanes;
     if (rsub >= rpb) return;
-    float ka[V], kb[V], kc[V];
+    float ka[V], kb[V], kc[V], rsc[V], rsh[V];
 #pragma unroll
     for (int k = 0; k < V; ++k) {
         const int c = lane * V + k;
-        const float is = inv_std[c], a = is * (gamma ? gamma[c] : 1.f);
+        const float is = inv_std[c], a = bn_scale(is, gamma ? gamma[c] : 1.f);
         const float m0 = training ? (float)(sums[c] / count) : 0.f;
         const float m1 = training ? (float)(sums[C + c] / count) : 0.f;
-        ka[k] = a;
+        ka[k] = a;                 // gamma as it is NOW (the reference's BN backward reads the live parameter, train.py:111-115)
         kb[k] = -a * is * m1;
         kc[k] = a * (mean[c] * is * m1 - m0);
+        rsc[k] = recompute ? fsc[c] : 0.f;      // the forward's affine, stored at forward time
+        rsh[k] = recompute ? fsh[c] : 0.f;
     }
-    const bool has_act = act != SSG_ACT_NONE;
+    const bool has_act = act != SSG_ACT_NONE && !recompute;
+    const bool rc_act = act != SSG_ACT_NONE && recompute;
     const long long rstride = (long long)gridDim.x * rpb;
     const long long col = (long long)lane * V;
     long long r = (long long)blockIdx.x * rpb + rsub;
@@ -429,6 +467,9 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_rows_kernel(const T* __restr
                 float fy[V]; vy[u].get(fy);
 #pragma unroll
                 for (int k = 0; k < V; ++k) d[k] *= act_grad_from_out(fy[k], act, slope);
+            } else if (rc_act) {
+#pragma unroll
+                for (int k = 0; k < V; ++k) d[k] *= act_grad_from_out(fmaf(fx[k], rsc[k], rsh[k]), act, slope);
             }
             const long long off = (r + u * rstride) * C + col;
             if (dres) { Vec<T> vr; vr.set(d); vr.store(dres + off); }
@@ -449,6 +490,9 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_rows_kernel(const T* __restr
             float fy[V]; vy.get(fy);
 #pragma unroll
             for (int k = 0; k < V; ++k) d[k] *= act_grad_from_out(fy[k], act, slope);
+        } else if (rc_act) {
+#pragma unroll
+            for (int k = 0; k < V; ++k) d[k] *= act_grad_from_out(fmaf(fx[k], rsc[k], rsh[k]), act, slope);
         }
         if (dres) { Vec<T> vr; vr.set(d); vr.store(dres + off); }
 #pragma unroll
@@ -469,11 +513,20 @@ static inline unsigned rows_grid(long long rows, int rpb) {
     return (unsigned)(b < 1 ? 1 : b);
 }
 
-__global__ void bn_param_grads_kernel(const double* sums, int C, float* dgamma, float* dbeta) {
+__global__ void bn_param_grads_kernel(const double* sums, int C, float* dgamma, float* dbeta, int accumulate = 0) {
     int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= C) return;
-    if (dbeta) dbeta[c] = (float)sums[c];
-    if (dgamma) dgamma[c] = (float)sums[C + c];
+    if (accumulate) {          // straight into the optimiser's gradient arena (zeroed by zero_grad; D runs two passes per step)
+        if (dbeta) dbeta[c] += (float)sums[c];
+        if (dgamma) dgamma[c] += (float)sums[C + c];
+    } else {
+        if (dbeta) dbeta[c] = (float)sums[c];
+        if (dgamma) dgamma[c] = (float)sums[C + c];
+    }
+}
+__global__ void accum_f64_f32_kernel(const double* __restrict__ src, float* __restrict__ dst, int n) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) dst[i] += (float)src[i];
 }
 
 }  // namespace ssg
@@ -492,6 +545,18 @@ int ssg_bn_finalize(const double* sums, double count, int c, float eps, float mo
     SSG_CHECK_ARG(c > 0 && count > 0, "bn_finalize: bad args");
     bn_finalize_kernel<<<(c + 127) / 128, 128, 0, (cudaStream_t)s>>>(sums, count, c, eps, momentum, sync_quirk, running_mean,
                                                                      running_var, mean, inv_std);
+    SSG_CHECK_LAUNCH();
+    return SSG_OK;
+}
+
+int ssg_bn_finalize_count(const double* sums, double count, int c, float eps, float momentum, int sync_quirk, float* running_mean,
+                          float* running_var, float* mean, float* inv_std, long long* num_batches_tracked, const float* gamma,
+                          const float* beta, float* sc_out, float* sh_out, ssg_stream_t s) {
+    SSG_CHECK_ARG(c > 0 && count > 0, "bn_finalize: bad args");
+    SSG_CHECK_ARG((sc_out == nullptr) == (sh_out == nullptr), "bn_finalize: sc_out and sh_out go together");
+    bn_finalize_kernel<<<(c + 127) / 128, 128, 0, (cudaStream_t)s>>>(sums, count, c, eps, momentum, sync_quirk, running_mean,
+                                                                     running_var, mean, inv_std, num_batches_tracked, gamma, beta,
+                                                                     sc_out, sh_out);
     SSG_CHECK_LAUNCH();
     return SSG_OK;
 }
@@ -556,6 +621,43 @@ int ssg_bn_bwd_apply(const void* dy, const void* y, const void* x, void* dx, voi
 
 int ssg_bn_param_grads(const double* sums, int c, float* dgamma, float* dbeta, ssg_stream_t s) {
     bn_param_grads_kernel<<<(c + 127) / 128, 128, 0, (cudaStream_t)s>>>(sums, c, dgamma, dbeta);
+    SSG_CHECK_LAUNCH();
+    return SSG_OK;
+}
+
+int ssg_bn_param_grads_acc(const double* sums, int c, float* dgamma, float* dbeta, ssg_stream_t s) {
+    bn_param_grads_kernel<<<(c + 127) / 128, 128, 0, (cudaStream_t)s>>>(sums, c, dgamma, dbeta, 1);
+    SSG_CHECK_LAUNCH();
+    return SSG_OK;
+}
+
+int ssg_accum_f64_f32(const double* src, float* dst, int n, ssg_stream_t s) {
+    SSG_CHECK_ARG(src && dst && n > 0, "accum_f64_f32: bad args");
+    accum_f64_f32_kernel<<<(n + 127) / 128, 128, 0, (cudaStream_t)s>>>(src, dst, n);
+    SSG_CHECK_LAUNCH();
+    return SSG_OK;
+}
+
+/* BN backward without re-reading the forward output: the activation mask is recomputed from x (no residual). */
+int ssg_bn_bwd_reduce_rc(const void* dy, const void* x, int dtype, long long rows, int c, const float* mean, const float* inv_std,
+                         const float* fwd_sc, const float* fwd_sh, int act, float slope, double* sums, ssg_stream_t s) {
+    SSG_CHECK_ARG(fwd_sc && fwd_sh, "bn_bwd_reduce_rc: the forward's sc / sh are required");
+    SSG_DISPATCH_DTYPE(dtype, return (launch_channel_reduce<T, 1>((const T*)dy, nullptr, (const T*)x, rows, c, mean, inv_std, act, slope,
+                                                                  1, sums, (cudaStream_t)s, fwd_sc, fwd_sh, 1)));
+    return SSG_OK;
+}
+
+int ssg_bn_bwd_apply_rc(const void* dy, const void* x, void* dx, int dtype, long long rows, int c, const float* mean,
+                        const float* inv_std, const float* gamma, const float* fwd_sc, const float* fwd_sh, const double* sums,
+                        double count, int act, float slope, int training, ssg_stream_t s) {
+    SSG_CHECK_ARG(rows > 0 && c > 0 && fwd_sc && fwd_sh, "bn_bwd_apply_rc: bad arguments");
+    SSG_DISPATCH_DTYPE(dtype, {
+        constexpr int V = Vec<T>::N;
+        SSG_CHECK_ARG(c % V == 0 && c / V <= 256, "bn_bwd_apply_rc: C=%d needs the row-strided kernel (C %% %d == 0, C / %d <= 256)", c, V, V);
+        const int rpb = 256 / (c / V);
+        bn_bwd_apply_rows_kernel<T><<<rows_grid(rows, rpb), 256, 0, (cudaStream_t)s>>>((const T*)dy, nullptr, (const T*)x, (T*)dx, nullptr, rows, c, mean,
+                                                                                       inv_std, gamma, sums, count, act, slope, training, fwd_sc, fwd_sh, 1);
+    });
     SSG_CHECK_LAUNCH();
     return SSG_OK;
 }

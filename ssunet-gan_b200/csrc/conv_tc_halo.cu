@@ -479,6 +479,7 @@ struct HaloWgradParams {
     int cout, cin;               // real channel extents of dw
     int tiles_x, tiles_y, m_tiles;
     int chunks0, chunks1;
+    int issuers;                 // 1 or 2 MMA-issuing warps (see the kernel)
 };
 
 constexpr int HW_XS = 4, HW_DS = 4;                    // ring slots
@@ -487,6 +488,46 @@ constexpr int HW_X_OFFSET = 0;
 constexpr int HW_DY_OFFSET = HW_XS * H_A_TILE_STRIDE;
 constexpr int HW_BAR_OFFSET = HW_DY_OFFSET + HW_DS * HW_DY_BYTES;
 constexpr int HW_TOTAL = HW_BAR_OFFSET + 256 + 1024;
+
+// Issue loop of the halo weight-gradient kernel for tap pairs [G_LO, G_HI): the whole warp walks the loop (uniform datapath),
+// the elected lane issues the MMAs and commits.
+template <int G_LO, int G_HI>
+__device__ __forceinline__ void halo_wgrad_issue(uint8_t* smem, uint64_t* x_full, uint64_t* dy_full, uint64_t* x_empty,
+                                                 uint64_t* dy_empty, uint64_t* acc_full, uint32_t tmem_base, int n_iter) {
+    constexpr uint32_t idesc = make_idesc_bf16(128, 64, 1, 1);     // both operands MN-major
+    const uint32_t leader = elect_one() ? 1u : 0u;
+    const uint32_t x_hi = desc_hi(1280, 2), dy_hi = desc_hi(1024, 2);
+    const uint32_t x_lo_base = desc_lo(smem_u32(smem + HW_X_OFFSET), 0);
+    const uint32_t dy_lo_base = desc_lo(smem_u32(smem + HW_DY_OFFSET), 1024);
+    for (int it = 0; it < n_iter; ++it) {
+        const int xs = it % HW_XS, ds = it % HW_DS;
+        mbar_wait(&x_full[xs], (it / HW_XS) & 1);
+        mbar_wait(&dy_full[ds], (it / HW_DS) & 1);
+        tc_fence_after();
+        const uint32_t xk = x_lo_base + (uint32_t)(xs * (H_A_TILE_STRIDE / 16));
+        const uint32_t dk = dy_lo_base + (uint32_t)(ds * (HW_DY_BYTES / 16));
+        const uint32_t keep = (uint32_t)it;
+        // Straight-line issue of the tile's MMAs (k outer, tap pair inner: consecutive MMAs accumulate into different
+        // TMEM accumulators); every descriptor is (slot base + compile-time constant), the leader flag predicates the
+        // instruction itself.  Pair g = taps 2g and 2g+1 (tap 8 is paired with a dummy second half whose rows are never
+        // stored).  16 pixels = two tile rows per MMA: x advances 2 halo rows (160 x 16 B), dy 2 box rows (128 x 16 B).
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+#pragma unroll
+            for (int g = G_LO; g < G_HI; ++g) {
+                const int ta = 2 * g, tb = g < 4 ? 2 * g + 1 : 8;
+                const int off_a = ((ta / 3) * 10 + ta % 3) * 128, off_b = ((tb / 3) * 10 + tb % 3) * 128;
+                const uint32_t lbo = g < 4 ? (uint32_t)(off_b - off_a) : 128u;
+                // start-address field += off_a / 16; LBO field (bits 16..29) = lbo / 16: both compile-time constants
+                umma_bf16_lohi_pred(tmem_base + (uint32_t)(g * 64), xk + (uint32_t)(k * 160 + ((off_a >> 4) | ((lbo >> 4) << 16))), x_hi,
+                                    dk + (uint32_t)(k * 128), dy_hi, idesc, k == 0 ? keep : 1u, leader);
+            }
+        }
+        umma_commit_pred(&x_empty[xs], leader);
+        umma_commit_pred(&dy_empty[ds], leader);
+    }
+    umma_commit_pred(acc_full, leader);
+}
 
 __global__ void __launch_bounds__(H_THREADS, 1) conv_tc_halo_wgrad_kernel(const __grid_constant__ CUtensorMap tmX0,
                                                                            const __grid_constant__ CUtensorMap tmX1,
@@ -507,9 +548,9 @@ __global__ void __launch_bounds__(H_THREADS, 1) conv_tc_halo_wgrad_kernel(const 
     const int n_iter = (p.m_tiles - (int)blockIdx.z + (int)gridDim.z - 1) / (int)gridDim.z;
 
     if (threadIdx.x == 0) {
-        for (int i = 0; i < HW_XS; ++i) { mbar_init(&x_full[i], 1); mbar_init(&x_empty[i], 1); }
-        for (int i = 0; i < HW_DS; ++i) { mbar_init(&dy_full[i], 1); mbar_init(&dy_empty[i], 1); }
-        mbar_init(acc_full, 1);
+        for (int i = 0; i < HW_XS; ++i) { mbar_init(&x_full[i], 1); mbar_init(&x_empty[i], p.issuers); }
+        for (int i = 0; i < HW_DS; ++i) { mbar_init(&dy_full[i], 1); mbar_init(&dy_empty[i], p.issuers); }
+        mbar_init(acc_full, p.issuers);
         fence_barrier_init();
     }
     if (warp == 2) tmem_alloc(tmem_slot, 512);
@@ -544,41 +585,18 @@ __global__ void __launch_bounds__(H_THREADS, 1) conv_tc_halo_wgrad_kernel(const 
                 tma_load_4d(smem + HW_DY_OFFSET + sl * HW_DY_BYTES, &tmDY, co0, tx * H_TW, ty * H_TH, img, &dy_full[sl]);
             }
         }
-    } else if (warp == 2) {
-        // whole warp walks the loop (uniform datapath); lane 0 issues the MMAs and commits
-        constexpr uint32_t idesc = make_idesc_bf16(128, 64, 1, 1);     // both operands MN-major
-        const uint32_t leader = elect_one() ? 1u : 0u;
-        const uint32_t x_hi = desc_hi(1280, 2), dy_hi = desc_hi(1024, 2);
-        const uint32_t x_lo_base = desc_lo(smem_u32(smem + HW_X_OFFSET), 0);
-        const uint32_t dy_lo_base = desc_lo(smem_u32(smem + HW_DY_OFFSET), 1024);
-        for (int it = 0; it < n_iter; ++it) {
-            const int xs = it % HW_XS, ds = it % HW_DS;
-            mbar_wait(&x_full[xs], (it / HW_XS) & 1);
-            mbar_wait(&dy_full[ds], (it / HW_DS) & 1);
-            tc_fence_after();
-            const uint32_t xk = x_lo_base + (uint32_t)(xs * (H_A_TILE_STRIDE / 16));
-            const uint32_t dk = dy_lo_base + (uint32_t)(ds * (HW_DY_BYTES / 16));
-            const uint32_t keep = (uint32_t)it;
-            // Straight-line issue of the tile's 40 MMAs (k outer, tap pair inner: consecutive MMAs accumulate into different
-            // TMEM accumulators); every descriptor is (slot base + compile-time constant), the leader flag predicates the
-            // instruction itself.  Pair g = taps 2g and 2g+1 (tap 8 is paired with a dummy second half whose rows are never
-            // stored).  16 pixels = two tile rows per MMA: x advances 2 halo rows (160 x 16 B), dy 2 box rows (128 x 16 B).
-#pragma unroll
-            for (int k = 0; k < 8; ++k) {
-#pragma unroll
-                for (int g = 0; g < 5; ++g) {
-                    const int ta = 2 * g, tb = g < 4 ? 2 * g + 1 : 8;
-                    const int off_a = ((ta / 3) * 10 + ta % 3) * 128, off_b = ((tb / 3) * 10 + tb % 3) * 128;
-                    const uint32_t lbo = g < 4 ? (uint32_t)(off_b - off_a) : 128u;
-                    // start-address field += off_a / 16; LBO field (bits 16..29) = lbo / 16: both compile-time constants
-                    umma_bf16_lohi_pred(tmem_base + (uint32_t)(g * 64), xk + (uint32_t)(k * 160 + ((off_a >> 4) | ((lbo >> 4) << 16))), x_hi,
-                                        dk + (uint32_t)(k * 128), dy_hi, idesc, k == 0 ? keep : 1u, leader);
-                }
-            }
-            umma_commit_pred(&x_empty[xs], leader);
-            umma_commit_pred(&dy_empty[ds], leader);
+    } else if (warp == 2 || (warp == 3 && p.issuers == 2)) {
+        // MMA issue.  ncu (profiles/r02_ncu_halo_wgrad_l0.txt): the single issuing warp spent a third of its time on the uniform
+        // datapath's dependent descriptor arithmetic (short scoreboard) between UTCHMMAs of only 32 tensor-clocks each.  With
+        // p.issuers == 2 the five tap-pair accumulators are split between warps 2 (pairs 0-2) and 3 (pairs 3-4): MMAs into
+        // different accumulators are independent, so two issue streams need no ordering; each stream commits its own MMAs to
+        // the ring's empty barriers (initialised with one arrival per issuer).
+        if (p.issuers == 2) {
+            if (warp == 2) halo_wgrad_issue<0, 3>(smem, x_full, dy_full, x_empty, dy_empty, acc_full, tmem_base, n_iter);
+            else halo_wgrad_issue<3, 5>(smem, x_full, dy_full, x_empty, dy_empty, acc_full, tmem_base, n_iter);
+        } else {
+            halo_wgrad_issue<0, 5>(smem, x_full, dy_full, x_empty, dy_empty, acc_full, tmem_base, n_iter);
         }
-        umma_commit_pred(acc_full, leader);
     } else if (warp >= 4) {
         const int q = warp & 3;
         const int row = q * 32 + lane;                  // accumulator row: tap half (row >> 6), ci (row & 63)
@@ -617,6 +635,8 @@ int run_wgrad_halo(const void* x0, int c0, const void* x1, int c1, const void* d
     p.dw = dw; p.N = n; p.H = h; p.W = w; p.cout = cout_real; p.cin = cin_real;
     p.tiles_x = (w + H_TW - 1) / H_TW; p.tiles_y = (h + H_TH - 1) / H_TH; p.m_tiles = n * p.tiles_x * p.tiles_y;
     p.chunks0 = (c0 + 63) / 64; p.chunks1 = (c1 + 63) / 64;
+    static const int issuers_env = getenv("SSG_WGRAD_ISSUERS") ? atoi(getenv("SSG_WGRAD_ISSUERS")) : 2;
+    p.issuers = issuers_env == 1 ? 1 : 2;
     CUtensorMap mx0, mx1, mdy;
     auto enc = [&](CUtensorMap* m, const void* ptr, int c, int bw, int bh) {
         uint64_t dims[4] = {(uint64_t)c, (uint64_t)w, (uint64_t)h, (uint64_t)n};

@@ -217,6 +217,17 @@ __global__ void __launch_bounds__(256) clamp_adam_dev_kernel(float* __restrict__
     const float step = lr / bc1;
     adam_span(p, g, m, v, n, stride, b1, b2, eps, bc2_sqrt, step, clip, gscale, wd);
 }
+// Hyper-parameters on the device as well: hp = {lr, beta1, beta2, eps, clip, grad_scale, weight_decay, -}.  A captured launch
+// then follows an LR schedule / a changed clip: the host rewrites the eight floats between replays.
+__global__ void __launch_bounds__(256) clamp_adam_hp_kernel(float* __restrict__ p, float* __restrict__ g, float* __restrict__ m,
+                                                             float* __restrict__ v, long long n, const float* __restrict__ hp,
+                                                             const float* __restrict__ step_dev) {
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    const float lr = hp[0], b1 = hp[1], b2 = hp[2], eps = hp[3], clip = hp[4], gscale = hp[5], wd = hp[6];
+    const float t = step_dev[0];
+    const float bc1 = 1.f - powf(b1, t), bc2_sqrt = sqrtf(1.f - powf(b2, t));
+    adam_span(p, g, m, v, n, stride, b1, b2, eps, bc2_sqrt, lr / bc1, clip, gscale, wd);
+}
 __global__ void scale_by_dev_kernel(const float* __restrict__ w, const float* __restrict__ sc, float* __restrict__ o, long long n) {
     const float s = sc[0];
     const long long stride = (long long)gridDim.x * blockDim.x;
@@ -321,6 +332,14 @@ int ssg_clamp_adam_wd_dev(float* p, float* g, float* m, float* v, long long n, f
     step_inc_kernel<<<1, 1, 0, (cudaStream_t)s>>>(step_dev);
     clamp_adam_dev_kernel<<<grid_for(n, 2048), 256, 0, (cudaStream_t)s>>>(p, g, m, v, n, lr, beta1, beta2, eps, step_dev, clip, grad_scale,
                                                                           weight_decay);
+    SSG_CHECK_LAUNCH();
+    return SSG_OK;
+}
+int ssg_clamp_adam_hp_dev(float* p, float* g, float* m, float* v, long long n, const float* hp_dev, float* step_dev, ssg_stream_t s) {
+    if (n <= 0) return SSG_OK;
+    SSG_CHECK_ARG(step_dev != nullptr && hp_dev != nullptr, "clamp_adam_hp_dev: step counter / hyper-parameters missing");
+    step_inc_kernel<<<1, 1, 0, (cudaStream_t)s>>>(step_dev);
+    clamp_adam_hp_kernel<<<grid_for(n, 2048), 256, 0, (cudaStream_t)s>>>(p, g, m, v, n, hp_dev, step_dev);
     SSG_CHECK_LAUNCH();
     return SSG_OK;
 }

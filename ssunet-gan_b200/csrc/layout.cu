@@ -146,6 +146,44 @@ __global__ void pack_weight_kernel(const float* __restrict__ w, T* __restrict__ 
     dst[i] = (k < cout && c < cin) ? from_f<T>(w[(((long long)k * cin + c) * kh + r) * kw + s] * sc) : from_f<T>(0.f);
 }
 
+// Every packed operand of a network in ONE launch (the per-tensor kernel above costs one launch per weight and layout: ~190 per
+// step).  A block finds its record by binary search over first_block and converts SSG_PACK_BLOCK_ELEMS destination elements.
+struct __align__(8) PackDesc {
+    const float* src;
+    void* dst;
+    int layout, cout, cin, ks, cout_p, cin_p;
+    long long first_block;
+};
+static_assert(sizeof(PackDesc) == SSG_PACK_DESC_BYTES, "PackDesc layout is part of the C ABI");
+
+template <typename T>
+__global__ void __launch_bounds__(256) pack_weights_multi_kernel(const PackDesc* __restrict__ descs, int n_descs) {
+    const long long b = blockIdx.x;
+    int lo = 0, hi = n_descs - 1;
+    while (lo < hi) {                       // last record with first_block <= b
+        const int mid = (lo + hi + 1) >> 1;
+        if (descs[mid].first_block <= b) lo = mid; else hi = mid - 1;
+    }
+    const PackDesc d = descs[lo];
+    const long long total = (long long)d.cout_p * d.cin_p * d.ks * d.ks;
+    const long long base = (b - d.first_block) * SSG_PACK_BLOCK_ELEMS;
+    T* dst = reinterpret_cast<T*>(d.dst);
+#pragma unroll
+    for (int j = 0; j < SSG_PACK_BLOCK_ELEMS / 256; ++j) {
+        const long long i = base + j * 256 + threadIdx.x;
+        if (i >= total) break;
+        int r, s, c, k;
+        long long t = i;
+        if (d.layout == SSG_W_RSKC) {
+            c = (int)(t % d.cin_p); t /= d.cin_p; k = (int)(t % d.cout_p); t /= d.cout_p; s = (int)(t % d.ks); r = (int)(t / d.ks);
+        } else {
+            k = (int)(t % d.cout_p); t /= d.cout_p; c = (int)(t % d.cin_p); t /= d.cin_p; s = (int)(t % d.ks); r = (int)(t / d.ks);
+            if (d.layout == SSG_W_RSCK_FLIP) { r = d.ks - 1 - r; s = d.ks - 1 - s; }
+        }
+        dst[i] = (k < d.cout && c < d.cin) ? from_f<T>(d.src[(((long long)k * d.cin + c) * d.ks + r) * d.ks + s]) : from_f<T>(0.f);
+    }
+}
+
 }  // namespace ssg
 using namespace ssg;
 
@@ -232,6 +270,12 @@ int ssg_pack_conv_weight_pad(const float* w, void* dst, int dtype, int layout, i
     unsigned g = (unsigned)((total + 255) / 256);
     SSG_DISPATCH_DTYPE(dtype, pack_weight_kernel<T><<<g, 256, 0, (cudaStream_t)s>>>(w, (T*)dst, layout, cout, cin, kh, kw, inv_scale_dev,
                                                                                     cout_p, cin_p));
+    SSG_CHECK_LAUNCH();
+    return SSG_OK;
+}
+int ssg_pack_conv_weights_multi(const void* descs_dev, int n_descs, long long total_blocks, int dtype, ssg_stream_t s) {
+    SSG_CHECK_ARG(descs_dev && n_descs > 0 && total_blocks > 0 && total_blocks < (1ll << 31), "pack_conv_weights_multi: bad args");
+    SSG_DISPATCH_DTYPE(dtype, pack_weights_multi_kernel<T><<<(unsigned)total_blocks, 256, 0, (cudaStream_t)s>>>((const PackDesc*)descs_dev, n_descs));
     SSG_CHECK_LAUNCH();
     return SSG_OK;
 }

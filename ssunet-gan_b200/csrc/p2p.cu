@@ -25,8 +25,15 @@ __device__ __forceinline__ unsigned ld_acquire_sys(const unsigned* p) {
     return v;
 }
 
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+
 __global__ void __launch_bounds__(512) p2p_allreduce_f64_kernel(double* __restrict__ data, int n, void* const* __restrict__ peers, int rank,
-                                                                 int world, int slot_doubles, unsigned* __restrict__ epoch) {
+                                                                 int world, int slot_doubles, unsigned* __restrict__ epoch,
+                                                                 long long timeout_ns, unsigned* __restrict__ status) {
     __shared__ unsigned e_s;
     if (threadIdx.x == 0) e_s = *epoch + 1u;
     __syncthreads();
@@ -45,9 +52,19 @@ __global__ void __launch_bounds__(512) p2p_allreduce_f64_kernel(double* __restri
         unsigned* pf = reinterpret_cast<unsigned*>(reinterpret_cast<double*>(peers[threadIdx.x]) + flags_off);
         st_release_sys(pf + slot * world + rank, e);
         const unsigned* mf = reinterpret_cast<const unsigned*>(reinterpret_cast<const double*>(peers[rank]) + flags_off) + slot * world + threadIdx.x;
+        // A peer that never arrives (rank skew beyond the bound, a dead rank) must not kill the context: after timeout_ns of
+        // wall clock the wait is abandoned, the failure is recorded in *status and the host raises when it next checks.
         unsigned spins = 0;
+        unsigned long long t0 = 0;
         while (ld_acquire_sys(mf) != e) {
-            if (++spins > (1u << 28)) __trap();                                  // a peer never arrived: fail the launch, do not hang
+            if ((++spins & 0x3ffu) == 0 && timeout_ns > 0) {
+                const unsigned long long now = globaltimer_ns();
+                if (t0 == 0) t0 = now;
+                else if (now - t0 > (unsigned long long)timeout_ns) {
+                    if (status) atomicCAS(status, 0u, 1u + threadIdx.x);
+                    break;
+                }
+            }
         }
     }
     __syncthreads();
@@ -75,7 +92,18 @@ int ssg_p2p_allreduce_f64(double* data, int n, void* const* peer_bufs_dev, int r
     SSG_CHECK_ARG(data && peer_bufs_dev && epoch_dev, "p2p_allreduce: null pointer");
     SSG_CHECK_ARG(world >= 1 && world <= 64 && rank >= 0 && rank < world, "p2p_allreduce: rank %d of %d", rank, world);
     SSG_CHECK_ARG(n > 0 && n <= slot_doubles, "p2p_allreduce: %d doubles do not fit a %d-double slot", n, slot_doubles);
-    p2p_allreduce_f64_kernel<<<1, 512, 0, (cudaStream_t)s>>>(data, n, peer_bufs_dev, rank, world, slot_doubles, epoch_dev);
+    p2p_allreduce_f64_kernel<<<1, 512, 0, (cudaStream_t)s>>>(data, n, peer_bufs_dev, rank, world, slot_doubles, epoch_dev, 0, nullptr);
+    SSG_CHECK_LAUNCH();
+    return SSG_OK;
+}
+
+int ssg_p2p_allreduce_f64_to(double* data, int n, void* const* peer_bufs_dev, int rank, int world, int slot_doubles, unsigned* epoch_dev,
+                             long long timeout_ns, unsigned* status_dev, ssg_stream_t s) {
+    SSG_CHECK_ARG(data && peer_bufs_dev && epoch_dev, "p2p_allreduce: null pointer");
+    SSG_CHECK_ARG(world >= 1 && world <= 64 && rank >= 0 && rank < world, "p2p_allreduce: rank %d of %d", rank, world);
+    SSG_CHECK_ARG(n > 0 && n <= slot_doubles, "p2p_allreduce: %d doubles do not fit a %d-double slot", n, slot_doubles);
+    p2p_allreduce_f64_kernel<<<1, 512, 0, (cudaStream_t)s>>>(data, n, peer_bufs_dev, rank, world, slot_doubles, epoch_dev, timeout_ns,
+                                                             status_dev);
     SSG_CHECK_LAUNCH();
     return SSG_OK;
 }

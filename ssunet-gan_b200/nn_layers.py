@@ -31,14 +31,19 @@ class BatchNorm2d(nn.BatchNorm2d):
 
     def forward(self, x, residual=None, act=ACT_NONE, slope=0.0, sums=None):
         training = self.training or (self.running_mean is None)
+        # the counter is advanced by the statistics kernel itself (ops.batch_norm(nbt=...)): no separate launch per layer
+        nbt = None
         if training and self.track_running_stats and self.num_batches_tracked is not None and not self.sync_quirk:
-            self.num_batches_tracked.add_(1)
+            nbt = self.num_batches_tracked
         momentum = self.momentum
-        if momentum is None:   # cumulative moving average
+        if momentum is None:   # cumulative moving average: the factor depends on the counter's host value
+            if nbt is not None:
+                nbt.add_(1)
+                nbt = None
             momentum = 1.0 / float(self.num_batches_tracked) if training else 0.0
         return ops.batch_norm(x, self.weight, self.bias, self.running_mean if self.track_running_stats else None,
                               self.running_var if self.track_running_stats else None, training, momentum, self.eps,
-                              residual, act, slope, self.sync_group, self.sync_quirk, sums)
+                              residual, act, slope, self.sync_group, self.sync_quirk, sums, nbt)
 
 
 class ReLU(nn.Module):

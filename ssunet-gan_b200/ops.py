@@ -46,9 +46,18 @@ def thin_pad(c):
     return (c + 7) // 8 * 8 if tc_mode() else c
 
 
-def bump_weight_epoch():
+_REGISTRIES = None     # weakref.WeakSet of live PackRegistry objects (created on first use)
+
+
+def bump_weight_epoch(source=None):
+    """Weights changed behind autograd's back: drop every packed-operand cache.  `source`: the PackRegistry of the optimiser
+    that made the change and is about to refresh its own operands itself (its entries stay untouched; every OTHER registry and
+    every per-tensor cache is invalidated only when nobody names a source, i.e. the change may have hit any parameter)."""
     global _WEIGHT_EPOCH
     _WEIGHT_EPOCH += 1
+    if source is None and _REGISTRIES is not None:
+        for reg in list(_REGISTRIES):
+            reg.gen += 1
 
 
 # ----------------------------------------------------------------------------------------------
@@ -146,11 +155,85 @@ def _as_storage(t, dtype=None):
 # ----------------------------------------------------------------------------------------------
 # packed weights
 # ----------------------------------------------------------------------------------------------
+class PackRegistry:
+    """Packed convolution operands of the parameters ONE optimiser owns (optim.FusedClampAdam).  Every (parameter, layout,
+    padded extents) gets a persistent buffer -- a stable address, so captured CUDA graphs keep reading it -- and after each
+    optimiser step `refresh()` re-packs ALL of them with one launch (ssg_pack_conv_weights_multi) instead of one launch per
+    weight and layout (~190 per step).  `get()` validates the entry against the parameter's version / the weight epoch and
+    re-packs that one operand in place when somebody else changed the weights (load_state_dict, the weight clamp)."""
+
+    def __init__(self):
+        global _REGISTRIES
+        import weakref
+        self.entries = {}
+        self._tables = None
+        self.gen = 0              # bumped by bump_weight_epoch() when somebody else may have changed this optimiser's weights
+        if _REGISTRIES is None:
+            _REGISTRIES = weakref.WeakSet()
+        _REGISTRIES.add(self)
+
+    def get(self, w, layout, dtype, cout_p, cin_p):
+        key = (id(w), layout, dtype, cout_p, cin_p)
+        e = self.entries.get(key)
+        token = (w._version, self.gen, w.data_ptr())
+        if e is None:
+            cout, cin, kh, kw = w.shape
+            out = torch.empty(cout_p * cin_p * kh * kw, dtype=dtype, device=w.device)
+            e = {"w": w, "out": out, "layout": layout, "dtype": dtype, "cout_p": cout_p, "cin_p": cin_p, "token": None}
+            self.entries[key] = e
+            self._tables = None
+        if e["token"] != token:
+            cout, cin, kh, kw = w.shape
+            call("ssg_pack_conv_weight_pad", w.detach(), e["out"], dtype_code(dtype), layout, cout, cin, kh, kw, cout_p, cin_p, None)
+            e["token"] = token
+        return e["out"]
+
+    def _build_tables(self):
+        import struct
+        block = 2048          # SSG_PACK_BLOCK_ELEMS
+        by_dtype = {}
+        for e in self.entries.values():
+            by_dtype.setdefault(e["dtype"], []).append(e)
+        tables = []
+        for dt, es in by_dtype.items():
+            raw, first = bytearray(), 0
+            for e in es:
+                cout, cin, kh, kw = e["w"].shape
+                raw += struct.pack("<QQiiiiiiq", e["w"].data_ptr(), e["out"].data_ptr(), e["layout"], cout, cin, kh, e["cout_p"],
+                                   e["cin_p"], first)
+                first += (e["cout_p"] * e["cin_p"] * kh * kw + block - 1) // block
+            dev = es[0]["out"].device
+            tables.append((dt, torch.frombuffer(raw, dtype=torch.uint8).to(dev), len(es), first, [(e, e["w"].data_ptr()) for e in es]))
+        self._tables = tables
+
+    def refresh(self):
+        """Re-pack every registered operand from the current parameter values (one launch per storage dtype)."""
+        if not self.entries:
+            return
+        if self._tables is None or any(e["w"].data_ptr() != q for t in self._tables for e, q in t[4]):
+            if torch.cuda.is_current_stream_capturing():
+                raise _lib.SsgError("PackRegistry: a packed operand was first used (or a parameter moved) during CUDA-graph capture; "
+                                    "run one eager warm-up iteration first")
+            self._build_tables()
+        for dt, table, n, blocks, _ in self._tables:
+            call("ssg_pack_conv_weights_multi", table, n, blocks, dtype_code(dt))
+        self.restamp()
+
+    def restamp(self):
+        """Mark every entry valid for the current weight epoch (the refresh kernels ran: eagerly or inside a replayed graph)."""
+        for e in self.entries.values():
+            w = e["w"]
+            e["token"] = (w._version, self.gen, w.data_ptr())
+
+
 def packed_weight(w, layout, dtype, inv_scale=None, cout_p=None, cin_p=None):
     """OIHW fp32 parameter -> kernel operand (optionally zero-padded to cout_p x cin_p channels), cached on the tensor
-    until it changes."""
+    until it changes.  Parameters owned by a FusedClampAdam live in its `PackRegistry` (refreshed by ONE launch per step)."""
     cout_p = cout_p or w.shape[0]
     cin_p = cin_p or w.shape[1]
+    reg = getattr(w, "_ssg_packs", None)
+    if reg is not None and inv_scale is None and w.dim() == 4 and w.shape[2] == w.shape[3]:
+        return reg.get(w, layout, dtype, cout_p, cin_p)
     key = (layout, dtype, cout_p, cin_p)
     token = (w._version, _WEIGHT_EPOCH, w.data_ptr())
     cache = getattr(w, "_ssg_pack", None)
@@ -236,6 +319,19 @@ def _add_into(buf, t):
     call("ssg_add", buf, t, buf, dtype_code(buf.dtype), buf.numel())
 
 
+def _arena_slot(param):
+    """`param.grad` when it is the parameter's slot of an optimiser's flat fp32 gradient arena (optim.FusedClampAdam, zeroed by
+    zero_grad) that a backward kernel may ADD into directly; autograd then gets None for the parameter and runs no AccumulateGrad
+    addition.  None in every other situation (no fused optimiser, create_graph, derived tensors such as SPADE's concatenated
+    gamma|beta weights)."""
+    if param is None or not param.is_leaf or torch.is_grad_enabled():
+        return None
+    g = param.grad
+    if g is None or getattr(g, "_ssg_arena", None) is None or g.dtype != torch.float32 or not g.is_contiguous():
+        return None
+    return g
+
+
 class _Conv2d(torch.autograd.Function):
     """nn.Conv2d (square kernel, symmetric padding, groups=1) with optional fused bias + activation.
     x may be stored with more channels than the weight has inputs, and the output may be stored with `cout_store`
@@ -266,6 +362,7 @@ class _Conv2d(torch.autograd.Function):
             call("ssg_conv2d_fwd_simt", x, wp, bias, y, dtype_code(dt), n, h, w, cin, cout, kh, kw, stride, pad, act, slope)
         ctx.save_for_backward(x, weight, y if act != ACT_NONE else None)
         ctx.cfg = (stride, pad, act, slope, bias is not None, use_tc)
+        ctx.bias_ref = bias
         if sums is not None:
             ctx.mark_non_differentiable(sums)
         return y, sums
@@ -306,9 +403,8 @@ class _Conv2d(torch.autograd.Function):
 
             dx = write() if ctx.dx_sink is None else ctx.dx_sink.contribute(write, accumulate)
         if ctx.needs_input_grad[1]:
-            slot = weight.grad if weight.is_leaf else None
-            if (use_tc and slot is not None and getattr(slot, "_ssg_arena", None) is not None and slot.dtype == torch.float32
-                    and slot.is_contiguous() and not torch.is_grad_enabled()):
+            slot = _arena_slot(weight)
+            if use_tc and slot is not None:
                 # the parameter's gradient lives in the optimiser's flat arena (optim.FusedClampAdam, zeroed by zero_grad):
                 # the tensor-core kernel adds straight into it -- no memset, no temporary, no accumulation kernel.  Autograd
                 # gets None for this input (its AccumulateGrad node has nothing left to do).
@@ -321,13 +417,21 @@ class _Conv2d(torch.autograd.Function):
                 dw = torch.empty_like(weight, dtype=torch.float32)
                 call("ssg_conv2d_wgrad_simt", x, dy, dw, dtype_code(dt), n, h, w, cin, cout, kh, kw, stride, pad)
         if has_bias and ctx.needs_input_grad[2]:
-            if colsum is not None and colsum.numel() == cout_s:
-                db = colsum[:cout].float()
-            else:
-                sums = torch.empty(2 * cout_s, dtype=torch.float64, device=x.device)
-                call("ssg_channel_stats", dy, dtype_code(dt), _rows(dy), cout_s, sums, 0)
-                db = sums[:cout].float()
+            db = _bias_grad(ctx.bias_ref, dy, colsum, cout, cout_s, dt)
         return dx, dw, db, None, None, None, None, None, None, None
+
+
+def _bias_grad(bias, dy, colsum, cout, cout_s, dt):
+    """Gradient of a convolution bias = per-channel sums of dy (already reduced by dy's producer when `colsum` is given).
+    Added straight into the optimiser's gradient arena when the bias lives there (returns None), else returned as fp32."""
+    if colsum is None or colsum.numel() != cout_s:
+        colsum = torch.empty(2 * cout_s, dtype=torch.float64, device=dy.device)
+        call("ssg_channel_stats", dy, dtype_code(dt), _rows(dy), cout_s, colsum, 0)
+    slot = _arena_slot(bias)
+    if slot is not None:
+        call("ssg_accum_f64_f32", colsum, slot, cout)
+        return None
+    return colsum[:cout].float()
 
 
 class CatPair(tuple):
@@ -367,6 +471,7 @@ class _Conv2dCat(torch.autograd.Function):
         conv_tc.forward(x0, weight, bias, y, stride, pad, act, slope, x1=x1, stats=sums)
         ctx.save_for_backward(x0, x1, weight, y if act != ACT_NONE else None)
         ctx.cfg = (stride, pad, act, slope, bias is not None)
+        ctx.bias_ref = bias
         ctx.dx_sink = dx_sink
         if sums is not None:
             ctx.mark_non_differentiable(sums)
@@ -403,20 +508,14 @@ class _Conv2dCat(torch.autograd.Function):
             if res is not None:
                 dx0, dx1 = res
         if ctx.needs_input_grad[2]:
-            slot = weight.grad if weight.is_leaf else None
-            if (slot is not None and getattr(slot, "_ssg_arena", None) is not None and slot.dtype == torch.float32
-                    and slot.is_contiguous() and not torch.is_grad_enabled()):
+            slot = _arena_slot(weight)
+            if slot is not None:
                 conv_tc.wgrad(x0, dy, slot, stride, pad, x1=x1, accumulate=True)      # straight into the optimiser's gradient arena
             else:
                 dw = torch.empty_like(weight, dtype=torch.float32)
                 conv_tc.wgrad(x0, dy, dw, stride, pad, x1=x1)
         if has_bias and ctx.needs_input_grad[3]:
-            if colsum is not None and colsum.numel() == cout_s:
-                db = colsum[:cout].float()
-            else:
-                sums = torch.empty(2 * cout_s, dtype=torch.float64, device=x0.device)
-                call("ssg_channel_stats", dy, dtype_code(dt), _rows(dy), cout_s, sums, 0)
-                db = sums[:cout].float()
+            db = _bias_grad(ctx.bias_ref, dy, colsum, cout, cout_s, dt)
         return dx0, dx1, dw, db, None, None, None, None, None, None, None
 
 
@@ -461,11 +560,32 @@ class PeerStatReducer:
         assert ptrs[self.rank] == self.buf.data_ptr() or True
         self.peers_dev = torch.tensor(ptrs, dtype=torch.int64, device=dev)      # device array of `world` pointers
         self.epoch = torch.zeros(1, dtype=torch.int32, device=dev)
+        # A peer that does not arrive within the bound (rank-0-only validation or checkpointing, a slow loader, a dead rank) makes
+        # the kernel give up the wait and raise this flag; the context stays usable and `check()` reports it.  NCCL would wait
+        # forever; SSG_P2P_TIMEOUT_S=0 asks for the same.
+        import os
+        self.timeout_ns = int(float(os.environ.get("SSG_P2P_TIMEOUT_S", "600")) * 1e9)
+        self.status = torch.zeros(1, dtype=torch.int32, device=dev)
         torch.cuda.synchronize()
         dist.barrier(group=pg)           # every rank's buffer is zeroed and mapped before the first exchange
 
     def all_reduce(self, t):
-        call("ssg_p2p_allreduce_f64", t, t.numel(), self.peers_dev, self.rank, self.world, self.SLOT_DOUBLES, self.epoch)
+        call("ssg_p2p_allreduce_f64_to", t, t.numel(), self.peers_dev, self.rank, self.world, self.SLOT_DOUBLES, self.epoch,
+             self.timeout_ns, self.status)
+
+    def check(self):
+        """Raise if an exchange timed out since the last check (host sync: call it where the step already reads a scalar)."""
+        st = int(self.status.item())
+        if st:
+            self.status.zero_()
+            raise _lib.SsgError("SyncBN peer-memory exchange: rank %d gave up waiting for rank %d after %.0f s; the statistics of that "
+                                "step are invalid" % (self.rank, st - 1, self.timeout_ns / 1e9))
+
+    @classmethod
+    def check_all(cls):
+        for inst in cls._instances.values():
+            if inst is not None:
+                inst.check()
 
     @classmethod
     def for_group(cls, group):
@@ -507,7 +627,7 @@ class _BatchNorm(torch.autograd.Function):
     ``group`` spans more than one rank.  ``sync_quirk`` selects batchnorm.py:127's clamp(eps)."""
 
     @staticmethod
-    def forward(ctx, x, gamma, beta, residual, running_mean, running_var, momentum, eps, act, slope, group, sync_quirk, sums):
+    def forward(ctx, x, gamma, beta, residual, running_mean, running_var, momentum, eps, act, slope, group, sync_quirk, sums, nbt):
         n, c, h, w = x.shape
         dt = x.dtype
         rows = _rows(x)
@@ -521,34 +641,50 @@ class _BatchNorm(torch.autograd.Function):
         count = float(rows * world)
         mean = torch.empty(c, dtype=torch.float32, device=dev)
         inv_std = torch.empty(c, dtype=torch.float32, device=dev)
-        call("ssg_bn_finalize", sums, count, c, eps, momentum if momentum is not None else 0.0, int(sync_quirk),
-             running_mean, running_var, mean, inv_std)
+        # layers without a residual: the backward re-derives the activation mask from x (ssg_bn_bwd_*_rc) and never reads y; the
+        # forward's affine (sc, sh) is stored by the finalize launch for that
+        vec = 8 if dt == torch.bfloat16 else 4
+        recompute = act != ACT_NONE and residual is None and c % vec == 0 and c // vec <= 256
+        scsh = torch.empty(2 * c, dtype=torch.float32, device=dev) if recompute else None
+        # `nbt`: nn.BatchNorm2d's num_batches_tracked, advanced by the same launch (was a separate ATen add per layer)
+        call("ssg_bn_finalize_count", sums, count, c, eps, momentum if momentum is not None else 0.0, int(sync_quirk),
+             running_mean, running_var, mean, inv_std, nbt, gamma, beta, scsh, scsh[c:] if recompute else None)
         y = empty_nhwc(n, c, h, w, dt, dev)
         call("ssg_bn_apply", x, residual, y, dtype_code(dt), rows, c, mean, inv_std, gamma, beta, act, slope)
-        ctx.save_for_backward(x, y if act != ACT_NONE else None, mean, inv_std, gamma)
-        ctx.cfg = (act, slope, group, count, residual is not None)
+        ctx.save_for_backward(x, y if (act != ACT_NONE and not recompute) else None, mean, inv_std, gamma, beta, scsh)
+        ctx.cfg = (act, slope, group, count, residual is not None, recompute)
         return y
 
     @staticmethod
     def backward(ctx, dy):
-        x, y, mean, inv_std, gamma = ctx.saved_tensors
-        act, slope, group, count, has_res = ctx.cfg
+        x, y, mean, inv_std, gamma, beta, scsh = ctx.saved_tensors
+        act, slope, group, count, has_res, recompute = ctx.cfg
         n, c, h, w = x.shape
         dt = x.dtype
         rows = _rows(x)
         dy = _as_storage(dy, dt)
         sums = torch.empty(2 * c, dtype=torch.float64, device=x.device)
-        call("ssg_bn_bwd_reduce", dy, y, x, dtype_code(dt), rows, c, mean, inv_std, act, slope, sums)
+        if recompute:
+            call("ssg_bn_bwd_reduce_rc", dy, x, dtype_code(dt), rows, c, mean, inv_std, scsh, scsh[c:], act, slope, sums)
+        else:
+            call("ssg_bn_bwd_reduce", dy, y, x, dtype_code(dt), rows, c, mean, inv_std, act, slope, sums)
         dgamma = dbeta = None
-        if gamma is not None:
-            dgamma = torch.empty(c, dtype=torch.float32, device=x.device)
-            dbeta = torch.empty(c, dtype=torch.float32, device=x.device)
-            call("ssg_bn_param_grads", sums, c, dgamma, dbeta)      # local sums: the gradient all-reduce adds ranks
+        if gamma is not None and (ctx.needs_input_grad[1] or ctx.needs_input_grad[2]):
+            sg, sb = _arena_slot(gamma), _arena_slot(beta)
+            if sg is not None and sb is not None and ctx.needs_input_grad[1] and ctx.needs_input_grad[2]:
+                call("ssg_bn_param_grads_acc", sums, c, sg, sb)      # local sums: the gradient all-reduce adds ranks
+            else:
+                dgamma = torch.empty(c, dtype=torch.float32, device=x.device)
+                dbeta = torch.empty(c, dtype=torch.float32, device=x.device)
+                call("ssg_bn_param_grads", sums, c, dgamma, dbeta)
         _all_reduce_sum(sums, group)
         dx = empty_nhwc(n, c, h, w, dt, x.device)
         dres = empty_nhwc(n, c, h, w, dt, x.device) if has_res else None
-        call("ssg_bn_bwd_apply", dy, y, x, dx, dres, dtype_code(dt), rows, c, mean, inv_std, gamma, sums, count, act, slope, 1)
-        return dx, dgamma, dbeta, dres, None, None, None, None, None, None, None, None, None
+        if recompute:
+            call("ssg_bn_bwd_apply_rc", dy, x, dx, dtype_code(dt), rows, c, mean, inv_std, gamma, scsh, scsh[c:], sums, count, act, slope, 1)
+        else:
+            call("ssg_bn_bwd_apply", dy, y, x, dx, dres, dtype_code(dt), rows, c, mean, inv_std, gamma, sums, count, act, slope, 1)
+        return dx, dgamma, dbeta, dres, None, None, None, None, None, None, None, None, None, None
 
 
 class _BatchNormEval(torch.autograd.Function):
@@ -586,14 +722,15 @@ class _BatchNormEval(torch.autograd.Function):
 
 
 def batch_norm(x, gamma, beta, running_mean, running_var, training, momentum=0.1, eps=1e-5, residual=None,
-               act=ACT_NONE, slope=0.0, group=None, sync_quirk=False, sums=None):
-    """sums: optional fp64 [sum x | sum x^2] already reduced by the producer of x (conv2d(..., want_stats=True))."""
+               act=ACT_NONE, slope=0.0, group=None, sync_quirk=False, sums=None, nbt=None):
+    """sums: optional fp64 [sum x | sum x^2] already reduced by the producer of x (conv2d(..., want_stats=True)).
+    nbt: the module's `num_batches_tracked` buffer when this (training) call must advance it."""
     x = to_nhwc(x)
     if residual is not None:
         residual = to_nhwc(residual)
     if training:
         return _BatchNorm.apply(x, gamma, beta, residual, running_mean, running_var, momentum, eps, act, slope, group, sync_quirk,
-                                sums)
+                                sums, nbt)
     return _BatchNormEval.apply(x, gamma, beta, residual, running_mean, running_var, eps, act, slope)
 
 
@@ -604,6 +741,10 @@ class _MaxPool(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x):
         n, c, h, w = x.shape
+        if h % 2 or w % 2:
+            # the reference's MaxPool2d(2, 2) drops an odd trailing row / column and MaxUnpool2d then restores the even size; every
+            # network on this path halves sizes that are multiples of 32, so odd extents are rejected instead of half-supported
+            raise _lib.SsgError("max_pool2x2: spatial size %d x %d must be even" % (h, w))
         y = empty_nhwc(n, c, h // 2, w // 2, x.dtype, x.device)
         code = torch.empty((n, h // 2, w // 2, c), dtype=torch.uint8, device=x.device)
         call("ssg_maxpool2x2_fwd", x, y, code, dtype_code(x.dtype), n, h, w, c)
@@ -618,11 +759,7 @@ class _MaxPool(torch.autograd.Function):
         n, c, oh, ow = dy.shape
         h, w = ctx.hw
         dy = _as_storage(dy)
-        if (h, w) == (2 * oh, 2 * ow):
-            dx = empty_nhwc(n, c, h, w, dy.dtype, dy.device)
-        else:   # odd sizes: the last row/col never entered a window
-            dx = torch.zeros((n, h, w, c), dtype=dy.dtype, device=dy.device).permute(0, 3, 1, 2)
-            raise _lib.SsgError("max_pool2x2 backward needs even spatial sizes")
+        dx = empty_nhwc(n, c, h, w, dy.dtype, dy.device)
         call("ssg_scatter2x2", dy, code, dx, dtype_code(dy.dtype), n, oh, ow, c)
         return dx
 

@@ -49,21 +49,28 @@ class DataParallelWithCallback(nn.Module):
         self.rank = dist.get_rank(process_group) if _dist_ready() else 0
         self.world_size = dist.get_world_size(process_group) if _dist_ready() else 1
         self._grad_hook_armed = False
-        if self.world_size > 1:
-            self._broadcast_state()
-        execute_replication_callbacks([module], [self.rank])
-        for m in module.modules():
-            if hasattr(m, "_set_process_group"):
-                m._set_process_group(process_group, self.world_size)
+        self._hook_handles = []
         self._params = [p for p in module.parameters() if p.requires_grad]
         if self.world_size > 1:
-            for p in self._params:
-                p.register_hook(self._make_hook())
+            # nn.DataParallel with ONE device calls the module directly (no replicate(), no callbacks): SyncBN then stays on its
+            # F.batch_norm path (+eps, num_batches_tracked advances).  Only a real multi-rank wrapper switches it to parallel mode.
+            self._broadcast_state()
+            execute_replication_callbacks([module], [self.rank])
+            for m in module.modules():
+                if hasattr(m, "_set_process_group"):
+                    m._set_process_group(process_group, self.world_size)
+            self._hook_handles = [p.register_hook(self._make_hook()) for p in self._params]
 
     def _broadcast_state(self):
         with torch.no_grad():
             for t in list(self.module.parameters()) + list(self.module.buffers()):
                 dist.broadcast(t.data, 0, group=self.process_group)
+
+    def _remove_hooks(self):
+        """Detach this wrapper's gradient hooks (convert_model re-wraps the network: the old wrapper must stop all-reducing)."""
+        for h in self._hook_handles:
+            h.remove()
+        self._hook_handles = []
 
     def _make_hook(self):
         def hook(grad):
@@ -85,8 +92,10 @@ class DataParallelWithCallback(nn.Module):
         from .optim import flat_arena_of
         arena = flat_arena_of(grads)
         if arena is not None:
+            # SUM over ranks; the 1/world factor rides into the fused clamp+Adam kernel as its gradient scale (applied before the
+            # clamp, as averaging before clip_gradient would) instead of a separate pass over the arena
             dist.all_reduce(arena, op=dist.ReduceOp.SUM, group=self.process_group)
-            arena.div_(self.world_size)
+            arena._ssg_grad_scale = 1.0 / self.world_size
             return
         flat = torch.cat([g.reshape(-1) for g in grads])
         dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.process_group)
@@ -100,7 +109,8 @@ class DataParallelWithCallback(nn.Module):
         return self.module(*inputs, **kwargs)
 
     def replicate(self, module, device_ids):
-        execute_replication_callbacks([module], [self.rank])
+        if self.world_size > 1:
+            execute_replication_callbacks([module], [self.rank])
         return [module]
 
 

@@ -7,7 +7,8 @@ process per GPU.
   * the discriminator's parameters do not accumulate gradients during the generator step — the
     reference computes them and `optimizer_d.zero_grad()` throws them away (train_seg_gan.py:225);
   * BCEDiceLoss and MSELoss are one fused pass;
-  * the IoU/Dice metrics can be skipped (`with_metrics=False`) — they force a host sync.
+  * the IoU/Dice metrics can be skipped (`with_metrics=False`) or left half-done on the device (`with_metrics="device"` +
+    `finish_metrics`): their host halves force a sync, which a captured CUDA graph cannot contain.
 Data parallelism: wrap G and D in `replicate.DataParallelWithCallback` (after
 `batchnorm.convert_model` for SyncBN); gradients are averaged over ranks when backward finishes.
 """
@@ -17,6 +18,7 @@ import torch
 
 from . import ops
 from .losses import BCEDiceAndContentLoss
+from . import metrics
 from .metrics import dice_coef, iou_score
 from .srgan_utils import clip_gradient
 
@@ -47,11 +49,17 @@ def gan_train_step(generator, discriminator, optimizer_g, optimizer_d, input, ta
     generator_output = ops.nan_to_zero(generator_output)                       # :190
     loss, content_loss = criterion(generator_output, target)                   # :194-195
     iou = dice = None
+    pending = None
     if with_metrics:
         out_m = generator_output[:, 1:num_classes].detach().contiguous()       # :191
         tar_m = target[:, 1:num_classes].contiguous()                          # :192
-        iou = iou_score(out_m, tar_m)                                          # :197
-        dice = dice_coef(out_m, tar_m)                                         # :198
+        if with_metrics == "device":
+            # device halves only (counts / pairwise leaf sums): no host sync here, so the step can be captured in a CUDA graph;
+            # `finish_metrics` completes them after the step's results are read back
+            pending = (metrics.iou_counts(out_m, tar_m),) + metrics.dice_leaf_sums(out_m, tar_m)
+        else:
+            iou = iou_score(out_m, tar_m)                                      # :197
+            dice = dice_coef(out_m, tar_m)                                     # :198
     saved = _set_requires_grad(discriminator, False)
     seg_discriminated = discriminator(generator_output)                        # :202
     _set_requires_grad(discriminator, True, saved)
@@ -74,9 +82,21 @@ def gan_train_step(generator, discriminator, optimizer_g, optimizer_d, input, ta
     if grad_clip is not None:
         clip_gradient(optimizer_d, grad_clip)                                  # :229-230
     optimizer_d.step()                                                         # :233
-    return OrderedDict([("loss", loss.detach()), ("content", content_loss.detach()), ("adv_g", adv_g),
-                        ("adv_d", adversarial_loss.detach()), ("iou", iou), ("dice", dice),
-                        ("logits", generator_output.detach())])
+    out = OrderedDict([("loss", loss.detach()), ("content", content_loss.detach()), ("adv_g", adv_g),
+                       ("adv_d", adversarial_loss.detach()), ("iou", iou), ("dice", dice),
+                       ("logits", generator_output.detach())])
+    if pending is not None:
+        out["metric_parts"] = pending
+    return out
+
+
+def finish_metrics(out):
+    """Host halves of iou_score / dice_coef (metrics.py:6-35) for a step run with with_metrics="device": reads the int64 counts
+    and the float32 leaf sums back and fills out["iou"], out["dice"] (bit-identical to the one-call metrics)."""
+    counts, leaf, n = out["metric_parts"]
+    out["iou"] = metrics.iou_from_counts(counts)
+    out["dice"] = metrics.dice_from_leaves(leaf, n)
+    return out
 
 
 def generator_fwd_bwd(generator, input, target):
@@ -96,15 +116,17 @@ class GraphedGanStep:
     count); BatchNorm running statistics, Adam moments, parameters and the NCCL all-reduces (SyncBN statistics, gradient
     arenas) are all updated by the replayed kernels exactly as in the eager step.  Construction leaves parameters, buffers
     and optimiser state exactly as it found them (the warm-up iterations are rolled back).  Returns the same OrderedDict of 0-dim
-    tensors as `gan_train_step` (static outputs: read them before the next call); IoU/Dice are not part of the graph
-    (they need a host round trip) -- compute them from `out["logits"]` when wanted."""
+    tensors as `gan_train_step` (static outputs: read them before the next call).  The device halves of iou_score / dice_coef
+    (train_seg_gan.py:197-198) ARE part of the graph (`with_metrics=True`, the default); `metrics()` reads the counts / leaf sums
+    back and finishes them on the host.  Learning rate, betas, eps and clip live in device memory and are refreshed from the
+    optimisers' param_groups before every replay, so LR schedulers keep working."""
 
     def __init__(self, generator, discriminator, optimizer_g, optimizer_d, batch_shape, target_shape=None, num_classes=3,
-                 warmup=3, **kw):
+                 warmup=3, with_metrics=True, **kw):
         from . import _lib
         dev = next(generator.parameters()).device
         self.g, self.d, self.og, self.od = generator, discriminator, optimizer_g, optimizer_d
-        self.kw = dict(kw, num_classes=num_classes, with_metrics=False)
+        self.kw = dict(kw, num_classes=num_classes, with_metrics="device" if with_metrics else False)
         self.x = torch.zeros(batch_shape, dtype=torch.float32, device=dev)
         tshape = target_shape or (batch_shape[0], num_classes, batch_shape[2], batch_shape[3])
         self.t = torch.zeros(tshape, dtype=torch.float32, device=dev)
@@ -129,7 +151,8 @@ class GraphedGanStep:
                 gan_train_step(self.g, self.d, self.og, self.od, self.x, self.t, **self.kw)
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
-        ops.bump_weight_epoch()            # every packed-weight cache entry is stale: the packs must be IN the graph
+        # Packed conv operands live in the optimisers' registries (persistent buffers refreshed by ONE launch after each Adam
+        # step, which IS captured below); the warm-up registered every operand the step uses.
         self.graph = torch.cuda.CUDAGraph()
         l0 = _lib.launch_count
         with torch.cuda.graph(self.graph):
@@ -142,15 +165,35 @@ class GraphedGanStep:
         optimizer_g.flat_g.zero_()
         optimizer_d.flat_g.zero_()
         ops.bump_weight_epoch()
+        optimizer_g.packs.refresh()        # the restored parameters' operands (the graph reads these buffers first thing)
+        optimizer_d.packs.refresh()
+        self._epoch_seen = ops._WEIGHT_EPOCH
 
     def load(self, input, target, non_blocking=True):
         self.x.copy_(input, non_blocking=non_blocking)
         self.t.copy_(target, non_blocking=non_blocking)
 
     def replay(self):
+        if ops._WEIGHT_EPOCH != self._epoch_seen:
+            # somebody changed the weights since the last replay (load_state_dict, a weight clamp, an eager step): the graph reads
+            # the registries' buffers directly, so bring them up to date first
+            self.og.packs.refresh()
+            self.od.packs.refresh()
+        self.og.sync_hyperparams()         # follow param_group changes (LR schedulers) made since the capture
+        self.od.sync_hyperparams()
         self.graph.replay()
-        ops.bump_weight_epoch()            # parameters changed behind autograd's back: drop eager packed-weight caches
+        self.og._step += 1
+        self.od._step += 1
+        ops.bump_weight_epoch()            # parameters changed behind autograd's back: drop eager packed-weight caches ...
+        self.og.packs.restamp()            # ... except the registries' operands, which the replayed graph just refreshed
+        self.od.packs.restamp()
+        self._epoch_seen = ops._WEIGHT_EPOCH
         return self.out
+
+    def metrics(self):
+        """(iou, dice) of the last replayed step: device -> host read of the counts / leaf sums + the host halves."""
+        finish_metrics(self.out)
+        return self.out["iou"], self.out["dice"]
 
     def __call__(self, input, target):
         self.load(input, target)

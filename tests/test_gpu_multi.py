@@ -36,8 +36,8 @@ def _worker(rank, world, port, use_nccl_stats, ret):
         ssg.set_compute_dtype(torch.float32)
         g = torch.Generator().manual_seed(3)
         C = 24
-        xb = torch.randn(6, C, 9, 7, generator=g) * 1.5 + 0.3
-        gy = torch.randn(6, C, 9, 7, generator=g)
+        xb = torch.randn(3 * world, C, 9, 7, generator=g) * 1.5 + 0.3
+        gy = torch.randn(3 * world, C, 9, 7, generator=g)
         gamma = 1 + 0.1 * torch.randn(C, generator=g)
         beta = 0.1 * torch.randn(C, generator=g)
 
@@ -83,11 +83,11 @@ def _worker(rank, world, port, use_nccl_stats, ret):
         dist.destroy_process_group()
 
 
+@pytest.mark.parametrize("world", [2, 8])
 @pytest.mark.parametrize("use_nccl_stats", [False, True])
-def test_syncbn_two_ranks_matches_full_batch(use_nccl_stats):
-    if torch.cuda.device_count() < 2:
-        pytest.skip("needs 2 GPUs")
-    world = 2
+def test_syncbn_two_ranks_matches_full_batch(use_nccl_stats, world):
+    if torch.cuda.device_count() < world:
+        pytest.skip("needs %d GPUs" % world)
     mgr = mp.Manager()
     ret = mgr.dict()
     mp.spawn(_worker, args=(world, _free_port(), use_nccl_stats, ret), nprocs=world, join=True)
@@ -96,3 +96,79 @@ def test_syncbn_two_ranks_matches_full_batch(use_nccl_stats):
         assert ok, "SyncBN over 2 ranks does not reproduce full-batch BN (rank %d)" % rank
         assert same_stats, "running statistics differ between ranks"
         assert used_p2p == (not use_nccl_stats), "expected the %s statistics exchange" % ("NCCL" if use_nccl_stats else "peer-memory")
+
+
+def _step_worker(rank, world, port, ret):
+    """One full G+D iteration, data-parallel over `world` ranks (SyncBN + gradient all-reduce), against the same iteration on the
+    whole batch on ONE device: SyncBN-DP over n GPUs with per-GPU batch b == single-device BN on batch n*b."""
+    import sys
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    try:
+        import ssunet_gan_b200 as ssg
+        import ssunet_oracle as O
+        from ssunet_gan_b200 import batchnorm, models_seg_gan, optim, replicate, train_step
+        ssg.set_compute_dtype(torch.float32)
+        ssg.set_conv_impl("simt")
+        b = 2
+        x, t = O.synthetic_batch(b * world, 3, 64, 64, seed=99, blobby=True)
+
+        def nets():
+            g = models_seg_gan.Generator({"arch": "UNet_R_SS_v2", "num_classes": 3, "input_channels": 3, "deep_supervision": False})
+            g.load_state_dict(O.portable_state_dict(O.unet_r_ss_v2_spec(3, 3, prefix="net.")))
+            d = models_seg_gan.Discriminator(3)
+            d.load_state_dict(O.portable_state_dict(O.discriminator_spec(3)))
+            return g.cuda().train(), d.cuda().train()
+
+        g, d = nets()
+        gp = replicate.DataParallelWithCallback(batchnorm.convert_model(g))
+        dp = replicate.DataParallelWithCallback(batchnorm.convert_model(d))
+        og = optim.FusedClampAdam(gp.parameters(), lr=2e-5)
+        od = optim.FusedClampAdam(dp.parameters(), lr=2e-5)
+        sl = slice(rank * b, (rank + 1) * b)
+        r = train_step.gan_train_step(gp, dp, og, od, x[sl].cuda(), t[sl].cuda(), with_metrics=False)
+        res = {"logits": r["logits"].cpu(), "gw": gp.module.net.final.weight.detach().cpu().clone(),
+               "dw": dp.module.fc2.weight.detach().cpu().clone(),
+               "g_c1": gp.module.net.conv0_0.conv1.weight.detach().cpu().clone()}
+        if rank == 0:
+            # the same iteration on the whole batch, one device, plain (unsynchronised) BatchNorm
+            g1, d1 = nets()
+            og1 = optim.FusedClampAdam(g1.parameters(), lr=2e-5)
+            od1 = optim.FusedClampAdam(d1.parameters(), lr=2e-5)
+            r1 = train_step.gan_train_step(g1, d1, og1, od1, x.cuda(), t.cuda(), with_metrics=False)
+            res["full_logits"] = r1["logits"].cpu()
+            res["full_gw"] = g1.net.final.weight.detach().cpu().clone()
+            res["full_dw"] = d1.fc2.weight.detach().cpu().clone()
+            res["full_g_c1"] = g1.net.conv0_0.conv1.weight.detach().cpu().clone()
+            res["init_gw"] = O.portable_state_dict(O.unet_r_ss_v2_spec(3, 3, prefix="net."))["net.final.weight"]
+        ret[rank] = res
+    finally:
+        torch.cuda.synchronize()
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 8])
+def test_gan_step_data_parallel_matches_full_batch(world):
+    if torch.cuda.device_count() < world:
+        pytest.skip("needs %d GPUs" % world)
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_step_worker, args=(world, _free_port(), ret), nprocs=world, join=True)
+    full = ret[0]
+    for rank in range(world):
+        got = ret[rank]["logits"].double()
+        want = full["full_logits"][rank * 2:(rank + 1) * 2].double()
+        err = float((got - want).norm() / want.norm())
+        assert err < 2e-4, "rank %d logits differ from the full-batch run: %.3e" % (rank, err)
+        # every rank took the same (averaged-gradient) Adam step: parameters identical across ranks
+        assert torch.equal(ret[rank]["gw"], ret[0]["gw"]) and torch.equal(ret[rank]["dw"], ret[0]["dw"])
+    # and that step is the full-batch step: one Adam update moves every element by <= lr, in the same direction
+    for k in ("gw", "dw", "g_c1"):
+        a, b = full[k], full["full_" + k]
+        assert float((a - b).abs().max()) < 4.1e-5
+        assert float(((a - b).abs() < 1e-7).float().mean()) > 0.97, k
+    assert float((full["gw"] - full["init_gw"]).abs().max()) > 1e-6
