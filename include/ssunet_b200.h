@@ -111,6 +111,14 @@ int ssg_conv2d_fwd_tc_has_stats(int ksize, int stride, int pad);
  * small stride-1 convolution over dy with 1, 2, 2 and 4 taps) written interleaved into dx. */
 int ssg_conv2d_dgrad_tc(const void* dy, const void* w_packed, void* dx, int n, int h, int w, int cin, int cout, int ksize,
                         int stride, int pad, ssg_stream_t s);
+/* Same for the stride-2 3x3 convolution, with the PRODUCER's activation backward folded into the epilogue: `producer_out` is the
+ * post-activation output (shaped like dx) of the layer whose output this convolution consumed -- i.e. this convolution's saved
+ * input x -- and dx is multiplied by act'(producer_out) before it is stored.  The discriminator's block 0 (conv + LeakyReLU, no
+ * BN: models_seg_gan.py:262-266) then needs no separate LeakyReLU-backward pass over its 16 x 512 x 512 x 64 gradient.  Valid
+ * only when x has no other consumer.  ssg_conv2d_dgrad_tc_mask_supported: geometries that offer it. */
+int ssg_conv2d_dgrad_tc_mask_supported(int ksize, int stride, int pad);
+int ssg_conv2d_dgrad_tc_mask(const void* dy, const void* w_packed, void* dx, const void* producer_out, int producer_act, float producer_slope,
+                             int n, int h, int w, int cin, int cout, int ksize, int stride, int pad, ssg_stream_t s);
 /* Same, but dx += gradient (TMA reduce-add in the epilogue, bf16 addition at the L2): the second consumer of an activation adds
  * its contribution into the buffer the first one wrote -- replaces autograd's separate addition pass for BasicBlock's
  * conv1 + shortcut (archs.py:229-234) and SPADE's x2map + modulation (normalization.py:112-120).  Only for the geometries
@@ -134,6 +142,17 @@ int ssg_conv2d_wgrad_tc(const void* x0, int c0, const void* x1, int c1, const vo
  * flat gradient arena (zeroed by zero_grad), which removes the per-layer memset, temporary and gradient-accumulation add. */
 int ssg_conv2d_wgrad_tc_acc(const void* x0, int c0, const void* x1, int c1, const void* dy, int cout, float* dw_oihw, int cout_real,
                             int cin_real, int n, int h, int w, int ksize, int stride, int pad, ssg_stream_t s);
+
+/* ---- 3x3 / stride 1 / pad 1 convolutions between thin activations (both stored with 8 channels, <= 8 real channels) ---------
+ * SPADE's mlp_shared (label_nc -> nhidden, normalization.py:93-95) at the two finest levels and its adjoints.  CUDA-core kernels,
+ * one pixel per thread, weights read from the fp32 OIHW parameter directly (no packed operand): a 128-row tensor-core tile for
+ * ~100 multiply-adds per pixel is all issue / drain overhead.  bf16 NHWC storage only. */
+int ssg_conv3x3_tiny_supported(int cin_stored, int cout_stored, int cin, int cout);
+int ssg_conv3x3_tiny_fwd(const void* x, const float* w_oihw, const float* bias, void* y, int n, int h, int w, int cin, int cout, int act,
+                         float slope, ssg_stream_t s);
+int ssg_conv3x3_tiny_dgrad(const void* dy, const float* w_oihw, void* dx, int n, int h, int w, int cin, int cout, ssg_stream_t s);
+/* dw (fp32 OIHW) and db (fp32, may be NULL) are ACCUMULATED into: pass zeroed buffers or gradient-arena slots. */
+int ssg_conv3x3_tiny_wgrad(const void* x, const void* dy, float* dw_oihw, float* db, int n, int h, int w, int cin, int cout, ssg_stream_t s);
 
 /* ---- per-channel statistics / batch norm -------------------------------------------------- */
 /* batchnorm.py:59-64 (_sum_ft of x and x**2): sums[0:C] = sum x, sums[C:2C] = sum x^2 (fp64,

@@ -59,6 +59,7 @@ for (name, key), a in agg.items():
 for name, ms in sorted(byname.items(), key=lambda kv: -kv[1])[:25]:
     print("  %-32s %8.3f ms %5.1f%%" % (name, ms, 100 * ms / inside))
 print()
-for (name, key), a in sorted(agg.items(), key=lambda kv: -kv[1][1])[:70]:
+TOP = int(os.environ.get("TOP", "70"))
+for (name, key), a in sorted(agg.items(), key=lambda kv: -kv[1][1])[:TOP]:
     tf = " %6.0f TF/s" % (a[2] / a[1] / 1e9) if a[2] else ""
     print("%-26s n=%2d %8.3f ms%s  %s" % (name, a[0], a[1], tf, key))

@@ -43,16 +43,28 @@ def can_accumulate(k, stride, pad):
     return bool(_lib.lib().ssg_conv2d_dgrad_tc_can_acc(int(k), int(stride), int(pad)))
 
 
-def dgrad(dy, weight, dx, stride, pad, accumulate=False):
+def can_mask(k, stride, pad):
+    """True when the data-gradient kernel can fold the producer's activation backward into its epilogue."""
+    return bool(_lib.lib().ssg_conv2d_dgrad_tc_mask_supported(int(k), int(stride), int(pad)))
+
+
+def dgrad(dy, weight, dx, stride, pad, accumulate=False, producer_out=None, producer_act=0, producer_slope=0.0):
     """dx (n, cin_s, h, w) from dy (n, cout_s, oh, ow); weights packed [tap][cin_s][cout_s] (K-major in cout).
-    accumulate: dx += ... (only for the geometries `can_accumulate` accepts)."""
+    accumulate: dx += ... (only for the geometries `can_accumulate` accepts).
+    producer_out: the post-activation output of the layer that produced this convolution's input (== the saved input x): dx is
+    multiplied by act'(producer_out) in the epilogue (only for the geometries `can_mask` accepts)."""
     from .ops import packed_weight
     n, cin_s, h, w = dx.shape
     cout, cin, k, _ = weight.shape
     cout_s = dy.shape[1]
     wp = packed_weight(weight, W_RSCK, torch.bfloat16, cout_p=cout_s, cin_p=cin_s)
-    call("ssg_conv2d_dgrad_tc_acc" if accumulate else "ssg_conv2d_dgrad_tc", dy, wp, dx, n, h, w, cin_s, cout_s, k, stride, pad,
-         flops=_flops(n, dy.shape[2], dy.shape[3], cin, cout, k))
+    fl = _flops(n, dy.shape[2], dy.shape[3], cin, cout, k)
+    if producer_out is not None:
+        assert not accumulate and tuple(producer_out.shape) == tuple(dx.shape)
+        call("ssg_conv2d_dgrad_tc_mask", dy, wp, dx, producer_out, int(producer_act), float(producer_slope), n, h, w, cin_s, cout_s, k,
+             stride, pad, flops=fl)
+        return
+    call("ssg_conv2d_dgrad_tc_acc" if accumulate else "ssg_conv2d_dgrad_tc", dy, wp, dx, n, h, w, cin_s, cout_s, k, stride, pad, flops=fl)
 
 
 def dgrad_split(dy, weight, dx0, dx1, stride, pad, accumulate=False):

@@ -48,7 +48,14 @@ struct ConvTcParams {
     int chunks0, chunks1;        // 64-channel chunks taken from x0 / x1
     int act;
     float slope;
-    TapClass cls[4];             // blockIdx.z selects the class
+    const bf16* mask;            // optional (data gradient): a tensor shaped like y holding the post-activation OUTPUT of the layer that
+    int mask_act;                // produced this convolution's input; the epilogue multiplies by act'(mask), i.e. the producer's
+    float mask_slope;            // activation backward (models_seg_gan.py:52-57 LeakyReLU) rides along instead of a separate pass
+    int ncls;                    // number of classes
+    int merge;                   // 1: ONE CTA computes all classes of its tile (one TMEM accumulator each) instead of one CTA per
+                                 // class: the stride-2 data gradient's four parity classes share their dy boxes (L2) and the CTA's
+                                 // fixed costs, and the nine k-blocks fill one pipeline (ncu: 8 % tensor activity, dy read 4 x before)
+    TapClass cls[4];             // blockIdx.z selects the class (merge == 0)
 };
 
 template <int BN>
@@ -83,15 +90,15 @@ __global__ void __launch_bounds__(NUM_THREADS) conv_tc_fwd_kernel(const __grid_c
     const int w0 = tx * TW, h0 = ty * TH, img0 = tn * (BM >> (p.tw_log2 + p.th_log2));
     const int n0 = blockIdx.y * BN;
     const int chunks = p.chunks0 + p.chunks1;
-    const TapClass& tcl = p.cls[blockIdx.z];
-    const int num_kb = tcl.ntaps * chunks;
+    const int cls0 = p.merge ? 0 : (int)blockIdx.z, ncls_here = p.merge ? p.ncls : 1;
+    const uint32_t tmem_cols = p.merge ? 4u * L::TMEM_COLS : L::TMEM_COLS;
 
     if (threadIdx.x == 0) {
         for (int i = 0; i < L::STAGES; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
         mbar_init(tmem_full_bar, 1);
         fence_barrier_init();
     }
-    if (warp == 2) tmem_alloc(tmem_slot, L::TMEM_COLS);
+    if (warp == 2) tmem_alloc(tmem_slot, tmem_cols);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -101,18 +108,23 @@ __global__ void __launch_bounds__(NUM_THREADS) conv_tc_fwd_kernel(const __grid_c
         if (lane == 0) {
             tma_prefetch_desc(&tmA0);
             tma_prefetch_desc(&tmB);
-            for (int kb = 0; kb < num_kb; ++kb) {
-                const int stage = kb % L::STAGES;
-                const uint32_t phase = (kb / L::STAGES) & 1;
-                mbar_wait(&empty_bar[stage], phase ^ 1);
-                mbar_expect_tx(&full_bar[stage], L::STAGE_BYTES);
-                const int tap = kb / chunks, ch = kb - tap * chunks;
-                const int cx = p.in_mul * w0 + tcl.dx[tap], cy = p.in_mul * h0 + tcl.dy[tap];
-                uint8_t* sa = smem + stage * L::STAGE_BYTES;
-                uint8_t* sb = sa + A_BYTES;
-                if (ch < p.chunks0) tma_load_4d(sa, &tmA0, ch * BK, cx, cy, img0, &full_bar[stage]);
-                else tma_load_4d(sa, &tmA1, (ch - p.chunks0) * BK, cx, cy, img0, &full_bar[stage]);
-                tma_load_3d(sb, &tmB, ch * BK, n0, tcl.wt[tap], &full_bar[stage]);
+            int g = 0;                               // k-block counter over all classes of this CTA (ring position)
+            for (int ci = 0; ci < ncls_here; ++ci) {
+                const TapClass& tcl = p.cls[cls0 + ci];
+                const int num_kb = tcl.ntaps * chunks;
+                for (int kb = 0; kb < num_kb; ++kb, ++g) {
+                    const int stage = g % L::STAGES;
+                    const uint32_t phase = (g / L::STAGES) & 1;
+                    mbar_wait(&empty_bar[stage], phase ^ 1);
+                    mbar_expect_tx(&full_bar[stage], L::STAGE_BYTES);
+                    const int tap = kb / chunks, ch = kb - tap * chunks;
+                    const int cx = p.in_mul * w0 + tcl.dx[tap], cy = p.in_mul * h0 + tcl.dy[tap];
+                    uint8_t* sa = smem + stage * L::STAGE_BYTES;
+                    uint8_t* sb = sa + A_BYTES;
+                    if (ch < p.chunks0) tma_load_4d(sa, &tmA0, ch * BK, cx, cy, img0, &full_bar[stage]);
+                    else tma_load_4d(sa, &tmA1, (ch - p.chunks0) * BK, cx, cy, img0, &full_bar[stage]);
+                    tma_load_3d(sb, &tmB, ch * BK, n0, tcl.wt[tap], &full_bar[stage]);
+                }
             }
         }
     } else if (warp == 1) {
@@ -120,23 +132,28 @@ __global__ void __launch_bounds__(NUM_THREADS) conv_tc_fwd_kernel(const __grid_c
         constexpr uint32_t idesc = make_idesc_bf16(BM, BN, 0, 0);
         const bool leader = elect_one();
         const uint32_t hi = desc_hi(1024, 2);
-        for (int kb = 0; kb < num_kb; ++kb) {
-            const int stage = kb % L::STAGES;
-            const uint32_t phase = (kb / L::STAGES) & 1;
-            mbar_wait(&full_bar[stage], phase);
-            tc_fence_after();
-            const uint32_t sa = smem_u32(smem + stage * L::STAGE_BYTES);
-            const uint32_t a_lo = desc_lo(sa, 16), b_lo = desc_lo(sa + A_BYTES, 16);
-            if (leader) {
-                umma_bf16_lohi(tmem_base, a_lo, hi, b_lo, hi, idesc, (uint32_t)kb);
+        int g = 0;
+        for (int ci = 0; ci < ncls_here; ++ci) {
+            const int num_kb = p.cls[cls0 + ci].ntaps * chunks;
+            const uint32_t d_tmem = tmem_base + (uint32_t)(ci * (int)L::TMEM_COLS);      // one accumulator per class
+            for (int kb = 0; kb < num_kb; ++kb, ++g) {
+                const int stage = g % L::STAGES;
+                const uint32_t phase = (g / L::STAGES) & 1;
+                mbar_wait(&full_bar[stage], phase);
+                tc_fence_after();
+                const uint32_t sa = smem_u32(smem + stage * L::STAGE_BYTES);
+                const uint32_t a_lo = desc_lo(sa, 16), b_lo = desc_lo(sa + A_BYTES, 16);
+                if (leader) {
+                    umma_bf16_lohi(d_tmem, a_lo, hi, b_lo, hi, idesc, (uint32_t)kb);
 #pragma unroll
-                for (int k = 1; k < BK / 16; ++k)   // +32 bytes (>>4 == 2) per 16-element K step inside the swizzle atom
-                    umma_bf16_lohi(tmem_base, a_lo + (uint32_t)(2 * k), hi, b_lo + (uint32_t)(2 * k), hi, idesc, 1u);
-                umma_commit(&empty_bar[stage]);     // frees the smem slot once these MMAs have read it
+                    for (int k = 1; k < BK / 16; ++k)   // +32 bytes (>>4 == 2) per 16-element K step inside the swizzle atom
+                        umma_bf16_lohi(d_tmem, a_lo + (uint32_t)(2 * k), hi, b_lo + (uint32_t)(2 * k), hi, idesc, 1u);
+                    umma_commit(&empty_bar[stage]);     // frees the smem slot once these MMAs have read it
+                }
+                __syncwarp();
             }
-            __syncwarp();
         }
-        if (leader) umma_commit(tmem_full_bar);     // accumulator complete
+        if (leader) umma_commit(tmem_full_bar);     // accumulators complete
         __syncwarp();
     } else {
         // ---- epilogue: warp w may touch TMEM lanes [32*(w%4), 32*(w%4)+32) ----
@@ -144,9 +161,6 @@ __global__ void __launch_bounds__(NUM_THREADS) conv_tc_fwd_kernel(const __grid_c
         const int m = q * 32 + lane;                // accumulator row == pixel index inside the tile
         const int twi = m & (TW - 1), thi = (m >> p.tw_log2) & (TH - 1), nbi = m >> (p.tw_log2 + p.th_log2);
         const int tx_ = w0 + twi, ty_ = h0 + thi, on = img0 + nbi;
-        const int ox = p.out_mul * tx_ + tcl.add_x, oy = p.out_mul * ty_ + tcl.add_y;
-        const bool row_ok = tx_ < p.W && ty_ < p.H && on < p.N && ox < p.out_W && oy < p.out_H;
-        bf16* yrow = p.y + (((long long)on * p.out_H + oy) * p.out_W + ox) * p.cout + n0;
         mbar_wait(tmem_full_bar, 0);
         tc_fence_after();
         const bool vec_ok = (p.cout % 8 == 0);
@@ -154,10 +168,18 @@ __global__ void __launch_bounds__(NUM_THREADS) conv_tc_fwd_kernel(const __grid_c
         // act(v) = max(v, v * neg): neg = 1 (identity), 0 (ReLU) or the LeakyReLU slope -- branch-free
         const float neg = p.act == SSG_ACT_RELU ? 0.f : (p.act == SSG_ACT_LEAKY ? p.slope : 1.f);
 #pragma unroll 1
+        for (int ci = 0; ci < ncls_here; ++ci) {
+        const TapClass& tcl = p.cls[cls0 + ci];
+        const int ox = p.out_mul * tx_ + tcl.add_x, oy = p.out_mul * ty_ + tcl.add_y;
+        const bool row_ok = tx_ < p.W && ty_ < p.H && on < p.N && ox < p.out_W && oy < p.out_H;
+        const long long row_off = (((long long)on * p.out_H + oy) * p.out_W + ox) * p.cout + n0;
+        bf16* yrow = p.y + row_off;
+        const bf16* mrow = p.mask ? p.mask + row_off : nullptr;
+#pragma unroll 1
         for (int c0 = 0; c0 < BN; c0 += 16) {
             if (n0 + c0 >= p.cout) break;
             uint32_t v[16];
-            tmem_ld_32x32b_x16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
+            tmem_ld_32x32b_x16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(ci * (int)L::TMEM_COLS + c0), v);
             tmem_ld_wait();
             if (!row_ok) continue;
             float f[16];
@@ -170,6 +192,22 @@ __global__ void __launch_bounds__(NUM_THREADS) conv_tc_fwd_kernel(const __grid_c
             }
 #pragma unroll
             for (int j = 0; j < 16; ++j) f[j] = fmaxf(f[j], f[j] * neg);
+            if (mrow != nullptr) {
+                if (vec_ok && n0 + c0 + 16 <= p.cout) {          // two 16-byte loads of the producer's output row
+                    Vec<bf16> m0, m1;
+                    m0.load(mrow + c0);
+                    m1.load(mrow + c0 + 8);
+                    float mv[16];
+                    m0.get(mv);
+                    m1.get(mv + 8);
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) f[j] *= act_grad_from_out(mv[j], p.mask_act, p.mask_slope);
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j)
+                        if (n0 + c0 + j < p.cout) f[j] *= act_grad_from_out(__bfloat162float(mrow[c0 + j]), p.mask_act, p.mask_slope);
+                }
+            }
             if (vec_ok && n0 + c0 + 16 <= p.cout) {
                 Vec<bf16> o;
                 o.set(f); o.store(yrow + c0);
@@ -183,10 +221,11 @@ __global__ void __launch_bounds__(NUM_THREADS) conv_tc_fwd_kernel(const __grid_c
                     if (n0 + c0 + j < p.cout) yrow[c0 + j] = __float2bfloat16_rn(f[j]);
             }
         }
+        }
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 2) tmem_dealloc(tmem_base, L::TMEM_COLS);
+    if (warp == 2) tmem_dealloc(tmem_base, tmem_cols);
 }
 
 // ---- host side ------------------------------------------------------------------------------------
@@ -241,7 +280,7 @@ static int launch_fwd(const CUtensorMap& a0, const CUtensorMap& a1, const CUtens
         SSG_CHECK_CUDA(cudaFuncSetAttribute(conv_tc_fwd_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
         attr_set = true;
     }
-    dim3 grid((unsigned)m_tiles, (unsigned)((p.cout + BN - 1) / BN), (unsigned)n_classes);
+    dim3 grid((unsigned)m_tiles, (unsigned)((p.cout + BN - 1) / BN), (unsigned)(p.merge ? 1 : n_classes));
     conv_tc_fwd_kernel<BN><<<grid, NUM_THREADS, L::TOTAL, st>>>(a0, a1, b, p);
     SSG_CHECK_LAUNCH();
     return SSG_OK;
@@ -275,7 +314,8 @@ static int encode_act_map(CUtensorMap* m, const void* ptr, int c, int n, int h, 
 // (oh, ow): destination dims; gemm_n: destination channels; weights are [taps][gemm_n][c0 + c1] bf16.
 static int run_conv(const void* x0, int c0, const void* x1, int c1, const void* w_packed, int w_taps, const float* bias, int bias_n,
                     void* y, int n, int sh, int sw, int th_, int tw_, int oh, int ow, int gemm_n, int in_mul, int out_mul,
-                    const TapClass* cls, int n_classes, int act, float slope, cudaStream_t st) {
+                    const TapClass* cls, int n_classes, int act, float slope, cudaStream_t st, const void* mask = nullptr,
+                    int mask_act = 0, float mask_slope = 0.f) {
     int twl, thl;
     pick_tile(th_, tw_, twl, thl);
     const int TW = 1 << twl, TH = 1 << thl, NB = BM / (TW * TH);
@@ -285,7 +325,11 @@ static int run_conv(const void* x0, int c0, const void* x1, int c1, const void* 
     p.cout = gemm_n; p.tw_log2 = twl; p.th_log2 = thl;
     p.tiles_x = (tw_ + TW - 1) / TW; p.tiles_y = (th_ + TH - 1) / TH;
     p.chunks0 = (c0 + 63) / 64; p.chunks1 = (c1 + 63) / 64; p.act = act; p.slope = slope;
+    p.mask = (const bf16*)mask; p.mask_act = mask_act; p.mask_slope = mask_slope;
     for (int i = 0; i < n_classes; ++i) p.cls[i] = cls[i];
+    static const bool no_merge = getenv("SSG_S2_MERGE") != nullptr && atoi(getenv("SSG_S2_MERGE")) == 0;      // A/B switch
+    p.ncls = n_classes;
+    p.merge = (n_classes > 1 && !no_merge) ? 1 : 0;
     const int tiles_n = (n + NB - 1) / NB;
     CUtensorMap ma0, ma1, mb;
     int rc = encode_act_map(&ma0, x0, c0, n, sh, sw, twl, thl, in_mul);
@@ -380,8 +424,26 @@ int ssg_conv2d_dgrad_tc_split(const void* dy, const void* w_packed, void* dx0, i
                          (cudaStream_t)s, accumulate ? 1 : 0, dx1, c0);
 }
 
+static int dgrad_tc_impl(const void* dy, const void* w_packed, void* dx, int n, int h, int w, int cin, int cout, int ksize, int stride,
+                         int pad, const void* mask, int mask_act, float mask_slope, ssg_stream_t s);
+
 int ssg_conv2d_dgrad_tc(const void* dy, const void* w_packed, void* dx, int n, int h, int w, int cin, int cout, int ksize, int stride,
                         int pad, ssg_stream_t s) {
+    return dgrad_tc_impl(dy, w_packed, dx, n, h, w, cin, cout, ksize, stride, pad, nullptr, 0, 0.f, s);
+}
+
+int ssg_conv2d_dgrad_tc_mask_supported(int ksize, int stride, int pad) { return (ksize == 3 && stride == 2) ? 1 : 0; }
+
+int ssg_conv2d_dgrad_tc_mask(const void* dy, const void* w_packed, void* dx, const void* producer_out, int producer_act, float producer_slope,
+                             int n, int h, int w, int cin, int cout, int ksize, int stride, int pad, ssg_stream_t s) {
+    SSG_CHECK_ARG(producer_out != nullptr && ssg_conv2d_dgrad_tc_mask_supported(ksize, stride, pad),
+                  "conv2d_dgrad_tc_mask: only the stride-2 3x3 data gradient carries the producer's activation backward (k=%d stride=%d)",
+                  ksize, stride);
+    return dgrad_tc_impl(dy, w_packed, dx, n, h, w, cin, cout, ksize, stride, pad, producer_out, producer_act, producer_slope, s);
+}
+
+static int dgrad_tc_impl(const void* dy, const void* w_packed, void* dx, int n, int h, int w, int cin, int cout, int ksize, int stride,
+                         int pad, const void* mask, int mask_act, float mask_slope, ssg_stream_t s) {
     SSG_CHECK_ARG(n > 0 && h > 0 && w > 0 && cin > 0 && cout > 0 && cout % 8 == 0 && cin % 8 == 0,
                   "conv2d_dgrad_tc: stored channel counts must be multiples of 8 (cin=%d cout=%d)", cin, cout);
     SSG_CHECK_ARG((ksize == 1 || ksize == 3) && pad >= 0 && pad < ksize && (stride == 1 || (stride == 2 && ksize == 3)),
@@ -413,7 +475,7 @@ int ssg_conv2d_dgrad_tc(const void* dy, const void* w_packed, void* dx, int n, i
         }
     const int th_ = (h + stride - 1) / stride, tw_ = (w + stride - 1) / stride;
     return run_conv(dy, cout, nullptr, 0, w_packed, ksize * ksize, nullptr, 0, dx, n, oh, ow, th_, tw_, h, w, cin, 1, stride, c, ncls, 0, 0.f,
-                    (cudaStream_t)s);
+                    (cudaStream_t)s, mask, mask_act, mask_slope);
 }
 
 }  // extern "C"

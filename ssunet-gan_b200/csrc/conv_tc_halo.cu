@@ -55,6 +55,7 @@ struct HaloParams {
     int accumulate;              // 1: y += result (TMA reduce-add) instead of y = result
     int split_c;                 // > 0 (multiple of 64): output channels [0, split_c) go to tmY, [split_c, cout) to tmY1 -- the
                                  // data gradient of a virtually concatenated input lands in its two source tensors
+    int issuers;                 // 1 or 2 MMA-issuing warps (2: the item's MT accumulators are split between warps 2 and 3)
 };
 
 // ACCS accumulator sets (2: epilogue overlaps the next item's MMAs).  RES: single-chunk (Cin <= 64) convolutions keep
@@ -81,6 +82,79 @@ struct HaloCfg {
     static_assert(TOTAL <= 227 * 1024, "shared memory budget");
 };
 
+// MMA-issue loop of conv_tc_halo_kernel for the M-tiles [mt0, mt0 + MTI) of every work item (MTI == MT: the only issuer).
+template <int MT, int BN, int ACCS, bool RES, int MTI>
+__device__ __forceinline__ void halo_issue(uint8_t* smem, uint64_t* a_full, uint64_t* a_empty, uint64_t* b_full, uint64_t* b_empty,
+                                           uint64_t* acc_full, uint64_t* acc_empty, uint64_t* b_free, uint32_t tmem_base,
+                                           const HaloParams& p, int chunks, int mt0) {
+    using C = HaloCfg<MT, BN, ACCS, RES>;
+    constexpr uint32_t idesc = make_idesc_bf16(128, BN, 0, 0);
+    const uint32_t leader = elect_one() ? 1u : 0u;
+    const uint32_t a_hi = desc_hi((uint32_t)p.halo_c * 128, 2), b_hi = desc_hi(1024, 2);
+    const uint32_t b_lo_base = desc_lo(smem_u32(smem + C::B_OFFSET), 16);
+    // taps in weight order t = r * k + s; the halo offset advances by one pixel per s and one halo row per r
+    // (mirrored for the data gradient) -- no division or table lookup on the issue path
+    const int step_s = p.flip ? -8 : 8, step_r = (p.flip ? -1 : 1) * (p.halo_c - p.ksize) * 8;
+    const uint32_t a_first = p.flip ? (uint32_t)((p.ksize - 1) * p.halo_c + p.ksize - 1) * 8 : 0u;        // 8 x 16 B per pixel
+    int ac = 0, bc = 0, it = 0, cur_n0 = -1, reloads = 0;
+    for (int item = blockIdx.x; item < p.total_items; item += gridDim.x, ++it) {
+        const int acc = it % ACCS;
+        bool fresh_b = !RES;            // RES: the resident weight tiles are awaited once, by the first item that uses them
+        if (RES) {
+            const int n0 = (p.n_major ? item / p.supers : item % p.n_tiles) * BN;
+            if (n0 != cur_n0) { cur_n0 = n0; ++reloads; fresh_b = true; }
+        }
+        mbar_wait(&acc_empty[acc], ((it / ACCS) & 1) ^ 1);
+        tc_fence_after();
+        const uint32_t d_base = tmem_base + (uint32_t)(acc * C::ACC_COLS + mt0 * BN);
+        for (int ch = 0; ch < chunks; ++ch, ++ac) {
+            const int st = ac % C::A_STAGES;
+            const int ksteps = ch == chunks - 1 ? p.k_last : 4;
+            mbar_wait(&a_full[st], (ac / C::A_STAGES) & 1);
+            tc_fence_after();
+            uint32_t a_lo = desc_lo(smem_u32(smem + st * C::A_STAGE_BYTES + mt0 * H_A_TILE_STRIDE), 16) + a_first;
+            int tq = 0;
+            for (int tap = 0; tap < p.ntaps; ++tap, ++bc) {
+                const int sl = RES ? tap : bc % C::B_SLOTS;
+                if (fresh_b) {
+                    mbar_wait(&b_full[sl], RES ? ((reloads - 1) & 1) : ((bc / C::B_SLOTS) & 1));
+                    tc_fence_after();
+                }
+                const uint32_t b_lo = b_lo_base + (uint32_t)(sl * (C::B_BYTES / 16));
+                const uint32_t keep = (uint32_t)(ch | tap);                                         // 0: first k-block of the item
+                // k outer, M-tile inner: consecutive MMAs accumulate into DIFFERENT TMEM accumulators
+                if (ksteps == 4) {
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+#pragma unroll
+                        for (int mt = 0; mt < MTI; ++mt)
+                            umma_bf16_lohi_pred(d_base + (uint32_t)(mt * BN), a_lo + (uint32_t)(mt * (H_A_TILE_STRIDE / 16) + 2 * k), a_hi,
+                                                b_lo + (uint32_t)(2 * k), b_hi, idesc, k == 0 ? keep : 1u, leader);
+                    }
+                } else {
+                    for (int k = 0; k < ksteps; ++k) {
+#pragma unroll
+                        for (int mt = 0; mt < MTI; ++mt)
+                            umma_bf16_lohi_pred(d_base + (uint32_t)(mt * BN), a_lo + (uint32_t)(mt * (H_A_TILE_STRIDE / 16) + 2 * k), a_hi,
+                                                b_lo + (uint32_t)(2 * k), b_hi, idesc, k == 0 ? keep : 1u, leader);
+                    }
+                }
+                if (!RES) umma_commit_pred(&b_empty[sl], leader);
+                a_lo += (uint32_t)step_s;
+                if (++tq == p.ksize) { tq = 0; a_lo += (uint32_t)step_r; }
+            }
+            umma_commit_pred(&a_empty[st], leader);
+        }
+        umma_commit_pred(&acc_full[acc], leader);
+        if (RES) {
+            // last item on these weights?  then tell the producer when its MMAs are done
+            const int nxt = item + (int)gridDim.x;
+            const bool last_use = nxt >= p.total_items || (p.n_major ? nxt / p.supers : nxt % p.n_tiles) * BN != cur_n0;
+            if (last_use) umma_commit_pred(b_free, leader);
+        }
+    }
+}
+
 template <int MT, int BN, int ACCS, bool RES>
 __global__ void __launch_bounds__(H_THREADS, 1) conv_tc_halo_kernel(const __grid_constant__ CUtensorMap tmA0,
                                                                      const __grid_constant__ CUtensorMap tmA1,
@@ -104,10 +178,11 @@ __global__ void __launch_bounds__(H_THREADS, 1) conv_tc_halo_kernel(const __grid
     const int tiles_per_img = p.tiles_x * p.tiles_y;
 
     if (threadIdx.x == 0) {
-        for (int i = 0; i < C::A_STAGES; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); }
-        for (int i = 0; i < C::B_SLOTS; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); }
-        for (int i = 0; i < ACCS; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 128); }
-        mbar_init(b_free, 1);
+        const int ni = (p.issuers == 2 && MT >= 2) ? 2 : 1;     // MMA-issuing warps: arrivals per consumer-side barrier
+        for (int i = 0; i < C::A_STAGES; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], ni); }
+        for (int i = 0; i < C::B_SLOTS; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], ni); }
+        for (int i = 0; i < ACCS; ++i) { mbar_init(&acc_full[i], ni); mbar_init(&acc_empty[i], 128); }
+        mbar_init(b_free, ni);
         fence_barrier_init();
     }
     if (warp == 2) tmem_alloc(tmem_slot, 512);
@@ -166,75 +241,18 @@ __global__ void __launch_bounds__(H_THREADS, 1) conv_tc_halo_kernel(const __grid
                     }
             }
         }
-    } else if (warp == 2) {
-        // ---- MMA issuer: the WHOLE warp walks the (warp-uniform) loop so that barrier addresses, descriptors and TMEM
-        // addresses live on the uniform datapath; lane 0 alone issues tcgen05.mma / tcgen05.commit ----
-        {
-            constexpr uint32_t idesc = make_idesc_bf16(128, BN, 0, 0);
-            const uint32_t leader = elect_one() ? 1u : 0u;
-            const uint32_t a_hi = desc_hi((uint32_t)p.halo_c * 128, 2), b_hi = desc_hi(1024, 2);
-            const uint32_t b_lo_base = desc_lo(smem_u32(smem + C::B_OFFSET), 16);
-            // taps in weight order t = r * k + s; the halo offset advances by one pixel per s and one halo row per r
-            // (mirrored for the data gradient) -- no division or table lookup on the issue path
-            const int step_s = p.flip ? -8 : 8, step_r = (p.flip ? -1 : 1) * (p.halo_c - p.ksize) * 8;
-            const uint32_t a_first = p.flip ? (uint32_t)((p.ksize - 1) * p.halo_c + p.ksize - 1) * 8 : 0u;        // 8 x 16 B per pixel
-            int ac = 0, bc = 0, it = 0, cur_n0 = -1, reloads = 0;
-            for (int item = blockIdx.x; item < p.total_items; item += gridDim.x, ++it) {
-                const int acc = it % ACCS;
-                bool fresh_b = !RES;            // RES: the resident weight tiles are awaited once, by the first item that uses them
-                if (RES) {
-                    const int n0 = (p.n_major ? item / p.supers : item % p.n_tiles) * BN;
-                    if (n0 != cur_n0) { cur_n0 = n0; ++reloads; fresh_b = true; }
-                }
-                mbar_wait(&acc_empty[acc], ((it / ACCS) & 1) ^ 1);
-                tc_fence_after();
-                const uint32_t d_base = tmem_base + (uint32_t)(acc * C::ACC_COLS);
-                for (int ch = 0; ch < chunks; ++ch, ++ac) {
-                    const int st = ac % C::A_STAGES;
-                    const int ksteps = ch == chunks - 1 ? p.k_last : 4;
-                    mbar_wait(&a_full[st], (ac / C::A_STAGES) & 1);
-                    tc_fence_after();
-                    uint32_t a_lo = desc_lo(smem_u32(smem + st * C::A_STAGE_BYTES), 16) + a_first;
-                    int tq = 0;
-                    for (int tap = 0; tap < p.ntaps; ++tap, ++bc) {
-                        const int sl = RES ? tap : bc % C::B_SLOTS;
-                        if (fresh_b) {
-                            mbar_wait(&b_full[sl], RES ? ((reloads - 1) & 1) : ((bc / C::B_SLOTS) & 1));
-                            tc_fence_after();
-                        }
-                        const uint32_t b_lo = b_lo_base + (uint32_t)(sl * (C::B_BYTES / 16));
-                        const uint32_t keep = (uint32_t)(ch | tap);                                         // 0: first k-block of the item
-                        // k outer, M-tile inner: consecutive MMAs accumulate into DIFFERENT TMEM accumulators
-                        if (ksteps == 4) {
-#pragma unroll
-                            for (int k = 0; k < 4; ++k) {
-#pragma unroll
-                                for (int mt = 0; mt < MT; ++mt)
-                                    umma_bf16_lohi_pred(d_base + (uint32_t)(mt * BN), a_lo + (uint32_t)(mt * (H_A_TILE_STRIDE / 16) + 2 * k), a_hi,
-                                                        b_lo + (uint32_t)(2 * k), b_hi, idesc, k == 0 ? keep : 1u, leader);
-                            }
-                        } else {
-                            for (int k = 0; k < ksteps; ++k) {
-#pragma unroll
-                                for (int mt = 0; mt < MT; ++mt)
-                                    umma_bf16_lohi_pred(d_base + (uint32_t)(mt * BN), a_lo + (uint32_t)(mt * (H_A_TILE_STRIDE / 16) + 2 * k), a_hi,
-                                                        b_lo + (uint32_t)(2 * k), b_hi, idesc, k == 0 ? keep : 1u, leader);
-                            }
-                        }
-                        if (!RES) umma_commit_pred(&b_empty[sl], leader);
-                        a_lo += (uint32_t)step_s;
-                        if (++tq == p.ksize) { tq = 0; a_lo += (uint32_t)step_r; }
-                    }
-                    umma_commit_pred(&a_empty[st], leader);
-                }
-                umma_commit_pred(&acc_full[acc], leader);
-                if (RES) {
-                    // last item on these weights?  then tell the producer when its MMAs are done
-                    const int nxt = item + (int)gridDim.x;
-                    const bool last_use = nxt >= p.total_items || (p.n_major ? nxt / p.supers : nxt % p.n_tiles) * BN != cur_n0;
-                    if (last_use) umma_commit_pred(b_free, leader);
-                }
-            }
+    } else if (warp == 2 || (warp == 3 && p.issuers == 2 && MT >= 2)) {
+        // ---- MMA issue: the WHOLE warp walks the (warp-uniform) loop so that barrier addresses, descriptors and TMEM
+        // addresses live on the uniform datapath; the elected lane alone issues tcgen05.mma / tcgen05.commit.
+        // With p.issuers == 2 the MT accumulators of an item are split between warps 2 and 3: MMAs into different accumulators
+        // are independent, so the two issue streams need no ordering; each commits its own MMAs to the rings' empty barriers
+        // (initialised with one arrival per issuer).  The thin instances (BN = 16: 8 tensor-clocks per MMA) and the BN = 64
+        // instances (32 clocks) were paced by ONE warp's descriptor arithmetic on the uniform datapath, not by the tensor pipe.
+        if (p.issuers == 2 && MT >= 2) {
+            halo_issue<MT, BN, ACCS, RES, (MT >= 2 ? MT / 2 : 1)>(smem, a_full, a_empty, b_full, b_empty, acc_full, acc_empty, b_free, tmem_base, p,
+                                                                   chunks, warp == 2 ? 0 : MT / 2);
+        } else {
+            halo_issue<MT, BN, ACCS, RES, MT>(smem, a_full, a_empty, b_full, b_empty, acc_full, acc_empty, b_free, tmem_base, p, chunks, 0);
         }
     } else if (warp >= 4) {
         // ---- epilogue: warp q owns TMEM lanes [32q, 32q + 32) = tile rows 4q .. 4q + 3 (a {64 ch, 8, 4, 1} box of y).
@@ -375,6 +393,10 @@ static int launch_halo(const CUtensorMap& a0, const CUtensorMap& a1, const CUten
     p.supers = (p.m_tiles + MT - 1) / MT;
     p.total_items = p.supers * p.n_tiles;
     p.n_major = RES ? 1 : 0;
+    // Two issuing warps wherever an item has >= 2 accumulators (measured: thin BN = 16 instances +20 %, BN = 64 +5-10 %, BN = 128
+    // +6 %); SSG_HALO_ISSUERS=1 restores the single issuer (A/B switch)
+    static const int issuers_env = getenv("SSG_HALO_ISSUERS") ? atoi(getenv("SSG_HALO_ISSUERS")) : 2;
+    p.issuers = (MT >= 2 && issuers_env != 1) ? 2 : 1;
     int grid = sm_count_cached();
     if (grid > p.total_items) grid = p.total_items;
     conv_tc_halo_kernel<MT, BN, ACCS, RES><<<grid, H_THREADS, C::TOTAL, st>>>(a0, a1, b, ym, ym1, p);

@@ -36,14 +36,21 @@ class ConvolutionalBlock(nn.Module):
         self._act = ACT_LEAKY if activation == "leakyrelu" else ACT_NONE
         self._has_bn = batch_norm is True
 
-    def forward(self, input):
+    def forward(self, input, input_act=None):
+        """input_act = (act, slope): `input` is the output of an activation-fused convolution with no BatchNorm (the previous
+        block's `fused_output_act`) and feeds nothing but this block; the data gradient then carries that activation's backward."""
         if not self._fusable:
             raise NotImplementedError("only None / LeakyReLU activations are on the seg-GAN path")
         conv = self.conv_block[0]
         if self._has_bn:
-            y, sums = conv(input, want_stats=self.training)
+            y, sums = conv(input, want_stats=self.training, input_act=input_act)
             return self.conv_block[1](y, act=self._act, slope=0.2, sums=sums)
-        return conv(input, act=self._act, slope=0.2)
+        return conv(input, act=self._act, slope=0.2, input_act=input_act)
+
+    @property
+    def fused_output_act(self):
+        """(act, slope) when this block's output comes straight out of the convolution's activation epilogue (no BatchNorm)."""
+        return (self._act, 0.2) if (not self._has_bn and self._act != ACT_NONE) else None
 
 
 class Generator(nn.Module):
@@ -88,8 +95,10 @@ class Discriminator(nn.Module):
 
     def forward(self, imgs):
         out = ops.to_nhwc(imgs, pad_channels=True)
-        for blk in self.conv_blocks:
-            out = blk(out)
+        prev_act = None
+        for blk in self.conv_blocks:        # a Sequential chain: every block's output feeds exactly the next block
+            out = blk(out, input_act=prev_act)
+            prev_act = blk.fused_output_act
         flat = ops.adaptive_avg_pool_flat(out, 6, 6)
         hid = self.fc1(flat, act=ACT_LEAKY, slope=0.2)
         logit = self.fc2(hid)

@@ -10,11 +10,12 @@ from ._lib import ACT_LEAKY, ACT_NONE, ACT_RELU  # noqa: F401
 class Conv2d(nn.Conv2d):
     """nn.Conv2d drop-in (square kernel, symmetric zero padding, dilation 1, groups 1)."""
 
-    def forward(self, x, act=ACT_NONE, slope=0.0, cout_store=None, want_stats=None, dx_sink=None):
+    def forward(self, x, act=ACT_NONE, slope=0.0, cout_store=None, want_stats=None, dx_sink=None, input_act=None):
         assert self.groups == 1 and self.dilation == (1, 1) and self.padding_mode == "zeros"
         assert self.kernel_size[0] == self.kernel_size[1] and self.stride[0] == self.stride[1]
         assert self.padding[0] == self.padding[1]
-        return ops.conv2d(x, self.weight, self.bias, self.stride[0], self.padding[0], act, slope, cout_store, want_stats, dx_sink)
+        return ops.conv2d(x, self.weight, self.bias, self.stride[0], self.padding[0], act, slope, cout_store, want_stats, dx_sink,
+                          input_act)
 
 
 class Linear(nn.Linear):

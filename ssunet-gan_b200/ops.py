@@ -338,8 +338,44 @@ class _Conv2d(torch.autograd.Function):
     >= Cout channels (thin_pad): the extra channels are zeros."""
 
     @staticmethod
-    def forward(ctx, x, weight, bias, stride, pad, act, slope, cout_store, want_stats, dx_sink=None):
+    def _backward_tiny(ctx, dy, x, weight, y, act, slope, has_bias):
+        """Backward of the thin -> thin 3x3 convolution (csrc/conv_tiny.cu): data gradient, and weight + bias gradient in one pass."""
+        n, _, h, w = x.shape
+        cout, cin = weight.shape[0], weight.shape[1]
+        dt = x.dtype
+        dy = _as_storage(dy, dt)
+        if act != ACT_NONE:
+            dz = torch.empty_like(dy)
+            call("ssg_act_bwd", dy, y, dz, dtype_code(dt), dy.numel(), act, slope)
+            dy = dz
+        dx = dw = db = None
+        if ctx.needs_input_grad[0]:
+            def write():
+                t = empty_nhwc(n, x.shape[1], h, w, dt, x.device)
+                call("ssg_conv3x3_tiny_dgrad", dy, weight.detach(), t, n, h, w, cin, cout)
+                return t
+            dx = write() if ctx.dx_sink is None else ctx.dx_sink.contribute(write, lambda buf: _add_into(buf, write()))
+        need_b = has_bias and ctx.needs_input_grad[2]
+        if ctx.needs_input_grad[1] or need_b:
+            wslot = _arena_slot(weight) if ctx.needs_input_grad[1] else None
+            bslot = _arena_slot(ctx.bias_ref) if need_b else None
+            if ctx.needs_input_grad[1] and wslot is None:
+                dw = torch.zeros_like(weight, dtype=torch.float32)
+            if need_b and bslot is None:
+                db = torch.zeros(cout, dtype=torch.float32, device=x.device)
+            wdst = wslot if wslot is not None else dw
+            if wdst is None:       # bias gradient only: the kernel still needs somewhere to put dW
+                wdst = torch.zeros_like(weight, dtype=torch.float32)
+            call("ssg_conv3x3_tiny_wgrad", x, dy, wdst, bslot if bslot is not None else db, n, h, w, cin, cout)
+        return dx, dw, db, None, None, None, None, None, None, None, None
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, stride, pad, act, slope, cout_store, want_stats, dx_sink=None, input_act=None):
         ctx.dx_sink = dx_sink
+        # input_act = (act, slope): the caller declares that x is the post-activation output of an activation-fused convolution
+        # and has NO other consumer; the data-gradient kernel may then apply that activation's backward in its epilogue and tag
+        # the gradient so that the producer's backward skips its own pass (Discriminator block 0 -> block 1)
+        ctx.input_act = input_act
         n, cin_s, h, w = x.shape
         cout, cin, kh, kw = weight.shape
         cout_s = cout_store or cout
@@ -348,8 +384,14 @@ class _Conv2d(torch.autograd.Function):
         dt = x.dtype
         y = empty_nhwc(n, cout_s, oh, ow, dt, x.device)
         use_tc = _tc_eligible(cin_s, cout_s, kh, stride, dt)
+        # thin -> thin 3x3 (SPADE's mlp_shared at the two finest levels): one-pixel-per-thread CUDA-core kernels (csrc/conv_tiny.cu)
+        use_tiny = bool(use_tc and kh == 3 and stride == 1 and pad == 1 and not want_stats
+                        and _lib.lib().ssg_conv3x3_tiny_supported(cin_s, cout_s, cin, cout))
         sums = None
-        if use_tc:
+        if use_tiny:
+            call("ssg_conv3x3_tiny_fwd", x, weight.detach(), bias.detach() if bias is not None else None, y, n, h, w, cin, cout, act, slope)
+            use_tc = False
+        elif use_tc:
             from . import conv_tc
             if want_stats and conv_tc.has_stats(kh, stride, pad):
                 # BatchNorm's sum / sum-of-squares (batchnorm.py:59-64) come out of the conv epilogue: no extra pass over y
@@ -362,6 +404,7 @@ class _Conv2d(torch.autograd.Function):
             call("ssg_conv2d_fwd_simt", x, wp, bias, y, dtype_code(dt), n, h, w, cin, cout, kh, kw, stride, pad, act, slope)
         ctx.save_for_backward(x, weight, y if act != ACT_NONE else None)
         ctx.cfg = (stride, pad, act, slope, bias is not None, use_tc)
+        ctx.use_tiny = use_tiny
         ctx.bias_ref = bias
         if sums is not None:
             ctx.mark_non_differentiable(sums)
@@ -371,13 +414,16 @@ class _Conv2d(torch.autograd.Function):
     def backward(ctx, dy, _dsums=None):
         x, weight, y = ctx.saved_tensors
         stride, pad, act, slope, has_bias, use_tc = ctx.cfg
+        if ctx.use_tiny:
+            return _Conv2d._backward_tiny(ctx, dy, x, weight, y, act, slope, has_bias)
         n, cin_s, h, w = x.shape
         cout, cin, kh, kw = weight.shape
         cout_s = dy.shape[1]
         dt = x.dtype
         colsum = getattr(dy, "_ssg_colsum", None)      # per-channel sums of dy already reduced by its producer (SPADE backward)
+        act_done = getattr(dy, "_ssg_act_applied", None) == (act, slope)      # the consumer's dgrad kernel already applied act'
         dy = _as_storage(dy, dt)
-        if act != ACT_NONE:
+        if act != ACT_NONE and not act_done:
             dz = torch.empty_like(dy)
             call("ssg_act_bwd", dy, y, dz, dtype_code(dt), dy.numel(), act, slope)
             dy = dz
@@ -386,9 +432,16 @@ class _Conv2d(torch.autograd.Function):
         if use_tc:
             from . import conv_tc
         if ctx.needs_input_grad[0]:
+            in_act = ctx.input_act
+            fuse_in = (in_act is not None and use_tc and ctx.dx_sink is None and in_act[0] != ACT_NONE and x.dtype == torch.bfloat16
+                       and conv_tc.can_mask(kh, stride, pad))
+
             def write():
                 t = empty_nhwc(n, cin_s, h, w, dt, x.device)
-                if use_tc:
+                if fuse_in:
+                    conv_tc.dgrad(dy, weight, t, stride, pad, producer_out=x, producer_act=in_act[0], producer_slope=in_act[1])
+                    t._ssg_act_applied = (in_act[0], in_act[1])
+                elif use_tc:
                     conv_tc.dgrad(dy, weight, t, stride, pad)
                 else:
                     wp = packed_weight(weight, W_RSKC, dt)
@@ -418,7 +471,7 @@ class _Conv2d(torch.autograd.Function):
                 call("ssg_conv2d_wgrad_simt", x, dy, dw, dtype_code(dt), n, h, w, cin, cout, kh, kw, stride, pad)
         if has_bias and ctx.needs_input_grad[2]:
             db = _bias_grad(ctx.bias_ref, dy, colsum, cout, cout_s, dt)
-        return dx, dw, db, None, None, None, None, None, None, None
+        return dx, dw, db, None, None, None, None, None, None, None, None
 
 
 def _bias_grad(bias, dy, colsum, cout, cout_s, dt):
@@ -519,7 +572,8 @@ class _Conv2dCat(torch.autograd.Function):
         return dx0, dx1, dw, db, None, None, None, None, None, None, None
 
 
-def conv2d(x, weight, bias=None, stride=1, pad=0, act=ACT_NONE, slope=0.0, cout_store=None, want_stats=None, dx_sink=None):
+def conv2d(x, weight, bias=None, stride=1, pad=0, act=ACT_NONE, slope=0.0, cout_store=None, want_stats=None, dx_sink=None,
+           input_act=None):
     """want_stats (True / False; None = plain call returning y): return `(y, sums)` where sums is the fp64
     [sum y | sum y^2] per-channel statistics of the output when requested and the kernel can produce them in its epilogue
     (else None)."""
@@ -528,7 +582,7 @@ def conv2d(x, weight, bias=None, stride=1, pad=0, act=ACT_NONE, slope=0.0, cout_
             y, sums = _Conv2dCat.apply(x[0], x[1], weight, bias, stride, pad, act, slope, cout_store, bool(want_stats), dx_sink)
             return (y, sums) if want_stats is not None else y
         x = x.materialise()
-    y, sums = _Conv2d.apply(to_nhwc(x), weight, bias, stride, pad, act, slope, cout_store, bool(want_stats), dx_sink)
+    y, sums = _Conv2d.apply(to_nhwc(x), weight, bias, stride, pad, act, slope, cout_store, bool(want_stats), dx_sink, input_act)
     return (y, sums) if want_stats is not None else y
 
 

@@ -87,7 +87,11 @@ THIN = [
     (2, 3, 64, 20, 24, 3, 1),     # archs.py:576 conv0_0.conv1 / models_seg_gan.py:267 block 0
     (2, 3, 64, 20, 24, 1, 1),     # BasicBlock shortcut on the image
     (1, 64, 3, 16, 16, 3, 1),     # SPADE.x2map (normalization.py:94)
-    (2, 3, 4, 12, 12, 3, 1),      # SPADE.mlp_shared, both sides thin
+    (2, 3, 4, 12, 12, 3, 1),      # SPADE.mlp_shared, both sides thin: csrc/conv_tiny.cu (one pixel per thread)
+    (2, 3, 8, 30, 22, 3, 1),      # level 1 (nhidden = 8)
+    (1, 4, 3, 17, 9, 3, 1),       # roles swapped
+    (1, 8, 8, 64, 40, 3, 1),
+    (3, 5, 7, 9, 11, 3, 1),       # odd channel counts inside the 8-channel storage
     (1, 4, 128, 18, 10, 3, 1),    # SPADE gamma|beta at level 0
     (1, 24, 768, 8, 8, 3, 1),     # level 3
     (2, 48, 192, 6, 6, 3, 1),

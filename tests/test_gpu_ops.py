@@ -217,9 +217,10 @@ def test_spade_modulate_and_head(dt):
     assert rel(y.float(), yr) < TOL[dt]
     assert rel(xc.grad, xr.grad) < TOL[dt] and rel(gbc.grad, gbr.grad) < TOL[dt]
     # adaptive avg pool (non-divisible 20 -> 6 and divisible 12 -> 6) + flatten order + linear
-    for hw in (20, 12, 3):
-        f = torch.randn(3, 32, hw, hw, generator=g)
-        wl = torch.randn(10, 32 * 36, generator=g) / 30
+    # (channel counts that are multiples of 64 take the staged backward kernel, the others the gather kernel)
+    for hw, ch in ((20, 32), (12, 32), (3, 32), (20, 64), (32, 128), (7, 64)):
+        f = torch.randn(3, ch, hw, hw, generator=g)
+        wl = torch.randn(10, ch * 36, generator=g) / 30
         bl = torch.randn(10, generator=g)
         fr, wr, br = f.clone().requires_grad_(True), wl.clone().requires_grad_(True), bl.clone().requires_grad_(True)
         or_ = F.leaky_relu(F.linear(F.adaptive_avg_pool2d(fr, (6, 6)).reshape(3, -1), wr, br), 0.2)
