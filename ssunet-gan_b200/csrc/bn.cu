@@ -599,7 +599,7 @@ int ssg_bn_bwd_reduce(const void* dy, const void* y, const void* x, int dtype, l
 int ssg_bn_bwd_apply(const void* dy, const void* y, const void* x, void* dx, void* dres, int dtype, long long rows, int c,
                      const float* mean, const float* inv_std, const float* gamma, const double* sums, double count, int act,
                      float slope, int training, ssg_stream_t s) {
-    SSG_CHECK_ARG(rows > 0 && c > 0 && c <= 2048, "bn_bwd_apply: bad shape");
+    SSG_CHECK_ARG(rows > 0 && c > 0 && c <= 2448, "bn_bwd_apply: bad shape (C <= 2448: the table-driven kernel keeps 5 C floats in 48 KB)");
     SSG_CHECK_ARG(act == SSG_ACT_NONE || y != nullptr, "bn_bwd_apply: activation needs the forward output");
     size_t smem = sizeof(float) * 5 * c;
     SSG_DISPATCH_DTYPE(dtype, {

@@ -502,32 +502,46 @@ struct HaloWgradParams {
     int tiles_x, tiles_y, m_tiles;
     int chunks0, chunks1;
     int issuers;                 // 1 or 2 MMA-issuing warps (see the kernel)
+    int splits;                  // split-K factor over the pixel tiles (gridDim.z = splits * passes)
 };
 
-constexpr int HW_XS = 4, HW_DS = 4;                    // ring slots
-constexpr int HW_DY_BYTES = 128 * 128;
-constexpr int HW_X_OFFSET = 0;
-constexpr int HW_DY_OFFSET = HW_XS * H_A_TILE_STRIDE;
-constexpr int HW_BAR_OFFSET = HW_DY_OFFSET + HW_DS * HW_DY_BYTES;
-constexpr int HW_TOTAL = HW_BAR_OFFSET + 256 + 1024;
+// BN = 64: one pass, five tap-pair accumulators of 64 columns (320 TMEM columns).  Each 128 x 64 x 16 MMA reads 4 KB of A and
+// 2 KB of B from shared memory for 32 tensor-clocks = 192 B/clk against the SM's 128 B/clk port: at most 67 % of the tensor
+// peak (ncu, profiles/r02_ncu_halo_wgrad_l0.txt: 44 % tensor-active, the issuing warp waiting on the MMA queue).
+// BN = 128 (Cout >= 128): a 128 x 128 x 16 MMA reads 4 + 4 KB for 64 tensor-clocks = 125 B/clk -- inside the port.  Five
+// 128-column accumulators would need 640 of the 512 TMEM columns, so the nine taps are covered by TWO passes (blockIdx.z & 1):
+// pass 0 = tap pairs 0-2 (384 columns), pass 1 = pairs 3-4 (256 columns); each pass streams its pixel tiles' x halo box and a
+// 128-channel dy box (two 64-channel TMA boxes, the second reached through the descriptor's leading-byte offset) once.
+template <int BN>
+struct HaloWgradCfg {
+    static constexpr int XS = 4, DS = (BN == 128) ? 3 : 4;    // ring slots
+    static constexpr int DY_BYTES = BN * 256;                // 128 pixels x BN channels x 2 B
+    static constexpr int X_OFFSET = 0;
+    static constexpr int DY_OFFSET = XS * H_A_TILE_STRIDE;
+    static constexpr int BAR_OFFSET = DY_OFFSET + DS * DY_BYTES;
+    static constexpr int TOTAL = BAR_OFFSET + 256 + 1024;
+    static constexpr int PASSES = (BN == 128) ? 2 : 1;
+    static_assert(TOTAL <= 227 * 1024, "shared memory budget");
+};
 
-// Issue loop of the halo weight-gradient kernel for tap pairs [G_LO, G_HI): the whole warp walks the loop (uniform datapath),
-// the elected lane issues the MMAs and commits.
-template <int G_LO, int G_HI>
+// Issue loop for tap pairs [G_LO, G_HI) whose accumulators start at TMEM column (g - G_BASE) * BN: the whole warp walks the loop
+// (uniform datapath), the elected lane issues the MMAs and commits.
+template <int BN, int G_LO, int G_HI, int G_BASE>
 __device__ __forceinline__ void halo_wgrad_issue(uint8_t* smem, uint64_t* x_full, uint64_t* dy_full, uint64_t* x_empty,
                                                  uint64_t* dy_empty, uint64_t* acc_full, uint32_t tmem_base, int n_iter) {
-    constexpr uint32_t idesc = make_idesc_bf16(128, 64, 1, 1);     // both operands MN-major
+    using C = HaloWgradCfg<BN>;
+    constexpr uint32_t idesc = make_idesc_bf16(128, BN, 1, 1);     // both operands MN-major
     const uint32_t leader = elect_one() ? 1u : 0u;
     const uint32_t x_hi = desc_hi(1280, 2), dy_hi = desc_hi(1024, 2);
-    const uint32_t x_lo_base = desc_lo(smem_u32(smem + HW_X_OFFSET), 0);
-    const uint32_t dy_lo_base = desc_lo(smem_u32(smem + HW_DY_OFFSET), 1024);
+    const uint32_t x_lo_base = desc_lo(smem_u32(smem + C::X_OFFSET), 0);
+    const uint32_t dy_lo_base = desc_lo(smem_u32(smem + C::DY_OFFSET), 16384);    // LBO: the second 64-channel box of a 128-wide co tile
     for (int it = 0; it < n_iter; ++it) {
-        const int xs = it % HW_XS, ds = it % HW_DS;
-        mbar_wait(&x_full[xs], (it / HW_XS) & 1);
-        mbar_wait(&dy_full[ds], (it / HW_DS) & 1);
+        const int xs = it % C::XS, ds = it % C::DS;
+        mbar_wait(&x_full[xs], (it / C::XS) & 1);
+        mbar_wait(&dy_full[ds], (it / C::DS) & 1);
         tc_fence_after();
         const uint32_t xk = x_lo_base + (uint32_t)(xs * (H_A_TILE_STRIDE / 16));
-        const uint32_t dk = dy_lo_base + (uint32_t)(ds * (HW_DY_BYTES / 16));
+        const uint32_t dk = dy_lo_base + (uint32_t)(ds * (C::DY_BYTES / 16));
         const uint32_t keep = (uint32_t)it;
         // Straight-line issue of the tile's MMAs (k outer, tap pair inner: consecutive MMAs accumulate into different
         // TMEM accumulators); every descriptor is (slot base + compile-time constant), the leader flag predicates the
@@ -541,7 +555,7 @@ __device__ __forceinline__ void halo_wgrad_issue(uint8_t* smem, uint64_t* x_full
                 const int off_a = ((ta / 3) * 10 + ta % 3) * 128, off_b = ((tb / 3) * 10 + tb % 3) * 128;
                 const uint32_t lbo = g < 4 ? (uint32_t)(off_b - off_a) : 128u;
                 // start-address field += off_a / 16; LBO field (bits 16..29) = lbo / 16: both compile-time constants
-                umma_bf16_lohi_pred(tmem_base + (uint32_t)(g * 64), xk + (uint32_t)(k * 160 + ((off_a >> 4) | ((lbo >> 4) << 16))), x_hi,
+                umma_bf16_lohi_pred(tmem_base + (uint32_t)((g - G_BASE) * BN), xk + (uint32_t)(k * 160 + ((off_a >> 4) | ((lbo >> 4) << 16))), x_hi,
                                     dk + (uint32_t)(k * 128), dy_hi, idesc, k == 0 ? keep : 1u, leader);
             }
         }
@@ -551,27 +565,34 @@ __device__ __forceinline__ void halo_wgrad_issue(uint8_t* smem, uint64_t* x_full
     umma_commit_pred(acc_full, leader);
 }
 
+template <int BN>
 __global__ void __launch_bounds__(H_THREADS, 1) conv_tc_halo_wgrad_kernel(const __grid_constant__ CUtensorMap tmX0,
                                                                            const __grid_constant__ CUtensorMap tmX1,
                                                                            const __grid_constant__ CUtensorMap tmDY,
                                                                            const HaloWgradParams p) {
+    using C = HaloWgradCfg<BN>;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    uint64_t* x_full = reinterpret_cast<uint64_t*>(smem + HW_BAR_OFFSET);
-    uint64_t* x_empty = x_full + HW_XS;
-    uint64_t* dy_full = x_empty + HW_XS;
-    uint64_t* dy_empty = dy_full + HW_DS;
-    uint64_t* acc_full = dy_empty + HW_DS;
+    uint64_t* x_full = reinterpret_cast<uint64_t*>(smem + C::BAR_OFFSET);
+    uint64_t* x_empty = x_full + C::XS;
+    uint64_t* dy_full = x_empty + C::XS;
+    uint64_t* dy_empty = dy_full + C::DS;
+    uint64_t* acc_full = dy_empty + C::DS;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_full + 1);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int chunk = blockIdx.x, co0 = blockIdx.y * 64;
+    const int chunk = blockIdx.x, co0 = blockIdx.y * BN;
+    const int pass = (C::PASSES == 2) ? (int)(blockIdx.z & 1) : 0;             // BN = 128: tap pairs 0-2 / 3-4
+    const int zsplit = (int)blockIdx.z / C::PASSES;
     const int tiles_per_img = p.tiles_x * p.tiles_y;
-    const int n_iter = (p.m_tiles - (int)blockIdx.z + (int)gridDim.z - 1) / (int)gridDim.z;
+    const int n_iter = (p.m_tiles - zsplit + p.splits - 1) / p.splits;
+    // this CTA's tap pairs and its MMA-issuing warps' shares of them
+    const int g_lo = (C::PASSES == 2 && pass == 1) ? 3 : 0;
+    const int g_hi = (C::PASSES == 2 && pass == 0) ? 3 : 5;
 
     if (threadIdx.x == 0) {
-        for (int i = 0; i < HW_XS; ++i) { mbar_init(&x_full[i], 1); mbar_init(&x_empty[i], p.issuers); }
-        for (int i = 0; i < HW_DS; ++i) { mbar_init(&dy_full[i], 1); mbar_init(&dy_empty[i], p.issuers); }
+        for (int i = 0; i < C::XS; ++i) { mbar_init(&x_full[i], 1); mbar_init(&x_empty[i], p.issuers); }
+        for (int i = 0; i < C::DS; ++i) { mbar_init(&dy_full[i], 1); mbar_init(&dy_empty[i], p.issuers); }
         mbar_init(acc_full, p.issuers);
         fence_barrier_init();
     }
@@ -584,13 +605,13 @@ __global__ void __launch_bounds__(H_THREADS, 1) conv_tc_halo_wgrad_kernel(const 
     if (warp == 0) {
         if (lane == 0) {
             for (int it = 0; it < n_iter; ++it) {
-                const int t = blockIdx.z + it * gridDim.z;
+                const int t = zsplit + it * p.splits;
                 const int img = t / tiles_per_img, rem = t - img * tiles_per_img;
                 const int ty = rem / p.tiles_x, tx = rem - ty * p.tiles_x;
-                const int sl = it % HW_XS;
-                mbar_wait(&x_empty[sl], ((it / HW_XS) & 1) ^ 1);
+                const int sl = it % C::XS;
+                mbar_wait(&x_empty[sl], ((it / C::XS) & 1) ^ 1);
                 mbar_expect_tx(&x_full[sl], 18 * 10 * 128);
-                uint8_t* dst = smem + HW_X_OFFSET + sl * H_A_TILE_STRIDE;
+                uint8_t* dst = smem + C::X_OFFSET + sl * H_A_TILE_STRIDE;
                 if (chunk < p.chunks0) tma_load_4d(dst, &tmX0, chunk * 64, tx * H_TW - 1, ty * H_TH - 1, img, &x_full[sl]);
                 else tma_load_4d(dst, &tmX1, (chunk - p.chunks0) * 64, tx * H_TW - 1, ty * H_TH - 1, img, &x_full[sl]);
             }
@@ -598,26 +619,43 @@ __global__ void __launch_bounds__(H_THREADS, 1) conv_tc_halo_wgrad_kernel(const 
     } else if (warp == 1) {
         if (lane == 0) {
             for (int it = 0; it < n_iter; ++it) {
-                const int t = blockIdx.z + it * gridDim.z;
+                const int t = zsplit + it * p.splits;
                 const int img = t / tiles_per_img, rem = t - img * tiles_per_img;
                 const int ty = rem / p.tiles_x, tx = rem - ty * p.tiles_x;
-                const int sl = it % HW_DS;
-                mbar_wait(&dy_empty[sl], ((it / HW_DS) & 1) ^ 1);
-                mbar_expect_tx(&dy_full[sl], HW_DY_BYTES);
-                tma_load_4d(smem + HW_DY_OFFSET + sl * HW_DY_BYTES, &tmDY, co0, tx * H_TW, ty * H_TH, img, &dy_full[sl]);
+                const int sl = it % C::DS;
+                mbar_wait(&dy_empty[sl], ((it / C::DS) & 1) ^ 1);
+                mbar_expect_tx(&dy_full[sl], C::DY_BYTES);
+#pragma unroll
+                for (int hb = 0; hb < BN / 64; ++hb)
+                    tma_load_4d(smem + C::DY_OFFSET + sl * C::DY_BYTES + hb * 16384, &tmDY, co0 + hb * 64, tx * H_TW, ty * H_TH, img, &dy_full[sl]);
             }
         }
     } else if (warp == 2 || (warp == 3 && p.issuers == 2)) {
-        // MMA issue.  ncu (profiles/r02_ncu_halo_wgrad_l0.txt): the single issuing warp spent a third of its time on the uniform
-        // datapath's dependent descriptor arithmetic (short scoreboard) between UTCHMMAs of only 32 tensor-clocks each.  With
-        // p.issuers == 2 the five tap-pair accumulators are split between warps 2 (pairs 0-2) and 3 (pairs 3-4): MMAs into
-        // different accumulators are independent, so two issue streams need no ordering; each stream commits its own MMAs to
-        // the ring's empty barriers (initialised with one arrival per issuer).
-        if (p.issuers == 2) {
-            if (warp == 2) halo_wgrad_issue<0, 3>(smem, x_full, dy_full, x_empty, dy_empty, acc_full, tmem_base, n_iter);
-            else halo_wgrad_issue<3, 5>(smem, x_full, dy_full, x_empty, dy_empty, acc_full, tmem_base, n_iter);
+        // MMA issue.  ncu (profiles/r02_ncu_halo_wgrad_l0.txt): a single issuing warp spent a third of its time on the uniform
+        // datapath's dependent descriptor arithmetic (short scoreboard) between UTCHMMAs.  With p.issuers == 2 the CTA's tap-pair
+        // accumulators are split between warps 2 and 3: MMAs into different accumulators are independent, so two issue streams
+        // need no ordering; each stream commits its own MMAs to the rings' empty barriers (one arrival per issuer).
+        if (C::PASSES == 1) {
+            if (p.issuers == 2) {
+                if (warp == 2) halo_wgrad_issue<BN, 0, 3, 0>(smem, x_full, dy_full, x_empty, dy_empty, acc_full, tmem_base, n_iter);
+                else halo_wgrad_issue<BN, 3, 5, 0>(smem, x_full, dy_full, x_empty, dy_empty, acc_full, tmem_base, n_iter);
+            } else {
+                halo_wgrad_issue<BN, 0, 5, 0>(smem, x_full, dy_full, x_empty, dy_empty, acc_full, tmem_base, n_iter);
+            }
+        } else if (pass == 0) {
+            if (p.issuers == 2) {
+                if (warp == 2) halo_wgrad_issue<BN, 0, 2, 0>(smem, x_full, dy_full, x_empty, dy_empty, acc_full, tmem_base, n_iter);
+                else halo_wgrad_issue<BN, 2, 3, 0>(smem, x_full, dy_full, x_empty, dy_empty, acc_full, tmem_base, n_iter);
+            } else {
+                halo_wgrad_issue<BN, 0, 3, 0>(smem, x_full, dy_full, x_empty, dy_empty, acc_full, tmem_base, n_iter);
+            }
         } else {
-            halo_wgrad_issue<0, 5>(smem, x_full, dy_full, x_empty, dy_empty, acc_full, tmem_base, n_iter);
+            if (p.issuers == 2) {
+                if (warp == 2) halo_wgrad_issue<BN, 3, 4, 3>(smem, x_full, dy_full, x_empty, dy_empty, acc_full, tmem_base, n_iter);
+                else halo_wgrad_issue<BN, 4, 5, 3>(smem, x_full, dy_full, x_empty, dy_empty, acc_full, tmem_base, n_iter);
+            } else {
+                halo_wgrad_issue<BN, 3, 5, 3>(smem, x_full, dy_full, x_empty, dy_empty, acc_full, tmem_base, n_iter);
+            }
         }
     } else if (warp >= 4) {
         const int q = warp & 3;
@@ -627,13 +665,13 @@ __global__ void __launch_bounds__(H_THREADS, 1) conv_tc_halo_wgrad_kernel(const 
         tc_fence_after();
         if (n_iter > 0) {
 #pragma unroll 1
-            for (int g = 0; g < 5; ++g) {
+            for (int g = g_lo; g < g_hi; ++g) {
                 const int tap = 2 * g + (row >> 6);
                 const bool row_ok = tap < 9 && ci < p.cin;
 #pragma unroll 1
-                for (int c0 = 0; c0 < 64; c0 += 32) {
+                for (int c0 = 0; c0 < BN; c0 += 32) {
                     uint32_t v[32];
-                    tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(g * 64 + c0), v);
+                    tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((g - g_lo) * BN + c0), v);
                     tmem_ld_wait();
                     if (!row_ok) continue;
                     float* dst = p.dw + ((long long)(co0 + c0) * p.cin + ci) * 9 + tap;
@@ -647,6 +685,27 @@ __global__ void __launch_bounds__(H_THREADS, 1) conv_tc_halo_wgrad_kernel(const 
     tc_fence_before();
     __syncthreads();
     if (warp == 2) tmem_dealloc(tmem_base, 512);
+}
+
+template <int BN>
+static int launch_wgrad_halo(const CUtensorMap& mx0, const CUtensorMap& mx1, const CUtensorMap& mdy, HaloWgradParams& p, int chunks,
+                             int cout_real, cudaStream_t st) {
+    using C = HaloWgradCfg<BN>;
+    static bool attr_set = false;
+    if (!attr_set) {
+        SSG_CHECK_CUDA(cudaFuncSetAttribute(conv_tc_halo_wgrad_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::TOTAL));
+        attr_set = true;
+    }
+    const int co_tiles = (cout_real + BN - 1) / BN;
+    const int ctas = chunks * co_tiles * C::PASSES;
+    int splits = (2 * sm_count_cached() + ctas - 1) / ctas;      // ~two waves of CTAs
+    if (splits > p.m_tiles) splits = p.m_tiles;
+    if (splits < 1) splits = 1;
+    p.splits = splits;
+    dim3 grid((unsigned)chunks, (unsigned)co_tiles, (unsigned)(splits * C::PASSES));
+    conv_tc_halo_wgrad_kernel<BN><<<grid, H_THREADS, C::TOTAL, st>>>(mx0, mx1, mdy, p);
+    SSG_CHECK_LAUNCH();
+    return SSG_OK;
 }
 
 // x0 | x1: stored channel counts c0 / c1 (multiples of 8); dy: stored channels cout_s.  dw must be zeroed by the caller.
@@ -675,19 +734,11 @@ int run_wgrad_halo(const void* x0, int c0, const void* x1, int c1, const void* d
     }
     rc = enc(&mdy, dy, cout_s, H_TW, H_TH);
     if (rc) return rc;
-    static bool attr_set = false;
-    if (!attr_set) {
-        SSG_CHECK_CUDA(cudaFuncSetAttribute(conv_tc_halo_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, HW_TOTAL));
-        attr_set = true;
-    }
-    const int chunks = p.chunks0 + p.chunks1, co_tiles = (cout_real + 63) / 64;
-    int splits = (2 * sm_count_cached() + chunks * co_tiles - 1) / (chunks * co_tiles);      // ~two waves of CTAs
-    if (splits > p.m_tiles) splits = p.m_tiles;
-    if (splits < 1) splits = 1;
-    dim3 grid((unsigned)chunks, (unsigned)co_tiles, (unsigned)splits);
-    conv_tc_halo_wgrad_kernel<<<grid, H_THREADS, HW_TOTAL, st>>>(mx0, mx1, mdy, p);
-    SSG_CHECK_LAUNCH();
-    return SSG_OK;
+    const int chunks = p.chunks0 + p.chunks1;
+    // SSG_WGRAD_BN=64 forces the one-pass 64-wide kernel everywhere (A/B switch)
+    static const bool force64 = getenv("SSG_WGRAD_BN") != nullptr && atoi(getenv("SSG_WGRAD_BN")) == 64;
+    if (cout_real >= 128 && cout_s >= 128 && !force64) return launch_wgrad_halo<128>(mx0, mx1, mdy, p, chunks, cout_real, st);
+    return launch_wgrad_halo<64>(mx0, mx1, mdy, p, chunks, cout_real, st);
 }
 
 // =====================================================================================================

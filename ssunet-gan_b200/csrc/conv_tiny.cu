@@ -44,12 +44,12 @@ __global__ void __launch_bounds__(128) conv3x3_tiny_kernel(const bf16* __restric
     if (threadIdx.x < CO) b_s[threadIdx.x] = (bias != nullptr && threadIdx.x < w_cout) ? bias[threadIdx.x] : 0.f;
     __syncthreads();
     const int groups_per_row = (wd + PX - 1) / PX;
-    const long long total = (long long)n * h * groups_per_row;
-    const long long stride = (long long)gridDim.x * blockDim.x;
-    for (long long gi = (long long)blockIdx.x * blockDim.x + threadIdx.x; gi < total; gi += stride) {
-        const int x0 = (int)(gi % groups_per_row) * PX;
-        const long long rowi = gi / groups_per_row;              // n * h + y
-        const int yy = (int)(rowi % h);
+    const int total = n * h * groups_per_row;                    // < 2^31 (checked by the launcher): 32-bit index arithmetic
+    const int stride = (int)(gridDim.x * blockDim.x);
+    for (int gi = (int)(blockIdx.x * blockDim.x + threadIdx.x); gi < total; gi += stride) {
+        const int rowi = gi / groups_per_row;                    // n * h + y
+        const int x0 = (gi - rowi * groups_per_row) * PX;
+        const int yy = rowi % h;
         float acc[PX][CO];
 #pragma unroll
         for (int q = 0; q < PX; ++q)
@@ -59,7 +59,7 @@ __global__ void __launch_bounds__(128) conv3x3_tiny_kernel(const bf16* __restric
         for (int r = 0; r < 3; ++r) {
             const int sy = yy + r - 1;
             const bool row_ok = sy >= 0 && sy < h;
-            const bf16* xr = x + ((rowi + (r - 1)) * wd) * 8;
+            const bf16* xr = x + ((long long)(rowi + (r - 1)) * wd) * 8;
             float f[PX + 2][CI];
 #pragma unroll
             for (int c = 0; c < PX + 2; ++c) {
@@ -92,18 +92,21 @@ __global__ void __launch_bounds__(128) conv3x3_tiny_kernel(const bf16* __restric
             for (int co = 0; co < CO; ++co) o[co] = apply_act(acc[q][co], act, slope);
             Vec<bf16> vo;
             vo.set(o);
-            vo.store(y + (rowi * wd + x0 + q) * 8);
+            vo.store(y + ((long long)rowi * wd + x0 + q) * 8);
         }
     }
 }
 
-// blockIdx.y = filter row r: one thread accumulates the 3 x CI x CO partial products of that row's taps over a strided set of
-// pixels (<= 96 registers), the block combines them through shared memory in a fixed order and adds once per block into dW
-// (fp32 atomics: a few hundred blocks).  Row 0's blocks also reduce the bias gradient.
+// blockIdx.y = filter row r: one thread accumulates the 3 x CI x CO partial products of that row's taps (<= 96 registers) over
+// runs of PXW = 8 consecutive pixels of an image row -- one index decomposition and PXW + 2 sliding x loads per run (the first
+// version decomposed a 64-bit pixel index per pixel: two emulated 64-bit divisions cost more than the arithmetic) -- then the block
+// combines the partials through shared memory in a fixed order and adds once per block into dW (fp32 atomics: a few hundred
+// blocks).  Row 0's blocks also reduce the bias gradient.
 template <int CI, int CO>
 __global__ void __launch_bounds__(128) conv3x3_tiny_wgrad_kernel(const bf16* __restrict__ x, const bf16* __restrict__ dy, float* __restrict__ dw,
                                                                   float* __restrict__ db, int n, int h, int wd, int w_cout, int w_cin) {
     constexpr int NW = 3 * CI * CO;
+    constexpr int PXW = 8;
     const int r = blockIdx.y;
     float acc[NW];
     float accb[CO];
@@ -111,25 +114,49 @@ __global__ void __launch_bounds__(128) conv3x3_tiny_wgrad_kernel(const bf16* __r
     for (int i = 0; i < NW; ++i) acc[i] = 0.f;
 #pragma unroll
     for (int i = 0; i < CO; ++i) accb[i] = 0.f;
-    const long long total = (long long)n * h * wd;
-    const long long stride = (long long)gridDim.x * blockDim.x;
-    for (long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x; p < total; p += stride) {
-        const int xx = (int)(p % wd);
-        const int yy = (int)((p / wd) % h);
-        float g[8];
-        load8(dy + p * 8, true, g);
-#pragma unroll
-        for (int co = 0; co < CO; ++co) accb[co] += g[co];
+    const int runs_per_row = (wd + PXW - 1) / PXW;
+    const int rows = n * h;                                  // < 2^31 / runs_per_row (checked by the launcher)
+    const int total = rows * runs_per_row;
+    const int stride = (int)(gridDim.x * blockDim.x);
+    for (int gi = (int)(blockIdx.x * blockDim.x + threadIdx.x); gi < total; gi += stride) {
+        const int rowi = gi / runs_per_row;
+        const int x0 = (gi - rowi * runs_per_row) * PXW;
+        const int yy = rowi % h;
         const int sy = yy + r - 1;
+        const bool row_ok = sy >= 0 && sy < h;
+        const bf16* xr = x + ((long long)(rowi + (r - 1)) * wd) * 8;
+        const bf16* gr = dy + ((long long)rowi * wd) * 8;
+        float f0[CI], f1[CI], f2[CI];                        // sliding window: x at columns q - 1, q, q + 1
+        {
+            float t[8];
+            load8(xr + (long long)(x0 - 1) * 8, row_ok && x0 - 1 >= 0, t);
 #pragma unroll
-        for (int s = 0; s < 3; ++s) {
-            const int sx = xx + s - 1;
-            float f[8];
-            load8(x + (p + (long long)(r - 1) * wd + (s - 1)) * 8, sy >= 0 && sy < h && sx >= 0 && sx < wd, f);
+            for (int ci = 0; ci < CI; ++ci) f0[ci] = t[ci];
+            load8(xr + (long long)x0 * 8, row_ok && x0 < wd, t);
+#pragma unroll
+            for (int ci = 0; ci < CI; ++ci) f1[ci] = t[ci];
+        }
+#pragma unroll
+        for (int q = 0; q < PXW; ++q) {
+            const int xc = x0 + q;
+            float t[8];
+            load8(xr + (long long)(xc + 1) * 8, row_ok && xc + 1 < wd, t);
+#pragma unroll
+            for (int ci = 0; ci < CI; ++ci) f2[ci] = t[ci];
+            float g[8];
+            load8(gr + (long long)xc * 8, xc < wd, g);
+#pragma unroll
+            for (int co = 0; co < CO; ++co) accb[co] += g[co];
 #pragma unroll
             for (int ci = 0; ci < CI; ++ci)
 #pragma unroll
-                for (int co = 0; co < CO; ++co) acc[(s * CI + ci) * CO + co] = fmaf(f[ci], g[co], acc[(s * CI + ci) * CO + co]);
+                for (int co = 0; co < CO; ++co) {
+                    acc[(0 * CI + ci) * CO + co] = fmaf(f0[ci], g[co], acc[(0 * CI + ci) * CO + co]);
+                    acc[(1 * CI + ci) * CO + co] = fmaf(f1[ci], g[co], acc[(1 * CI + ci) * CO + co]);
+                    acc[(2 * CI + ci) * CO + co] = fmaf(f2[ci], g[co], acc[(2 * CI + ci) * CO + co]);
+                }
+#pragma unroll
+            for (int ci = 0; ci < CI; ++ci) { f0[ci] = f1[ci]; f1[ci] = f2[ci]; }
         }
     }
     // warp tree (shuffles), then the four warps' results through shared memory
@@ -162,6 +189,7 @@ static int launch_tiny(const void* x, const float* w, const float* bias, void* y
                        float slope, cudaStream_t st) {
     constexpr int PX = (CI * CO <= 16) ? 4 : 2;
     const long long total = (long long)n * h * ((wd + PX - 1) / PX);
+    SSG_CHECK_ARG(total < (1ll << 31), "conv3x3_tiny: tensor too large for 32-bit group indexing");
     conv3x3_tiny_kernel<CI, CO, DGRAD, PX><<<grid_for(total, 128, 16), 128, 0, st>>>((const bf16*)x, w, bias, (bf16*)y, n, h, wd, w_cout, w_cin, act, slope);
     SSG_CHECK_LAUNCH();
     return SSG_OK;
@@ -202,8 +230,9 @@ int ssg_conv3x3_tiny_dgrad(const void* dy, const float* w_oihw, void* dx, int n,
 int ssg_conv3x3_tiny_wgrad(const void* x, const void* dy, float* dw_oihw, float* db, int n, int h, int w, int cin, int cout, ssg_stream_t s) {
     SSG_CHECK_ARG(x && dy && dw_oihw && n > 0 && h > 0 && w > 0 && cin >= 1 && cin <= 8 && cout >= 1 && cout <= 8, "conv3x3_tiny_wgrad: bad args");
     const int ci = round48(cin), co = round48(cout);
-    const long long total = (long long)n * h * w;
-    const dim3 g(grid_for(total, 128 * 32, 3), 3);         // >= 32 pixels per thread: the block reduction stays a small share
+    const long long total = (long long)n * h * ((w + 7) / 8);                  // 8-pixel runs
+    SSG_CHECK_ARG(total < (1ll << 31), "conv3x3_tiny_wgrad: tensor too large for 32-bit run indexing");
+    const dim3 g(grid_for(total, 128 * 4, 4), 3);          // >= 4 runs (32 pixels) per thread: the block reduction stays a small share
     cudaStream_t st = (cudaStream_t)s;
     if (ci == 4 && co == 4) conv3x3_tiny_wgrad_kernel<4, 4><<<g, 128, 0, st>>>((const bf16*)x, (const bf16*)dy, dw_oihw, db, n, h, w, cout, cin);
     else if (ci == 4 && co == 8) conv3x3_tiny_wgrad_kernel<4, 8><<<g, 128, 0, st>>>((const bf16*)x, (const bf16*)dy, dw_oihw, db, n, h, w, cout, cin);

@@ -987,7 +987,8 @@ def spade_modulate(x, gb, dx_sink=None):
 
 
 # ----------------------------------------------------------------------------------------------
-# fused self-conditioned SPADE (csrc/spade_fused.cu) -- OPT-IN until it has been validated on the GPU
+# fused self-conditioned SPADE (csrc/spade_fused.cu) -- OPT-IN: both versions are validated on B200 (tests/test_gpu_spade_fused.py)
+# and both are slower than the chain of tensor-core convolutions (profiles/r02_spade_fused.txt)
 # ----------------------------------------------------------------------------------------------
 import os as _os
 
@@ -996,8 +997,8 @@ _SPADE_FUSED = {"1": 1, "2": 2}.get(_os.environ.get("SSG_SPADE_FUSED", ""), 0)
 
 def set_spade_fused(enabled):
     """Route self-conditioned SPADE blocks with 64 / 128 channels through the one-kernel forward.
-    True / 1: version 1 (verified on B200, slower than the chain); 2: version 2 where it applies (C = 64, label_nc <= 3;
-    persistent CTAs, weights-stationary x2map -- written after v1's measurement, still to be run), version 1 elsewhere."""
+    True / 1: version 1; 2: version 2 where it applies (C = 64, label_nc <= 3; persistent CTAs, weights-stationary x2map),
+    version 1 elsewhere.  Both verified on B200, both slower than the default chain (1.63 / 1.57 ms against 1.25 ms at level 0)."""
     global _SPADE_FUSED
     _SPADE_FUSED = int(enabled)
 

@@ -1,11 +1,11 @@
-"""Opt-in one-kernel SPADE forward (csrc/spade_fused.cu) against the unfused chain of the same module: forward
-and every gradient.  The kernel is not the default path yet, so this file only runs when SSG_SPADE_FUSED_TEST=1."""
-import os
-
+"""One-kernel SPADE forward (csrc/spade_fused.cu; both versions) against the unfused chain of the same module:
+forward and every gradient.  Both versions are numerically right on B200 and both are SLOWER than the chain (level 0: 1.63 /
+1.57 ms against 1.25 ms; level 1: 0.96 / 0.96 against 0.59, profiles/r02_spade_fused.txt), so they stay off the default path;
+the tests run unconditionally so that the opt-in switch (`SSG_SPADE_FUSED`, `ops.set_spade_fused`) never rots."""
 import pytest
 import torch
 
-pytestmark = [pytest.mark.gpu, pytest.mark.skipif(os.environ.get("SSG_SPADE_FUSED_TEST") != "1", reason="opt-in kernel: set SSG_SPADE_FUSED_TEST=1")]
+pytestmark = pytest.mark.gpu
 
 
 def rel(a, b):
@@ -50,7 +50,9 @@ def test_spade_fused_matches_unfused_chain(c, hw, version):
     assert rel(dx1, dx2) < 1e-2, rel(dx1, dx2)
     assert g1.keys() == g2.keys()
     for k in g1:
-        assert rel(g1[k], g2[k]) < 2e-2, (k, rel(g1[k], g2[k]))
+        # (the chain's mlp_shared runs on the fp32-weight CUDA-core kernels, csrc/conv_tiny.cu; the fused kernel's backward on the
+        # bf16-weight tensor-core ones: two bf16-level roundings apart)
+        assert rel(g1[k], g2[k]) < 4e-2, (k, rel(g1[k], g2[k]))
     with torch.no_grad():          # inference: no gamma|beta tensor is written
         ops.set_spade_fused(version)
         try:
