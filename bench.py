@@ -509,11 +509,12 @@ def main():
                      "by_entry_point": {k: {"tflops": round(v["flops"] / (v["ms"] / 1e3) / 1e12, 1) if v["ms"] > 0 else None,
                                             "ms_per_step": round(v["ms"] / prof_steps, 3), "launches_per_step": v["n"] // prof_steps}
                                         for k, v in sorted(prof.get("by_name", {}).items())}})
-    # DRAM traffic of the dominant kernel (largest share of the step: the halo weight-gradient kernel), per launch, from the
-    # committed `ncu --set full` capture of that kernel (profiles/r02_traffic.json, written by profiles/traffic_from_ncu.py)
+    # DRAM traffic of the dominant kernel family (conv_tc_halo_kernel: 36 % of the step's device time in the launch list,
+    # profiles/r02_launches_summary.txt), per launch, from the committed `ncu --set full` capture of its level-0 instance
+    # (profiles/r02_traffic.json, written by profiles/traffic_from_ncu.py from the .ncu-rep files)
     try:
         tr = json.load(open(os.path.join(ROOT, "profiles", "r02_traffic.json")))["kernels"]
-        top = [k for k in tr if k["capture"].endswith("halo_wgrad_l0")][0]
+        top = ([k for k in tr if k["capture"].endswith("halo_fwd_l0_2issuers")] or [k for k in tr if k["capture"].endswith("halo_wgrad_l0")])[0]
         roof["traffic"] = top["dram_bytes"]
         roof["traffic_detail"] = {"kernel": top["kernel"], "launch": top["what"], "dram_bytes": top["dram_bytes"],
                                   "algorithmic_bytes": top["algorithmic_bytes"], "source": "profiles/r02_traffic.json (" + top["capture"] + ".ncu-rep)",

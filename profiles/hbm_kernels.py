@@ -96,8 +96,26 @@ def main():
         lambda: call("ssg_bn_bwd_apply", dy, y, x, dx, None, DT, R, c, mean, istd, gam, sums, float(R), 1, 0.0, 1))
     rec("bn_bwd_apply + dres", "autograd of archs.py:233", 5 * E,
         lambda: call("ssg_bn_bwd_apply", dy, y, x, dx, dres, DT, R, c, mean, istd, gam, sums, float(R), 1, 0.0, 1))
+    scsh = torch.cat([istd * gam, bet - mean * istd * gam]).contiguous()
+    rec("bn_bwd_reduce (mask recomputed from x)", "autograd of archs.py:231 (no residual)", 2 * E,
+        lambda: call("ssg_bn_bwd_reduce_rc", dy, x, DT, R, c, mean, istd, scsh, scsh[c:], 1, 0.0, sums))
+    rec("bn_bwd_apply (mask recomputed from x)", "autograd of archs.py:231 (no residual)", 3 * E,
+        lambda: call("ssg_bn_bwd_apply_rc", dy, x, dx, DT, R, c, mean, istd, gam, scsh, scsh[c:], sums, float(R), 1, 0.0, 1))
     if args.only == "bn":
         return
+    # ---- thin -> thin 3x3 (SPADE mlp_shared at level 0): 16 x 512 x 512 x 8 bf16 both sides ----
+    xt = torch.randn(R, 8, device=dev).to(BF)
+    yt = torch.empty_like(xt)
+    wt = torch.randn(4, 3, 3, 3, device=dev) * 0.2
+    bt = torch.randn(4, device=dev) * 0.1
+    dwt, dbt = torch.zeros_like(wt), torch.zeros_like(bt)
+    rec("conv3x3 thin->thin fwd (3 -> 4 ch)", "normalization.py:93-95 (mlp_shared)", 2 * R * 16,
+        lambda: call("ssg_conv3x3_tiny_fwd", xt, wt, bt, yt, n, h, w, 3, 4, 1, 0.0))
+    rec("conv3x3 thin->thin dgrad", "autograd of normalization.py:93-95", 2 * R * 16,
+        lambda: call("ssg_conv3x3_tiny_dgrad", yt, wt, xt, n, h, w, 3, 4))
+    rec("conv3x3 thin->thin wgrad + bias grad", "autograd of normalization.py:93-95", 2 * R * 16,
+        lambda: call("ssg_conv3x3_tiny_wgrad", xt, yt, dwt, dbt, n, h, w, 3, 4))
+    del xt, yt
     gb = torch.randn(R, 2 * c, device=dev).to(BF)
     dgb = torch.empty_like(gb)
     rec("spade_modulate fwd", "normalization.py:120", 4 * E, lambda: call("ssg_spade_modulate_fwd", x, gb, y, DT, R, c))
@@ -115,6 +133,14 @@ def main():
     cat = torch.empty(n * 512 * 512, 192, dtype=BF, device=dev)
     rec("concat2 (skip | up)", "archs.py:667", 2 * (E + up.numel() * 2), lambda: call("ssg_concat2", x, 64, up, 128, cat, DT, R))
     del x128, up, cat, yp, code
+    # ---- discriminator head: adaptive 6x6 average pool of 16 x 32 x 32 x 512 + flatten, and its backward ----
+    xp = torch.randn(16 * 32 * 32, 512, device=dev).to(BF)
+    yp2 = torch.empty(16, 512 * 36, dtype=BF, device=dev)
+    rec("adaptive_avgpool 6x6 + flatten fwd", "models_seg_gan.py:277-279", xp.numel() * 2 + yp2.numel() * 2,
+        lambda: call("ssg_adaptive_avgpool_flat_fwd", xp, yp2, DT, 16, 32, 32, 512, 6, 6), "17 MB: launch-latency share")
+    rec("adaptive_avgpool 6x6 + flatten bwd", "autograd of models_seg_gan.py:277-279", xp.numel() * 2 + yp2.numel() * 2,
+        lambda: call("ssg_adaptive_avgpool_flat_bwd", yp2, xp, DT, 16, 32, 32, 512, 6, 6), "17 MB: launch-latency share")
+    del xp, yp2
     # ---- losses / metrics on 16 x 3 x 512 x 512 fp32 logits + masks ----
     lg = torch.randn(16, 3 * 512 * 512, device=dev)
     tg = (torch.rand(16, 3 * 512 * 512, device=dev) > 0.5).float()

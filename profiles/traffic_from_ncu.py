@@ -1,7 +1,7 @@
 """DRAM traffic per launch of the captured kernels (one `ncu --set full` capture each, profiles/capture_r02.sh) next to their
 algorithmic bytes -> profiles/r02_traffic.json (bench.py's roofline.traffic reads the dominant kernel's row from it).
 
-    python profiles/traffic_from_ncu.py gpurun_out r02a
+    python profiles/traffic_from_ncu.py gpurun_out r02a r02b
 """
 import csv
 import json
@@ -25,6 +25,13 @@ CASES = {
     "halo_dgrad_l0": ("conv0_0.conv2 data gradient, 16x512x512, 64<-64, 3x3", 2 * E, 2.0 * 16 * 512 * 512 * 64 * 64 * 9),
     "bn_bwd_apply": ("BN backward apply (dy, y, x -> dx), 16x512x512x64", 4 * E, 0.0),
     "bn_bwd_reduce": ("BN backward reduce (dy, y, x -> sums), 16x512x512x64", 3 * E, 0.0),
+    # second batch of captures (profiles/capture_r02b.sh): the kernels changed in round 2
+    "halo_wgrad128_l1c": ("conv1_1.conv1 weight gradient, 128-wide co tiles in two tap-pair passes", 16 * 256 * 256 * (384 + 128) * 2 + 384 * 128 * 9 * 4,
+                          2.0 * 16 * 256 * 256 * 384 * 128 * 9),
+    "halo_wgrad64_l0": ("conv0_0.conv2 weight gradient, two issuing warps", 2 * E + 64 * 64 * 9 * 4, 2.0 * 16 * 512 * 512 * 64 * 64 * 9),
+    "s2_dgrad_merged_l0": ("D block1 data gradient, stride 2, four parity classes in one CTA", E + E // 4, 2.0 * 16 * 256 * 256 * 64 * 64 * 9),
+    "halo_fwd_l0_2issuers": ("conv0_0.conv2 forward, two issuing warps", 2 * E, 2.0 * 16 * 512 * 512 * 64 * 64 * 9),
+    "halo_thin_x2map_fwd": ("SPADE x2map forward 64 -> 3 (stored 8), 16x512x512", E + E // 8, 2.0 * 16 * 512 * 512 * 64 * 3 * 9),
 }
 
 
@@ -42,12 +49,14 @@ def read(rep):
 
 
 def main():
-    d, tag = sys.argv[1], sys.argv[2]
+    d, tags = sys.argv[1], sys.argv[2:]
     res = []
     for name, (what, alg, flops) in CASES.items():
-        rep = os.path.join(d, "%s_%s.ncu-rep" % (tag, name))
-        if not os.path.exists(rep):
+        hits = [(t, os.path.join(d, "%s_%s.ncu-rep" % (t, name))) for t in tags]
+        hits = [(t, r) for t, r in hits if os.path.exists(r)]
+        if not hits:
             continue
+        tag, rep = hits[0]
         m = read(rep)
         m.update({"capture": "%s_%s" % (tag, name), "what": what, "algorithmic_bytes": alg,
                   "dram_bytes": m["dram_read_bytes"] + m["dram_write_bytes"]})

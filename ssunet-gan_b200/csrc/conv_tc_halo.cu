@@ -502,7 +502,8 @@ struct HaloWgradParams {
     int tiles_x, tiles_y, m_tiles;
     int chunks0, chunks1;
     int issuers;                 // 1 or 2 MMA-issuing warps (see the kernel)
-    int splits;                  // split-K factor over the pixel tiles (gridDim.z = splits * passes)
+    int splits0, splits1;        // split-K factors over the pixel tiles of pass 0 / pass 1 (gridDim.z = splits0 + splits1; one pass:
+                                 // splits1 == 0).  Pass 0 carries three tap pairs, pass 1 two: 3 : 2 splits equalise the CTAs' run times
 };
 
 // BN = 64: one pass, five tap-pair accumulators of 64 columns (320 TMEM columns).  Each 128 x 64 x 16 MMA reads 4 KB of A and
@@ -582,10 +583,11 @@ __global__ void __launch_bounds__(H_THREADS, 1) conv_tc_halo_wgrad_kernel(const 
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int chunk = blockIdx.x, co0 = blockIdx.y * BN;
-    const int pass = (C::PASSES == 2) ? (int)(blockIdx.z & 1) : 0;             // BN = 128: tap pairs 0-2 / 3-4
-    const int zsplit = (int)blockIdx.z / C::PASSES;
+    const int pass = (C::PASSES == 2 && (int)blockIdx.z >= p.splits0) ? 1 : 0;          // BN = 128: tap pairs 0-2 / 3-4
+    const int zsplit = pass ? (int)blockIdx.z - p.splits0 : (int)blockIdx.z;
+    const int nsplit = pass ? p.splits1 : p.splits0;
     const int tiles_per_img = p.tiles_x * p.tiles_y;
-    const int n_iter = (p.m_tiles - zsplit + p.splits - 1) / p.splits;
+    const int n_iter = (p.m_tiles - zsplit + nsplit - 1) / nsplit;
     // this CTA's tap pairs and its MMA-issuing warps' shares of them
     const int g_lo = (C::PASSES == 2 && pass == 1) ? 3 : 0;
     const int g_hi = (C::PASSES == 2 && pass == 0) ? 3 : 5;
@@ -605,7 +607,7 @@ __global__ void __launch_bounds__(H_THREADS, 1) conv_tc_halo_wgrad_kernel(const 
     if (warp == 0) {
         if (lane == 0) {
             for (int it = 0; it < n_iter; ++it) {
-                const int t = zsplit + it * p.splits;
+                const int t = zsplit + it * nsplit;
                 const int img = t / tiles_per_img, rem = t - img * tiles_per_img;
                 const int ty = rem / p.tiles_x, tx = rem - ty * p.tiles_x;
                 const int sl = it % C::XS;
@@ -619,7 +621,7 @@ __global__ void __launch_bounds__(H_THREADS, 1) conv_tc_halo_wgrad_kernel(const 
     } else if (warp == 1) {
         if (lane == 0) {
             for (int it = 0; it < n_iter; ++it) {
-                const int t = zsplit + it * p.splits;
+                const int t = zsplit + it * nsplit;
                 const int img = t / tiles_per_img, rem = t - img * tiles_per_img;
                 const int ty = rem / p.tiles_x, tx = rem - ty * p.tiles_x;
                 const int sl = it % C::DS;
@@ -697,12 +699,40 @@ static int launch_wgrad_halo(const CUtensorMap& mx0, const CUtensorMap& mx1, con
         attr_set = true;
     }
     const int co_tiles = (cout_real + BN - 1) / BN;
-    const int ctas = chunks * co_tiles * C::PASSES;
-    int splits = (2 * sm_count_cached() + ctas - 1) / ctas;      // ~two waves of CTAs
-    if (splits > p.m_tiles) splits = p.m_tiles;
-    if (splits < 1) splits = 1;
-    p.splits = splits;
-    dim3 grid((unsigned)chunks, (unsigned)co_tiles, (unsigned)(splits * C::PASSES));
+    const int pairs = chunks * co_tiles;
+    // Split-K factor z = CTAs per (chunk, co tile).  One CTA per SM is resident (shared memory), so CTAs beyond the SM count run
+    // as a second wave -- and every CTA ends with the same fixed-size flush of its accumulators (40 960 fp32 reductions into L2,
+    // ~22 % of a level-0 launch in the ncu source page: profiles/r02_ncu_halo_wgrad_l0.txt).  Pick the z that minimises
+    //     waves(z) * (tiles per CTA + flush), flush expressed in tile times,
+    // instead of round 1's fixed "two waves".
+    const int sms = sm_count_cached();
+    const long long flush_tiles = (BN == 128) ? 40 : 24;
+    int best_z = 1;
+    long long best_cost = -1;
+    const int z_max = (2 * sms + pairs - 1) / pairs + 1;
+    for (int zc = C::PASSES; zc <= z_max && zc <= p.m_tiles * C::PASSES; ++zc) {
+        const long long waves = ((long long)pairs * zc + sms - 1) / sms;
+        const long long per_cta = ((long long)p.m_tiles * C::PASSES + zc - 1) / zc;      // two-pass: z CTAs share 2 x m_tiles tile-passes
+        const long long cost = waves * (per_cta + flush_tiles);
+        if (best_cost < 0 || cost < best_cost) { best_cost = cost; best_z = zc; }
+    }
+    static const int z_env = getenv("SSG_WGRAD_WAVES") ? atoi(getenv("SSG_WGRAD_WAVES")) : 0;      // A/B: 2 = round 1's two waves
+    int z = z_env == 2 ? (2 * sms + pairs - 1) / pairs : best_z;
+    if (C::PASSES == 1) {
+        if (z > p.m_tiles) z = p.m_tiles;
+        if (z < 1) z = 1;
+        p.splits0 = z; p.splits1 = 0;
+    } else {
+        if (z < 2) z = 2;
+        int s0 = (3 * z + 2) / 5;                                 // pass 0: three tap pairs, pass 1: two
+        if (s0 < 1) s0 = 1;
+        int s1 = z - s0;
+        if (s1 < 1) s1 = 1;
+        if (s0 > p.m_tiles) s0 = p.m_tiles;
+        if (s1 > p.m_tiles) s1 = p.m_tiles;
+        p.splits0 = s0; p.splits1 = s1;
+    }
+    dim3 grid((unsigned)chunks, (unsigned)co_tiles, (unsigned)(p.splits0 + p.splits1));
     conv_tc_halo_wgrad_kernel<BN><<<grid, H_THREADS, C::TOTAL, st>>>(mx0, mx1, mdy, p);
     SSG_CHECK_LAUNCH();
     return SSG_OK;
