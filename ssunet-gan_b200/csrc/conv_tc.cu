@@ -652,9 +652,16 @@ static int launch_wgrad(const CUtensorMap& x0, const CUtensorMap& x1, const CUte
     }
     const int groups = (p.units + 2 * C::G - 1) / (2 * C::G);
     const int co_tiles = (p.cout + BN - 1) / BN;
-    int splits = (sm_count_cached() + groups * co_tiles - 1) / (groups * co_tiles);   // ~one CTA per SM (512 TMEM columns each)
-    if (splits > p.m_tiles) splits = p.m_tiles;
-    if (splits < 1) splits = 1;
+    // Split-K factor: one CTA per SM is resident (512 TMEM columns each) and every CTA ends with a fixed-size flush of its
+    // accumulators into L2, so pick the factor that minimises waves * (tiles per CTA + flush) -- see run_wgrad_halo
+    const int pairs = groups * co_tiles, sms = sm_count_cached();
+    int splits = 1;
+    long long best = -1;
+    for (int zc = 1; zc <= (2 * sms + pairs - 1) / pairs + 1 && zc <= p.m_tiles; ++zc) {
+        const long long waves = ((long long)pairs * zc + sms - 1) / sms;
+        const long long cost = waves * ((p.m_tiles + zc - 1) / zc + 24);
+        if (best < 0 || cost < best) { best = cost; splits = zc; }
+    }
     dim3 grid((unsigned)groups, (unsigned)co_tiles, (unsigned)splits);
     conv_tc_wgrad_kernel<BN><<<grid, NUM_THREADS, C::TOTAL, st>>>(x0, x1, dy, p);
     SSG_CHECK_LAUNCH();

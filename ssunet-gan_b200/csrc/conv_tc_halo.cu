@@ -660,6 +660,11 @@ __global__ void __launch_bounds__(H_THREADS, 1) conv_tc_halo_wgrad_kernel(const 
             }
         }
     } else if (warp >= 4) {
+        // ---- flush: fp32 reductions straight from the accumulator registers into dW (OIHW).  (A staged variant -- 32 output
+        // channels at a time through the idle operand rings as [co][ci][tap], then contiguous reductions -- was built, verified
+        // and measured in round 2: no faster at level 0 and 5-30 % slower on the deep layers, where its two block barriers and
+        // the shared-memory round trip outweigh the coalescing.  What the flush costs is its COUNT: see the split-K choice in
+        // launch_wgrad_halo.)
         const int q = warp & 3;
         const int row = q * 32 + lane;                  // accumulator row: tap half (row >> 6), ci (row & 63)
         const int ci = chunk * 64 + (row & 63);
@@ -899,7 +904,8 @@ static int launch_thin_wgrad(const CUtensorMap& mx, const CUtensorMap& mdy, cons
         SSG_CHECK_CUDA(cudaFuncSetAttribute(conv_tc_thin_wgrad_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, TOTAL));
         attr_set = true;
     }
-    int splits = (2 * sm_count_cached() + co_tiles - 1) / co_tiles;      // ~two waves of CTAs
+    // one wave of CTAs (one CTA per SM is resident): a second wave would pay the accumulator flush and the pipeline fill again
+    int splits = sm_count_cached() / co_tiles;
     if (splits > p.m_tiles) splits = p.m_tiles;
     if (splits < 1) splits = 1;
     dim3 grid((unsigned)co_tiles, (unsigned)splits);

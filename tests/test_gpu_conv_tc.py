@@ -92,6 +92,7 @@ THIN = [
     (1, 4, 3, 17, 9, 3, 1),       # roles swapped
     (1, 8, 8, 64, 40, 3, 1),
     (3, 5, 7, 9, 11, 3, 1),       # odd channel counts inside the 8-channel storage
+    (2, 3, 4, 100, 70, 3, 1),     # width not a multiple of the 4- / 8-pixel runs
     (1, 4, 128, 18, 10, 3, 1),    # SPADE gamma|beta at level 0
     (1, 24, 768, 8, 8, 3, 1),     # level 3
     (2, 48, 192, 6, 6, 3, 1),
