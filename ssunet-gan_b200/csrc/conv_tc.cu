@@ -58,21 +58,24 @@ struct ConvTcParams {
     TapClass cls[4];             // blockIdx.z selects the class (merge == 0)
 };
 
-template <int BN>
+// ST: ring depth.  0 = the default, 3 stages (round 1 used 4 below BN = 128: with 3 a third CTA fits per SM, and these CTAs are
+// short -- 9 k-blocks for a stride-2 layer with Cin = 64 -- so residency beats depth: D block 1 forward 0.182 -> 0.163 ms, data
+// gradient 0.311 -> 0.284 ms); SSG_PLAIN_STAGES=2 / 3 overrides (A/B switch)
+template <int BN, int ST = 0>
 struct SmemLayout {
     static constexpr int B_BYTES = BN * BK * 2;
     static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-    static constexpr int STAGES = (BN >= 128) ? 3 : 4;
+    static constexpr int STAGES = ST > 0 ? ST : 3;
     static constexpr int BAR_OFFSET = STAGES * STAGE_BYTES;
     static constexpr int TOTAL = BAR_OFFSET + 256 + 1024;   // + barriers + alignment slack
     static constexpr uint32_t TMEM_COLS = BN < 32 ? 32 : BN;
 };
 
-template <int BN>
+template <int BN, int ST>
 __global__ void __launch_bounds__(NUM_THREADS) conv_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmA0,
                                                                    const __grid_constant__ CUtensorMap tmA1,
                                                                    const __grid_constant__ CUtensorMap tmB, const ConvTcParams p) {
-    using L = SmemLayout<BN>;
+    using L = SmemLayout<BN, ST>;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::BAR_OFFSET);
@@ -271,19 +274,28 @@ int encode_bf16_map(CUtensorMap* map, const void* ptr, int rank, const uint64_t*
 
 static int ilog2_ceil(int v) { int l = 0; while ((1 << l) < v) ++l; return l; }
 
-template <int BN>
-static int launch_fwd(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b, const ConvTcParams& p, int m_tiles,
-                      int n_classes, cudaStream_t st) {
-    using L = SmemLayout<BN>;
+template <int BN, int ST>
+static int launch_fwd_st(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b, const ConvTcParams& p, int m_tiles,
+                         int n_classes, cudaStream_t st) {
+    using L = SmemLayout<BN, ST>;
     static bool attr_set = false;
     if (!attr_set) {
-        SSG_CHECK_CUDA(cudaFuncSetAttribute(conv_tc_fwd_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
+        SSG_CHECK_CUDA(cudaFuncSetAttribute(conv_tc_fwd_kernel<BN, ST>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
         attr_set = true;
     }
     dim3 grid((unsigned)m_tiles, (unsigned)((p.cout + BN - 1) / BN), (unsigned)(p.merge ? 1 : n_classes));
-    conv_tc_fwd_kernel<BN><<<grid, NUM_THREADS, L::TOTAL, st>>>(a0, a1, b, p);
+    conv_tc_fwd_kernel<BN, ST><<<grid, NUM_THREADS, L::TOTAL, st>>>(a0, a1, b, p);
     SSG_CHECK_LAUNCH();
     return SSG_OK;
+}
+
+template <int BN>
+static int launch_fwd(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b, const ConvTcParams& p, int m_tiles,
+                      int n_classes, cudaStream_t st) {
+    static const int st_env = getenv("SSG_PLAIN_STAGES") ? atoi(getenv("SSG_PLAIN_STAGES")) : 0;
+    if (st_env == 2) return launch_fwd_st<BN, 2>(a0, a1, b, p, m_tiles, n_classes, st);
+    if (st_env == 3) return launch_fwd_st<BN, 3>(a0, a1, b, p, m_tiles, n_classes, st);
+    return launch_fwd_st<BN, 0>(a0, a1, b, p, m_tiles, n_classes, st);
 }
 
 }  // namespace tc
