@@ -28,6 +28,8 @@ CASES = {
     # second batch of captures (profiles/capture_r02b.sh): the kernels changed in round 2
     "halo_wgrad128_l1c": ("conv1_1.conv1 weight gradient, 128-wide co tiles in two tap-pair passes", 16 * 256 * 256 * (384 + 128) * 2 + 384 * 128 * 9 * 4,
                           2.0 * 16 * 256 * 256 * 384 * 128 * 9),
+    "halo_wgrad64_l0c": ("conv0_1.conv1 weight gradient (192 -> 64 over the virtual concat), one wave of CTAs", 16 * 512 * 512 * (192 + 64) * 2 + 192 * 64 * 9 * 4,
+                         2.0 * 16 * 512 * 512 * 192 * 64 * 9),
     "halo_wgrad64_l0": ("conv0_0.conv2 weight gradient, two issuing warps", 2 * E + 64 * 64 * 9 * 4, 2.0 * 16 * 512 * 512 * 64 * 64 * 9),
     "s2_dgrad_merged_l0": ("D block1 data gradient, stride 2, four parity classes in one CTA", E + E // 4, 2.0 * 16 * 256 * 256 * 64 * 64 * 9),
     "halo_fwd_l0_2issuers": ("conv0_0.conv2 forward, two issuing warps", 2 * E, 2.0 * 16 * 512 * 512 * 64 * 64 * 9),
