@@ -268,3 +268,28 @@ def test_cat_pair_is_a_tuple_of_two_sources():
     # on the CPU (no tensor-core path) concat_channels refuses rather than silently materialising with torch
     with pytest.raises(ops._lib.SsgError):
         ops.concat_channels(a, b, virtual=True)
+
+
+def test_reference_arm_reproduces_the_survey_scalars():
+    """bench.py's CPU arm drives the reference's OWN modules (baseline/_ref, staged by baseline/make_ref.py) through the literal
+    loop body; on 2 x 3 x 128 x 128 / seed 1234 it must give the six scalars SURVEY.md §8c recorded from the reference."""
+    import importlib.util
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location("ssg_ref_step", os.path.join(root, "baseline", "ref_step.py"))
+    ref_step = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(ref_step)
+    if not ref_step.available():
+        pytest.skip("baseline/_ref is not staged (run python baseline/make_ref.py where /root/reference is visible)")
+    import torch
+
+    def make_batch(b, c, h, w, seed=0):
+        g = torch.Generator().manual_seed(seed)
+        x = torch.randn(b, c, h, w, generator=g)
+        t = (torch.rand(b, 3, h, w, generator=g) > 0.5).float()
+        return x, t
+
+    times, first, init = ref_step.timed_steps(2, 128, steps=1, make_batch=make_batch)
+    want = {"loss": 0.9099170, "content": 1.5091802, "adv_g": 0.6497294, "adv_d": 1.3694998, "iou": 0.32644978, "dice": 0.4970036}
+    for k, v in want.items():
+        assert abs(first[k] - v) < 2e-6 * max(1.0, abs(v)), (k, first[k], v)
+    assert len(init[0]) == 269 and len(times) == 1
