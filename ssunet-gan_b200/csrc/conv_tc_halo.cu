@@ -56,14 +56,16 @@ struct HaloParams {
     int split_c;                 // > 0 (multiple of 64): output channels [0, split_c) go to tmY, [split_c, cout) to tmY1 -- the
                                  // data gradient of a virtually concatenated input lands in its two source tensors
     int issuers;                 // 1 or 2 MMA-issuing warps (2: the item's MT accumulators are split between warps 2 and 3)
+    int lean;                    // resident-weights instances, 3 x 3, one chunk: the straight-line issue path (halo_issue_res3)
 };
 
 // ACCS accumulator sets (2: epilogue overlaps the next item's MMAs).  RES: single-chunk (Cin <= 64) convolutions keep
 // all nine weight tiles of the current N tile resident in shared memory instead of streaming them per work item.
-template <int MT, int BN, int ACCS, bool RES>
+template <int MT, int BN, int ACCS, bool RES, int EW = 1>
 struct HaloCfg {
-    static constexpr int OUT_BYTES = 4 * 4096 + 4 * 512;   // epilogue staging: one 32-pixel x 64-channel bf16 box per warp
-                                                           // + one BN-float bias row per warp
+    static constexpr int THREADS = 128 + 128 * EW;         // four role warps + EW epilogue warp groups
+    static constexpr int OUT_BYTES = EW * (4 * 4096 + 4 * 512);   // epilogue staging: one 32-pixel x 64-channel bf16 box per warp
+                                                                  // + one BN-float bias row per warp
     static constexpr int BUDGET = 227 * 1024 - 256 - 1024 - OUT_BYTES;
     static constexpr int B_BYTES = BN * 128;
     static constexpr int A_STAGE_BYTES = MT * H_A_TILE_STRIDE;
@@ -78,16 +80,17 @@ struct HaloCfg {
     static constexpr int TOTAL = BAR_OFFSET + 256 + 1024;
     static constexpr int ACC_COLS = MT * BN;           // TMEM columns of one accumulator set
     static_assert(ACCS * ACC_COLS <= 512, "accumulator sets must fit in TMEM");
+    static_assert(EW == 1 || (EW == 2 && MT % 2 == 0), "two epilogue groups split an item's M-tiles");
     static_assert(B_SLOTS >= 2 && B_SLOTS <= B_SLOTS_RAW && A_STAGES >= 2, "operand rings do not fit");
     static_assert(TOTAL <= 227 * 1024, "shared memory budget");
 };
 
 // MMA-issue loop of conv_tc_halo_kernel for the M-tiles [mt0, mt0 + MTI) of every work item (MTI == MT: the only issuer).
-template <int MT, int BN, int ACCS, bool RES, int MTI>
+template <int MT, int BN, int ACCS, bool RES, int EW, int MTI>
 __device__ __forceinline__ void halo_issue(uint8_t* smem, uint64_t* a_full, uint64_t* a_empty, uint64_t* b_full, uint64_t* b_empty,
                                            uint64_t* acc_full, uint64_t* acc_empty, uint64_t* b_free, uint32_t tmem_base,
                                            const HaloParams& p, int chunks, int mt0) {
-    using C = HaloCfg<MT, BN, ACCS, RES>;
+    using C = HaloCfg<MT, BN, ACCS, RES, EW>;
     constexpr uint32_t idesc = make_idesc_bf16(128, BN, 0, 0);
     const uint32_t leader = elect_one() ? 1u : 0u;
     const uint32_t a_hi = desc_hi((uint32_t)p.halo_c * 128, 2), b_hi = desc_hi(1024, 2);
@@ -155,13 +158,139 @@ __device__ __forceinline__ void halo_issue(uint8_t* smem, uint64_t* a_full, uint
     }
 }
 
-template <int MT, int BN, int ACCS, bool RES>
-__global__ void __launch_bounds__(H_THREADS, 1) conv_tc_halo_kernel(const __grid_constant__ CUtensorMap tmA0,
-                                                                     const __grid_constant__ CUtensorMap tmA1,
-                                                                     const __grid_constant__ CUtensorMap tmB,
-                                                                     const __grid_constant__ CUtensorMap tmY,
-                                                                     const __grid_constant__ CUtensorMap tmY1, const HaloParams p) {
-    using C = HaloCfg<MT, BN, ACCS, RES>;
+// Lean issue path of the streaming (non-resident) instances: the tap loop is unrolled over the KS x KS compile-time halo offsets, the
+// ring positions are carried as (slot, phase) pairs instead of being re-derived by division, and full 64-channel chunks take a
+// branch-free body.  Same protocol as halo_issue (one b_full wait and one b_empty commit per weight tile).
+template <int MT, int BN, int ACCS, int EW, int MTI, int KS>
+__device__ __forceinline__ void halo_issue_stream(uint8_t* smem, uint64_t* a_full, uint64_t* a_empty, uint64_t* b_full, uint64_t* b_empty,
+                                                  uint64_t* acc_full, uint64_t* acc_empty, uint32_t tmem_base, const HaloParams& p,
+                                                  int chunks, int mt0) {
+    using C = HaloCfg<MT, BN, ACCS, false, EW>;
+    constexpr uint32_t idesc = make_idesc_bf16(128, BN, 0, 0);
+    constexpr int HC = H_TW + KS - 1;
+    constexpr int LAST = ((KS - 1) * HC + KS - 1) * 8;
+    const uint32_t leader = elect_one() ? 1u : 0u;
+    const uint32_t a_hi = desc_hi((uint32_t)HC * 128, 2), b_hi = desc_hi(1024, 2);
+    const uint32_t b_lo_base = desc_lo(smem_u32(smem + C::B_OFFSET), 16);
+    const uint32_t a_lo_base = desc_lo(smem_u32(smem + mt0 * H_A_TILE_STRIDE), 16) + (p.flip ? (uint32_t)LAST : 0u);
+    const int sgn = p.flip ? -1 : 1;
+    int ast = 0, bsl = 0, acc = 0;
+    uint32_t aph = 0, bph = 0, cph = 1;                  // phases of the A ring, the B ring and the accumulator-empty barriers
+    for (int item = blockIdx.x; item < p.total_items; item += gridDim.x) {
+        mbar_wait(&acc_empty[acc], cph);
+        tc_fence_after();
+        const uint32_t d_base = tmem_base + (uint32_t)(acc * C::ACC_COLS + mt0 * BN);
+        for (int ch = 0; ch < chunks; ++ch) {
+            const bool full = ch != chunks - 1 || p.k_last == 4;
+            mbar_wait(&a_full[ast], aph);
+            tc_fence_after();
+            const uint32_t a_st = a_lo_base + (uint32_t)(ast * (C::A_STAGE_BYTES / 16));
+            uint32_t a_row = a_st;
+#pragma unroll 1
+            for (int r = 0; r < KS; ++r, a_row += (uint32_t)(sgn * HC * 8)) {      // filter rows rolled (code size), columns unrolled
+#pragma unroll
+                for (int sx = 0; sx < KS; ++sx) {
+                    mbar_wait(&b_full[bsl], bph);
+                    tc_fence_after();
+                    const uint32_t a_lo = a_row + (uint32_t)(sgn * sx * 8);
+                    const uint32_t b_lo = b_lo_base + (uint32_t)(bsl * (C::B_BYTES / 16));
+                    const uint32_t keep = sx ? 1u : (uint32_t)(ch | r);                            // 0: first k-block of the item
+                    if (full) {
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) {
+#pragma unroll
+                            for (int mt = 0; mt < MTI; ++mt)
+                                umma_bf16_lohi_pred(d_base + (uint32_t)(mt * BN), a_lo + (uint32_t)(mt * (H_A_TILE_STRIDE / 16) + 2 * k), a_hi,
+                                                    b_lo + (uint32_t)(2 * k), b_hi, idesc, k == 0 ? keep : 1u, leader);
+                        }
+                    } else {
+                        for (int k = 0; k < p.k_last; ++k) {
+#pragma unroll
+                            for (int mt = 0; mt < MTI; ++mt)
+                                umma_bf16_lohi_pred(d_base + (uint32_t)(mt * BN), a_lo + (uint32_t)(mt * (H_A_TILE_STRIDE / 16) + 2 * k), a_hi,
+                                                    b_lo + (uint32_t)(2 * k), b_hi, idesc, k == 0 ? keep : 1u, leader);
+                        }
+                    }
+                    umma_commit_pred(&b_empty[bsl], leader);
+                    if (++bsl == C::B_SLOTS) { bsl = 0; bph ^= 1u; }
+                }
+            }
+            umma_commit_pred(&a_empty[ast], leader);
+            if (++ast == C::A_STAGES) { ast = 0; aph ^= 1u; }
+        }
+        umma_commit_pred(&acc_full[acc], leader);
+        if (++acc == ACCS) { acc = 0; cph ^= 1u; }
+    }
+}
+
+// Lean issue path of the resident-weights instances (one 64-channel chunk, 3 x 3 taps): the nine tap offsets, the K steps of the
+// chunk and the weight slots are compile-time, the wait for the resident weights is peeled out of the tap loop, and the body is
+// straight-line code -- 9 * KSTEPS * MTI MMAs per item with one add per descriptor.  The generic loop above spends ~280 cycles per tap
+// on its branches and barrier bookkeeping (ncu source view, profiles/r02_ncu_halo_thin_in_dconv0_fwd.txt): for Cin = 8 that is
+// 2.5 K cycles per item around 0.6 K tensor-clocks of MMAs, for Cin = 64 it equals the MMAs' own 2.3 K tensor-clocks.
+template <int MT, int BN, int ACCS, int EW, int MTI, int KSTEPS>
+__device__ __forceinline__ void halo_issue_res3(uint8_t* smem, uint64_t* a_full, uint64_t* a_empty, uint64_t* b_full, uint64_t* acc_full,
+                                                uint64_t* acc_empty, uint64_t* b_free, uint32_t tmem_base, const HaloParams& p, int mt0) {
+    using C = HaloCfg<MT, BN, ACCS, true, EW>;
+    constexpr uint32_t idesc = make_idesc_bf16(128, BN, 0, 0);
+    constexpr int HC = H_TW + 2;                                   // halo pitch in pixels
+    constexpr int LAST = (2 * HC + 2) * 8;                         // descriptor offset (16-byte units) of halo pixel (2, 2)
+    const uint32_t leader = elect_one() ? 1u : 0u;
+    const uint32_t a_hi = desc_hi((uint32_t)HC * 128, 2), b_hi = desc_hi(1024, 2);
+    const uint32_t b_lo_base = desc_lo(smem_u32(smem + C::B_OFFSET), 16);
+    const uint32_t a_lo_base = desc_lo(smem_u32(smem + mt0 * H_A_TILE_STRIDE), 16) + (p.flip ? (uint32_t)LAST : 0u);
+    const int sgn = p.flip ? -1 : 1;
+    int it = 0, cur_n0 = -1, reloads = 0;
+    for (int item = blockIdx.x; item < p.total_items; item += gridDim.x, ++it) {
+        const int acc = it % ACCS, st = it % C::A_STAGES;
+        const int n0 = (p.n_major ? item / p.supers : item % p.n_tiles) * BN;
+        if (n0 != cur_n0) {                                        // new N tile: its nine weight tiles have been (re)loaded
+            cur_n0 = n0; ++reloads;
+#pragma unroll
+            for (int tap = 0; tap < 9; ++tap) mbar_wait(&b_full[tap], (reloads - 1) & 1);
+        }
+        mbar_wait(&acc_empty[acc], ((it / ACCS) & 1) ^ 1);
+        mbar_wait(&a_full[st], (it / C::A_STAGES) & 1);
+        tc_fence_after();
+        const uint32_t d_base = tmem_base + (uint32_t)(acc * C::ACC_COLS + mt0 * BN);
+        const uint32_t a_st = a_lo_base + (uint32_t)(st * (C::A_STAGE_BYTES / 16));
+#pragma unroll
+        for (int tap = 0; tap < 9; ++tap) {
+            const uint32_t a_lo = a_st + (uint32_t)(sgn * (((tap / 3) * HC + tap % 3) * 8));
+            const uint32_t b_lo = b_lo_base + (uint32_t)(tap * (C::B_BYTES / 16));
+#pragma unroll
+            for (int k = 0; k < KSTEPS; ++k) {
+#pragma unroll
+                for (int mt = 0; mt < MTI; ++mt)
+                    umma_bf16_lohi_pred(d_base + (uint32_t)(mt * BN), a_lo + (uint32_t)(mt * (H_A_TILE_STRIDE / 16) + 2 * k), a_hi,
+                                        b_lo + (uint32_t)(2 * k), b_hi, idesc, (tap | k) ? 1u : 0u, leader);
+            }
+        }
+        umma_commit_pred(&a_empty[st], leader);
+        umma_commit_pred(&acc_full[acc], leader);
+        const int nxt = item + (int)gridDim.x;                     // last item on these weights?  then tell the producer when its MMAs are done
+        if (nxt >= p.total_items || (p.n_major ? nxt / p.supers : nxt % p.n_tiles) * BN != cur_n0) umma_commit_pred(b_free, leader);
+    }
+}
+
+template <int MT, int BN, int ACCS, int EW, int MTI>
+__device__ __forceinline__ void halo_issue_res3_k(uint8_t* smem, uint64_t* a_full, uint64_t* a_empty, uint64_t* b_full, uint64_t* acc_full,
+                                                  uint64_t* acc_empty, uint64_t* b_free, uint32_t tmem_base, const HaloParams& p, int mt0) {
+    switch (p.k_last) {
+        case 1: halo_issue_res3<MT, BN, ACCS, EW, MTI, 1>(smem, a_full, a_empty, b_full, acc_full, acc_empty, b_free, tmem_base, p, mt0); break;
+        case 2: halo_issue_res3<MT, BN, ACCS, EW, MTI, 2>(smem, a_full, a_empty, b_full, acc_full, acc_empty, b_free, tmem_base, p, mt0); break;
+        case 3: halo_issue_res3<MT, BN, ACCS, EW, MTI, 3>(smem, a_full, a_empty, b_full, acc_full, acc_empty, b_free, tmem_base, p, mt0); break;
+        default: halo_issue_res3<MT, BN, ACCS, EW, MTI, 4>(smem, a_full, a_empty, b_full, acc_full, acc_empty, b_free, tmem_base, p, mt0); break;
+    }
+}
+
+template <int MT, int BN, int ACCS, bool RES, int EW>
+__global__ void __launch_bounds__(128 + 128 * EW, 1) conv_tc_halo_kernel(const __grid_constant__ CUtensorMap tmA0,
+                                                                          const __grid_constant__ CUtensorMap tmA1,
+                                                                          const __grid_constant__ CUtensorMap tmB,
+                                                                          const __grid_constant__ CUtensorMap tmY,
+                                                                          const __grid_constant__ CUtensorMap tmY1, const HaloParams p) {
+    using C = HaloCfg<MT, BN, ACCS, RES, EW>;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint64_t* a_full = reinterpret_cast<uint64_t*>(smem + C::BAR_OFFSET);
@@ -181,7 +310,7 @@ __global__ void __launch_bounds__(H_THREADS, 1) conv_tc_halo_kernel(const __grid
         const int ni = (p.issuers == 2 && MT >= 2) ? 2 : 1;     // MMA-issuing warps: arrivals per consumer-side barrier
         for (int i = 0; i < C::A_STAGES; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], ni); }
         for (int i = 0; i < C::B_SLOTS; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], ni); }
-        for (int i = 0; i < ACCS; ++i) { mbar_init(&acc_full[i], ni); mbar_init(&acc_empty[i], 128); }
+        for (int i = 0; i < ACCS; ++i) { mbar_init(&acc_full[i], ni); mbar_init(&acc_empty[i], 128 * EW); }
         mbar_init(b_free, ni);
         fence_barrier_init();
     }
@@ -248,19 +377,49 @@ __global__ void __launch_bounds__(H_THREADS, 1) conv_tc_halo_kernel(const __grid
         // are independent, so the two issue streams need no ordering; each commits its own MMAs to the rings' empty barriers
         // (initialised with one arrival per issuer).  The thin instances (BN = 16: 8 tensor-clocks per MMA) and the BN = 64
         // instances (32 clocks) were paced by ONE warp's descriptor arithmetic on the uniform datapath, not by the tensor pipe.
-        if (p.issuers == 2 && MT >= 2) {
-            halo_issue<MT, BN, ACCS, RES, (MT >= 2 ? MT / 2 : 1)>(smem, a_full, a_empty, b_full, b_empty, acc_full, acc_empty, b_free, tmem_base, p,
+        bool done = false;
+        if constexpr (RES) {
+            if (p.lean) {
+                if (p.issuers == 2 && MT >= 2)
+                    halo_issue_res3_k<MT, BN, ACCS, EW, (MT >= 2 ? MT / 2 : 1)>(smem, a_full, a_empty, b_full, acc_full, acc_empty, b_free, tmem_base,
+                                                                                 p, warp == 2 ? 0 : MT / 2);
+                else
+                    halo_issue_res3_k<MT, BN, ACCS, EW, MT>(smem, a_full, a_empty, b_full, acc_full, acc_empty, b_free, tmem_base, p, 0);
+                done = true;
+            }
+        }
+        if constexpr (!RES) {
+            if (p.lean) {
+                constexpr int MTI2 = MT >= 2 ? MT / 2 : 1;
+                const bool two = p.issuers == 2 && MT >= 2;
+                const int m0 = (two && warp == 3) ? MT / 2 : 0;
+                if (p.ksize == 3) {
+                    if (two) halo_issue_stream<MT, BN, ACCS, EW, MTI2, 3>(smem, a_full, a_empty, b_full, b_empty, acc_full, acc_empty, tmem_base, p, chunks, m0);
+                    else halo_issue_stream<MT, BN, ACCS, EW, MT, 3>(smem, a_full, a_empty, b_full, b_empty, acc_full, acc_empty, tmem_base, p, chunks, 0);
+                } else {
+                    if (two) halo_issue_stream<MT, BN, ACCS, EW, MTI2, 1>(smem, a_full, a_empty, b_full, b_empty, acc_full, acc_empty, tmem_base, p, chunks, m0);
+                    else halo_issue_stream<MT, BN, ACCS, EW, MT, 1>(smem, a_full, a_empty, b_full, b_empty, acc_full, acc_empty, tmem_base, p, chunks, 0);
+                }
+                done = true;
+            }
+        }
+        if (done) {
+        } else if (p.issuers == 2 && MT >= 2) {
+            halo_issue<MT, BN, ACCS, RES, EW, (MT >= 2 ? MT / 2 : 1)>(smem, a_full, a_empty, b_full, b_empty, acc_full, acc_empty, b_free, tmem_base, p,
                                                                    chunks, warp == 2 ? 0 : MT / 2);
         } else {
-            halo_issue<MT, BN, ACCS, RES, MT>(smem, a_full, a_empty, b_full, b_empty, acc_full, acc_empty, b_free, tmem_base, p, chunks, 0);
+            halo_issue<MT, BN, ACCS, RES, EW, MT>(smem, a_full, a_empty, b_full, b_empty, acc_full, acc_empty, b_free, tmem_base, p, chunks, 0);
         }
     } else if (warp >= 4) {
         // ---- epilogue: warp q owns TMEM lanes [32q, 32q + 32) = tile rows 4q .. 4q + 3 (a {64 ch, 8, 4, 1} box of y).
         // TMEM -> registers -> bias / activation -> bf16 -> swizzled smem staging -> ONE TMA store per (tile, 64 channels):
         // full-line coalesced writes, clipped to the image / channel bounds by the TMA unit.
-        const int q = warp & 3;
-        uint8_t* stage = smem + C::OUT_OFFSET + q * 4096;
-        float* bias_s = reinterpret_cast<float*>(smem + C::OUT_OFFSET + 4 * 4096 + q * 512);
+        // EW == 2: a second group of four warps (8..11, the same TMEM lane quarters) takes the odd M-tiles of every item -- with
+        // Cin <= 64 an item's MMAs (<= 2.3 K tensor-clocks) are shorter than ONE warp group's drain of its 2 x 128 x 64 outputs
+        // (~4 K clocks of TMEM load -> convert -> stage -> TMA store latency), so the epilogue paced those layers.
+        const int q = warp & 3, grp = EW == 2 ? ((warp - 4) >> 2) : 0, slot = grp * 4 + q;
+        uint8_t* stage = smem + C::OUT_OFFSET + slot * 4096;
+        float* bias_s = reinterpret_cast<float*>(smem + C::OUT_OFFSET + EW * 4 * 4096 + slot * 512);
         uint8_t* my_row = stage + lane * 128;
         const int sw = lane & 7;
         const bool has_bias = p.bias != nullptr;
@@ -303,7 +462,7 @@ __global__ void __launch_bounds__(H_THREADS, 1) conv_tc_halo_kernel(const __grid
             mbar_wait(&acc_full[acc], (it / ACCS) & 1);
             tc_fence_after();
 #pragma unroll 1
-            for (int mt = 0; mt < MT; ++mt) {
+            for (int mt = grp; mt < MT; mt += EW) {
                 const int t = super * MT + mt;
                 if (t >= p.m_tiles) break;
                 const int img = t / tiles_per_img, rem = t - img * tiles_per_img;
@@ -380,13 +539,13 @@ __global__ void __launch_bounds__(H_THREADS, 1) conv_tc_halo_kernel(const __grid
     if (warp == 2) tmem_dealloc(tmem_base, 512);
 }
 
-template <int MT, int BN, int ACCS, bool RES>
+template <int MT, int BN, int ACCS, bool RES, int EW = 1>
 static int launch_halo(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b, const CUtensorMap& ym, const CUtensorMap& ym1,
                        HaloParams& p, cudaStream_t st) {
-    using C = HaloCfg<MT, BN, ACCS, RES>;
+    using C = HaloCfg<MT, BN, ACCS, RES, EW>;
     static bool attr_set = false;
     if (!attr_set) {
-        SSG_CHECK_CUDA(cudaFuncSetAttribute(conv_tc_halo_kernel<MT, BN, ACCS, RES>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::TOTAL));
+        SSG_CHECK_CUDA(cudaFuncSetAttribute(conv_tc_halo_kernel<MT, BN, ACCS, RES, EW>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::TOTAL));
         attr_set = true;
     }
     p.n_tiles = (p.cout + BN - 1) / BN;
@@ -397,9 +556,13 @@ static int launch_halo(const CUtensorMap& a0, const CUtensorMap& a1, const CUten
     // +6 %); SSG_HALO_ISSUERS=1 restores the single issuer (A/B switch)
     static const int issuers_env = getenv("SSG_HALO_ISSUERS") ? atoi(getenv("SSG_HALO_ISSUERS")) : 2;
     p.issuers = (MT >= 2 && issuers_env != 1) ? 2 : 1;
+    static const bool lean_off = getenv("SSG_HALO_LEAN") && atoi(getenv("SSG_HALO_LEAN")) == 0;       // A/B switch
+    static const bool lean_stream_off = getenv("SSG_HALO_LEAN_STREAM") && atoi(getenv("SSG_HALO_LEAN_STREAM")) == 0;
+    if (RES) p.lean = (p.ksize == 3 && p.chunks0 + p.chunks1 == 1 && !lean_off) ? 1 : 0;
+    else p.lean = ((p.ksize == 3 || p.ksize == 1) && !lean_off && !lean_stream_off) ? 1 : 0;
     int grid = sm_count_cached();
     if (grid > p.total_items) grid = p.total_items;
-    conv_tc_halo_kernel<MT, BN, ACCS, RES><<<grid, H_THREADS, C::TOTAL, st>>>(a0, a1, b, ym, ym1, p);
+    conv_tc_halo_kernel<MT, BN, ACCS, RES, EW><<<grid, C::THREADS, C::TOTAL, st>>>(a0, a1, b, ym, ym1, p);
     SSG_CHECK_LAUNCH();
     return SSG_OK;
 }
@@ -473,6 +636,14 @@ int run_conv_halo(const void* x0, int c0, const void* x1, int c1, const void* w_
     }
     static const char* res_env = getenv("SSG_HALO_RES");          // "264" (default) or "164"
     if (shape == 264 && res_env && atoi(res_env) == 164) return launch_halo<1, 64, 4, true>(ma0, ma1, mb, my, my1, p, st);
+    // Epilogue warp groups of the resident-weights instance.  Thin inputs (<= 32 channels: SPADE's gamma|beta convolution, the
+    // discriminator's first layer) issue <= 18 short MMAs per item and are paced by the drain of the 2 x 128 x 64 outputs: two
+    // groups (0.240 -> 0.162 ms on 16 x 512^2 x 8 -> 64).  With 64 input channels the second group's instructions compete with the
+    // MMA-issuing warps for the same schedulers and the kernel gets SLOWER (0.274 -> 0.310 ms): one group.
+    // SSG_HALO_EPI = 1: always one group, 22: always two (A/B switches)
+    static const int epi_env = getenv("SSG_HALO_EPI") ? atoi(getenv("SSG_HALO_EPI")) : 2;
+    if (shape == 264 && epi_env == 2 && p.k_last <= 2) return launch_halo<2, 64, 2, true, 2>(ma0, ma1, mb, my, my1, p, st);
+    if (shape == 264 && epi_env == 22) return launch_halo<2, 64, 2, true, 2>(ma0, ma1, mb, my, my1, p, st);
     if (shape == 264) return launch_halo<2, 64, 2, true>(ma0, ma1, mb, my, my1, p, st);
     if (shape == 2128) return launch_halo<2, 128, 2, false>(ma0, ma1, mb, my, my1, p, st);
     if (shape == 416) return launch_halo<4, 16, 2, false>(ma0, ma1, mb, my, my1, p, st);
