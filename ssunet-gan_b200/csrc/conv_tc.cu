@@ -252,6 +252,9 @@ int run_wgrad_halo(const void* x0, int c0, const void* x1, int c1, const void* d
                    int n, int h, int w, cudaStream_t st);
 int run_wgrad_thin(const void* x, const void* dy, int cout_s, float* dw, int cout_real, int cin_real, int n, int h, int w,
                    cudaStream_t st);
+bool dgrad_s2_halo_supported(int h, int w, int cin, int cout);
+int run_dgrad_s2_halo(const void* dy, int cout, const void* w_packed, void* dx, int n, int h, int w, int cin, const void* mask,
+                      int mask_act, float mask_slope, cudaStream_t st);
 int encode_bf16_map(CUtensorMap* map, const void* ptr, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
                     const uint32_t* box, CUtensorMapSwizzle swizzle, const uint32_t* elem_strides);
 
@@ -466,6 +469,8 @@ static int dgrad_tc_impl(const void* dy, const void* w_packed, void* dx, int n, 
         // dx[i] = sum_r dy[i + pad - r] W[r]: halo origin i0 - pad, tap r reads halo row (k - 1 - r)
         return run_conv_halo(dy, cout, nullptr, 0, w_packed, ksize * ksize, nullptr, 0, dx, n, h, w, cin, ksize, 1, 0, 0.f, nullptr,
                              (cudaStream_t)s);
+    if (stride == 2 && ksize == 3 && pad == 1 && use_halo_kernel() && dgrad_s2_halo_supported(h, w, cin, cout))
+        return run_dgrad_s2_halo(dy, cout, w_packed, dx, n, h, w, cin, mask, mask_act, mask_slope, (cudaStream_t)s);
     TapClass c[4];
     memset(c, 0, sizeof(c));
     int ncls = 0;

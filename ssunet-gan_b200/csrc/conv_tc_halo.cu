@@ -650,6 +650,317 @@ int run_conv_halo(const void* x0, int c0, const void* x1, int c1, const void* w_
     return launch_halo<4, 64, 2, false>(ma0, ma1, mb, my, my1, p, st);
 }
 
+// =====================================================================================================
+// Data gradient of the 3 x 3 / stride-2 / pad-1 convolutions (the discriminator's down-sampling layers, models_seg_gan.py:38-39)
+// on the halo formulation.  dx[2i + py, 2j + px] = sum over the taps (r, s) with r == 1 (py == 0) or r in {0, 2} (py == 1), same
+// for s / px, of dy[i + (r == 0), j + (s == 0)] W[r][s]: every tap belongs to exactly ONE output-parity class, and all four
+// classes read the same 17 x 9 pixel halo box of dy.  A work item = (16 x 8 tile of dy positions, 64-wide tile of dx channels):
+// ONE TMA box of dy per 64-channel chunk feeds nine MMA groups into FOUR accumulators (one per parity class, 4 x 64 TMEM columns;
+// two sets), and the epilogue stores each class through its own tensor map -- dx seen as {C, W/2, H/2, N} with doubled pixel
+// strides and the base advanced by (py, px) -- so every store is full 128-byte lines.  The plain kernel (conv_tc.cu) loads a shifted
+// dy tile per tap and class (9 x 16 KB + 9 weight tiles per 128 positions: L2-bandwidth bound, profiles/r02_ncu_s2_dgrad_merged_l0.txt).
+// Warps: 0 = dy producer, 1 = weight producer, 2 = issuer of class (1,1)'s four taps, 3 = issuer of the other five taps,
+// 4..11 = two epilogue groups (classes {0, 2} and {1, 3}).  Optional mask: the producer layer's activation backward (act'(out)).
+// =====================================================================================================
+struct S2DgradParams {
+    int N, OH, OW;               // dy dims (tile space)
+    int H, W;                    // dx dims (2 * OH, 2 * OW)
+    int cin;                     // dx channels: GEMM N extent
+    int tiles_x, tiles_y, m_tiles, n_tiles, total_items;
+    int chunks, k_last;          // 64-channel chunks of dy (GEMM K) and live 16-channel K steps of the last one
+    int res;                     // chunks == 1: the nine weight tiles of an N tile stay resident, items walk M fastest
+    const bf16* mask;            // optional, shaped like dx
+    int mask_act;
+    float mask_slope;
+};
+
+struct S2DgradCfg {
+    static constexpr int THREADS = 384;
+    static constexpr int A_STAGE_BYTES = 20480;             // 17 x 9 x 128 B = 19584, rounded up to 1024
+    static constexpr int A_BOX_BYTES = 17 * 9 * 128;
+    static constexpr int A_STAGES = 5;
+    static constexpr int B_BYTES = 64 * 128;
+    static constexpr int B_OFFSET = A_STAGES * A_STAGE_BYTES;
+    static constexpr int OUT_OFFSET = B_OFFSET + 9 * B_BYTES;
+    static constexpr int OUT_BYTES = 8 * 4096;
+    static constexpr int BAR_OFFSET = OUT_OFFSET + OUT_BYTES;
+    static constexpr int TOTAL = BAR_OFFSET + 512 + 1024;
+    static_assert(TOTAL <= 227 * 1024, "shared memory budget");
+};
+
+// tap t = 3 r + s: parity class (r != 1) * 2 + (s != 1), halo offset ((r == 0) * 9 + (s == 0)) pixels, first tap of its class?
+__device__ __forceinline__ constexpr int s2d_class(int t) { return ((t / 3) != 1 ? 2 : 0) + ((t % 3) != 1 ? 1 : 0); }
+__device__ __forceinline__ constexpr int s2d_aoff(int t) { return (((t / 3) == 0 ? 9 : 0) + ((t % 3) == 0 ? 1 : 0)) * 8; }
+__device__ __forceinline__ constexpr bool s2d_first(int t) { return t == 0 || t == 1 || t == 3 || t == 4; }
+
+template <int WHICH>    // 0: the four taps of class (1,1); 1: the other five
+__device__ __forceinline__ void s2d_issue(uint8_t* smem, uint64_t* a_full, uint64_t* a_empty, uint64_t* b_full, uint64_t* b_empty,
+                                          uint64_t* acc_full, uint64_t* acc_empty, uint64_t* b_free, uint32_t tmem_base,
+                                          const S2DgradParams& p) {
+    using C = S2DgradCfg;
+    constexpr uint32_t idesc = make_idesc_bf16(128, 64, 0, 0);
+    const uint32_t leader = elect_one() ? 1u : 0u;
+    const uint32_t a_hi = desc_hi(9 * 128, 2), b_hi = desc_hi(1024, 2);
+    const uint32_t b_lo_base = desc_lo(smem_u32(smem + C::B_OFFSET), 16);
+    const uint32_t a_lo_base = desc_lo(smem_u32(smem), 16);
+    const int supers = p.m_tiles;
+    int ast = 0, acc = 0, cur_n0 = -1, reloads = 0;
+    uint32_t aph = 0, cph = 1, bph = 0;
+    for (int item = blockIdx.x; item < p.total_items; item += gridDim.x) {
+        const int n0 = (p.res ? item / supers : item % p.n_tiles) * 64;
+        bool fresh = !p.res;
+        if (p.res && n0 != cur_n0) { cur_n0 = n0; ++reloads; fresh = true; }
+        mbar_wait(&acc_empty[acc], cph);
+        tc_fence_after();
+        const uint32_t d_base = tmem_base + (uint32_t)(acc * 256);
+        for (int ch = 0; ch < p.chunks; ++ch) {
+            const bool full = ch != p.chunks - 1 || p.k_last == 4;
+            mbar_wait(&a_full[ast], aph);
+            tc_fence_after();
+            const uint32_t a_st = a_lo_base + (uint32_t)(ast * (C::A_STAGE_BYTES / 16));
+#pragma unroll
+            for (int t = 0; t < 9; ++t) {
+                if ((s2d_class(t) == 3) != (WHICH == 0)) continue;
+                if (fresh) {
+                    mbar_wait(&b_full[t], p.res ? (uint32_t)((reloads - 1) & 1) : bph);
+                    tc_fence_after();
+                }
+                const uint32_t a_lo = a_st + (uint32_t)s2d_aoff(t);
+                const uint32_t b_lo = b_lo_base + (uint32_t)(t * (C::B_BYTES / 16));
+                const uint32_t d = d_base + (uint32_t)(s2d_class(t) * 64);
+                const uint32_t keep = s2d_first(t) ? (uint32_t)ch : 1u;
+                if (full) {
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
+                        umma_bf16_lohi_pred(d, a_lo + (uint32_t)(2 * k), a_hi, b_lo + (uint32_t)(2 * k), b_hi, idesc, k == 0 ? keep : 1u, leader);
+                } else {
+                    for (int k = 0; k < p.k_last; ++k)
+                        umma_bf16_lohi_pred(d, a_lo + (uint32_t)(2 * k), a_hi, b_lo + (uint32_t)(2 * k), b_hi, idesc, k == 0 ? keep : 1u, leader);
+                }
+                if (!p.res) umma_commit_pred(&b_empty[t], leader);
+            }
+            umma_commit_pred(&a_empty[ast], leader);
+            if (++ast == C::A_STAGES) { ast = 0; aph ^= 1u; }
+            bph ^= 1u;
+        }
+        umma_commit_pred(&acc_full[acc], leader);
+        if (++acc == 2) { acc = 0; cph ^= 1u; }
+        if (p.res) {
+            const int nxt = item + (int)gridDim.x;
+            if (nxt >= p.total_items || (nxt / supers) * 64 != cur_n0) umma_commit_pred(b_free, leader);
+        }
+    }
+}
+
+__global__ void __launch_bounds__(S2DgradCfg::THREADS, 1) conv_tc_halo_s2dgrad_kernel(const __grid_constant__ CUtensorMap tmA,
+                                                                                        const __grid_constant__ CUtensorMap tmB,
+                                                                                        const __grid_constant__ CUtensorMap tmY0,
+                                                                                        const __grid_constant__ CUtensorMap tmY1,
+                                                                                        const __grid_constant__ CUtensorMap tmY2,
+                                                                                        const __grid_constant__ CUtensorMap tmY3,
+                                                                                        const S2DgradParams p) {
+    using C = S2DgradCfg;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint64_t* a_full = reinterpret_cast<uint64_t*>(smem + C::BAR_OFFSET);
+    uint64_t* a_empty = a_full + C::A_STAGES;
+    uint64_t* b_full = a_empty + C::A_STAGES;
+    uint64_t* b_empty = b_full + 9;
+    uint64_t* acc_full = b_empty + 9;
+    uint64_t* acc_empty = acc_full + 2;
+    uint64_t* b_free = acc_empty + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(b_free + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int tiles_per_img = p.tiles_x * p.tiles_y;
+    const int supers = p.m_tiles;
+
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < C::A_STAGES; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 2); }
+        for (int i = 0; i < 9; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 2); mbar_init(&acc_empty[i], 256); }
+        mbar_init(b_free, 2);
+        fence_barrier_init();
+    }
+    if (warp == 2) tmem_alloc(tmem_slot, 512);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
+
+    if (warp == 0) {
+        if (lane == 0) {
+            tma_prefetch_desc(&tmA);
+            int ast = 0;
+            uint32_t aph = 1;
+            for (int item = blockIdx.x; item < p.total_items; item += gridDim.x) {
+                const int t = p.res ? item % supers : item / p.n_tiles;
+                const int img = t / tiles_per_img, rem = t - img * tiles_per_img;
+                const int ty = rem / p.tiles_x, tx = rem - ty * p.tiles_x;
+                for (int ch = 0; ch < p.chunks; ++ch) {
+                    mbar_wait(&a_empty[ast], aph);
+                    mbar_expect_tx(&a_full[ast], C::A_BOX_BYTES);
+                    tma_load_4d(smem + ast * C::A_STAGE_BYTES, &tmA, ch * 64, tx * H_TW, ty * H_TH, img, &a_full[ast]);
+                    if (++ast == C::A_STAGES) { ast = 0; aph ^= 1u; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            tma_prefetch_desc(&tmB);
+            int cur_n0 = -1, reloads = 0;
+            uint32_t bph = 1;
+            for (int item = blockIdx.x; item < p.total_items; item += gridDim.x) {
+                const int n0 = (p.res ? item / supers : item % p.n_tiles) * 64;
+                if (p.res) {
+                    if (n0 == cur_n0) continue;
+                    if (reloads > 0) mbar_wait(b_free, (uint32_t)((reloads - 1) & 1));
+                    cur_n0 = n0; ++reloads;
+                    for (int t = 0; t < 9; ++t) {
+                        mbar_expect_tx(&b_full[t], C::B_BYTES);
+                        tma_load_3d(smem + C::B_OFFSET + t * C::B_BYTES, &tmB, 0, n0, t, &b_full[t]);
+                    }
+                    continue;
+                }
+                for (int ch = 0; ch < p.chunks; ++ch, bph ^= 1u)
+                    for (int t = 0; t < 9; ++t) {
+                        mbar_wait(&b_empty[t], bph);
+                        mbar_expect_tx(&b_full[t], C::B_BYTES);
+                        tma_load_3d(smem + C::B_OFFSET + t * C::B_BYTES, &tmB, ch * 64, n0, t, &b_full[t]);
+                    }
+            }
+        }
+    } else if (warp == 2) {
+        s2d_issue<0>(smem, a_full, a_empty, b_full, b_empty, acc_full, acc_empty, b_free, tmem_base, p);
+    } else if (warp == 3) {
+        s2d_issue<1>(smem, a_full, a_empty, b_full, b_empty, acc_full, acc_empty, b_free, tmem_base, p);
+    } else {
+        // ---- epilogue: group g = classes {g, g + 2} (px = g, py = 0 / 1); warp q of a group owns tile rows 4q .. 4q + 3 ----
+        const int q = warp & 3, grp = (warp - 4) >> 2, slot = grp * 4 + q;
+        uint8_t* stage = smem + C::OUT_OFFSET + slot * 4096;
+        uint8_t* my_row = stage + lane * 128;
+        const int sw = lane & 7;
+        int acc = 0;
+        uint32_t fph = 0;
+        for (int item = blockIdx.x; item < p.total_items; item += gridDim.x) {
+            const int t = p.res ? item % supers : item / p.n_tiles;
+            const int n0 = (p.res ? item / supers : item % p.n_tiles) * 64;
+            const int img = t / tiles_per_img, rem = t - img * tiles_per_img;
+            const int ty = rem / p.tiles_x, tx = rem - ty * p.tiles_x;
+            const int oy = ty * H_TH + 4 * q + (lane >> 3), ox = tx * H_TW + (lane & 7);       // this lane's dy position
+            const bool pix_ok = oy < p.OH && ox < p.OW;
+            mbar_wait(&acc_full[acc], fph);
+            tc_fence_after();
+#pragma unroll 1
+            for (int py = 0; py < 2; ++py) {
+                const int cls = py * 2 + grp;
+                uint32_t v[64];
+                const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * 256 + cls * 64);
+                tmem_ld_32x32b_x32(t_addr, v);
+                tmem_ld_32x32b_x32(t_addr + 32u, v + 32);
+                tmem_ld_wait();
+                if (p.mask != nullptr && pix_ok) {
+                    const bf16* mrow = p.mask + ((((long long)img * p.H + (2 * oy + py)) * p.W + (2 * ox + grp)) * p.cin + n0);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        if (n0 + j * 8 < p.cin) {
+                            const uint4 m4 = __ldg(reinterpret_cast<const uint4*>(mrow + j * 8));
+                            const uint32_t mw[4] = {m4.x, m4.y, m4.z, m4.w};
+#pragma unroll
+                            for (int e = 0; e < 4; ++e) {
+                                const float m0 = __uint_as_float(mw[e] << 16), m1 = __uint_as_float(mw[e] & 0xffff0000u);
+                                v[j * 8 + 2 * e] = __float_as_uint(__uint_as_float(v[j * 8 + 2 * e]) * act_grad_from_out(m0, p.mask_act, p.mask_slope));
+                                v[j * 8 + 2 * e + 1] =
+                                    __float_as_uint(__uint_as_float(v[j * 8 + 2 * e + 1]) * act_grad_from_out(m1, p.mask_act, p.mask_slope));
+                            }
+                        }
+                    }
+                }
+                if (lane == 0) tma_store_wait_read();
+                __syncwarp();
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    uint32_t w4[4];
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        const __nv_bfloat162 hh = __floats2bfloat162_rn(__uint_as_float(v[j * 8 + 2 * e]), __uint_as_float(v[j * 8 + 2 * e + 1]));
+                        w4[e] = *reinterpret_cast<const uint32_t*>(&hh);
+                    }
+                    *reinterpret_cast<uint4*>(my_row + ((j ^ sw) << 4)) = make_uint4(w4[0], w4[1], w4[2], w4[3]);
+                }
+                fence_proxy_async();
+                __syncwarp();
+                if (lane == 0) {
+                    const CUtensorMap* ymap = cls == 0 ? &tmY0 : (cls == 1 ? &tmY1 : (cls == 2 ? &tmY2 : &tmY3));
+                    tma_store_4d(ymap, stage, n0, tx * H_TW, ty * H_TH + 4 * q, img);
+                    tma_store_commit();
+                }
+            }
+            tc_fence_before();
+            mbar_arrive(&acc_empty[acc]);
+            if (++acc == 2) { acc = 0; fph ^= 1u; }
+        }
+        if (lane == 0) tma_store_wait_all();
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) tmem_dealloc(tmem_base, 512);
+}
+
+bool dgrad_s2_halo_supported(int h, int w, int cin, int cout) {
+    static const bool off = getenv("SSG_S2_HALO") && atoi(getenv("SSG_S2_HALO")) == 0;        // A/B switch: the plain kernel
+    return !off && h % 2 == 0 && w % 2 == 0 && h >= 2 && w >= 2 && cin % 8 == 0 && cout % 8 == 0;
+}
+
+int run_dgrad_s2_halo(const void* dy, int cout, const void* w_packed, void* dx, int n, int h, int w, int cin, const void* mask,
+                      int mask_act, float mask_slope, cudaStream_t st) {
+    using C = S2DgradCfg;
+    S2DgradParams p;
+    memset(&p, 0, sizeof(p));
+    p.N = n; p.H = h; p.W = w; p.OH = h / 2; p.OW = w / 2; p.cin = cin;
+    p.tiles_x = (p.OW + H_TW - 1) / H_TW; p.tiles_y = (p.OH + H_TH - 1) / H_TH; p.m_tiles = n * p.tiles_x * p.tiles_y;
+    p.n_tiles = (cin + 63) / 64;
+    p.total_items = p.m_tiles * p.n_tiles;
+    p.chunks = (cout + 63) / 64;
+    p.k_last = (cout - 64 * (p.chunks - 1) + 15) / 16;
+    p.res = p.chunks == 1 ? 1 : 0;
+    p.mask = (const bf16*)mask; p.mask_act = mask_act; p.mask_slope = mask_slope;
+    CUtensorMap ma, mb, my[4];
+    {
+        uint64_t dims[4] = {(uint64_t)cout, (uint64_t)p.OW, (uint64_t)p.OH, (uint64_t)n};
+        uint64_t str[3] = {(uint64_t)cout * 2, (uint64_t)p.OW * cout * 2, (uint64_t)p.OH * p.OW * cout * 2};
+        uint32_t box[4] = {64, 9, 17, 1};
+        int rc = encode_bf16_map(&ma, dy, 4, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B, nullptr);
+        if (rc) return rc;
+    }
+    {
+        uint64_t dims[3] = {(uint64_t)cout, (uint64_t)cin, 9};
+        uint64_t str[2] = {(uint64_t)cout * 2, (uint64_t)cin * cout * 2};
+        uint32_t box[3] = {64, 64, 1};
+        int rc = encode_bf16_map(&mb, w_packed, 3, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B, nullptr);
+        if (rc) return rc;
+    }
+    for (int cls = 0; cls < 4; ++cls) {
+        const int py = cls >> 1, px = cls & 1;
+        uint64_t dims[4] = {(uint64_t)cin, (uint64_t)p.OW, (uint64_t)p.OH, (uint64_t)n};
+        uint64_t str[3] = {(uint64_t)cin * 4, (uint64_t)w * cin * 4, (uint64_t)h * w * cin * 2};
+        uint32_t box[4] = {64, H_TW, 4, 1};
+        int rc = encode_bf16_map(&my[cls], (const uint8_t*)dx + ((size_t)py * w + px) * cin * 2, 4, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B,
+                                 nullptr);
+        if (rc) return rc;
+    }
+    static bool attr_set = false;
+    if (!attr_set) {
+        SSG_CHECK_CUDA(cudaFuncSetAttribute(conv_tc_halo_s2dgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, C::TOTAL));
+        attr_set = true;
+    }
+    int grid = sm_count_cached();
+    if (grid > p.total_items) grid = p.total_items;
+    conv_tc_halo_s2dgrad_kernel<<<grid, C::THREADS, C::TOTAL, st>>>(ma, mb, my[0], my[1], my[2], my[3], p);
+    SSG_CHECK_LAUNCH();
+    return SSG_OK;
+}
+
 }  // namespace tc
 }  // namespace ssg
 

@@ -34,6 +34,12 @@ CASES = [
     (1, 256, 64, 34, 18, 3, 2),
     (2, 64, 64, 15, 13, 3, 2),    # odd spatial dims: last row / column handled by the parity classes
     (1, 64, 64, 140, 132, 3, 2),  # > 64 output columns: two column tiles
+    # halo-form stride-2 data gradient (even sizes): more work items than SMs; one dy chunk with three dx-channel tiles (resident
+    # weights reloaded mid-CTA); three dy chunks (weights streamed); ragged tiles; channel tails
+    (2, 64, 64, 200, 168, 3, 2),
+    (1, 192, 64, 200, 168, 3, 2),
+    (1, 64, 192, 136, 104, 3, 2),
+    (2, 72, 40, 36, 28, 3, 2),
     # persistent halo kernel: more work items than SMs, several N tiles per CTA (resident-weight reload when Cin <= 64)
     (1, 64, 192, 200, 168, 3),
     (2, 128, 128, 150, 100, 3),
@@ -80,6 +86,33 @@ def test_conv_tc_virtual_concat():
     y = ops.empty_nhwc(2, 64, 20, 20, torch.bfloat16)
     conv_tc.forward(ac, wt.cuda(), None, y, 1, 1, 0, 0.0, x1=bc)
     assert rel(y.float(), yr) < 6e-3
+
+
+@pytest.mark.parametrize("cfg", [(2, 64, 64, 64, 48), (1, 64, 128, 200, 168), (1, 128, 128, 40, 24)])
+def test_conv_tc_stride2_dgrad_carries_producer_activation(cfg):
+    """models_seg_gan.py:38-39,52-57: conv -> LeakyReLU -> stride-2 conv.  The stride-2 data gradient multiplies by the LeakyReLU
+    derivative of the first layer's output in its epilogue (`input_act`); compare with autograd on the unfused fp32 chain."""
+    import ssunet_gan_b200 as ssg
+    from ssunet_gan_b200 import ops
+    n, c1, c2, h, w = cfg
+    ssg.set_compute_dtype(torch.bfloat16)
+    ssg.set_conv_impl("auto")
+    g = torch.Generator().manual_seed(c1 + c2 + h)
+    x = torch.randn(n, 16, h, w, generator=g).bfloat16().float()
+    w1 = (torch.randn(c1, 16, 3, 3, generator=g) / 12.0).bfloat16().float()
+    w2 = (torch.randn(c2, c1, 3, 3, generator=g) / math.sqrt(9 * c1)).bfloat16().float()
+    xr, w1r, w2r = x.clone().requires_grad_(True), w1.clone().requires_grad_(True), w2.clone().requires_grad_(True)
+    yr = F.conv2d(F.leaky_relu(F.conv2d(xr, w1r, None, 1, 1), 0.2), w2r, None, 2, 1)
+    gy = torch.randn(yr.shape, generator=g).bfloat16().float()
+    yr.backward(gy)
+    xc, w1c, w2c = x.cuda().requires_grad_(True), w1.cuda().requires_grad_(True), w2.cuda().requires_grad_(True)
+    mid = ops.conv2d(xc, w1c, None, 1, 1, ops.ACT_LEAKY, 0.2)
+    y = ops.conv2d(mid, w2c, None, 2, 1, ops.ACT_NONE, 0.0, input_act=(ops.ACT_LEAKY, 0.2))
+    y.backward(gy.cuda().bfloat16())
+    assert rel(y.float(), yr) < 8e-3
+    assert rel(xc.grad, xr.grad) < 1.2e-2
+    assert rel(w1c.grad, w1r.grad) < 1.2e-2
+    assert rel(w2c.grad, w2r.grad) < 8e-3
 
 
 THIN = [
