@@ -640,6 +640,7 @@ int run_conv_halo(const void* x0, int c0, const void* x1, int c1, const void* w_
     // discriminator's first layer) issue <= 18 short MMAs per item and are paced by the drain of the 2 x 128 x 64 outputs: two
     // groups (0.240 -> 0.162 ms on 16 x 512^2 x 8 -> 64).  With 64 input channels the second group's instructions compete with the
     // MMA-issuing warps for the same schedulers and the kernel gets SLOWER (0.274 -> 0.310 ms): one group.
+    // (Two groups on the 128-wide streaming instance cost it an operand stage and lose: 0.130 -> 0.172 ms on a 1 x 1 768 -> 256 at 128^2.)
     // SSG_HALO_EPI = 1: always one group, 22: always two (A/B switches)
     static const int epi_env = getenv("SSG_HALO_EPI") ? atoi(getenv("SSG_HALO_EPI")) : 2;
     if (shape == 264 && epi_env == 2 && p.k_last <= 2) return launch_halo<2, 64, 2, true, 2>(ma0, ma1, mb, my, my1, p, st);

@@ -10,7 +10,10 @@ constexpr int MCH = 8;
 // vectors (float4 weights, 4 x bf16 / float4 activations), MROWS batch rows at a time, so every weight element is read
 // once per MROWS rows and feeds MROWS FMAs; block-level tree reduction at the end.  (The first version gave each warp one
 // feature and issued one 2-byte activation load per FMA: 0.58 ms for fc1 at batch 16; the weight read alone is 12 us.)
-constexpr int LIN_JB = 2, LIN_MROWS = 16, LIN_THREADS = 256;
+// JB = 4 features per block: every block re-reads the whole activation matrix from L2 (590 KB for fc1 at batch 16), so with
+// JB = 2 the 512 blocks moved 300 MB of activations around 75 MB of weights (0.124 ms); the k loop is unrolled by two so that
+// eight 16-byte weight loads per thread are in flight.
+constexpr int LIN_JB = 4, LIN_MROWS = 16, LIN_THREADS = 256;
 
 __device__ __forceinline__ void load4f(const float* p, float* f) {
     const float4 v = *reinterpret_cast<const float4*>(p);
@@ -23,7 +26,7 @@ __device__ __forceinline__ void load4f(const bf16* p, float* f) {
 }
 
 template <typename T>
-__global__ void __launch_bounds__(LIN_THREADS) linear_fwd_kernel(const T* __restrict__ x, const float* __restrict__ w,
+__global__ void __launch_bounds__(LIN_THREADS, 2) linear_fwd_kernel(const T* __restrict__ x, const float* __restrict__ w,
                                                                   const float* __restrict__ bias, T* __restrict__ y, int m, int k,
                                                                   int nout, int act, float slope, const float* __restrict__ inv_scale) {
     __shared__ float red[LIN_THREADS / 32][LIN_JB * LIN_MROWS];
@@ -38,13 +41,7 @@ __global__ void __launch_bounds__(LIN_THREADS) linear_fwd_kernel(const T* __rest
 #pragma unroll
             for (int i = 0; i < LIN_MROWS; ++i) acc[j][i] = 0.f;
         if (vec) {
-            for (int kk = threadIdx.x * 4; kk < k; kk += LIN_THREADS * 4) {
-                float wv[LIN_JB][4];
-#pragma unroll
-                for (int j = 0; j < LIN_JB; ++j) {
-                    if (j0 + j < nout) load4f(w + (long long)(j0 + j) * k + kk, wv[j]);
-                    else wv[j][0] = wv[j][1] = wv[j][2] = wv[j][3] = 0.f;
-                }
+            auto body = [&](int kk, const float (&wv)[LIN_JB][4]) {
 #pragma unroll
                 for (int i = 0; i < LIN_MROWS; ++i) {
                     if (m0 + i < m) {
@@ -55,6 +52,26 @@ __global__ void __launch_bounds__(LIN_THREADS) linear_fwd_kernel(const T* __rest
                             acc[j][i] = fmaf(wv[j][0], xv[0], fmaf(wv[j][1], xv[1], fmaf(wv[j][2], xv[2], fmaf(wv[j][3], xv[3], acc[j][i]))));
                     }
                 }
+            };
+            auto loadw = [&](int kk, float (&wv)[LIN_JB][4]) {
+#pragma unroll
+                for (int j = 0; j < LIN_JB; ++j) {
+                    if (j0 + j < nout) load4f(w + (long long)(j0 + j) * k + kk, wv[j]);
+                    else wv[j][0] = wv[j][1] = wv[j][2] = wv[j][3] = 0.f;
+                }
+            };
+            int kk = threadIdx.x * 4;
+            for (; kk + LIN_THREADS * 4 < k; kk += LIN_THREADS * 8) {       // two k positions per trip: 2 x JB weight loads in flight
+                float wa[LIN_JB][4], wb[LIN_JB][4];
+                loadw(kk, wa);
+                loadw(kk + LIN_THREADS * 4, wb);
+                body(kk, wa);
+                body(kk + LIN_THREADS * 4, wb);
+            }
+            for (; kk < k; kk += LIN_THREADS * 4) {
+                float wa[LIN_JB][4];
+                loadw(kk, wa);
+                body(kk, wa);
             }
         } else {
             for (int kk = threadIdx.x; kk < k; kk += LIN_THREADS) {
@@ -194,7 +211,7 @@ __global__ void __launch_bounds__(256) linear_wgrad_kernel(const T* __restrict__
     if (kk < k) {
         for (int i = 0; i < m; ++i) {
             float xv[4];
-            if (kk + 3 < k) load4f(x + (long long)i * k + kk, xv);
+            if (kk + 3 < k && (k & 3) == 0) load4f(x + (long long)i * k + kk, xv);       // rows are 8 / 16-byte aligned only when k % 4 == 0
             else {
 #pragma unroll
                 for (int e = 0; e < 4; ++e) xv[e] = kk + e < k ? to_f(x[(long long)i * k + kk + e]) : 0.f;

@@ -363,3 +363,29 @@ def test_spectral_norm_matches_reference(golden_dir):
     conv(torch.from_numpy(z["x"]).cuda())
     assert torch.equal(u_before, conv.weight_u)          # no power iteration in eval mode
     assert rel(conv.weight, torch.from_numpy(z["w1"])) < 1e-5
+
+
+@pytest.mark.parametrize("cfg", [(16, 18432, 1024), (5, 1000, 37), (3, 103, 5), (20, 4096, 9), (16, 1024, 1)])
+@pytest.mark.parametrize("dt", [torch.float32, torch.bfloat16])
+def test_linear_matches_torch(cfg, dt):
+    """Discriminator head (models_seg_gan.py:277-283: fc 18432 -> 1024, LeakyReLU, fc 1024 -> 1): weight-streaming kernels
+    against F.linear in fp32, forward and all three gradients; vector / scalar k paths, feature tails, more than 16 rows."""
+    from ssunet_gan_b200 import ops
+    m, k, n = cfg
+    g = torch.Generator().manual_seed(m + k + n)
+    x = torch.randn(m, k, generator=g).to(dt).float()
+    w = torch.randn(n, k, generator=g) / math.sqrt(k)
+    b = torch.randn(n, generator=g)
+    xr, wr, br = x.clone().requires_grad_(True), w.clone().requires_grad_(True), b.clone().requires_grad_(True)
+    yr = F.leaky_relu(F.linear(xr, wr, br), 0.2)
+    gy = torch.randn(yr.shape, generator=g).to(dt).float()
+    yr.backward(gy)
+    xc, wc, bc = x.cuda().to(dt).requires_grad_(True), w.cuda().requires_grad_(True), b.cuda().requires_grad_(True)
+    y = ops.linear(xc, wc, bc, ops.ACT_LEAKY, 0.2)
+    y.backward(gy.cuda().to(dt))
+    tol = 1e-5 if dt == torch.float32 else 6e-3
+    rel = lambda a, r: float((a.detach().double().cpu() - r.detach().double()).norm() / (r.detach().double().norm() + 1e-30))
+    assert rel(y.float(), yr) < tol
+    assert rel(xc.grad.float(), xr.grad) < tol
+    assert rel(wc.grad, wr.grad) < tol
+    assert rel(bc.grad, br.grad) < tol
