@@ -850,9 +850,22 @@ __global__ void __launch_bounds__(S2DgradCfg::THREADS, 1) conv_tc_halo_s2dgrad_k
             const int ty = rem / p.tiles_x, tx = rem - ty * p.tiles_x;
             const int oy = ty * H_TH + 4 * q + (lane >> 3), ox = tx * H_TW + (lane & 7);       // this lane's dy position
             const bool pix_ok = oy < p.OH && ox < p.OW;
+            // the producer's output rows of BOTH classes are requested before the wait for the accumulator: their DRAM latency
+            // (the epilogue's only global loads) then overlaps the item's MMAs instead of stalling every store step
+            uint4 mk[2][8];
+            const bool use_mask = p.mask != nullptr && pix_ok;
+            if (use_mask) {
+#pragma unroll
+                for (int py = 0; py < 2; ++py) {
+                    const bf16* mrow = p.mask + ((((long long)img * p.H + (2 * oy + py)) * p.W + (2 * ox + grp)) * p.cin + n0);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j)
+                        mk[py][j] = (n0 + j * 8 < p.cin) ? __ldg(reinterpret_cast<const uint4*>(mrow + j * 8)) : make_uint4(0, 0, 0, 0);
+                }
+            }
             mbar_wait(&acc_full[acc], fph);
             tc_fence_after();
-#pragma unroll 1
+#pragma unroll
             for (int py = 0; py < 2; ++py) {
                 const int cls = py * 2 + grp;
                 uint32_t v[64];
@@ -860,12 +873,11 @@ __global__ void __launch_bounds__(S2DgradCfg::THREADS, 1) conv_tc_halo_s2dgrad_k
                 tmem_ld_32x32b_x32(t_addr, v);
                 tmem_ld_32x32b_x32(t_addr + 32u, v + 32);
                 tmem_ld_wait();
-                if (p.mask != nullptr && pix_ok) {
-                    const bf16* mrow = p.mask + ((((long long)img * p.H + (2 * oy + py)) * p.W + (2 * ox + grp)) * p.cin + n0);
+                if (use_mask) {
 #pragma unroll
                     for (int j = 0; j < 8; ++j) {
                         if (n0 + j * 8 < p.cin) {
-                            const uint4 m4 = __ldg(reinterpret_cast<const uint4*>(mrow + j * 8));
+                            const uint4 m4 = mk[py][j];
                             const uint32_t mw[4] = {m4.x, m4.y, m4.z, m4.w};
 #pragma unroll
                             for (int e = 0; e < 4; ++e) {
