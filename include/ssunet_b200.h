@@ -68,10 +68,11 @@ int ssg_pack_conv_weight_pad(const float* w_oihw, void* dst, int dtype, int layo
 /* Every packed operand of a network refreshed by ONE launch (after the optimiser step: srgan_utils.py:192-195 + Adam changed all
  * weights).  descs_dev: DEVICE array of n_descs records of SSG_PACK_DESC_BYTES bytes, little-endian, no padding:
  *   u64 src (fp32 OIHW), u64 dst, i32 layout, i32 cout, i32 cin, i32 ksize, i32 cout_p, i32 cin_p, i64 first_block
- * `first_block` is the running sum of ceil(cout_p*cin_p*ksize^2 / SSG_PACK_BLOCK_ELEMS) over the preceding records and
- * total_blocks the sum over all of them. */
+ * One block converts one SSG_PACK_TILE x SSG_PACK_TILE (output x input channel) tile with all ksize^2 taps: `first_block` is the
+ * running sum of ceil(cout_p / SSG_PACK_TILE) * ceil(cin_p / SSG_PACK_TILE) over the preceding records and total_blocks the sum
+ * over all of them.  ksize must be 1 or 3 (other kernels: ssg_pack_conv_weight_pad). */
 #define SSG_PACK_DESC_BYTES 48
-#define SSG_PACK_BLOCK_ELEMS 2048
+#define SSG_PACK_TILE 32
 int ssg_pack_conv_weights_multi(const void* descs_dev, int n_descs, long long total_blocks, int dtype, ssg_stream_t s);
 
 /* ---- convolution, CUDA-core implicit GEMM (any shape; the only path for tiny channel counts) */

@@ -147,7 +147,11 @@ __global__ void pack_weight_kernel(const float* __restrict__ w, T* __restrict__ 
 }
 
 // Every packed operand of a network in ONE launch (the per-tensor kernel above costs one launch per weight and layout: ~190 per
-// step).  A block finds its record by binary search over first_block and converts SSG_PACK_BLOCK_ELEMS destination elements.
+// step).  A block finds its record by binary search over first_block and converts ONE tile of SSG_PACK_TILE x SSG_PACK_TILE
+// (output x input) channels with all ks^2 taps through shared memory: the OIHW source is read in contiguous runs of
+// 32 * ks^2 floats per output channel and both destination layouts are written in 32-element runs.  (The first version computed
+// one destination element per thread straight from the source: a 36-byte read stride, i.e. nine L2 sectors fetched per 128
+// useful bytes -- 0.40 ms per step for the generator's 2 x 34 M packed elements; the tile version moves the same bytes once.)
 struct __align__(8) PackDesc {
     const float* src;
     void* dst;
@@ -156,8 +160,42 @@ struct __align__(8) PackDesc {
 };
 static_assert(sizeof(PackDesc) == SSG_PACK_DESC_BYTES, "PackDesc layout is part of the C ABI");
 
+template <typename T, int TAPS>
+__device__ __forceinline__ void pack_tile(const PackDesc& d, int tb, float (*tile)[SSG_PACK_TILE * 9 + 1]) {
+    constexpr int TL = SSG_PACK_TILE, ROW = TL * TAPS;
+    const int tiles_c = (d.cin_p + TL - 1) / TL;
+    const int k0 = (tb / tiles_c) * TL, c0 = (tb % tiles_c) * TL;
+    const int run = (d.cin - c0 < TL ? (d.cin - c0 > 0 ? d.cin - c0 : 0) : TL) * TAPS;     // live floats per source row of the tile
+    const float* src = d.src + ((long long)k0 * d.cin + c0) * TAPS;
+    for (int e = threadIdx.x; e < TL * ROW; e += 256) {
+        const int k = e / ROW, off = e - k * ROW;
+        tile[k][off] = (k0 + k < d.cout && off < run) ? src[(long long)k * d.cin * TAPS + off] : 0.f;
+    }
+    __syncthreads();
+    T* dst = reinterpret_cast<T*>(d.dst);
+    const int lane = threadIdx.x & 31, grp = threadIdx.x >> 5;        // a warp writes one 32-element run; 8 runs per pass
+    if (d.layout == SSG_W_RSKC) {           // [tap][k][c], c fastest
+        if (c0 + lane < d.cin_p) {
+            for (int r = grp; r < TL * TAPS; r += 8) {
+                const int k = r % TL, tap = r / TL;
+                if (k0 + k < d.cout_p) dst[((long long)tap * d.cout_p + k0 + k) * d.cin_p + c0 + lane] = from_f<T>(tile[k][lane * TAPS + tap]);
+            }
+        }
+    } else {                                // [tap][c][k], k fastest (optionally with the taps mirrored)
+        const bool flip = d.layout == SSG_W_RSCK_FLIP;
+        if (k0 + lane < d.cout_p) {
+            for (int r = grp; r < TL * TAPS; r += 8) {
+                const int c = r % TL, tap = r / TL;
+                if (c0 + c < d.cin_p)
+                    dst[((long long)tap * d.cin_p + c0 + c) * d.cout_p + k0 + lane] = from_f<T>(tile[lane][c * TAPS + (flip ? TAPS - 1 - tap : tap)]);
+            }
+        }
+    }
+}
+
 template <typename T>
 __global__ void __launch_bounds__(256) pack_weights_multi_kernel(const PackDesc* __restrict__ descs, int n_descs) {
+    __shared__ float tile[SSG_PACK_TILE][SSG_PACK_TILE * 9 + 1];
     const long long b = blockIdx.x;
     int lo = 0, hi = n_descs - 1;
     while (lo < hi) {                       // last record with first_block <= b
@@ -165,23 +203,8 @@ __global__ void __launch_bounds__(256) pack_weights_multi_kernel(const PackDesc*
         if (descs[mid].first_block <= b) lo = mid; else hi = mid - 1;
     }
     const PackDesc d = descs[lo];
-    const long long total = (long long)d.cout_p * d.cin_p * d.ks * d.ks;
-    const long long base = (b - d.first_block) * SSG_PACK_BLOCK_ELEMS;
-    T* dst = reinterpret_cast<T*>(d.dst);
-#pragma unroll
-    for (int j = 0; j < SSG_PACK_BLOCK_ELEMS / 256; ++j) {
-        const long long i = base + j * 256 + threadIdx.x;
-        if (i >= total) break;
-        int r, s, c, k;
-        long long t = i;
-        if (d.layout == SSG_W_RSKC) {
-            c = (int)(t % d.cin_p); t /= d.cin_p; k = (int)(t % d.cout_p); t /= d.cout_p; s = (int)(t % d.ks); r = (int)(t / d.ks);
-        } else {
-            k = (int)(t % d.cout_p); t /= d.cout_p; c = (int)(t % d.cin_p); t /= d.cin_p; s = (int)(t % d.ks); r = (int)(t / d.ks);
-            if (d.layout == SSG_W_RSCK_FLIP) { r = d.ks - 1 - r; s = d.ks - 1 - s; }
-        }
-        dst[i] = (k < d.cout && c < d.cin) ? from_f<T>(d.src[(((long long)k * d.cin + c) * d.ks + r) * d.ks + s]) : from_f<T>(0.f);
-    }
+    if (d.ks == 3) pack_tile<T, 9>(d, (int)(b - d.first_block), tile);      // ks is 1 or 3 (checked by the caller)
+    else pack_tile<T, 1>(d, (int)(b - d.first_block), tile);
 }
 
 }  // namespace ssg
@@ -275,6 +298,7 @@ int ssg_pack_conv_weight_pad(const float* w, void* dst, int dtype, int layout, i
 }
 int ssg_pack_conv_weights_multi(const void* descs_dev, int n_descs, long long total_blocks, int dtype, ssg_stream_t s) {
     SSG_CHECK_ARG(descs_dev && n_descs > 0 && total_blocks > 0 && total_blocks < (1ll << 31), "pack_conv_weights_multi: bad args");
+    // (records with ksize other than 1 or 3 are not accepted: the caller packs those with ssg_pack_conv_weight_pad)
     SSG_DISPATCH_DTYPE(dtype, pack_weights_multi_kernel<T><<<(unsigned)total_blocks, 256, 0, (cudaStream_t)s>>>((const PackDesc*)descs_dev, n_descs));
     SSG_CHECK_LAUNCH();
     return SSG_OK;

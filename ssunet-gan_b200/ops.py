@@ -190,7 +190,7 @@ class PackRegistry:
 
     def _build_tables(self):
         import struct
-        block = 2048          # SSG_PACK_BLOCK_ELEMS
+        tile = 32             # SSG_PACK_TILE: one block per 32 x 32 channel tile (all taps)
         by_dtype = {}
         for e in self.entries.values():
             by_dtype.setdefault(e["dtype"], []).append(e)
@@ -201,7 +201,7 @@ class PackRegistry:
                 cout, cin, kh, kw = e["w"].shape
                 raw += struct.pack("<QQiiiiiiq", e["w"].data_ptr(), e["out"].data_ptr(), e["layout"], cout, cin, kh, e["cout_p"],
                                    e["cin_p"], first)
-                first += (e["cout_p"] * e["cin_p"] * kh * kw + block - 1) // block
+                first += ((e["cout_p"] + tile - 1) // tile) * ((e["cin_p"] + tile - 1) // tile)
             dev = es[0]["out"].device
             tables.append((dt, torch.frombuffer(raw, dtype=torch.uint8).to(dev), len(es), first, [(e, e["w"].data_ptr()) for e in es]))
         self._tables = tables
@@ -232,7 +232,7 @@ def packed_weight(w, layout, dtype, inv_scale=None, cout_p=None, cin_p=None):
     cout_p = cout_p or w.shape[0]
     cin_p = cin_p or w.shape[1]
     reg = getattr(w, "_ssg_packs", None)
-    if reg is not None and inv_scale is None and w.dim() == 4 and w.shape[2] == w.shape[3]:
+    if reg is not None and inv_scale is None and w.dim() == 4 and w.shape[2] == w.shape[3] and w.shape[2] in (1, 3):
         return reg.get(w, layout, dtype, cout_p, cin_p)
     key = (layout, dtype, cout_p, cin_p)
     token = (w._version, _WEIGHT_EPOCH, w.data_ptr())

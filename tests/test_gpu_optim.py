@@ -150,3 +150,27 @@ def test_graphed_step_follows_param_group_changes():
     assert og._step == 2
     sd = og.state_dict()
     assert float(sd["state"][0]["step"]) == 2.0
+
+
+def test_multi_pack_equals_per_tensor_pack():
+    """`ssg_pack_conv_weights_multi` (one launch, 32 x 32 channel tiles through shared memory) against the per-tensor kernel: all
+    three layouts, 1 x 1 and 3 x 3, channel counts off the tile size, zero-padded channel extents."""
+    from ssunet_gan_b200 import ops
+    from ssunet_gan_b200._lib import W_RSKC, W_RSCK, W_RSCK_FLIP
+    g = torch.Generator(device="cuda").manual_seed(5)
+    reg = ops.PackRegistry()
+    cases = []
+    for (cout, cin, k, cout_p, cin_p) in [(64, 64, 3, 64, 64), (70, 40, 3, 72, 40), (3, 64, 3, 8, 64), (128, 3, 3, 128, 8),
+                                          (200, 96, 1, 200, 96), (33, 31, 1, 40, 32), (8, 8, 3, 8, 8)]:
+        w = torch.randn(cout, cin, k, k, device="cuda", generator=g)
+        for layout in (W_RSKC, W_RSCK, W_RSCK_FLIP):
+            for dt in (torch.bfloat16, torch.float32):
+                cases.append((w, layout, dt, cout_p, cin_p, reg.get(w, layout, dt, cout_p, cin_p)))
+    for c in cases:
+        c[-1].fill_(7.0)               # `get` packed each operand with the per-tensor kernel: wipe it, the multi kernel must rewrite all
+    reg.refresh()
+    for w, layout, dt, cout_p, cin_p, got in cases:
+        cout, cin, k, _ = w.shape
+        ref = torch.empty(cout_p * cin_p * k * k, dtype=dt, device="cuda")
+        ops.call("ssg_pack_conv_weight_pad", w, ref, ops.dtype_code(dt), layout, cout, cin, k, k, cout_p, cin_p, None)
+        assert torch.equal(got, ref), (tuple(w.shape), layout, dt, cout_p, cin_p)
