@@ -20,6 +20,26 @@ from .xresidualblock import xResidualBlock  # noqa: F401
 __all__ = ["UNet", "NestedUNet", "SSUNet", "UNet_ori", "UNet_B_SS", "AttUNet", "UNet_R_SS", "UNet_R_SS_v2"]   # archs.py:8
 
 
+def _fold_eval_bn(conv, bn):
+    """Eval-mode BatchNorm folded into the convolution in front of it (inference only: archs.py:229-231 with running statistics):
+    bn(conv(x, W)) = conv(x, W * s) + (beta - mean * s), s = gamma / sqrt(var + eps).  Cached on the conv module until a weight,
+    a BN parameter or a running statistic changes (in-place updates by replayed graphs / fused optimisers bump ops._WEIGHT_EPOCH)."""
+    key = (conv.weight._version, conv.weight.data_ptr(), bn.weight._version, bn.bias._version, bn.running_mean._version,
+           bn.running_var._version, ops._WEIGHT_EPOCH)
+    hit = getattr(conv, "_ssg_folded_bn", None)
+    if hit is not None and hit[0] == key:
+        return hit[1], hit[2]
+    with torch.no_grad():
+        s = bn.weight.float() * torch.rsqrt(bn.running_var.float() + bn.eps)
+        w = (conv.weight.float() * s.view(-1, 1, 1, 1)).contiguous()
+        b = (bn.bias.float() - bn.running_mean.float() * s).contiguous()
+    conv._ssg_folded_bn = (key, w, b)
+    return w, b
+
+
+FOLD_EVAL_BN = True       # set False to keep the separate eval-mode BN pass (A/B switch for the inference leg)
+
+
 class BasicBlock(nn.Module):
     """relu(bn2(conv2(relu(bn1(conv1 x)))) + shortcut(x))   (archs.py:205-241).
     BN-apply + ReLU and BN-apply + residual-add + ReLU are single fused passes."""
@@ -48,8 +68,14 @@ class BasicBlock(nn.Module):
             x = ops.to_nhwc(x)
         # x feeds conv1 and the 1x1 shortcut: one gradient buffer for both (the second data-gradient kernel adds in its epilogue)
         sink = ops.grad_sink_for(x) if len(self.shortcut) else None
-        y1, s1 = self.conv1(x, want_stats=self.training, dx_sink=sink)  # BN statistics are reduced in the conv epilogue when possible
-        out = self.bn1(y1, act=ACT_RELU, sums=s1)
+        if (FOLD_EVAL_BN and not self.training and not torch.is_grad_enabled() and self.bn1.running_mean is not None
+                and self.bn1.weight is not None):
+            # inference: bn1 + ReLU ride in conv1's epilogue (scaled weights, bias, activation) -- one activation pass less per block
+            w1, b1 = _fold_eval_bn(self.conv1, self.bn1)
+            out = ops.conv2d(x, w1, b1, self.conv1.stride[0], 1, ACT_RELU, 0.0)
+        else:
+            y1, s1 = self.conv1(x, want_stats=self.training, dx_sink=sink)  # BN statistics are reduced in the conv epilogue when possible
+            out = self.bn1(y1, act=ACT_RELU, sums=s1)
         y2, s2 = self.conv2(out, want_stats=self.training)
         sc = self.shortcut[0](x, dx_sink=sink) if len(self.shortcut) else x
         return self.bn2(y2, residual=sc, act=ACT_RELU, sums=s2)

@@ -236,3 +236,45 @@ def test_supervised_step_vs_reference_golden(golden_dir, name, ds, hw, dtype, im
             if sd[key].is_floating_point() and not _bias_before_bn(key):      # those random-walk by +-lr on rounding noise
                 np.testing.assert_allclose(_csum(sd[key])[1:], c[1:], rtol=3e-4, atol=2e-4)
         np.testing.assert_allclose(sd[str(z["probe_key"])].cpu().numpy(), z["probe"], rtol=0, atol=2.1e-4)
+
+
+@pytest.mark.parametrize("dtype,tol", [(torch.float32, 2e-5), (torch.bfloat16, 8e-3)])
+@pytest.mark.parametrize("planes", [(64, 64), (96, 128)])
+def test_basic_block_eval_bn_fold_equals_unfolded(dtype, tol, planes):
+    """Inference: bn1 + ReLU folded into conv1 (scaled weights + bias + activation in the epilogue, archs.py:229-231 with running
+    statistics) against the separate eval-mode BN pass and against torch's fp32 modules; the fold follows later weight changes."""
+    import torch.nn.functional as F
+    import ssunet_gan_b200 as ssg
+    from ssunet_gan_b200 import archs
+    ssg.set_compute_dtype(dtype)
+    cin, cout = planes
+    torch.manual_seed(11)
+    blk = archs.BasicBlock(cin, cout).cuda()
+    with torch.no_grad():
+        for bn in (blk.bn1, blk.bn2):
+            bn.weight.uniform_(0.5, 1.5); bn.bias.normal_(0, 0.3)
+            bn.running_mean.normal_(0, 0.5); bn.running_var.uniform_(0.5, 2.0)
+    blk.eval()
+    x = torch.randn(2, cin, 40, 24, device="cuda")
+
+    def torch_ref():
+        y = F.relu(F.batch_norm(F.conv2d(x, blk.conv1.weight, None, 1, 1), blk.bn1.running_mean, blk.bn1.running_var, blk.bn1.weight,
+                                blk.bn1.bias, False, 0.0, blk.bn1.eps))
+        y = F.batch_norm(F.conv2d(y, blk.conv2.weight, None, 1, 1), blk.bn2.running_mean, blk.bn2.running_var, blk.bn2.weight,
+                         blk.bn2.bias, False, 0.0, blk.bn2.eps)
+        sc = F.conv2d(x, blk.shortcut[0].weight) if len(blk.shortcut) else x
+        return F.relu(y + sc)
+
+    rel = lambda a, b: float((a.float() - b.float()).norm() / b.float().norm())
+    with torch.no_grad():
+        ref = torch_ref()
+        folded = blk(x).float()
+        archs.FOLD_EVAL_BN = False
+        try:
+            plain = blk(x).float()
+        finally:
+            archs.FOLD_EVAL_BN = True
+        assert rel(folded, ref) < tol and rel(plain, ref) < tol
+        blk.conv1.weight.mul_(0.5)                       # the cached fold must notice
+        assert rel(blk(x).float(), torch_ref()) < tol
+    ssg.set_compute_dtype(torch.bfloat16)
