@@ -238,6 +238,7 @@ def test_supervised_step_vs_reference_golden(golden_dir, name, ds, hw, dtype, im
         np.testing.assert_allclose(sd[str(z["probe_key"])].cpu().numpy(), z["probe"], rtol=0, atol=2.1e-4)
 
 
+@pytest.mark.gpu
 @pytest.mark.parametrize("dtype,tol", [(torch.float32, 2e-5), (torch.bfloat16, 8e-3)])
 @pytest.mark.parametrize("planes", [(64, 64), (96, 128)])
 def test_basic_block_eval_bn_fold_equals_unfolded(dtype, tol, planes):
