@@ -514,7 +514,8 @@ def main():
     # (profiles/r02_traffic.json, written by profiles/traffic_from_ncu.py from the .ncu-rep files)
     try:
         tr = json.load(open(os.path.join(ROOT, "profiles", "r02_traffic.json")))["kernels"]
-        top = ([k for k in tr if k["capture"].endswith("halo_fwd_l0_2issuers")] or [k for k in tr if k["capture"].endswith("halo_wgrad_l0")])[0]
+        top = ([k for k in tr if k["capture"].endswith("halo_fwd_l0_lean")] or [k for k in tr if k["capture"].endswith("halo_fwd_l0_2issuers")]
+               or [k for k in tr if k["capture"].endswith("halo_wgrad_l0")])[0]
         roof["traffic"] = top["dram_bytes"]
         roof["traffic_detail"] = {"kernel": top["kernel"], "launch": top["what"], "dram_bytes": top["dram_bytes"],
                                   "algorithmic_bytes": top["algorithmic_bytes"], "source": "profiles/r02_traffic.json (" + top["capture"] + ".ncu-rep)",

@@ -34,6 +34,17 @@ CASES = {
     "s2_dgrad_merged_l0": ("D block1 data gradient, stride 2, four parity classes in one CTA", E + E // 4, 2.0 * 16 * 256 * 256 * 64 * 64 * 9),
     "halo_fwd_l0_2issuers": ("conv0_0.conv2 forward, two issuing warps", 2 * E, 2.0 * 16 * 512 * 512 * 64 * 64 * 9),
     "halo_thin_x2map_fwd": ("SPADE x2map forward 64 -> 3 (stored 8), 16x512x512", E + E // 8, 2.0 * 16 * 512 * 512 * 64 * 3 * 9),
+    # third batch (profiles/capture_r02d.sh, capture_r02e.sh): thin-input forward before / after the straight-line issue path and the
+    # second epilogue group, the level-0 forward after it, the halo-form stride-2 data gradient
+    "halo_thin_in_dconv0_fwd": ("D block0 forward 3 (stored 8) -> 64, 16x512x512, generic issue loop, one epilogue group", E + E // 8,
+                                2.0 * 16 * 512 * 512 * 3 * 64 * 9),
+    "halo_thin_in_gb_fwd": ("SPADE gamma|beta forward 4 (stored 8) -> 128, 16x512x512, generic issue loop, one epilogue group", 2 * E + E // 8,
+                            2.0 * 16 * 512 * 512 * 4 * 128 * 9),
+    "halo_thin_in_dconv0_fwd_lean": ("D block0 forward 3 (stored 8) -> 64, straight-line issue + two epilogue groups", E + E // 8,
+                                     2.0 * 16 * 512 * 512 * 3 * 64 * 9),
+    "halo_fwd_l0_lean": ("conv0_0.conv2 forward, straight-line issue path", 2 * E, 2.0 * 16 * 512 * 512 * 64 * 64 * 9),
+    "s2_dgrad_halo_l0": ("D block1 data gradient, stride 2, halo formulation (one dy box, four class accumulators)", E + E // 4,
+                         2.0 * 16 * 256 * 256 * 64 * 64 * 9),
 }
 
 
