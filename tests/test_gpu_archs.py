@@ -258,15 +258,17 @@ def test_basic_block_eval_bn_fold_equals_unfolded(dtype, tol, planes):
     blk.eval()
     x = torch.randn(2, cin, 40, 24, device="cuda")
 
-    def torch_ref():
-        y = F.relu(F.batch_norm(F.conv2d(x, blk.conv1.weight, None, 1, 1), blk.bn1.running_mean, blk.bn1.running_var, blk.bn1.weight,
-                                blk.bn1.bias, False, 0.0, blk.bn1.eps))
-        y = F.batch_norm(F.conv2d(y, blk.conv2.weight, None, 1, 1), blk.bn2.running_mean, blk.bn2.running_var, blk.bn2.weight,
-                         blk.bn2.bias, False, 0.0, blk.bn2.eps)
-        sc = F.conv2d(x, blk.shortcut[0].weight) if len(blk.shortcut) else x
-        return F.relu(y + sc)
+    def torch_ref():               # float64 on the host (cuDNN's fp32 convolutions default to TF32: 1e-4, not a reference)
+        d = lambda t: t.detach().double().cpu()
+        xd = d(x)
+        y = F.relu(F.batch_norm(F.conv2d(xd, d(blk.conv1.weight), None, 1, 1), d(blk.bn1.running_mean), d(blk.bn1.running_var),
+                                d(blk.bn1.weight), d(blk.bn1.bias), False, 0.0, blk.bn1.eps))
+        y = F.batch_norm(F.conv2d(y, d(blk.conv2.weight), None, 1, 1), d(blk.bn2.running_mean), d(blk.bn2.running_var), d(blk.bn2.weight),
+                         d(blk.bn2.bias), False, 0.0, blk.bn2.eps)
+        sc = F.conv2d(xd, d(blk.shortcut[0].weight)) if len(blk.shortcut) else xd
+        return F.relu(y + sc).cuda()
 
-    rel = lambda a, b: float((a.float() - b.float()).norm() / b.float().norm())
+    rel = lambda a, b: float((a.double() - b.double()).norm() / b.double().norm())
     with torch.no_grad():
         ref = torch_ref()
         folded = blk(x).float()
