@@ -376,7 +376,8 @@ def main():
     # roofline leg: the dominant kernels (tcgen05 convolutions) timed one by one with CUDA events on the launching stream,
     # live, over eager steps of the same workload (a captured graph cannot carry per-kernel events)
     prof_steps = 2
-    PROF = ["ssg_conv2d_fwd_tc", "ssg_conv2d_dgrad_tc", "ssg_conv2d_dgrad_tc_acc", "ssg_conv2d_dgrad_tc_split", "ssg_conv2d_wgrad_tc", "ssg_conv2d_wgrad_tc_acc"]
+    PROF = ["ssg_conv2d_fwd_tc", "ssg_conv2d_dgrad_tc", "ssg_conv2d_dgrad_tc_acc", "ssg_conv2d_dgrad_tc_split", "ssg_conv2d_dgrad_tc_mask",
+            "ssg_conv2d_wgrad_tc", "ssg_conv2d_wgrad_tc_acc"]
     train_step.gan_train_step(g, d, og, od, dev[0][0], dev[0][1], with_metrics="device")
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

@@ -147,13 +147,23 @@ class FusedClampAdam(torch.optim.Optimizer):
         call("ssg_clamp_", self.flat_p, self.flat_p.numel(), float(clip))
         ops.bump_weight_epoch()
 
+    def wait_gradients(self):
+        """Join a gradient all-reduce that a data-parallel wrapper left running on the arena (replicate.py: `async_gradients`):
+        the current stream waits for it (capturable: an event dependency, not a host block)."""
+        work = getattr(self.flat_g, "_ssg_pending", None)
+        if work is not None:
+            work.wait()
+            self.flat_g._ssg_pending = None
+
     def zero_grad(self, set_to_none=False):
         self._check_bindings()
+        self.wait_gradients()
         self.flat_g.zero_()
 
     @torch.no_grad()
     def step(self, closure=None, grad_scale=None):
         self._check_bindings()
+        self.wait_gradients()
         group = self.param_groups[0]
         b1, b2 = group["betas"]
         self._step += 1

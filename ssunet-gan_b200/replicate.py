@@ -49,6 +49,10 @@ class DataParallelWithCallback(nn.Module):
         self.rank = dist.get_rank(process_group) if _dist_ready() else 0
         self.world_size = dist.get_world_size(process_group) if _dist_ready() else 1
         self._grad_hook_armed = False
+        # True: the arena all-reduce is left RUNNING when backward returns (NCCL's stream); optim.FusedClampAdam.step / zero_grad
+        # join it.  train_step.gan_train_step sets it around the generator's backward so that the reduction of G's gradients runs
+        # beside the discriminator phase, which does not read them.
+        self.async_gradients = False
         self._hook_handles = []
         self._params = [p for p in module.parameters() if p.requires_grad]
         if self.world_size > 1:
@@ -94,7 +98,10 @@ class DataParallelWithCallback(nn.Module):
         if arena is not None:
             # SUM over ranks; the 1/world factor rides into the fused clamp+Adam kernel as its gradient scale (applied before the
             # clamp, as averaging before clip_gradient would) instead of a separate pass over the arena
-            dist.all_reduce(arena, op=dist.ReduceOp.SUM, group=self.process_group)
+            if self.async_gradients:
+                arena._ssg_pending = dist.all_reduce(arena, op=dist.ReduceOp.SUM, group=self.process_group, async_op=True)
+            else:
+                dist.all_reduce(arena, op=dist.ReduceOp.SUM, group=self.process_group)
             arena._ssg_grad_scale = 1.0 / self.world_size
             return
         flat = torch.cat([g.reshape(-1) for g in grads])

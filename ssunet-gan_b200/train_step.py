@@ -12,6 +12,7 @@ process per GPU.
 Data parallelism: wrap G and D in `replicate.DataParallelWithCallback` (after
 `batchnorm.convert_model` for SyncBN); gradients are averaged over ranks when backward finishes.
 """
+import os
 from collections import OrderedDict
 
 import torch
@@ -25,6 +26,7 @@ from .srgan_utils import clip_gradient
 ALPA = 1e-4      # train_seg_gan.py:172
 BETA = 1e-3      # train_seg_gan.py:173
 GRAD_CLIP = 0.8  # train_seg_gan.py:174
+OVERLAP_GRAD_SYNC = os.environ.get("SSG_OVERLAP_GRAD_SYNC", "1") != "0"      # see gan_train_step
 
 
 def _set_requires_grad(module, flag, saved=None):
@@ -66,10 +68,27 @@ def gan_train_step(generator, discriminator, optimizer_g, optimizer_d, input, ta
     adversarial_loss = ops.bce_with_logits_const(seg_discriminated, 1.0)       # :204
     perceptual_loss = loss + alpa * content_loss + beta * adversarial_loss     # :205
     optimizer_g.zero_grad()                                                    # :207
-    perceptual_loss.backward()                                                 # :208
-    if grad_clip is not None:
-        clip_gradient(optimizer_g, grad_clip)                                  # :211-212
-    optimizer_g.step()                                                         # :215
+    # Data parallel (replicate.DataParallelWithCallback on a flat-arena optimiser): the all-reduce of G's gradients is left
+    # running on NCCL's stream and G's clamp + Adam moves behind the discriminator phase -- nothing in :217-226 reads G's
+    # parameters or gradients (generator_output is already computed), so the result is the same and the reduction overlaps
+    # D's two forwards and its backward.  OVERLAP_GRAD_SYNC = False keeps the reference's order.
+    overlap = (OVERLAP_GRAD_SYNC and getattr(generator, "world_size", 1) > 1 and hasattr(generator, "async_gradients")
+               and hasattr(optimizer_g, "wait_gradients"))
+    if overlap:
+        generator.async_gradients = True
+    try:
+        perceptual_loss.backward()                                             # :208
+    finally:
+        if overlap:
+            generator.async_gradients = False
+
+    def update_generator():
+        if grad_clip is not None:
+            clip_gradient(optimizer_g, grad_clip)                              # :211-212
+        optimizer_g.step()                                                     # :215
+
+    if not overlap:
+        update_generator()
     adv_g = adversarial_loss.detach()
 
     # ---- discriminator update (train_seg_gan.py:217-233) ----
@@ -78,7 +97,16 @@ def gan_train_step(generator, discriminator, optimizer_g, optimizer_d, input, ta
     adversarial_loss = ops.bce_with_logits_const(sr_discriminated, 0.0) + \
         ops.bce_with_logits_const(hr_discriminated, 1.0)                       # :221-222
     optimizer_d.zero_grad()                                                    # :225
-    adversarial_loss.backward()                                                # :226
+    overlap_d = overlap and getattr(discriminator, "world_size", 1) > 1 and hasattr(discriminator, "async_gradients")
+    if overlap_d:
+        discriminator.async_gradients = True       # D's reduction runs beside G's deferred clamp + Adam + operand re-packing
+    try:
+        adversarial_loss.backward()                                            # :226
+    finally:
+        if overlap_d:
+            discriminator.async_gradients = False
+    if overlap:
+        update_generator()
     if grad_clip is not None:
         clip_gradient(optimizer_d, grad_clip)                                  # :229-230
     optimizer_d.step()                                                         # :233

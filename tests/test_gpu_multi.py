@@ -134,6 +134,21 @@ def _step_worker(rank, world, port, ret):
         res = {"logits": r["logits"].cpu(), "gw": gp.module.net.final.weight.detach().cpu().clone(),
                "dw": dp.module.fc2.weight.detach().cpu().clone(),
                "g_c1": gp.module.net.conv0_0.conv1.weight.detach().cpu().clone()}
+        # the same data-parallel iteration in the reference's order (G's clamp + Adam before the discriminator phase, blocking
+        # all-reduces): the overlapped order used above must land on the same parameters
+        train_step.OVERLAP_GRAD_SYNC = False
+        try:
+            g2, d2 = nets()
+            gp2 = replicate.DataParallelWithCallback(batchnorm.convert_model(g2))
+            dp2 = replicate.DataParallelWithCallback(batchnorm.convert_model(d2))
+            og2 = optim.FusedClampAdam(gp2.parameters(), lr=2e-5)
+            od2 = optim.FusedClampAdam(dp2.parameters(), lr=2e-5)
+            train_step.gan_train_step(gp2, dp2, og2, od2, x[sl].cuda(), t[sl].cuda(), with_metrics=False)
+            res["seq_gw"] = gp2.module.net.final.weight.detach().cpu().clone()
+            res["seq_dw"] = dp2.module.fc2.weight.detach().cpu().clone()
+            res["seq_g_c1"] = gp2.module.net.conv0_0.conv1.weight.detach().cpu().clone()
+        finally:
+            train_step.OVERLAP_GRAD_SYNC = True
         if rank == 0:
             # the same iteration on the whole batch, one device, plain (unsynchronised) BatchNorm
             g1, d1 = nets()
@@ -170,6 +185,11 @@ def test_gan_step_data_parallel_matches_full_batch(world):
         assert err < 1e-2, "rank %d logits differ from the full-batch run: %.3e" % (rank, err)
         # every rank took the same (averaged-gradient) Adam step: parameters identical across ranks
         assert torch.equal(ret[rank]["gw"], ret[0]["gw"]) and torch.equal(ret[rank]["dw"], ret[0]["dw"])
+        # overlapped gradient all-reduce (G's update behind the discriminator phase) == the sequential order, up to the
+        # atomics' summation order: an Adam step moves an element by <= lr = 2e-5, so a sign flip of a ~0 gradient costs <= 4e-5
+        for k in ("gw", "dw", "g_c1"):
+            dlt = (ret[rank][k].double() - ret[rank]["seq_" + k].double()).abs()
+            assert float(dlt.max()) <= 4.1e-5 and float(dlt.mean()) < 2e-7, (k, float(dlt.max()), float(dlt.mean()))
     # and that step is the full-batch step: one Adam update moves every element by <= lr, in the same direction
     for k in ("gw", "dw", "g_c1"):
         a, b = full[k], full["full_" + k]
