@@ -293,3 +293,24 @@ def test_reference_arm_reproduces_the_survey_scalars():
     for k, v in want.items():
         assert abs(first[k] - v) < 2e-6 * max(1.0, abs(v)), (k, first[k], v)
     assert len(init[0]) == 269 and len(times) == 1
+
+
+def test_eval_bn_fold_math_on_cpu():
+    """archs._fold_eval_bn (inference: bn1 folded into conv1, archs.py:229-231 with running statistics) is plain tensor algebra:
+    conv(x, W * s) + (beta - mean * s) == bn_eval(conv(x, W)); and the cache follows in-place weight changes."""
+    import torch.nn.functional as F
+    from ssunet_gan_b200 import archs
+    torch.manual_seed(3)
+    conv = torch.nn.Conv2d(5, 7, 3, padding=1, bias=False)
+    bn = torch.nn.BatchNorm2d(7)
+    with torch.no_grad():
+        bn.weight.uniform_(0.5, 1.5); bn.bias.normal_(); bn.running_mean.normal_(); bn.running_var.uniform_(0.5, 2.0)
+    bn.eval()
+    x = torch.randn(2, 5, 9, 11)
+    w, b = archs._fold_eval_bn(conv, bn)
+    with torch.no_grad():
+        assert torch.allclose(F.conv2d(x, w, b, 1, 1), bn(conv(x)), atol=1e-5)
+        assert archs._fold_eval_bn(conv, bn)[0] is w                      # cached
+        conv.weight.mul_(2.0)                                             # version counter moves: recomputed
+        w2, b2 = archs._fold_eval_bn(conv, bn)
+        assert w2 is not w and torch.allclose(F.conv2d(x, w2, b2, 1, 1), bn(conv(x)), atol=1e-5)
