@@ -12,7 +12,7 @@ SHAPES = [  # name, cin, cout, hw, k, stride
     ("conv4_1.conv1", 1024, 512, 32, 3, 1), ("conv5_0.conv2", 768, 768, 16, 3, 1), ("short1_1 1x1", 384, 128, 256, 1, 1),
     ("D.block1 s2", 64, 64, 512, 3, 2), ("D.block3 s2", 128, 128, 256, 3, 2), ("spade gb L0", 8, 128, 512, 3, 1), ("x2map L0", 64, 8, 512, 3, 1),
     ("D.conv0", 8, 64, 512, 3, 1), ("spade gb L1", 8, 256, 256, 3, 1), ("conv0_0 dgradsplit", 192, 64, 512, 3, 1),
-    ("short0_1 1x1", 192, 64, 512, 1, 1), ("short2_1 1x1", 768, 256, 128, 1, 1),
+    ("final 1x1", 64, 8, 512, 1, 1), ("short0_1 1x1", 192, 64, 512, 1, 1), ("short2_1 1x1", 768, 256, 128, 1, 1),
 ]
 which = sys.argv[1:] or ["fwd", "dgrad", "wgrad"]
 ONLY = os.environ.get("ONLY")

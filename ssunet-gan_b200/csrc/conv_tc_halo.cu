@@ -471,13 +471,22 @@ __global__ void __launch_bounds__(128 + 128 * EW, 1) conv_tc_halo_kernel(const _
 #pragma unroll
                 for (int h0 = 0; h0 < BN; h0 += 64) {
                     if (n0 + h0 >= p.cout) break;
+                    // thin outputs (BN = 16: SPADE's x2map, the logits head, data gradients into 8-channel maps): only the 16 live
+                    // accumulator columns are read, converted and staged -- the store's other channels are clipped by the TMA
+                    // unit anyway (a full 64-column step per M-tile made these instances epilogue-bound: 4 steps per item)
+                    constexpr int CW = BN < 64 ? BN : 64, NJ = CW / 8;
                     uint32_t v[64];
-                    tmem_ld_32x32b_x32(t_addr + (uint32_t)h0, v);
-                    tmem_ld_32x32b_x32(t_addr + (uint32_t)(h0 + 32), v + 32);
+                    if constexpr (CW == 64) {
+                        tmem_ld_32x32b_x32(t_addr + (uint32_t)h0, v);
+                        tmem_ld_32x32b_x32(t_addr + (uint32_t)(h0 + 32), v + 32);
+                    } else {
+                        static_assert(CW == 16, "narrow epilogue: BN = 16");
+                        tmem_ld_32x32b_x16(t_addr + (uint32_t)h0, v);
+                    }
                     tmem_ld_wait();
                     if (has_bias) {
 #pragma unroll
-                        for (int e = 0; e < 64; e += 4) {
+                        for (int e = 0; e < CW; e += 4) {
                             const float4 b4 = *reinterpret_cast<const float4*>(bias_s + h0 + e);
                             v[e] = __float_as_uint(__uint_as_float(v[e]) + b4.x);
                             v[e + 1] = __float_as_uint(__uint_as_float(v[e + 1]) + b4.y);
@@ -488,7 +497,7 @@ __global__ void __launch_bounds__(128 + 128 * EW, 1) conv_tc_halo_kernel(const _
                     if (lane == 0) tma_store_wait_read();          // the previous store has finished reading the staging box
                     __syncwarp();
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) {                   // 8 channels = one 16-byte chunk
+                    for (int j = 0; j < NJ; ++j) {                  // 8 channels = one 16-byte chunk
                         uint32_t w4[4];
 #pragma unroll
                         for (int e = 0; e < 4; ++e) {
