@@ -314,3 +314,35 @@ def test_eval_bn_fold_math_on_cpu():
         conv.weight.mul_(2.0)                                             # version counter moves: recomputed
         w2, b2 = archs._fold_eval_bn(conv, bn)
         assert w2 is not w and torch.allclose(F.conv2d(x, w2, b2, 1, 1), bn(conv(x)), atol=1e-5)
+
+
+def test_stride2_dgrad_parity_class_table_on_cpu():
+    """The tap -> (output-parity class, dy offset) table of csrc/conv_tc_halo.cu's stride-2 data-gradient kernel
+    (`s2d_class`, `s2d_aoff`, `s2d_first`), restated in numpy and checked against autograd of F.conv2d(stride 2, pad 1):
+    dx[2i + py, 2j + px] = sum over the taps of class (py, px) of dy[i + (r == 0), j + (s == 0)] . W[r][s]  (models_seg_gan.py:38-39)."""
+    import torch.nn.functional as F
+    torch.manual_seed(7)
+    n, cin, cout, h, w = 2, 5, 4, 12, 8
+    x = torch.randn(n, cin, h, w, dtype=torch.float64, requires_grad=True)
+    wt = torch.randn(cout, cin, 3, 3, dtype=torch.float64)
+    y = F.conv2d(x, wt, None, 2, 1)
+    dy = torch.randn_like(y)
+    y.backward(dy)
+    oh, ow = h // 2, w // 2
+    dyp = np.zeros((n, cout, oh + 1, ow + 1))                       # the halo box: one extra row / column, zero outside the image
+    dyp[:, :, :oh, :ow] = dy.numpy()
+    wn = wt.numpy()
+    dx = np.zeros((n, cin, h, w))
+    seen = {}
+    for t in range(9):
+        r, s = divmod(t, 3)
+        cls = (2 if r != 1 else 0) + (1 if s != 1 else 0)           # s2d_class
+        di, dj = int(r == 0), int(s == 0)                           # s2d_aoff = (di * 9 + dj) pixels of the 17 x 9 halo box
+        first = t in (0, 1, 3, 4)                                   # s2d_first
+        assert first == (cls not in seen)
+        seen[cls] = True
+        py, px = cls >> 1, cls & 1
+        contrib = np.einsum("nkij,kc->ncij", dyp[:, :, di:di + oh, dj:dj + ow], wn[:, :, r, s])
+        dx[:, :, py::2, px::2] += contrib
+    assert sorted(seen) == [0, 1, 2, 3]
+    assert np.allclose(dx, x.grad.numpy(), atol=1e-10)
