@@ -197,7 +197,7 @@ def run_reference(args, cfg):
 
 def workload_name(cfg, batch, size, world):
     return ("seg-GAN G+D step: UNet_R_SS_v2 (config_v1, input_channels=%d) + SRGAN discriminator, batch %d x %d x %d x %d per GPU%s [BASELINE %s]"
-            % (cfg["cin"], batch, cfg["cin"], size, size, "" if world == 1 else ", SyncBN statistics over NVLink peer memory + NCCL gradient all-reduce",
+            % (cfg["cin"], batch, cfg["cin"], size, size, "" if world == 1 else ", SyncBN statistics over NVLink peer memory + NCCL gradient all-reduces beside the discriminator phase",
                cfg["baseline"]))
 
 
